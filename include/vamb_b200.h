@@ -1,0 +1,114 @@
+/* vamb_b200 -- C ABI of the B200 (sm_100a) kernels behind the vamb hot path.
+ *
+ * Drop-in boundary.  The reference (RasmussenLab/vamb) is
+ * pure Python + PyTorch and has no FFI of its own; the functions below are what a
+ * ctypes binding inside vamb/encode.py and vamb/cluster.py would bind to replace the
+ * tensor expressions cited next to each entry point.  INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / C++ types.  Pointers are DEVICE pointers
+ *     unless the name ends in `_host` (then: pinned host memory).
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), except
+ *     the `*_sync` entry points, which end with one cudaStreamSynchronize.
+ *   - return value: 0 = ok, non-zero = failure; vk_last_error() (thread-local) has the
+ *     message.  Nothing throws, nothing allocates persistent device memory: all
+ *     buffers are owned by the caller (the Python host code holds them as tensors).
+ *   - "vk arithmetic v1"  fixes the floating-point evaluation
+ *     order of every reduction so that results are bit-identical to oracle/.
+ */
+#ifndef VAMB_B200_H
+#define VAMB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VK_ABI_VERSION 1
+#define VK_NBINS 60          /* ceil(0.3 / 0.005), vamb/cluster.py:231 */
+#define VK_MAX_CAND 32       /* candidates evaluated per vk_eval_candidates launch */
+#define VK_PROBE_INLINE 2040 /* `within` ids returned inline with the probe header */
+
+const char *vk_last_error(void);
+int vk_abi_version(void);
+/* sm_100a-only build: returns 0 when the current device can run these kernels. */
+int vk_check_device(void);
+
+/* ------------------------------------------------------------------ clustering */
+
+/* Result header of one probe; lives in device memory, copied to pinned host memory.
+ * All sums are exact integers, hence independent of the order of accumulation. */
+typedef struct vk_probe_header {
+    uint64_t density_fx;      /* sum len_i * (0.05f - d_i) over kept rows with d_i <= 0.05f, units 2^-29 */
+    uint64_t hist[VK_NBINS];  /* sum of len_i per distance bin over kept rows with 0 <= d_i <= 0.3f       */
+    int32_t n_within;         /* kept rows with d <= 0.05f  (cluster.py:625)                               */
+    int32_t n_lt;             /* kept rows with d <  0.05f  (cluster.py:457, loner test)                   */
+    int32_t n_nl;             /* kept rows with d <= nl_radius (entries appended to the neighbour list)    */
+    int32_t rank;             /* kept rows with row index < medoid row (the reference's packed index)      */
+    int32_t within[VK_PROBE_INLINE]; /* unordered row ids with d <= 0.05f (first VK_PROBE_INLINE of them)  */
+} vk_probe_header;
+
+/* vamb/cluster.py:653-669 (_normalize), in place: zero rows -> 1/D, row /= (|row| * sqrt 2). */
+int vk_normalize_rows(float *matrix, int64_t n, int d, void *stream);
+
+/* Per-row check that 2*|row|^2 is within `tol` of 1; *n_bad (device int32) receives the count. */
+int vk_check_normalized(const float *matrix, int64_t n, int d, float tol, int32_t *n_bad, void *stream);
+
+/* One seed->all-contigs pass: vamb/cluster.py:672-676 (_calc_distances) fused with
+ * :619-629 (within-radius set + local density), :457-481 (loner count + weighted
+ * histogram) and the collection of the neighbour list {kept rows with d <= nl_radius}
+ * that vk_eval_candidates / vk_select_members consume.  `edges` = the 61 fp32 bin edges.
+ * `hdr` is zeroed by the call.  within ids beyond VK_PROBE_INLINE go to `within_overflow`
+ * (capacity n) at positions [VK_PROBE_INLINE, n_within). */
+int vk_probe(const float *matrix, const float *lengths, const uint8_t *kept, int64_t n, int d,
+             int64_t medoid_row, float nl_radius, const float *edges,
+             vk_probe_header *hdr, int32_t *within_overflow,
+             int32_t *nl_rows, float *nl_dists, void *stream);
+
+/* vk_probe + copy of the header to `hdr_host` (pinned) + stream synchronize. */
+int vk_probe_sync(const float *matrix, const float *lengths, const uint8_t *kept, int64_t n, int d,
+                  int64_t medoid_row, float nl_radius, const float *edges,
+                  vk_probe_header *hdr, int32_t *within_overflow,
+                  int32_t *nl_rows, float *nl_dists, vk_probe_header *hdr_host, void *stream);
+
+/* Local densities of up to VK_MAX_CAND candidate medoids in one pass over the neighbour
+ * list (the <= maxsteps sample_medoid calls of one wander_medoid round,
+ * vamb/cluster.py:427-448, whose densities are independent of each other).  Only list
+ * entries with nl_dists <= prune_radius are visited (a row within 0.05 of
+ * a candidate that is itself within 0.05 of the medoid lies within 0.19 of the medoid).
+ * out_host[k] = density_fx of candidate k (pinned host, 2*VK_MAX_CAND uint64: densities
+ * then counts).  Ends with a stream synchronize. */
+int vk_eval_candidates_sync(const float *matrix, const float *lengths, int d,
+                            const int32_t *nl_rows, const float *nl_dists, int32_t n_nl,
+                            float prune_radius, const int32_t *cand_rows_host, int n_cand,
+                            uint64_t *out_dev, uint64_t *out_host, void *stream);
+
+/* vamb/cluster.py:640-650 (_smaller_indices) + :308-309 (kept_mask[point] = 0):
+ * appends orig_ids[row] of every neighbour-list entry with d <= threshold to `members`
+ * (unordered), clears kept[row], returns the count through members_host[0] and the ids
+ * through members_host[1..] (pinned, capacity_host int32 entries; ids beyond that stay in
+ * `members` on the device).  Ends with a stream synchronize. */
+int vk_select_members_sync(const int32_t *nl_rows, const float *nl_dists, int32_t n_nl, float threshold,
+                           const int32_t *orig_ids, uint8_t *kept, int32_t *members /* [1 + n_nl] */,
+                           int32_t *members_host, int32_t capacity_host, void *stream);
+
+/* kept[rows[i]] = 0 for i < n (rows: device int32). */
+int vk_mask_clear(uint8_t *kept, const int32_t *rows, int32_t n, void *stream);
+
+/* vamb/cluster.py:318-335 (pack) / vambcore.overwrite_matrix: stable row compaction of
+ * (matrix, lengths, orig_ids) by `kept` into the *_out buffers; kept_out[0..n_out) = 1.
+ * tile_scratch: int32[2 + ceil(n / 1024)].  *n_out_host (pinned int64) receives the new
+ * row count.  Ends with a stream synchronize. */
+int vk_compact_rows_sync(const float *matrix, const float *lengths, const int32_t *orig_ids,
+                         const uint8_t *kept, int64_t n, int d,
+                         float *matrix_out, float *lengths_out, int32_t *orig_out, uint8_t *kept_out,
+                         int32_t *tile_scratch, int64_t *n_out_host, void *stream);
+
+/* Full distance vector (vamb/cluster.py:672-676) -- used by tests and the roofline bench. */
+int vk_distances(const float *matrix, int64_t n, int d, int64_t medoid_row, float *dists, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAMB_B200_H */

@@ -1,0 +1,76 @@
+"""CPU suite for the drop-in boundary: the C-ABI library loads and exports every declared
+symbol, and argument validation raises the reference's exceptions before any GPU work."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from vamb_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "vamb_b200.h")).read()
+    declared = set(re.findall(r"\b(vk_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(_lib.lib, name), f"{name} declared in include/vamb_b200.h but not exported"
+    assert declared == set(_lib.declared_symbols())
+    assert _lib.lib.vk_abi_version() == _lib.VK_ABI_VERSION
+
+
+def test_probe_header_layout_matches_binding():
+    from vamb_b200 import _lib
+
+    assert _lib.HDR_SIZE == 8 + 8 * 60 + 16 + 4 * _lib.VK_PROBE_INLINE
+
+
+def test_no_cpu_fallback():
+    import torch
+    from vamb_b200 import _lib
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.VkError):
+        _lib.require_device()
+
+
+class TestClusterBadParams:
+    # test/test_cluster.py:15-36
+    rng = np.random.RandomState(5)
+    data = rng.random((64, 40)).astype(np.float32)
+    lens = rng.randint(500, 1000, size=64)
+
+    def test_bad_params(self):
+        import vamb_b200.cluster as vc
+
+        with pytest.raises(ValueError):
+            vc.ClusterGenerator(self.data.astype(np.float64), self.lens)
+        with pytest.raises(ValueError):
+            vc.ClusterGenerator(self.data, self.lens, maxsteps=0)
+        with pytest.raises(ValueError):
+            vc.ClusterGenerator(self.data, self.lens, windowsize=0)
+        with pytest.raises(ValueError):
+            vc.ClusterGenerator(self.data, self.lens, minsuccesses=0)
+        with pytest.raises(ValueError):
+            vc.ClusterGenerator(self.data, self.lens, minsuccesses=5, windowsize=4)
+        with pytest.raises(ValueError):
+            vc.ClusterGenerator(np.random.random((0, 40)), np.array([], dtype=int))
+        with pytest.raises(ValueError):
+            vc.ClusterGenerator(self.data, self.lens[:-1])
+
+    def test_cluster_kind(self):
+        import vamb_b200.cluster as vc
+
+        assert vc.Cluster(1, 0, np.array([1]), 0.1, None, None, 0, 0).kind_str == "loner"
+        assert vc.Cluster(1, 0, np.array([1]), 0.1, None, 0.06, 0, 0).kind_str == "fallback"
+        assert vc.Cluster(1, 0, np.array([1]), 0.1, 0.3, 0.04, 0, 0).kind_str == "normal"
+
+    def test_edges_and_pdf_match_oracle(self):
+        import vamb_b200.cluster as vc
+        from oracle import cluster_oracle as co
+
+        assert np.array_equal(vc._histogram_edges(), co.linspace_edges())
+        assert np.array_equal(vc._NORMALPDF, co.NORMALPDF)

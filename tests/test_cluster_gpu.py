@@ -1,0 +1,203 @@
+"""GPU suite: the CUDA clusterer (through the C ABI) against the oracle and the golden
+fixtures made by the reference.  Integer / index results are compared bit-exactly."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from tests import _util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vk():
+    from vamb_b200 import _lib
+
+    _lib.require_device()
+    return _lib
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("d", [3, 32, 40, 283])
+def test_normalize_and_distances_bit_exact(vk, d):
+    from oracle import cluster_oracle as co
+
+    rng = np.random.default_rng(d)
+    n = 20011
+    m = rng.standard_normal((n, d)).astype(np.float32)
+    m[5] = 0.0
+    host = m.copy()
+    co.normalize(host)
+    dm = _dev(m)
+    s = torch.cuda.current_stream().cuda_stream
+    vk.check(vk.lib.vk_normalize_rows(dm.data_ptr(), n, d, s))
+    torch.cuda.synchronize()
+    assert np.array_equal(dm.cpu().numpy().view(np.uint32), host.view(np.uint32))
+    for idx in (0, 5, n - 1, 777):
+        out = torch.empty(n, dtype=torch.float32, device="cuda")
+        vk.check(vk.lib.vk_distances(dm.data_ptr(), n, d, idx, out.data_ptr(), s))
+        torch.cuda.synchronize()
+        ref = co.calc_distances(host, idx)
+        assert np.array_equal(out.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.parametrize("d,n", [(32, 30000), (40, 5000), (283, 3000)])
+def test_probe_header_matches_oracle(vk, d, n):
+    from oracle import cluster_oracle as co
+    from vamb_b200 import synth
+
+    lat, lens = synth.make_latent(n, d, seed=d, spread=0.2)
+    host = lat.copy()
+    co.normalize(host)
+    lens32 = lens.astype(np.float32)
+    rng = np.random.default_rng(0)
+    kept = (rng.random(n) > 0.3).astype(np.uint8)
+    dm, dl, dk = _dev(host), _dev(lens32), _dev(kept)
+    hdr = torch.zeros(vk.HDR_SIZE, dtype=torch.uint8, device="cuda")
+    hdr_host = torch.zeros(vk.HDR_SIZE, dtype=torch.uint8).pin_memory()
+    over = torch.empty(n, dtype=torch.int32, device="cuda")
+    nl_rows = torch.empty(n, dtype=torch.int32, device="cuda")
+    nl_d = torch.empty(n, dtype=torch.float32, device="cuda")
+    edges = co.linspace_edges()
+    de = _dev(edges)
+    s = torch.cuda.current_stream().cuda_stream
+    lib = co._load_lib()
+    for medoid in np.flatnonzero(kept)[[0, 10, -1]]:
+        vk.check(vk.lib.vk_probe_sync(dm.data_ptr(), dl.data_ptr(), dk.data_ptr(), n, d, int(medoid), 0.3,
+                                      de.data_ptr(), hdr.data_ptr(), over.data_ptr(), nl_rows.data_ptr(),
+                                      nl_d.data_ptr(), hdr_host.data_ptr(), s))
+        h = hdr_host.numpy()
+        dens = int(h[0:8].view(np.uint64)[0])
+        hist = h[8:8 + 480].view(np.uint64)
+        n_within, n_lt, n_nl, rank = (int(x) for x in h[488:504].view(np.int32))
+        # oracle on the kept rows only (the reference's CPU path has physically removed the others)
+        sel = np.flatnonzero(kept)
+        sub = np.ascontiguousarray(host[sel])
+        dist = co.calc_distances(sub, int(np.searchsorted(sel, medoid)))
+        idx = np.empty(len(sel), dtype=np.int64)
+        od = ctypes.c_uint64(0)
+        cnt = lib.ok_sample(co._p(dist, ctypes.c_float), co._p(np.ascontiguousarray(lens32[sel]), ctypes.c_float),
+                            len(sel), ctypes.c_float(0.05), co._p(idx, ctypes.c_int64), ctypes.byref(od))
+        oh = np.zeros(60, dtype=np.uint64)
+        o_nlt = lib.ok_hist(co._p(dist, ctypes.c_float), co._p(np.ascontiguousarray(lens32[sel]), ctypes.c_float),
+                            len(sel), co._p(edges, ctypes.c_float), 60, ctypes.c_float(0.05), co._p(oh, ctypes.c_uint64))
+        assert n_within == cnt and dens == od.value and n_lt == o_nlt
+        assert np.array_equal(hist, oh)
+        assert rank == int(np.searchsorted(sel, medoid))
+        within = np.sort(h[504:504 + 4 * min(n_within, vk.VK_PROBE_INLINE)].view(np.int32))
+        if n_within <= vk.VK_PROBE_INLINE:
+            assert np.array_equal(sel[idx[:cnt]], within)
+        assert n_nl == int(np.count_nonzero(dist <= np.float32(0.3)))
+        got = np.sort(nl_rows[:n_nl].cpu().numpy())
+        assert np.array_equal(got, sel[dist <= np.float32(0.3)])
+
+
+@pytest.mark.parametrize("name", list(_util.CLUSTER_CASES))
+def test_cuda_clusterer_matches_reference_golden(name):
+    import vamb_b200.cluster as vc
+
+    g, lat, lens, rng_seed = _util.load_cluster_golden(name)
+    clusters = list(vc.ClusterGenerator(lat, lens, rng_seed=rng_seed, **_util.CLUSTER_CASES[name]))
+    _util.assert_clusters_equal_golden(clusters, g)
+
+
+@pytest.mark.parametrize("n,d,spread,seed", [(20000, 32, 0.1, 21), (50000, 32, 0.3, 22), (8000, 283, 0.1, 23)])
+def test_cuda_clusterer_matches_oracle_larger(n, d, spread, seed):
+    import vamb_b200.cluster as vc
+    from oracle import cluster_oracle as co
+    from vamb_b200 import synth
+
+    lat, lens = synth.make_latent(n, d, seed, spread)
+    oc = list(co.OracleClusterGenerator(lat, lens, rng_seed=seed))
+    gc = list(vc.ClusterGenerator(lat, lens, rng_seed=seed))
+    _util.assert_clusters_equal(gc, oc)
+
+
+def test_forced_packing_and_unpruned_paths_agree():
+    """pack() at every cluster and the no-pruning path give the same clusters."""
+    import vamb_b200.cluster as vc
+    from vamb_b200 import synth
+
+    lat, lens = synth.make_latent(6000, 32, 31, 0.3)
+    base = list(vc.ClusterGenerator(lat, lens, rng_seed=1))
+    gen = vc.ClusterGenerator(lat, lens, rng_seed=1)
+    gen._pack_fraction = 2.0  # pack after every emitted cluster, like the reference's CPU path
+    _util.assert_clusters_equal(list(gen), base)
+    gen = vc.ClusterGenerator(lat, lens, rng_seed=1)
+    gen._prune_radius = float("inf")
+    gen._nl_radius = float("inf")
+    _util.assert_clusters_equal(list(gen), base)
+
+
+# ---- the reference's own acceptance tests for this boundary (test/test_cluster.py) ----
+class TestReferenceClusterSuite:
+    rng = np.random.RandomState(5)
+    data = rng.random((1024, 40)).astype(np.float32)
+    lens = rng.randint(500, 1000, size=1024)
+
+    def test_basics(self):
+        import vamb_b200.cluster as vc
+
+        clstr = vc.ClusterGenerator(self.data, self.lens)
+        assert clstr is iter(clstr)
+        x = next(clstr)
+        assert isinstance(x, vc.Cluster)
+        clusters = list(clstr)
+        clusters.append(x)
+        assert sum(len(c.members) for c in clusters) == len(self.data)
+        mems = set()
+        for c in clusters:
+            mems.update(c.members)
+        assert mems == set(range(len(self.data)))
+
+    def test_matches_oracle_with_ties(self):
+        import vamb_b200.cluster as vc
+        from oracle import cluster_oracle as co
+
+        order = np.argsort(self.lens)[::-1]
+        oc = list(co.OracleClusterGenerator(self.data, self.lens, order=order))
+        gc = list(vc.ClusterGenerator(self.data, self.lens))
+        _util.assert_clusters_equal(gc, oc)
+
+    def test_destruction(self):
+        import vamb_b200.cluster as vc
+
+        copy = self.data.copy()
+        clstr = vc.ClusterGenerator(self.data, self.lens)
+        assert np.any(np.abs(self.data - clstr.matrix.numpy()) > 0.001)
+        clstr = vc.ClusterGenerator(copy, self.lens, destroy=True)
+        assert np.all(np.abs(copy - clstr.matrix.numpy()) < 1e-6)
+        assert np.any(np.abs(self.data - clstr.matrix.numpy()) > 0.001)
+
+    def test_normalization(self):
+        import vamb_b200.cluster as vc
+        from hashlib import md5
+
+        def xor_rows_hash(matrix):
+            m = np.frombuffer(matrix.copy().data, dtype=np.uint32)
+            m.shape = matrix.shape
+            v = m[0].copy()
+            for i in range(1, len(m)):
+                v ^= m[i]
+            return md5(v).digest().hex()
+
+        before = md5(self.data.data.tobytes()).digest().hex()
+        vc.ClusterGenerator(self.data, self.lens)
+        assert before == md5(self.data.data.tobytes()).digest().hex()
+        cp = self.data.copy()
+        vc.ClusterGenerator(cp, self.lens, destroy=True)
+        assert before != md5(cp.data.tobytes()).digest().hex()
+        bx = xor_rows_hash(cp)
+        vc.ClusterGenerator(cp, self.lens, destroy=True, normalized=True)
+        assert bx == xor_rows_hash(cp)
+
+    def test_cluster(self):
+        import vamb_b200.cluster as vc
+
+        x = next(vc.ClusterGenerator(self.data, self.lens))
+        assert isinstance(x.members, np.ndarray)

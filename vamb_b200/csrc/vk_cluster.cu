@@ -1,0 +1,602 @@
+// vamb_b200 clustering kernels (sm_100a).  HBM-streaming integer/compare work: no tensor
+// cores; the rules that matter are coalescing (8 lanes x float4 = one 128 B row, one warp =
+// 4 consecutive rows = 512 contiguous bytes per load instruction), several independent
+// loads in flight per thread, shared-memory staging of the sparse outputs, and a persistent
+// grid sized to the SM count.
+//
+// Replaces (reference file:line, RasmussenLab/vamb):
+//   normalize_rows_kernel   vamb/cluster.py:653-669   _normalize
+//   probe_kernel            vamb/cluster.py:672-676   _calc_distances
+//                           vamb/cluster.py:619-629   sample_medoid (within set, density)
+//                           vamb/cluster.py:457-481   find_threshold (loner count, histogram)
+//   eval_candidates_kernel  vamb/cluster.py:427-448   the sample_medoid calls of one wander round
+//   select_members_kernel   vamb/cluster.py:640-650, 308-309   _smaller_indices + kept_mask update
+//   compact_*_kernel        vamb/cluster.py:318-335   pack (vambcore.overwrite_matrix)
+#include <stdarg.h>
+#include <string.h>
+
+#include "vk_common.cuh"
+
+// ------------------------------------------------------------------ error plumbing
+static thread_local char g_err[512] = "";
+
+void vk_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *vk_last_error(void) { return g_err; }
+extern "C" int vk_abi_version(void) { return VK_ABI_VERSION; }
+
+int vk_num_sms() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+    }
+    return sms;
+}
+
+extern "C" int vk_check_device(void) {
+    int dev = 0, major = 0, minor = 0;
+    VK_CUDA(cudaGetDevice(&dev));
+    VK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    VK_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+    if (major != 10) {
+        vk_set_error("vamb_b200 kernels are built for sm_100a only; device is sm_%d%d", major, minor);
+        return 1;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------ normalize
+// One thread per row (one-off pass).  ss = sum_k (double)x_k^2 in ascending k (products exact).
+__global__ void __launch_bounds__(256) normalize_rows_kernel(float *__restrict__ m, int64_t n, int d) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    float *x = m + row * (int64_t)d;
+    bool allzero = true;
+    for (int k = 0; k < d; ++k)
+        if (x[k] != 0.0f) { allzero = false; break; }
+    const float fill = (float)(1.0 / (double)d);
+    double ss = 0.0;
+    for (int k = 0; k < d; ++k) {
+        const double v = allzero ? (double)fill : (double)x[k];
+        ss += v * v;
+    }
+    const float nrm = (float)sqrt(ss);
+    const float den = __fmul_rn(nrm, 1.41421356237309504880f);
+    for (int k = 0; k < d; ++k) {
+        const float v = allzero ? fill : x[k];
+        x[k] = __fdiv_rn(v, den);
+    }
+}
+
+extern "C" int vk_normalize_rows(float *matrix, int64_t n, int d, void *stream) {
+    if (n <= 0) return 0;
+    const int threads = 256;
+    const int64_t blocks = (n + threads - 1) / threads;
+    normalize_rows_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(matrix, n, d);
+    VK_LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void __launch_bounds__(256) check_normalized_kernel(const float *__restrict__ m, int64_t n, int d,
+                                                               float tol, int32_t *n_bad) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    const float *x = m + row * (int64_t)d;
+    double ss = 0.0;
+    for (int k = 0; k < d; ++k) ss += (double)x[k] * (double)x[k];
+    if (!(fabs(2.0 * ss - 1.0) <= (double)tol)) atomicAdd(n_bad, 1);
+}
+
+extern "C" int vk_check_normalized(const float *matrix, int64_t n, int d, float tol, int32_t *n_bad, void *stream) {
+    VK_CUDA(cudaMemsetAsync(n_bad, 0, sizeof(int32_t), (cudaStream_t)stream));
+    if (n <= 0) return 0;
+    const int64_t blocks = (n + 255) / 256;
+    check_normalized_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(matrix, n, d, tol, n_bad);
+    VK_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ probe
+constexpr int PB_THREADS = 256;
+constexpr int PB_GROUPS = PB_THREADS / 8;  // rows per pass
+constexpr int PB_R = 4;                    // independent rows (float4 loads) in flight per lane
+constexpr int PB_TILE = 512;               // rows per tile (= PB_GROUPS * PB_R * 4 passes)
+constexpr int PB_MAX_D = 1024;             // generic path: query vector staged in shared memory
+
+__device__ __forceinline__ int hist_bin(float dd, const float *edges) {
+    // upper_bound(edges, dd) - 1 with the last bin right-inclusive (torch.histogram, linear bins
+    // + local search against the fp32 edge table).  Caller guarantees edges[0] <= dd <= edges[60].
+    int b = (int)(dd * 200.0f);
+    b = max(0, min(VK_NBINS - 1, b));
+    while (b > 0 && dd < edges[b]) --b;
+    while (b < VK_NBINS - 1 && dd >= edges[b + 1]) ++b;
+    return b;
+}
+
+struct ProbeAcc {
+    u64 dens;
+    unsigned nlt;
+    unsigned rank;
+};
+
+template <int DFIX>
+__global__ void __launch_bounds__(PB_THREADS, 4)
+probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths,
+             const uint8_t *__restrict__ kept, int64_t n, int d_rt, int64_t mrow, float nl_radius,
+             const float *__restrict__ edges_g, vk_probe_header *hdr, int32_t *within_overflow,
+             int32_t *nl_rows, float *nl_dists, int n_tiles) {
+    const int d = DFIX ? DFIX : d_rt;
+    __shared__ float s_edges[VK_NBINS + 1];
+    __shared__ u64 s_hist[VK_NBINS];
+    __shared__ int32_t s_nl_rows[PB_TILE];
+    __shared__ float s_nl_d[PB_TILE];
+    __shared__ int s_nl_cnt, s_nl_base;
+    __shared__ ProbeAcc s_acc;
+    __shared__ __align__(16) float s_q[DFIX ? DFIX : PB_MAX_D];
+
+    const int tid = threadIdx.x;
+    const int lane8 = tid & 7;
+    const int g = tid >> 3;
+    const unsigned gmask = group8_mask();
+    const bool vec4 = (d & 3) == 0;
+
+    if (tid <= VK_NBINS) s_edges[tid] = edges_g[tid];
+    if (tid < VK_NBINS) s_hist[tid] = 0ull;
+    if (tid == 0) { s_nl_cnt = 0; s_acc.dens = 0ull; s_acc.nlt = 0u; s_acc.rank = 0u; }
+    for (int k = tid; k < d; k += PB_THREADS) s_q[k] = matrix[mrow * (int64_t)d + k];
+    __syncthreads();
+
+    float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (DFIX == 32) qv = *reinterpret_cast<const float4 *>(s_q + 4 * lane8);
+    const float e_lo = s_edges[0], e_hi = s_edges[VK_NBINS];
+    const float rad = 0.05f;
+
+    u64 t_dens = 0ull;
+    unsigned t_nlt = 0u, t_rank = 0u;
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row0 = (int64_t)tile * PB_TILE;
+#pragma unroll 1
+        for (int it = 0; it < PB_TILE / (PB_GROUPS * PB_R); ++it) {
+            float acc[PB_R];
+            int64_t rows[PB_R];
+            if (DFIX == 32) {
+                float4 v[PB_R];
+#pragma unroll
+                for (int k = 0; k < PB_R; ++k) {
+                    rows[k] = row0 + (int64_t)(it * PB_R + k) * PB_GROUPS + g;
+                    v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rows[k] < n) v[k] = ldg_stream4(matrix + rows[k] * 32 + 4 * lane8);
+                }
+#pragma unroll
+                for (int k = 0; k < PB_R; ++k) acc[k] = chain4(v[k], qv);
+            } else {
+#pragma unroll
+                for (int k = 0; k < PB_R; ++k) {
+                    rows[k] = row0 + (int64_t)(it * PB_R + k) * PB_GROUPS + g;
+                    acc[k] = 0.0f;
+                    if (rows[k] < n) acc[k] = lane_chain_generic(matrix + rows[k] * (int64_t)d, s_q, d, lane8, vec4);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < PB_R; ++k) acc[k] = group8_sum(acc[k], gmask);
+
+            if (lane8 == 0) {
+#pragma unroll
+                for (int k = 0; k < PB_R; ++k) {
+                    const int64_t row = rows[k];
+                    if (row >= n) continue;
+                    if (!kept[row]) continue;
+                    float dd = __fsub_rn(0.5f, acc[k]);
+                    if (row == mrow) dd = 0.0f;
+                    if (row < mrow) ++t_rank;
+                    if (dd < rad) ++t_nlt;
+                    const bool in_hist = (dd >= e_lo) && (dd <= e_hi);
+                    const bool within = dd <= rad;
+                    float len = 0.0f;
+                    if (in_hist || within) len = __ldg(lengths + row);
+                    if (within) {
+                        t_dens += __float2ull_rz(len) * closeness_fx(rad, dd);
+                        const int pos = atomicAdd(&hdr->n_within, 1);
+                        if (pos < VK_PROBE_INLINE) hdr->within[pos] = (int32_t)row;
+                        else within_overflow[pos] = (int32_t)row;
+                    }
+                    if (in_hist) atomicAdd(&s_hist[hist_bin(dd, s_edges)], __float2ull_rz(len));
+                    if (dd <= nl_radius) {
+                        const int slot = atomicAdd(&s_nl_cnt, 1);
+                        s_nl_rows[slot] = (int32_t)row;
+                        s_nl_d[slot] = dd;
+                    }
+                }
+            }
+        }
+        // flush this tile's neighbour-list entries: one global reservation per tile
+        __syncthreads();
+        const int cnt = s_nl_cnt;
+        if (cnt > 0) {
+            if (tid == 0) s_nl_base = atomicAdd(&hdr->n_nl, cnt);
+            __syncthreads();
+            const int base = s_nl_base;
+            for (int i = tid; i < cnt; i += PB_THREADS) {
+                nl_rows[base + i] = s_nl_rows[i];
+                nl_dists[base + i] = s_nl_d[i];
+            }
+            __syncthreads();
+            if (tid == 0) s_nl_cnt = 0;
+            __syncthreads();
+        }
+    }
+
+    if (lane8 == 0 && (t_dens | t_nlt | t_rank)) {
+        if (t_dens) atomicAdd(&s_acc.dens, t_dens);
+        if (t_nlt) atomicAdd(&s_acc.nlt, t_nlt);
+        if (t_rank) atomicAdd(&s_acc.rank, t_rank);
+    }
+    __syncthreads();
+    if (tid < VK_NBINS) {
+        const u64 h = s_hist[tid];
+        if (h) atomicAdd(reinterpret_cast<u64 *>(&hdr->hist[tid]), h);
+    }
+    if (tid == 64) {
+        if (s_acc.dens) atomicAdd(reinterpret_cast<u64 *>(&hdr->density_fx), s_acc.dens);
+        if (s_acc.nlt) atomicAdd(&hdr->n_lt, (int)s_acc.nlt);
+        if (s_acc.rank) atomicAdd(&hdr->rank, (int)s_acc.rank);
+    }
+}
+
+static int probe_grid(int n_tiles) {
+    const int cap = vk_num_sms() * 4;
+    return n_tiles < cap ? n_tiles : cap;
+}
+
+extern "C" int vk_probe(const float *matrix, const float *lengths, const uint8_t *kept, int64_t n, int d,
+                        int64_t medoid_row, float nl_radius, const float *edges, vk_probe_header *hdr,
+                        int32_t *within_overflow, int32_t *nl_rows, float *nl_dists, void *stream) {
+    if (n <= 0 || medoid_row < 0 || medoid_row >= n) {
+        vk_set_error("vk_probe: bad arguments (n=%lld, medoid_row=%lld)", (long long)n, (long long)medoid_row);
+        return 1;
+    }
+    if (d < 1 || d > PB_MAX_D) {
+        vk_set_error("vk_probe: d=%d outside [1, %d]", d, PB_MAX_D);
+        return 1;
+    }
+    if (n > 2147483647LL) {
+        vk_set_error("vk_probe: n=%lld exceeds int32 row ids", (long long)n);
+        return 1;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    // only the accumulators need zeroing, not the inline id list
+    VK_CUDA(cudaMemsetAsync(hdr, 0, offsetof(vk_probe_header, within), s));
+    const int n_tiles = (int)((n + PB_TILE - 1) / PB_TILE);
+    const int grid = probe_grid(n_tiles);
+    if (d == 32)
+        probe_kernel<32><<<grid, PB_THREADS, 0, s>>>(matrix, lengths, kept, n, d, medoid_row, nl_radius, edges,
+                                                     hdr, within_overflow, nl_rows, nl_dists, n_tiles);
+    else
+        probe_kernel<0><<<grid, PB_THREADS, 0, s>>>(matrix, lengths, kept, n, d, medoid_row, nl_radius, edges,
+                                                    hdr, within_overflow, nl_rows, nl_dists, n_tiles);
+    VK_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int vk_probe_sync(const float *matrix, const float *lengths, const uint8_t *kept, int64_t n, int d,
+                             int64_t medoid_row, float nl_radius, const float *edges, vk_probe_header *hdr,
+                             int32_t *within_overflow, int32_t *nl_rows, float *nl_dists,
+                             vk_probe_header *hdr_host, void *stream) {
+    if (vk_probe(matrix, lengths, kept, n, d, medoid_row, nl_radius, edges, hdr, within_overflow, nl_rows,
+                 nl_dists, stream))
+        return 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    VK_CUDA(cudaMemcpyAsync(hdr_host, hdr, sizeof(vk_probe_header), cudaMemcpyDeviceToHost, s));
+    VK_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+// ------------------------------------------------------------------ plain distance vector
+template <int DFIX>
+__global__ void __launch_bounds__(PB_THREADS, 4)
+distances_kernel(const float *__restrict__ matrix, int64_t n, int d_rt, int64_t mrow, float *__restrict__ dists,
+                 int n_tiles) {
+    const int d = DFIX ? DFIX : d_rt;
+    __shared__ __align__(16) float s_q[DFIX ? DFIX : PB_MAX_D];
+    const int tid = threadIdx.x, lane8 = tid & 7, g = tid >> 3;
+    const unsigned gmask = group8_mask();
+    const bool vec4 = (d & 3) == 0;
+    for (int k = tid; k < d; k += PB_THREADS) s_q[k] = matrix[mrow * (int64_t)d + k];
+    __syncthreads();
+    float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (DFIX == 32) qv = *reinterpret_cast<const float4 *>(s_q + 4 * lane8);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row0 = (int64_t)tile * PB_TILE;
+#pragma unroll 1
+        for (int it = 0; it < PB_TILE / (PB_GROUPS * PB_R); ++it) {
+            float acc[PB_R];
+            int64_t rows[PB_R];
+            if (DFIX == 32) {
+                float4 v[PB_R];
+#pragma unroll
+                for (int k = 0; k < PB_R; ++k) {
+                    rows[k] = row0 + (int64_t)(it * PB_R + k) * PB_GROUPS + g;
+                    v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rows[k] < n) v[k] = ldg_stream4(matrix + rows[k] * 32 + 4 * lane8);
+                }
+#pragma unroll
+                for (int k = 0; k < PB_R; ++k) acc[k] = chain4(v[k], qv);
+            } else {
+#pragma unroll
+                for (int k = 0; k < PB_R; ++k) {
+                    rows[k] = row0 + (int64_t)(it * PB_R + k) * PB_GROUPS + g;
+                    acc[k] = 0.0f;
+                    if (rows[k] < n) acc[k] = lane_chain_generic(matrix + rows[k] * (int64_t)d, s_q, d, lane8, vec4);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < PB_R; ++k) {
+                acc[k] = group8_sum(acc[k], gmask);
+                if (lane8 == 0 && rows[k] < n) dists[rows[k]] = rows[k] == mrow ? 0.0f : __fsub_rn(0.5f, acc[k]);
+            }
+        }
+    }
+}
+
+extern "C" int vk_distances(const float *matrix, int64_t n, int d, int64_t medoid_row, float *dists, void *stream) {
+    if (n <= 0 || medoid_row < 0 || medoid_row >= n || d < 1 || d > PB_MAX_D) {
+        vk_set_error("vk_distances: bad arguments");
+        return 1;
+    }
+    const int n_tiles = (int)((n + PB_TILE - 1) / PB_TILE);
+    const int grid = probe_grid(n_tiles);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (d == 32) distances_kernel<32><<<grid, PB_THREADS, 0, s>>>(matrix, n, d, medoid_row, dists, n_tiles);
+    else distances_kernel<0><<<grid, PB_THREADS, 0, s>>>(matrix, n, d, medoid_row, dists, n_tiles);
+    VK_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ candidate evaluation
+struct CandRows {
+    int32_t rows[VK_MAX_CAND];
+};
+
+constexpr int EC_THREADS = 256;
+
+__global__ void __launch_bounds__(EC_THREADS)
+eval_candidates_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths, int d,
+                       const int32_t *__restrict__ nl_rows, const float *__restrict__ nl_dists, int n_nl,
+                       float prune_radius, CandRows cand, int n_cand, u64 *out) {
+    extern __shared__ __align__(16) float s_qs[];  // [n_cand][dpad]
+    __shared__ u64 s_dens[VK_MAX_CAND];
+    __shared__ unsigned s_cnt[VK_MAX_CAND];
+    const int tid = threadIdx.x, lane8 = tid & 7, g = tid >> 3;
+    const unsigned gmask = group8_mask();
+    const int dpad = (d + 3) & ~3;
+    const bool vec4 = (d & 3) == 0;
+    for (int i = tid; i < n_cand * dpad; i += EC_THREADS) {
+        const int k = i / dpad, c = i - k * dpad;
+        s_qs[i] = c < d ? matrix[(int64_t)cand.rows[k] * d + c] : 0.0f;
+    }
+    if (tid < VK_MAX_CAND) { s_dens[tid] = 0ull; s_cnt[tid] = 0u; }
+    __syncthreads();
+
+    const float rad = 0.05f;
+    const int groups_total = gridDim.x * (EC_THREADS / 8);
+    for (int j = blockIdx.x * (EC_THREADS / 8) + g; j < n_nl; j += groups_total) {
+        const float dj = nl_dists[j];
+        if (!(dj <= prune_radius)) continue;  // uniform within the 8-lane group
+        const int row = nl_rows[j];
+        const float *x = matrix + (int64_t)row * d;
+        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool fast = (d == 32);
+        if (fast) xv = ldg_stream4(x + 4 * lane8);
+        u64 lenq = 0ull;
+        if (lane8 == 0) lenq = __float2ull_rz(__ldg(lengths + row));
+        for (int k = 0; k < n_cand; ++k) {
+            const float *q = s_qs + k * dpad;
+            float acc;
+            if (fast) acc = chain4(xv, *reinterpret_cast<const float4 *>(q + 4 * lane8));
+            else acc = lane_chain_generic(x, q, d, lane8, vec4);
+            acc = group8_sum(acc, gmask);
+            if (lane8 == 0) {
+                float dd = __fsub_rn(0.5f, acc);
+                if (row == cand.rows[k]) dd = 0.0f;
+                if (dd <= rad) {
+                    atomicAdd(&s_dens[k], lenq * closeness_fx(rad, dd));
+                    atomicAdd(&s_cnt[k], 1u);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < n_cand) {
+        if (s_dens[tid]) atomicAdd(&out[tid], s_dens[tid]);
+        if (s_cnt[tid]) atomicAdd(&out[VK_MAX_CAND + tid], (u64)s_cnt[tid]);
+    }
+}
+
+extern "C" int vk_eval_candidates_sync(const float *matrix, const float *lengths, int d, const int32_t *nl_rows,
+                                       const float *nl_dists, int32_t n_nl, float prune_radius,
+                                       const int32_t *cand_rows_host, int n_cand, uint64_t *out_dev,
+                                       uint64_t *out_host, void *stream) {
+    if (n_cand < 1 || n_cand > VK_MAX_CAND) {
+        vk_set_error("vk_eval_candidates_sync: n_cand=%d outside [1, %d]", n_cand, VK_MAX_CAND);
+        return 1;
+    }
+    if (d < 1 || d > PB_MAX_D) {
+        vk_set_error("vk_eval_candidates_sync: d=%d outside [1, %d]", d, PB_MAX_D);
+        return 1;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    CandRows cand;
+    memset(&cand, 0, sizeof(cand));
+    for (int k = 0; k < n_cand; ++k) cand.rows[k] = cand_rows_host[k];
+    VK_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(uint64_t) * 2 * VK_MAX_CAND, s));
+    if (n_nl > 0) {
+        const int dpad = (d + 3) & ~3;
+        const size_t smem = sizeof(float) * (size_t)n_cand * dpad;
+        if (smem > 48 * 1024) {
+            VK_CUDA(cudaFuncSetAttribute(eval_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        const int per_block = EC_THREADS / 8;
+        int grid = (n_nl + per_block - 1) / per_block;
+        const int cap = vk_num_sms() * 4;
+        if (grid > cap) grid = cap;
+        eval_candidates_kernel<<<grid, EC_THREADS, smem, s>>>(matrix, lengths, d, nl_rows, nl_dists, n_nl,
+                                                              prune_radius, cand, n_cand, (u64 *)out_dev);
+        VK_LAUNCH_CHECK();
+    }
+    VK_CUDA(cudaMemcpyAsync(out_host, out_dev, sizeof(uint64_t) * 2 * VK_MAX_CAND, cudaMemcpyDeviceToHost, s));
+    VK_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+// ------------------------------------------------------------------ member selection
+__global__ void __launch_bounds__(256)
+select_members_kernel(const int32_t *__restrict__ nl_rows, const float *__restrict__ nl_dists, int n_nl,
+                      float threshold, const int32_t *__restrict__ orig_ids, uint8_t *kept, int32_t *members) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool hit = i < n_nl && nl_dists[i] <= threshold;
+    const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+    if (ballot == 0u) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&members[0], __popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (hit) {
+        const int row = nl_rows[i];
+        members[1 + base + __popc(ballot & ((1u << lane) - 1u))] = orig_ids[row];
+        kept[row] = 0;
+    }
+}
+
+extern "C" int vk_select_members_sync(const int32_t *nl_rows, const float *nl_dists, int32_t n_nl, float threshold,
+                                      const int32_t *orig_ids, uint8_t *kept, int32_t *members,
+                                      int32_t *members_host, int32_t capacity_host, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (capacity_host < 2) {
+        vk_set_error("vk_select_members_sync: capacity_host must be >= 2");
+        return 1;
+    }
+    VK_CUDA(cudaMemsetAsync(members, 0, sizeof(int32_t), s));
+    if (n_nl > 0) {
+        const int grid = (n_nl + 255) / 256;
+        select_members_kernel<<<grid, 256, 0, s>>>(nl_rows, nl_dists, n_nl, threshold, orig_ids, kept, members);
+        VK_LAUNCH_CHECK();
+    }
+    const int64_t first = (int64_t)n_nl + 1 < capacity_host ? (int64_t)n_nl + 1 : capacity_host;
+    VK_CUDA(cudaMemcpyAsync(members_host, members, sizeof(int32_t) * (size_t)first, cudaMemcpyDeviceToHost, s));
+    VK_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+__global__ void mask_clear_kernel(uint8_t *kept, const int32_t *rows, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) kept[rows[i]] = 0;
+}
+
+extern "C" int vk_mask_clear(uint8_t *kept, const int32_t *rows, int32_t n, void *stream) {
+    if (n <= 0) return 0;
+    mask_clear_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(kept, rows, n);
+    VK_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ stable row compaction
+constexpr int CP_TILE = 1024;
+
+// tile_scratch[0] = ticket, [1] = total kept, [2 + t] = kept count of tile t, turned into an
+// exclusive prefix by the last block to finish.
+__global__ void __launch_bounds__(CP_TILE)
+compact_count_kernel(const uint8_t *__restrict__ kept, int64_t n, int32_t *tile_scratch, int n_tiles) {
+    __shared__ int s_warp[CP_TILE / 32];
+    __shared__ int s_last;
+    const int tid = threadIdx.x;
+    const int64_t row = (int64_t)blockIdx.x * CP_TILE + tid;
+    const bool p = row < n && kept[row];
+    const unsigned b = __ballot_sync(0xffffffffu, p);
+    if ((tid & 31) == 0) s_warp[tid >> 5] = __popc(b);
+    __syncthreads();
+    if (tid == 0) {
+        int c = 0;
+        for (int w = 0; w < CP_TILE / 32; ++w) c += s_warp[w];
+        tile_scratch[2 + blockIdx.x] = c;
+        __threadfence();
+        s_last = (atomicAdd(&tile_scratch[0], 1) == n_tiles - 1);
+    }
+    __syncthreads();
+    if (s_last && tid == 0) {
+        __threadfence();
+        int run = 0;
+        for (int t = 0; t < n_tiles; ++t) {
+            const int c = ((volatile int32_t *)tile_scratch)[2 + t];
+            tile_scratch[2 + t] = run;
+            run += c;
+        }
+        tile_scratch[1] = run;
+        tile_scratch[0] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(CP_TILE)
+compact_scatter_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths,
+                       const int32_t *__restrict__ orig_ids, const uint8_t *__restrict__ kept, int64_t n, int d,
+                       float *__restrict__ matrix_out, float *__restrict__ lengths_out,
+                       int32_t *__restrict__ orig_out, uint8_t *__restrict__ kept_out,
+                       const int32_t *__restrict__ tile_scratch) {
+    __shared__ int s_warp[CP_TILE / 32];
+    __shared__ int s_dest[CP_TILE];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t row0 = (int64_t)blockIdx.x * CP_TILE;
+    const int64_t row = row0 + tid;
+    const bool p = row < n && kept[row];
+    const unsigned b = __ballot_sync(0xffffffffu, p);
+    if (lane == 0) s_warp[warp] = __popc(b);
+    __syncthreads();
+    int off = tile_scratch[2 + blockIdx.x];
+    for (int w = 0; w < warp; ++w) off += s_warp[w];
+    const int dest = p ? off + __popc(b & ((1u << lane) - 1u)) : -1;
+    s_dest[tid] = dest;
+    if (p) {
+        lengths_out[dest] = lengths[row];
+        orig_out[dest] = orig_ids[row];
+        kept_out[dest] = 1;
+    }
+    __syncthreads();
+    // rows are copied warp-cooperatively so that both sides stay coalesced
+    for (int r = warp; r < CP_TILE; r += CP_TILE / 32) {
+        const int dst = s_dest[r];
+        if (dst < 0) continue;
+        const float *src = matrix + (row0 + r) * (int64_t)d;
+        float *out = matrix_out + (int64_t)dst * d;
+        for (int k = lane; k < d; k += 32) out[k] = src[k];
+    }
+}
+
+extern "C" int vk_compact_rows_sync(const float *matrix, const float *lengths, const int32_t *orig_ids,
+                                    const uint8_t *kept, int64_t n, int d, float *matrix_out, float *lengths_out,
+                                    int32_t *orig_out, uint8_t *kept_out, int32_t *tile_scratch,
+                                    int64_t *n_out_host, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n <= 0) {
+        *n_out_host = 0;
+        return 0;
+    }
+    const int n_tiles = (int)((n + CP_TILE - 1) / CP_TILE);
+    VK_CUDA(cudaMemsetAsync(tile_scratch, 0, sizeof(int32_t) * 2, s));
+    compact_count_kernel<<<n_tiles, CP_TILE, 0, s>>>(kept, n, tile_scratch, n_tiles);
+    VK_LAUNCH_CHECK();
+    compact_scatter_kernel<<<n_tiles, CP_TILE, 0, s>>>(matrix, lengths, orig_ids, kept, n, d, matrix_out,
+                                                       lengths_out, orig_out, kept_out, tile_scratch);
+    VK_LAUNCH_CHECK();
+    int32_t total = 0;
+    VK_CUDA(cudaMemcpyAsync(&total, tile_scratch + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    VK_CUDA(cudaStreamSynchronize(s));
+    *n_out_host = total;
+    return 0;
+}

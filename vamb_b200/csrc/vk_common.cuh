@@ -1,0 +1,91 @@
+// Shared helpers for the vamb_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/vamb_b200.h"
+
+typedef unsigned long long u64;
+
+void vk_set_error(const char *fmt, ...);
+
+#define VK_CUDA(call)                                                                      \
+    do {                                                                                   \
+        cudaError_t _e = (call);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            vk_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+            return 1;                                                                      \
+        }                                                                                  \
+    } while (0)
+
+#define VK_LAUNCH_CHECK()                                                                  \
+    do {                                                                                   \
+        cudaError_t _e = cudaGetLastError();                                               \
+        if (_e != cudaSuccess) {                                                           \
+            vk_set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return 1;                                                                      \
+        }                                                                                  \
+    } while (0)
+
+int vk_num_sms();
+
+// ---- streaming (read-once) global loads: bypass L1 allocation ----
+__device__ __forceinline__ float4 ldg_stream4(const float *p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+// ---- "vk arithmetic v1": the 8-lane dot product -------------------------------------
+// Chunk c (elements 4c..4c+3) belongs to lane (c & 7) of an 8-lane group; every lane runs
+// one fmaf chain over its chunks in increasing c; the eight partial sums are combined by
+// an xor butterfly (1, 2, 4).  oracle/csrc/oracle_kernels.c:dot8 is the same order.
+__device__ __forceinline__ float group8_sum(float acc, unsigned mask) {
+    acc = __fadd_rn(acc, __shfl_xor_sync(mask, acc, 1));
+    acc = __fadd_rn(acc, __shfl_xor_sync(mask, acc, 2));
+    acc = __fadd_rn(acc, __shfl_xor_sync(mask, acc, 4));
+    return acc;
+}
+
+__device__ __forceinline__ unsigned group8_mask() {
+    return 0xFFu << (threadIdx.x & 24);  // lanes of this thread's 8-lane group within its warp
+}
+
+// partial (per-lane) chain for generic D; x = row base (global), q = query (shared)
+__device__ __forceinline__ float lane_chain_generic(const float *__restrict__ x, const float *q, int d,
+                                                    int lane8, bool vec4) {
+    float acc = 0.0f;
+    const int nchunk = (d + 3) >> 2;
+    for (int c = lane8; c < nchunk; c += 8) {
+        const int k0 = c << 2;
+        if (vec4) {
+            const float4 v = ldg_stream4(x + k0);
+            const float4 w = *reinterpret_cast<const float4 *>(q + k0);
+            acc = __fmaf_rn(v.x, w.x, acc);
+            acc = __fmaf_rn(v.y, w.y, acc);
+            acc = __fmaf_rn(v.z, w.z, acc);
+            acc = __fmaf_rn(v.w, w.w, acc);
+        } else {
+            const int k1 = min(k0 + 4, d);
+            for (int k = k0; k < k1; ++k) acc = __fmaf_rn(__ldg(x + k), q[k], acc);
+        }
+    }
+    return acc;
+}
+
+__device__ __forceinline__ float chain4(const float4 v, const float4 w) {
+    float acc = __fmaf_rn(v.x, w.x, 0.0f);
+    acc = __fmaf_rn(v.y, w.y, acc);
+    acc = __fmaf_rn(v.z, w.z, acc);
+    acc = __fmaf_rn(v.w, w.w, acc);
+    return acc;
+}
+
+// closeness (0.05f - d) is always a multiple of 2^-29 -> exact integer in those units
+__device__ __forceinline__ u64 closeness_fx(float radius, float d) {
+    const float c = __fsub_rn(radius, d);
+    return __float2ull_rz(c * 536870912.0f);
+}
