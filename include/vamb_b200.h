@@ -40,7 +40,12 @@ int vk_check_device(void);
 /* Result header of one probe; lives in device memory, copied to pinned host memory.
  * All sums are exact integers, hence independent of the order of accumulation. */
 typedef struct vk_probe_header {
-    uint64_t density_fx;      /* sum len_i * (0.05f - d_i) over kept rows with d_i <= 0.05f, units 2^-29 */
+    /* local density = sum len_i * (0.05f - d_i) over kept rows with d_i <= 0.05f, exact, in units of
+     * 2^-29: c_i = (0.05f - d_i) * 2^29 is an integer < 2^25; density = density_hi * 4096 + density_lo
+     * with density_lo = sum len_i * (c_i & 4095), density_hi = sum len_i * (c_i >> 12).  Exact while the
+     * total sequence length is below 2^50. */
+    uint64_t density_lo;
+    uint64_t density_hi;
     uint64_t hist[VK_NBINS];  /* sum of len_i per distance bin over kept rows with 0 <= d_i <= 0.3f       */
     int32_t n_within;         /* kept rows with d <= 0.05f  (cluster.py:625)                               */
     int32_t n_lt;             /* kept rows with d <  0.05f  (cluster.py:457, loner test)                   */
@@ -77,8 +82,7 @@ int vk_probe_sync(const float *matrix, const float *lengths, const uint8_t *kept
  * vamb/cluster.py:427-448, whose densities are independent of each other).  Only list
  * entries with nl_dists <= prune_radius are visited (a row within 0.05 of
  * a candidate that is itself within 0.05 of the medoid lies within 0.19 of the medoid).
- * out_host[k] = density_fx of candidate k (pinned host, 2*VK_MAX_CAND uint64: densities
- * then counts).  Ends with a stream synchronize. */
+ * out_host (pinned host, 3*VK_MAX_CAND uint64) = density_lo[k], then density_hi[k], then counts[k].  Ends with a stream synchronize. */
 int vk_eval_candidates_sync(const float *matrix, const float *lengths, int d,
                             const int32_t *nl_rows, const float *nl_dists, int32_t n_nl,
                             float prune_radius, const int32_t *cand_rows_host, int n_cand,

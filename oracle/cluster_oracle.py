@@ -246,12 +246,12 @@ class OracleClusterGenerator:
             _p(self.matrix, ctypes.c_float), n, self.matrix.shape[1], int(medoid), _p(d, ctypes.c_float)
         )
         idx = np.empty(n, dtype=np.int64)
-        dens = ctypes.c_uint64(0)
+        dens = (ctypes.c_uint64 * 2)()
         cnt = self.lib.ok_sample(
             _p(d, ctypes.c_float), _p(self.lens, ctypes.c_float), n,
-            ctypes.c_float(MEDOID_RADIUS), _p(idx, ctypes.c_int64), ctypes.byref(dens),
+            ctypes.c_float(MEDOID_RADIUS), _p(idx, ctypes.c_int64), dens,
         )
-        return idx[:cnt], d, int(dens.value)
+        return idx[:cnt], d, (int(dens[1]) << 12) + int(dens[0])
 
     # ---- cluster.py:415-450 ----
     def wander_medoid(self, seed: int):

@@ -70,23 +70,26 @@ OK_EXPORT void ok_dists(const float *m, int64_t n, int d, int64_t idx, float *ou
 
 /* cluster.py:625-629.  within = dists <= radius (fp32 compare); indices ascending;
  * density = sum len_i * (radius - d_i).  closeness is a multiple of 2^-29 (radius is
- * 0.05f), lengths are integers, so the sum is accumulated EXACTLY as an unsigned
- * 64-bit integer in units of 2^-29 (order independent).  Returns the count. */
+ * 0.05f), lengths are integers, so the sum is accumulated EXACTLY in integers, in units of
+ * 2^-29 (order independent): density = hi * 4096 + lo with lo = sum len * (c & 4095),
+ * hi = sum len * (c >> 12).  Returns the count. */
 OK_EXPORT int64_t ok_sample(const float *dists, const float *lens, int64_t n, float radius,
-                            int64_t *idx_out, uint64_t *density_fx) {
+                            int64_t *idx_out, uint64_t *density_lo_hi) {
     int64_t cnt = 0;
-    uint64_t acc = 0;
+    uint64_t lo = 0, hi = 0;
     for (int64_t i = 0; i < n; ++i) {
         float dd = dists[i];
         if (dd <= radius) {
             float c = radius - dd;
             uint64_t cq = (uint64_t)((double)c * 536870912.0); /* exact: c is k * 2^-29 */
-            acc += (uint64_t)lens[i] * cq;
+            lo += (uint64_t)lens[i] * (cq & 4095u);
+            hi += (uint64_t)lens[i] * (cq >> 12);
             if (idx_out) idx_out[cnt] = i;
             ++cnt;
         }
     }
-    *density_fx = acc;
+    density_lo_hi[0] = lo;
+    density_lo_hi[1] = hi;
     return cnt;
 }
 

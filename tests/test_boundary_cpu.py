@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
 def test_probe_header_layout_matches_binding():
     from vamb_b200 import _lib
 
-    assert _lib.HDR_SIZE == 8 + 8 * 60 + 16 + 4 * _lib.VK_PROBE_INLINE
+    assert _lib.HDR_SIZE == 16 + 8 * 60 + 16 + 4 * _lib.VK_PROBE_INLINE
 
 
 def test_no_cpu_fallback():

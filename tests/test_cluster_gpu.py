@@ -72,24 +72,24 @@ def test_probe_header_matches_oracle(vk, d, n):
                                       de.data_ptr(), hdr.data_ptr(), over.data_ptr(), nl_rows.data_ptr(),
                                       nl_d.data_ptr(), hdr_host.data_ptr(), s))
         h = hdr_host.numpy()
-        dens = int(h[0:8].view(np.uint64)[0])
-        hist = h[8:8 + 480].view(np.uint64)
-        n_within, n_lt, n_nl, rank = (int(x) for x in h[488:504].view(np.int32))
+        dens = (int(h[8:16].view(np.uint64)[0]) << 12) + int(h[0:8].view(np.uint64)[0])
+        hist = h[vk.HDR_HIST:vk.HDR_HIST + 480].view(np.uint64)
+        n_within, n_lt, n_nl, rank = (int(x) for x in h[vk.HDR_NWITHIN:vk.HDR_NWITHIN + 16].view(np.int32))
         # oracle on the kept rows only (the reference's CPU path has physically removed the others)
         sel = np.flatnonzero(kept)
         sub = np.ascontiguousarray(host[sel])
         dist = co.calc_distances(sub, int(np.searchsorted(sel, medoid)))
         idx = np.empty(len(sel), dtype=np.int64)
-        od = ctypes.c_uint64(0)
+        od = (ctypes.c_uint64 * 2)()
         cnt = lib.ok_sample(co._p(dist, ctypes.c_float), co._p(np.ascontiguousarray(lens32[sel]), ctypes.c_float),
-                            len(sel), ctypes.c_float(0.05), co._p(idx, ctypes.c_int64), ctypes.byref(od))
+                            len(sel), ctypes.c_float(0.05), co._p(idx, ctypes.c_int64), od)
         oh = np.zeros(60, dtype=np.uint64)
         o_nlt = lib.ok_hist(co._p(dist, ctypes.c_float), co._p(np.ascontiguousarray(lens32[sel]), ctypes.c_float),
                             len(sel), co._p(edges, ctypes.c_float), 60, ctypes.c_float(0.05), co._p(oh, ctypes.c_uint64))
-        assert n_within == cnt and dens == od.value and n_lt == o_nlt
+        assert n_within == cnt and dens == (int(od[1]) << 12) + int(od[0]) and n_lt == o_nlt
         assert np.array_equal(hist, oh)
         assert rank == int(np.searchsorted(sel, medoid))
-        within = np.sort(h[504:504 + 4 * min(n_within, vk.VK_PROBE_INLINE)].view(np.int32))
+        within = np.sort(h[vk.HDR_WITHIN:vk.HDR_WITHIN + 4 * min(n_within, vk.VK_PROBE_INLINE)].view(np.int32))
         if n_within <= vk.VK_PROBE_INLINE:
             assert np.array_equal(sel[idx[:cnt]], within)
         assert n_nl == int(np.count_nonzero(dist <= np.float32(0.3)))

@@ -58,7 +58,7 @@ def kernels(n, d=32):
         med, best = time_kernel(fn)
         print(f"n={n} d={d} {name}: median {med*1e3:.1f} us best {best*1e3:.1f} us -> {nbytes/med/1e6:.0f} GB/s (median), {nbytes/best/1e6:.0f} GB/s (best)")
     h = hdr.cpu().numpy()
-    print("  last probe n_nl", h[496:500].view(np.int32)[0], "n_within", h[488:492].view(np.int32)[0])
+    print("  last probe n_nl", h[_lib.HDR_NNL:_lib.HDR_NNL+4].view(np.int32)[0], "n_within", h[_lib.HDR_NWITHIN:_lib.HDR_NWITHIN+4].view(np.int32)[0])
 
 
 def cluster_e2e(n, spread=0.1, max_clusters=None):

@@ -18,9 +18,10 @@ VK_MAX_CAND = 32
 VK_PROBE_INLINE = 2040
 
 # byte offsets inside vk_probe_header (include/vamb_b200.h)
-HDR_DENSITY = 0
-HDR_HIST = 8
-HDR_NWITHIN = 8 + 8 * VK_NBINS
+HDR_DENSITY_LO = 0
+HDR_DENSITY_HI = 8
+HDR_HIST = 16
+HDR_NWITHIN = 16 + 8 * VK_NBINS
 HDR_NLT = HDR_NWITHIN + 4
 HDR_NNL = HDR_NWITHIN + 8
 HDR_RANK = HDR_NWITHIN + 12

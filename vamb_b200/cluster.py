@@ -188,8 +188,8 @@ class ClusterGenerator:
         len32 = lengths.astype(_np.float32)  # torch.Tensor(lengths), vamb/cluster.py:277
         if n and not (_np.all(len32 >= 0) and _np.all(len32 == _np.floor(len32))):
             raise ValueError("lengths must be non-negative integral values (contig lengths)")
-        if float(len32.astype(_np.float64).sum()) >= 2.0 ** 38:
-            raise ValueError("total sequence length >= 2^38 is outside the exact-density range")
+        if float(len32.astype(_np.float64).sum()) >= 2.0 ** 50:
+            raise ValueError("total sequence length >= 2^50 is outside the exact-density range")
         if n >= 2 ** 31:
             raise ValueError("more than 2^31 - 1 observations are not supported")
 
@@ -218,8 +218,8 @@ class ClusterGenerator:
         self._hdr = _torch.zeros(_lib.HDR_SIZE, dtype=_torch.uint8, device=dev)
         self._hdr_host = _torch.zeros(_lib.HDR_SIZE, dtype=_torch.uint8).pin_memory()
         self._hdr_np = self._hdr_host.numpy()
-        self._cand_out = _torch.zeros(2 * _lib.VK_MAX_CAND, dtype=_torch.int64, device=dev)
-        self._cand_out_host = _torch.zeros(2 * _lib.VK_MAX_CAND, dtype=_torch.int64).pin_memory()
+        self._cand_out = _torch.zeros(3 * _lib.VK_MAX_CAND, dtype=_torch.int64, device=dev)
+        self._cand_out_host = _torch.zeros(3 * _lib.VK_MAX_CAND, dtype=_torch.int64).pin_memory()
         self._members = _torch.empty(n + 1, dtype=_torch.int32, device=dev)
         self._members_host = _torch.zeros(4096, dtype=_torch.int32).pin_memory()
         self._tile_scratch = _torch.zeros(2 + (n + 1023) // 1024, dtype=_torch.int32, device=dev)
@@ -290,7 +290,8 @@ class ClusterGenerator:
         h = self._hdr_np
         p = _Probe()
         p.medoid = int(row)
-        p.density = int(h[_lib.HDR_DENSITY:_lib.HDR_DENSITY + 8].view(_np.uint64)[0])
+        dens = h[_lib.HDR_DENSITY_LO:_lib.HDR_DENSITY_LO + 16].view(_np.uint64)
+        p.density = (int(dens[1]) << 12) + int(dens[0])  # exact, in units of 2^-29
         p.hist = h[_lib.HDR_HIST:_lib.HDR_HIST + 8 * _NBINS].view(_np.uint64).copy()
         counts = h[_lib.HDR_NWITHIN:_lib.HDR_NWITHIN + 16].view(_np.int32)
         p.n_within, p.n_lt, p.n_nl, p.rank = (int(x) for x in counts)
@@ -316,8 +317,9 @@ class ClusterGenerator:
                     self._cand_out.data_ptr(), self._cand_out_host.data_ptr(), self._stream,
                 )
             )
-            dens = self._cand_out_host.numpy()[: len(chunk)].view(_np.uint64)
-            out.extend(int(x) for x in dens)
+            res = self._cand_out_host.numpy().view(_np.uint64)
+            lo, hi = res[: len(chunk)], res[_lib.VK_MAX_CAND:_lib.VK_MAX_CAND + len(chunk)]
+            out.extend((int(h) << 12) + int(l) for l, h in zip(lo, hi))
         return out
 
     def _select_members(self, probe: _Probe, threshold: float) -> _np.ndarray:

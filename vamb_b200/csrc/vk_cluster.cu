@@ -122,6 +122,7 @@ __device__ __forceinline__ int hist_bin(float dd, const float *edges) {
 
 struct ProbeAcc {
     u64 dens;
+    u64 dens_hi;
     unsigned nlt;
     unsigned rank;
 };
@@ -149,7 +150,7 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
 
     if (tid <= VK_NBINS) s_edges[tid] = edges_g[tid];
     if (tid < VK_NBINS) s_hist[tid] = 0ull;
-    if (tid == 0) { s_nl_cnt = 0; s_acc.dens = 0ull; s_acc.nlt = 0u; s_acc.rank = 0u; }
+    if (tid == 0) { s_nl_cnt = 0; s_acc.dens = 0ull; s_acc.dens_hi = 0ull; s_acc.nlt = 0u; s_acc.rank = 0u; }
     for (int k = tid; k < d; k += PB_THREADS) s_q[k] = matrix[mrow * (int64_t)d + k];
     __syncthreads();
 
@@ -158,7 +159,7 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
     const float e_lo = s_edges[0], e_hi = s_edges[VK_NBINS];
     const float rad = 0.05f;
 
-    u64 t_dens = 0ull;
+    u64 t_dens = 0ull, t_dens_hi = 0ull;
     unsigned t_nlt = 0u, t_rank = 0u;
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -203,7 +204,7 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
                     float len = 0.0f;
                     if (in_hist || within) len = __ldg(lengths + row);
                     if (within) {
-                        t_dens += __float2ull_rz(len) * closeness_fx(rad, dd);
+                        density_add(t_dens, t_dens_hi, __float2ull_rz(len), closeness_fx(rad, dd));
                         const int pos = atomicAdd(&hdr->n_within, 1);
                         if (pos < VK_PROBE_INLINE) hdr->within[pos] = (int32_t)row;
                         else within_overflow[pos] = (int32_t)row;
@@ -234,8 +235,9 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
         }
     }
 
-    if (lane8 == 0 && (t_dens | t_nlt | t_rank)) {
+    if (lane8 == 0 && (t_dens | t_dens_hi | t_nlt | t_rank)) {
         if (t_dens) atomicAdd(&s_acc.dens, t_dens);
+        if (t_dens_hi) atomicAdd(&s_acc.dens_hi, t_dens_hi);
         if (t_nlt) atomicAdd(&s_acc.nlt, t_nlt);
         if (t_rank) atomicAdd(&s_acc.rank, t_rank);
     }
@@ -245,7 +247,8 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
         if (h) atomicAdd(reinterpret_cast<u64 *>(&hdr->hist[tid]), h);
     }
     if (tid == 64) {
-        if (s_acc.dens) atomicAdd(reinterpret_cast<u64 *>(&hdr->density_fx), s_acc.dens);
+        if (s_acc.dens) atomicAdd(reinterpret_cast<u64 *>(&hdr->density_lo), s_acc.dens);
+        if (s_acc.dens_hi) atomicAdd(reinterpret_cast<u64 *>(&hdr->density_hi), s_acc.dens_hi);
         if (s_acc.nlt) atomicAdd(&hdr->n_lt, (int)s_acc.nlt);
         if (s_acc.rank) atomicAdd(&hdr->rank, (int)s_acc.rank);
     }
@@ -373,6 +376,7 @@ eval_candidates_kernel(const float *__restrict__ matrix, const float *__restrict
                        float prune_radius, CandRows cand, int n_cand, u64 *out) {
     extern __shared__ __align__(16) float s_qs[];  // [n_cand][dpad]
     __shared__ u64 s_dens[VK_MAX_CAND];
+    __shared__ u64 s_dens_hi[VK_MAX_CAND];
     __shared__ unsigned s_cnt[VK_MAX_CAND];
     const int tid = threadIdx.x, lane8 = tid & 7, g = tid >> 3;
     const unsigned gmask = group8_mask();
@@ -382,7 +386,7 @@ eval_candidates_kernel(const float *__restrict__ matrix, const float *__restrict
         const int k = i / dpad, c = i - k * dpad;
         s_qs[i] = c < d ? matrix[(int64_t)cand.rows[k] * d + c] : 0.0f;
     }
-    if (tid < VK_MAX_CAND) { s_dens[tid] = 0ull; s_cnt[tid] = 0u; }
+    if (tid < VK_MAX_CAND) { s_dens[tid] = 0ull; s_dens_hi[tid] = 0ull; s_cnt[tid] = 0u; }
     __syncthreads();
 
     const float rad = 0.05f;
@@ -407,7 +411,9 @@ eval_candidates_kernel(const float *__restrict__ matrix, const float *__restrict
                 float dd = __fsub_rn(0.5f, acc);
                 if (row == cand.rows[k]) dd = 0.0f;
                 if (dd <= rad) {
-                    atomicAdd(&s_dens[k], lenq * closeness_fx(rad, dd));
+                    const u64 cq = closeness_fx(rad, dd);
+                    atomicAdd(&s_dens[k], lenq * (cq & 4095ull));
+                    atomicAdd(&s_dens_hi[k], lenq * (cq >> 12));
                     atomicAdd(&s_cnt[k], 1u);
                 }
             }
@@ -416,7 +422,8 @@ eval_candidates_kernel(const float *__restrict__ matrix, const float *__restrict
     __syncthreads();
     if (tid < n_cand) {
         if (s_dens[tid]) atomicAdd(&out[tid], s_dens[tid]);
-        if (s_cnt[tid]) atomicAdd(&out[VK_MAX_CAND + tid], (u64)s_cnt[tid]);
+        if (s_dens_hi[tid]) atomicAdd(&out[VK_MAX_CAND + tid], s_dens_hi[tid]);
+        if (s_cnt[tid]) atomicAdd(&out[2 * VK_MAX_CAND + tid], (u64)s_cnt[tid]);
     }
 }
 
@@ -436,7 +443,7 @@ extern "C" int vk_eval_candidates_sync(const float *matrix, const float *lengths
     CandRows cand;
     memset(&cand, 0, sizeof(cand));
     for (int k = 0; k < n_cand; ++k) cand.rows[k] = cand_rows_host[k];
-    VK_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(uint64_t) * 2 * VK_MAX_CAND, s));
+    VK_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(uint64_t) * 3 * VK_MAX_CAND, s));
     if (n_nl > 0) {
         const int dpad = (d + 3) & ~3;
         const size_t smem = sizeof(float) * (size_t)n_cand * dpad;
@@ -451,7 +458,7 @@ extern "C" int vk_eval_candidates_sync(const float *matrix, const float *lengths
                                                               prune_radius, cand, n_cand, (u64 *)out_dev);
         VK_LAUNCH_CHECK();
     }
-    VK_CUDA(cudaMemcpyAsync(out_host, out_dev, sizeof(uint64_t) * 2 * VK_MAX_CAND, cudaMemcpyDeviceToHost, s));
+    VK_CUDA(cudaMemcpyAsync(out_host, out_dev, sizeof(uint64_t) * 3 * VK_MAX_CAND, cudaMemcpyDeviceToHost, s));
     VK_CUDA(cudaStreamSynchronize(s));
     return 0;
 }

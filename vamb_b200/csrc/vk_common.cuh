@@ -89,3 +89,9 @@ __device__ __forceinline__ u64 closeness_fx(float radius, float d) {
     const float c = __fsub_rn(radius, d);
     return __float2ull_rz(c * 536870912.0f);
 }
+
+// exact density accumulation split into two 64-bit sums (see vk_probe_header)
+__device__ __forceinline__ void density_add(u64 &lo, u64 &hi, u64 len, u64 cq) {
+    lo += len * (cq & 4095ull);
+    hi += len * (cq >> 12);
+}
