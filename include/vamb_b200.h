@@ -112,6 +112,96 @@ int vk_compact_rows_sync(const float *matrix, const float *lengths, const int32_
 /* Full distance vector (vamb/cluster.py:672-676) -- used by tests and the roofline bench. */
 int vk_distances(const float *matrix, int64_t n, int d, int64_t medoid_row, float *dists, void *stream);
 
+
+/* ------------------------------------------------------------------ VAE (vamb/encode.py) */
+
+#define VK_VAE_MAX_LAYERS 10 /* linear layers: len(nhiddens) encoder + mu + len(nhiddens) decoder + output */
+#define VK_VAE_ROW_TILE 64   /* batch rows per partial-statistics tile */
+
+enum { VK_LAYER_HIDDEN = 0, VK_LAYER_MU = 1, VK_LAYER_OUT = 2 };   /* vk_vae_layer.kind    */
+enum { VK_IN_DATA = 0, VK_IN_BN = 1, VK_IN_Z = 2 };                /* vk_vae_layer.in_kind */
+
+/* Device-resident control block: everything a replayed CUDA graph must read at run time. */
+typedef struct vk_vae_ctl {
+    double d;              /* D-Adaptation distance estimate (dadaptation DAdaptAdam: group['d'])            */
+    double num_w;          /* group['numerator_weighted']                                                     */
+    double loss_sums[5];   /* running sums of (loss, ab, ce, sse, kld) over the steps since the last reset    */
+    double wbar;           /* mean of the batch weights (the reference's [B]x[B,1] broadcast, encode.py:349)  */
+    int64_t step;          /* optimiser steps taken (Philox counter)                                          */
+    int64_t epoch_step0;   /* value of `step` at the start of the current epoch                               */
+    int64_t n_loss_steps;  /* number of steps accumulated in loss_sums                                        */
+    uint64_t seed;         /* Philox key / Feistel key base                                                   */
+    int32_t epoch;         /* current epoch (selects the row permutation)                                     */
+    int32_t tickets[2 * VK_VAE_MAX_LAYERS + 4]; /* last-block-done counters (self-resetting)                  */
+} vk_vae_ctl;
+
+/* One Linear (+ LeakyReLU + Dropout + BatchNorm1d) block, encode.py:259-295.  All pointers device. */
+typedef struct vk_vae_layer {
+    int32_t k_in, n_out;
+    int32_t kind, in_kind;
+    int64_t w_off, b_off;       /* float offsets into the parameter / gradient / optimiser arenas: W[n_out,k_in], b */
+    int64_t g_off, beta_off;    /* BatchNorm weight / bias offsets (-1 when kind != hidden)                        */
+    float *running_mean, *running_var;
+    int64_t *num_batches_tracked;
+    float *act;                 /* hidden: P = dropout(leakyrelu(x W^T + b)) [bmax, n_out]; mu: MU; out: R          */
+    float *dact;                /* hidden: dL/dBN(P); mu: dL/dmu; out: dL/dR                     [bmax, n_out]      */
+    double *fwd_part;           /* [ceil(bmax/ROW_TILE)][2][n_out] column sums of P and P^2 per row tile            */
+    double *bwd_part;           /* [ceil(bmax/ROW_TILE)][2][n_out] column sums of dH and dH*Phat per row tile        */
+    float *bn_a, *bn_c;         /* BN(P) = P * bn_a + bn_c  (batch statistics in training, running in eval)         */
+    float *bn_mean, *bn_rstd;   /* batch mean and 1/sqrt(var + eps) of the current step                             */
+    float *bn_m1, *bn_m2;       /* mean_b dH and mean_b dH*Phat of the current step                                 */
+} vk_vae_layer;
+
+typedef struct vk_vae {
+    int32_t n_layers, nsamples, ntnf, nlatent, d_in, bmax;
+    float dropout, slope;
+    float ce_w, ab_w, sse_w, kld_w;     /* encode.py:334-343 */
+    int64_t n_rows;                     /* rows of the resident dataset                       */
+    const float *data;                  /* [n_rows, d_in] = depths | tnf | total abundance    */
+    const float *weights;               /* [n_rows] contig weights (encode.py:122-126)        */
+    int64_t n_params;
+    float *params, *grads, *exp_avg, *exp_avg_sq, *s; /* flat arenas, module.parameters() order */
+    float *z;                           /* [bmax, nlatent] mu + eps                            */
+    int64_t *batch_rows;                /* [bmax] dataset row of every batch row               */
+    double *opt_part;                   /* [2 * 1024] optimiser block partials                 */
+    double *loss_part;                  /* [5 * 1024] loss block partials                      */
+    vk_vae_ctl *ctl;
+    vk_vae_layer layers[VK_VAE_MAX_LAYERS];
+} vk_vae;
+
+/* Optional host-injected randomness for parity tests (all device pointers, NULL = on-device RNG). */
+typedef struct vk_vae_inject {
+    const int64_t *batch_idx;                   /* [batch] dataset rows; NULL = epoch permutation       */
+    const float *eps;                           /* [batch, nlatent] reparameterisation noise             */
+    const uint8_t *keep[VK_VAE_MAX_LAYERS];     /* [batch, n_out] dropout keep-masks per hidden layer    */
+} vk_vae_inject;
+
+int64_t vk_vae_sizeof(int which); /* 0: vk_vae, 1: vk_vae_layer, 2: vk_vae_ctl, 3: vk_vae_inject */
+
+/* One optimiser step (encode.py:401-419): batch gather, forward (:259-314), loss (:316-357) and
+ * its backward, D-Adaptation Adam update (dadaptation.DAdaptAdam.step).  `net` and `inject` are HOST
+ * structs holding device pointers.  Stream-ordered, graph-capturable, no host synchronisation. */
+int vk_vae_train_step(const vk_vae *net, int batch, const vk_vae_inject *inject, void *stream);
+
+/* Forward only on rows [row0, row0 + batch) of the resident dataset (or inject->batch_idx).
+ * training != 0: batch statistics + dropout (encode.py:306-314 in train mode) and the loss kernel;
+ * training == 0: running statistics, no dropout.  Results stay in layer.act buffers. */
+int vk_vae_forward(const vk_vae *net, int64_t row0, int batch, int training, int with_loss,
+                   const vk_vae_inject *inject, void *stream);
+
+/* encode.py:442-484: eval-mode mu of rows [row0, row0 + n) with the low `mask_bits` mantissa bits
+ * cleared (vambtools.py:324-330), written to latent_out[n, nlatent] (device). */
+int vk_vae_encode(const vk_vae *net, int64_t row0, int64_t n, int mask_bits, float *latent_out, void *stream);
+
+/* Eval-mode BatchNorm affine from the running statistics into bn_a / bn_c. */
+int vk_vae_prepare_eval(const vk_vae *net, void *stream);
+
+/* Standalone D-Adaptation Adam step on the arenas (used after a gradient all-reduce). */
+int vk_vae_dadapt_step(const vk_vae *net, void *stream);
+
+/* Backward + gradients only (no optimiser): used by the multi-GPU path and by the tests. */
+int vk_vae_grad_step(const vk_vae *net, int batch, const vk_vae_inject *inject, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,213 @@
+"""GPU suite: the CUDA VAE path (through the C ABI) against the reference-made golden fixtures
+and the torch-fp32 oracle.  Floating point: per-step losses within 2e-5 relative, gradients /
+parameters within 2e-5 of the tensor norm (fp32 accumulation-order noise), eval-mode mu within
+1e-4 absolute before bit masking (BASELINE.json north_star tolerance)."""
+import io
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+from oracle.make_golden_vae import VAE_CASES, vae_inputs  # noqa: E402  (fixture definitions only)
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def unpack_keep(packed, batch, n):
+    return np.unpackbits(packed)[: batch * n].reshape(batch, n)
+
+
+@pytest.mark.parametrize("case", VAE_CASES, ids=[c[0] for c in VAE_CASES])
+def test_train_steps_and_encode_match_reference_golden(case):
+    import vamb_b200.encode as ve
+    from oracle import vae_oracle as vo
+
+    name, S, nh, nl, dp, n, batch, nsteps, seed = case
+    g = np.load(os.path.join(GOLDEN, f"vae_{name}.npz"))
+    rpkm, tnfs, lens = vae_inputs(S, n, seed)
+    dl = ve.make_dataloader(rpkm.copy(), tnfs.copy(), lens, batchsize=batch)
+    vae = ve.VAE(S, nhiddens=nh, nlatent=nl, dropout=dp, seed=seed)
+    # same seed -> the reference's initial weights, bit for bit
+    init = vo.init_state(S, vae.nhiddens, nl, seed)
+    sd = vae.state_dict()
+    assert list(sd.keys()) == list(init.keys())
+    for k in init:
+        assert torch.equal(sd[k].cpu(), init[k]), k
+    vae._reset_optimizer()
+    hidden = vae.nhiddens + vae.nhiddens[::-1]
+    for step in range(nsteps):
+        keeps = None
+        if vae.dropout > 0:
+            keeps = [unpack_keep(g[f"keep{li}"][step], batch, hidden[li]) for li in range(len(hidden))]
+        losses = vae._step_injected(dl.dataset.tensors, g["batch_idx"][step], g["eps"][step], keeps)
+        assert np.allclose(losses, g["losses"][step], rtol=2e-5, atol=1e-7), (step, losses, g["losses"][step])
+        assert abs(vae.dadapt_d - g["d"][step]) <= 2e-4 * g["d"][step], (step, vae.dadapt_d, g["d"][step])
+    sd = vae.state_dict()
+    L = len(vae.nhiddens)
+    assert rel(sd["mu.weight"].cpu().numpy(), g["mu_weight"]) < 2e-5
+    assert rel(sd["outputlayer.bias"].cpu().numpy(), g["out_bias"]) < 2e-5
+    assert rel(sd["encoderlayers.0.weight"].cpu().numpy()[:8], g["enc0_weight_head"]) < 2e-5
+    assert rel(sd["encodernorms.0.running_mean"].cpu().numpy(), g["bn0_running_mean"]) < 2e-5
+    assert rel(sd["encodernorms.0.running_var"].cpu().numpy(), g["bn0_running_var"]) < 2e-5
+    assert rel(sd[f"decodernorms.{L - 1}.weight"].cpu().numpy(), g["bn_last_weight"]) < 2e-5
+    assert int(sd["encodernorms.0.num_batches_tracked"]) == nsteps
+    # encode: eval mode, low 12 mantissa bits cleared
+    lat = vae.encode(dl)
+    assert lat.shape == (n, nl) and lat.dtype == np.float32 and lat.flags.owndata
+    assert np.all(lat.view(np.uint32) & 0xFFF == 0)
+    gl = g["latent"]
+    assert np.all(np.abs(lat - gl) <= 1e-4 + np.abs(gl) * 2.0 ** -11)
+
+
+def test_gradients_match_oracle_default_network():
+    """One fwd+bwd at B=256 on the bin-default network (S=50, 512-512-32): every gradient tensor."""
+    import vamb_b200.encode as ve
+    from oracle import vae_oracle as vo
+
+    S, n, B = 50, 1000, 256
+    rpkm, tnfs, lens = vae_inputs(S, n, 7)
+    dl = ve.make_dataloader(rpkm.copy(), tnfs.copy(), lens, batchsize=B)
+    d, t, a, w = dl.dataset.tensors
+    vae = ve.VAE(S, seed=2)
+    o = vo.OracleVAE(S, seed=2)
+    idx = torch.from_numpy(np.random.default_rng(0).choice(n, B, replace=False))
+    torch.manual_seed(5)
+    lo, grads, eps, keeps = o.grads(d[idx], t[idx], a[idx], w[idx])
+    losses = vae._step_injected(dl.dataset.tensors, idx.numpy(), eps.numpy(), [k.numpy() for k in keeps], optimize=False)
+    assert np.allclose(losses, lo, rtol=2e-5, atol=1e-7)
+    got = vae._grad_dict()
+    for k, gref in grads.items():
+        assert rel(got[k].cpu().numpy(), gref.numpy()) < 3e-5, k
+
+
+def test_odd_batch_and_many_steps_match_oracle():
+    """B not a multiple of the tile size, 12 steps: parameters track the oracle."""
+    import vamb_b200.encode as ve
+    from oracle import vae_oracle as vo
+
+    S, n, B = 4, 500, 77
+    rpkm, tnfs, lens = vae_inputs(S, n, 9)
+    dl = ve.make_dataloader(rpkm.copy(), tnfs.copy(), lens, batchsize=B)
+    d, t, a, w = dl.dataset.tensors
+    vae = ve.VAE(S, nhiddens=[96, 33], nlatent=7, seed=1)
+    vae._reset_optimizer()
+    o = vo.OracleVAE(S, nhiddens=[96, 33], nlatent=7, seed=1)
+    rng = np.random.default_rng(1)
+    for step in range(12):
+        idx = torch.from_numpy(rng.choice(n, B, replace=False))
+        torch.manual_seed(50 + step)
+        lo, eps, keeps = o.train_step(d[idx], t[idx], a[idx], w[idx])
+        losses = vae._step_injected(dl.dataset.tensors, idx.numpy(), eps.numpy(), [k.numpy() for k in keeps])
+        assert np.allclose(losses, lo, rtol=1e-4, atol=1e-6), (step, losses, lo)
+    sd = vae.state_dict()
+    for k, v in o.state.items():
+        if k.endswith("num_batches_tracked"):
+            assert int(sd[k]) == int(v)
+        else:
+            assert rel(sd[k].cpu().numpy(), v.numpy()) < 2e-4, k
+    assert abs(vae.dadapt_d - o.d) <= 1e-3 * o.d
+    lat_raw = vae._encode_device(dl.dataset.tensors, mask_bits=0)
+    _, oraw = o.encode(d, t, a)
+    assert np.abs(lat_raw - oraw).max() < 1e-4
+
+
+def test_forward_api_eval_and_train():
+    import vamb_b200.encode as ve
+    from oracle import vae_oracle as vo
+
+    S, n = 6, 130
+    rpkm, tnfs, lens = vae_inputs(S, n, 11)
+    dl = ve.make_dataloader(rpkm.copy(), tnfs.copy(), lens, batchsize=64)
+    d, t, a, w = dl.dataset.tensors
+    vae = ve.VAE(S, nhiddens=[64, 64], nlatent=8, seed=3)
+    o = vo.OracleVAE(S, nhiddens=[64, 64], nlatent=8, seed=3)
+    vae.eval()
+    do, to, ao, mu = vae(d, t, a)
+    rd, rt, ra, rmu, _, _ = vo.forward(o.state, d, t, a, S, o.dropout, False, eps=torch.zeros(n, 8))
+    assert mu.shape == (n, 8) and do.shape == (n, S) and to.shape == (n, 103) and ao.shape == (n, 1)
+    assert np.abs(mu.numpy() - rmu.numpy()).max() < 1e-5
+    assert np.allclose(do.sum(1).numpy(), 1.0, atol=1e-5)
+    loss = vae.calc_loss(d, do, t, to, a, ao, mu, w)
+    assert all(np.isfinite(float(x)) for x in loss)
+
+
+# ---- the reference's TestVAE (test/test_encode.py:122-185) on the CUDA path ----
+class TestReferenceVAESuite:
+    tnfs = np.random.RandomState(1).random((128, 103)).astype(np.float32)
+    rpkm = np.random.RandomState(2).random((128, 14)).astype(np.float32)
+    lens = np.random.RandomState(3).randint(2000, 5000, size=128)
+
+    def test_loss_falls(self):
+        import vamb_b200.encode as ve
+
+        vae = ve.VAE(self.rpkm.shape[1])
+        rpkm_copy, tnfs_copy = self.rpkm.copy(), self.tnfs.copy()
+        dl = ve.make_dataloader(rpkm_copy, tnfs_copy, self.lens, batchsize=16, destroy=True)
+        di, ti, ai, we = next(iter(dl))
+        vae.train()
+        do, to, ao, mu = vae(di, ti, ai)
+        before = vae.calc_loss(di, do, ti, to, ai, ao, mu, we)[0]
+        vae.trainmodel(dl, nepochs=3, batchsteps=[1, 2])
+        vae.train()
+        do, to, ao, mu = vae(di, ti, ai)
+        after = vae.calc_loss(di, do, ti, to, ai, ao, mu, we)[0]
+        assert float(after) < float(before)
+
+    def test_save_load_and_encoding(self):
+        import vamb_b200.encode as ve
+
+        vae = ve.VAE(self.rpkm.shape[1])
+        dl = ve.make_dataloader(self.rpkm.copy(), self.tnfs.copy(), self.lens, batchsize=16)
+        vae.trainmodel(dl, nepochs=2, batchsteps=None)
+        enc1 = vae.encode(dl)
+        assert enc1.dtype == np.float32 and enc1.shape == (len(self.rpkm), vae.nlatent)
+        buf = io.BytesIO()
+        vae.save(buf)
+        buf.seek(0)
+        vae2 = ve.VAE.load(buf)
+        enc2 = vae2.encode(dl)
+        assert np.all(np.abs(enc1 - enc2) < 1e-6)
+        # the file is loadable as plain tensors with the reference's key set
+        buf.seek(0)
+        dct = torch.load(buf, weights_only=True)
+        assert set(dct) == {"nsamples", "alpha", "beta", "dropout", "nhiddens", "nlatent", "state"}
+        assert "encodernorms.1.num_batches_tracked" in dct["state"]
+
+    def test_trainmodel_arg_errors(self):
+        import vamb_b200.encode as ve
+
+        vae = ve.VAE(self.rpkm.shape[1])
+        dl = ve.make_dataloader(self.rpkm.copy(), self.tnfs.copy(), self.lens, batchsize=16)
+        with pytest.raises(ValueError):
+            vae.trainmodel(dl, nepochs=0)
+        with pytest.raises(ValueError):
+            vae.trainmodel(dl, nepochs=3, batchsteps=[1.5])
+        with pytest.raises(ValueError):
+            vae.trainmodel(dl, nepochs=3, batchsteps=[3])
+
+
+def test_graph_replay_training_is_deterministic_and_learns():
+    """Enough steps per epoch to go through the CUDA-graph path; same seed -> same bits."""
+    import vamb_b200.encode as ve
+    from vamb_b200 import synth
+
+    ab, tnf, lens = synth.make_contigs(80000, 8, seed=0)
+    lats = []
+    for _ in range(2):
+        dl = ve.make_dataloader(ab.copy(), tnf.copy(), lens, batchsize=256)
+        vae = ve.VAE(8, seed=4)
+        vae.trainmodel(dl, nepochs=3, batchsteps=[2])
+        first = vae._last_epoch_losses
+        lats.append(vae.encode(dl))
+        assert np.all(np.isfinite(lats[-1]))
+    assert np.array_equal(lats[0], lats[1])
+    # planted genomes: the loss after 3 epochs is well below the untrained level
+    assert first[0] < 0.9

@@ -76,9 +76,18 @@ def _bind():
 _bind()
 
 
+# bound (with argtypes) in vamb_b200/encode.py next to the ctypes mirrors of their structs
+_VAE_SYMBOLS = [
+    "vk_vae_sizeof", "vk_vae_train_step", "vk_vae_grad_step", "vk_vae_forward", "vk_vae_encode",
+    "vk_vae_prepare_eval", "vk_vae_dadapt_step",
+]
+for _name in _VAE_SYMBOLS:
+    getattr(lib, _name)  # AttributeError = stale .so
+
+
 def declared_symbols() -> list:
     """Every entry point include/vamb_b200.h declares (checked by the CPU test-suite)."""
-    return ["vk_last_error", "vk_abi_version"] + list(_SIGNATURES)
+    return ["vk_last_error", "vk_abi_version"] + list(_SIGNATURES) + _VAE_SYMBOLS
 
 
 def check(status: int) -> None:

@@ -1,0 +1,826 @@
+// vamb_b200 VAE kernels, fp32 CUDA-core path (sm_100a).
+//
+// One optimiser step of vamb/encode.py (VAE.trainepoch :401-419) = 15 stream-ordered launches:
+//   batch_rows  | fwd x (2L+2) | loss | bwd x (2L+2) (wgrad + dgrad tiles in ONE grid) | dadapt
+// with every element-wise stage fused into the operand loads / epilogues of the GEMM tiles:
+//   * BatchNorm is never materialised: producers write P = dropout(leakyrelu(xW^T+b)) plus
+//     per-row-tile column sums; the LAST block to finish (ticket) folds them into the per-feature
+//     affine (a, c) and the running statistics; consumers apply P*a + c while loading.
+//   * the BatchNorm / dropout / LeakyReLU backward is applied while loading dH as a GEMM operand;
+//     its two batch reductions (sum dH, sum dH*Phat) are column sums of the dgrad epilogue.
+//   * bias gradients come out of the wgrad GEMM through a virtual all-ones input column.
+// All reductions are two-stage with a fixed order (no floating-point atomics): same inputs ->
+// same bits.  This file is the exact-fp32 reference path; vk_vae_tc.cu (tcgen05, 3xTF32) replaces
+// the GEMM core for large batches.
+//
+// Reference lines (RasmussenLab/vamb): encode.py:259-273 _encode, :276-286 reparameterize,
+// :288-304 _decode, :316-357 calc_loss, :442-484 encode; dadaptation==3.2 DAdaptAdam.step.
+#include "vk_common.cuh"
+
+// ------------------------------------------------------------------ small device helpers
+__device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                           uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ float u32_to_unit(uint32_t x) {  // (0, 1]
+    return ((float)(x >> 8) + 1.0f) * (1.0f / 16777216.0f);
+}
+
+// Feistel permutation of [0, n) by cycle walking over [0, 2^(2*half_bits)).
+__device__ __forceinline__ uint64_t feistel_perm(uint64_t i, uint64_t n, int half_bits, uint64_t key) {
+    const uint32_t mask = (1u << half_bits) - 1u;
+    uint64_t x = i;
+    do {
+        uint32_t l = (uint32_t)(x >> half_bits) & mask, r = (uint32_t)x & mask;
+#pragma unroll
+        for (int round = 0; round < 4; ++round) {
+            uint32_t f = (r ^ (uint32_t)(key >> (16 * round))) * 0x9E3779B1u;
+            f ^= f >> 15; f *= 0x85EBCA6Bu; f ^= f >> 13;
+            const uint32_t nl = r, nr = (l ^ f) & mask;
+            l = nl; r = nr;
+        }
+        x = ((uint64_t)l << half_bits) | r;
+    } while (x >= n);
+    return x;
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+// ------------------------------------------------------------------ batch rows + mean weight
+// mode 0: rows from inject->batch_idx; 1: epoch permutation; 2: contiguous [row0, row0+B)
+__global__ void __launch_bounds__(256)
+batch_rows_kernel(int64_t *batch_rows, const int64_t *batch_idx, const float *weights, vk_vae_ctl *ctl, int B,
+                  int64_t n_rows, int mode, int64_t row0, int steps_per_epoch) {
+    __shared__ double s_w[256];
+    const int tid = threadIdx.x;
+    double acc = 0.0;
+    int half_bits = 1;
+    while ((1ull << (2 * half_bits)) < (uint64_t)n_rows) ++half_bits;
+    const uint64_t key = mix64(ctl->seed ^ (0x5851F42D4C957F2Dull * (uint64_t)(ctl->epoch + 1)));
+    int64_t pos0 = 0;
+    if (mode == 1) {
+        int64_t t = ctl->step - ctl->epoch_step0;
+        if (steps_per_epoch > 0) t %= steps_per_epoch;
+        pos0 = t * (int64_t)B;
+    }
+    for (int b = tid; b < B; b += 256) {
+        int64_t r;
+        if (mode == 0) r = batch_idx[b];
+        else if (mode == 1) r = (int64_t)feistel_perm((uint64_t)(pos0 + b), (uint64_t)n_rows, half_bits, key);
+        else r = row0 + b;
+        batch_rows[b] = r;
+        acc += (double)weights[r];
+    }
+    s_w[tid] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 256; ++i) t += s_w[i];
+        ctl->wbar = t / (double)B;
+    }
+}
+
+// ------------------------------------------------------------------ operand loaders
+// at(r, c): element (row r, column c) of the logical [rows, cols] operand, 0 outside.
+struct LdPlain {
+    const float *p; int ld, rows, cols;
+    __device__ __forceinline__ float at(int r, int c) const {
+        return (r < rows && c < cols) ? __ldg(p + (int64_t)r * ld + c) : 0.0f;
+    }
+};
+struct LdAffine {  // BatchNorm applied on load: P * a + c
+    const float *p; const float *a; const float *sh; int ld, rows, cols;
+    __device__ __forceinline__ float at(int r, int c) const {
+        if (r >= rows || c >= cols) return 0.0f;
+        return __fmaf_rn(__ldg(p + (int64_t)r * ld + c), __ldg(a + c), __ldg(sh + c));
+    }
+};
+struct LdData {  // gathered dataset rows
+    const float *data; const int64_t *rows_idx; int ld, rows, cols;
+    __device__ __forceinline__ float at(int r, int c) const {
+        return (r < rows && c < cols) ? __ldg(data + rows_idx[r] * (int64_t)ld + c) : 0.0f;
+    }
+};
+struct LdDY {  // dL/dY of a hidden block from dL/dBN(P): BatchNorm, dropout and LeakyReLU backward
+    const float *dh; const float *p; const float *g; const float *mean; const float *rstd;
+    const float *m1; const float *m2; int ld, rows, cols; float inv_keep, slope; int has_dropout;
+    __device__ __forceinline__ float at(int r, int c) const {
+        if (r >= rows || c >= cols) return 0.0f;
+        const int64_t o = (int64_t)r * ld + c;
+        const float pv = __ldg(p + o);
+        if (has_dropout && pv == 0.0f) return 0.0f;  // dropped unit
+        const float rs = __ldg(rstd + c);
+        const float ph = (pv - __ldg(mean + c)) * rs;
+        float v = __ldg(g + c) * rs * (__ldg(dh + o) - __ldg(m1 + c) - ph * __ldg(m2 + c));
+        v *= inv_keep;
+        return pv > 0.0f ? v : v * slope;
+    }
+};
+// generic input activation of a layer (data / BN(P) / z) with an optional all-ones extra column
+struct LdInput {
+    int in_kind; LdData d; LdAffine a; LdPlain z; int ones_col;  // ones_col < 0: none
+    __device__ __forceinline__ float at(int r, int c) const {
+        if (c == ones_col) return r < (in_kind == VK_IN_DATA ? d.rows : in_kind == VK_IN_BN ? a.rows : z.rows) ? 1.0f : 0.0f;
+        if (in_kind == VK_IN_DATA) return d.at(r, c);
+        if (in_kind == VK_IN_BN) return a.at(r, c);
+        return z.at(r, c);
+    }
+};
+// generic dL/dY of a layer: hidden -> LdDY, mu / out -> plain
+struct LdGradOut {
+    int hidden; LdDY h; LdPlain pl;
+    __device__ __forceinline__ float at(int r, int c) const { return hidden ? h.at(r, c) : pl.at(r, c); }
+};
+
+// ------------------------------------------------------------------ 64x64x16 fp32 GEMM tile
+constexpr int GT = 256;       // threads: 16 x 16, each a TM x TN micro-tile
+constexpr int BK = 16;
+constexpr int SMEM_GEMM_FLOATS = 2 * BK * (64 + 4) * 2;
+
+// C[m, n] = sum_k A(m, k) * B(n, k).  AT: A stored [k][m] (at(k, m)); else [m][k].  Same for B.
+template <int BM, int BN, bool AT, bool BT, class LA, class LB>
+__device__ __forceinline__ void gemm_block(int K, int m0, int n0, const LA &la, const LB &lb,
+                                           float (&acc)[BM / 16][BN / 16], float *smem) {
+    constexpr int TM = BM / 16, TN = BN / 16, LDA = BM + 4, LDB = BN + 4;
+    float *As = smem;
+    float *Bs = smem + 2 * BK * LDA;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    float ra[TM], rb[TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
+
+    auto gload = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            if (!AT) { const int k = tid & 15, m = (tid >> 4) + 16 * i; ra[i] = la.at(m0 + m, k0 + k); }
+            else { const int m = tid % BM, k = tid / BM + (GT / BM) * i; ra[i] = la.at(k0 + k, m0 + m); }
+        }
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            if (!BT) { const int k = tid & 15, n = (tid >> 4) + 16 * j; rb[j] = lb.at(n0 + n, k0 + k); }
+            else { const int n = tid % BN, k = tid / BN + (GT / BN) * j; rb[j] = lb.at(k0 + k, n0 + n); }
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            int m, k;
+            if (!AT) { k = tid & 15; m = (tid >> 4) + 16 * i; }
+            else { m = tid % BM; k = tid / BM + (GT / BM) * i; }
+            As[(buf * BK + k) * LDA + m] = ra[i];
+        }
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            int n, k;
+            if (!BT) { k = tid & 15; n = (tid >> 4) + 16 * j; }
+            else { n = tid % BN; k = tid / BN + (GT / BN) * j; }
+            Bs[(buf * BK + k) * LDB + n] = rb[j];
+        }
+    };
+
+    const int nk = (K + BK - 1) / BK;
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    for (int kt = 0; kt < nk; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < nk) gload((kt + 1) * BK);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float a[TM], b[TN];
+            const float *ap = As + (buf * BK + k) * LDA + ty * TM;
+            const float *bp = Bs + (buf * BK + k) * LDB + tx * TN;
+#pragma unroll
+            for (int i = 0; i < TM; ++i) a[i] = ap[i];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) b[j] = bp[j];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = __fmaf_rn(a[i], b[j], acc[i][j]);
+        }
+        if (kt + 1 < nk) sstore(buf ^ 1);
+        __syncthreads();
+    }
+}
+
+// column sums of a 64x64 tile held as 4x4 micro-tiles: deterministic two-stage reduction.
+// v0/v1[j] = this thread's partial over its TM rows.  Writes out0/out1[col] for col < 64.
+template <int TN>
+__device__ __forceinline__ void tile_colsum2(const float (&v0)[TN], const float (&v1)[TN], double *s_red,
+                                             double *out0, double *out1, int n0, int N) {
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    constexpr int BN = TN * 16;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+        s_red[(0 * 16 + ty) * BN + tx * TN + j] = (double)v0[j];
+        s_red[(1 * 16 + ty) * BN + tx * TN + j] = (double)v1[j];
+    }
+    __syncthreads();
+    if (tid < 2 * BN) {
+        const int which = tid / BN, col = tid % BN;
+        double t = 0.0;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) t += s_red[(which * 16 + r) * BN + col];
+        if (n0 + col < N) (which ? out1 : out0)[n0 + col] = t;
+    }
+    __syncthreads();
+}
+
+// "last block done": returns true in every thread of the block that finishes last.
+__device__ __forceinline__ bool last_block_done(int32_t *ticket, int total) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int t = atomicAdd(ticket, 1);
+        s_last = (t == total - 1);
+        if (s_last) *ticket = 0;  // self-reset for the next launch
+    }
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last != 0;
+}
+
+// ------------------------------------------------------------------ forward layer
+struct FwdArgs {
+    LdInput in;           // input activation [B, K]
+    const float *W, *bias;  // [N, K], [N]
+    int B, K, N, kind, training;
+    float *out;           // P / MU / R  [B, N]
+    // hidden
+    float dropout; const uint8_t *keep; double *part;
+    float *bn_a, *bn_c, *bn_mean, *bn_rstd; const float *gamma, *beta;
+    float *running_mean, *running_var; int64_t *nbt;
+    // mu
+    float *z; const float *eps; int add_eps; int mask_bits; float *latent_out;
+    vk_vae_ctl *ctl; int layer_id; float slope;
+};
+
+__global__ void __launch_bounds__(GT) fwd_layer_kernel(FwdArgs a) {
+    __shared__ __align__(16) float s_gemm[SMEM_GEMM_FLOATS];
+    __shared__ double s_red[2 * 16 * 64];
+    float acc[4][4];
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    LdPlain w{a.W, a.K, a.N, a.K};
+    gemm_block<64, 64, false, false>(a.K, m0, n0, a.in, w, acc, s_gemm);
+
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const uint32_t k0 = (uint32_t)a.ctl->seed, k1 = (uint32_t)(a.ctl->seed >> 32);
+    const uint32_t step_lo = (uint32_t)a.ctl->step, step_hi = (uint32_t)(a.ctl->step >> 32);
+    float cs[4] = {0.f, 0.f, 0.f, 0.f}, cq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= a.B) continue;
+        uint32_t rnd[4] = {0u, 0u, 0u, 0u};
+        const int nq = n0 / 4 + tx;
+        if (a.kind == VK_LAYER_HIDDEN && a.training && a.dropout > 0.0f && a.keep == nullptr)
+            philox4x32((uint32_t)m, (uint32_t)nq, step_lo, step_hi ^ ((uint32_t)(a.layer_id + 1) << 24), k0, k1, rnd);
+        if (a.kind == VK_LAYER_MU && a.add_eps && a.eps == nullptr)
+            philox4x32((uint32_t)m, (uint32_t)nq, step_lo, step_hi ^ 0x7F000000u, k0, k1, rnd);
+        float nrm[4] = {0.f, 0.f, 0.f, 0.f};
+        if (a.kind == VK_LAYER_MU && a.add_eps && a.eps == nullptr) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float u1 = u32_to_unit(rnd[2 * h]), u2 = u32_to_unit(rnd[2 * h + 1]);
+                const float r = sqrtf(-2.0f * logf(u1));
+                float sn, cn;
+                sincosf(6.28318530717958647692f * u2, &sn, &cn);
+                nrm[2 * h] = r * cn;
+                nrm[2 * h + 1] = r * sn;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= a.N) continue;
+            const float y = acc[i][j] + __ldg(a.bias + n);
+            const int64_t o = (int64_t)m * a.N + n;
+            if (a.kind == VK_LAYER_HIDDEN) {
+                float p = y > 0.0f ? y : y * a.slope;
+                if (a.training && a.dropout > 0.0f) {
+                    bool kp;
+                    if (a.keep) kp = a.keep[o] != 0;
+                    else kp = u32_to_unit(rnd[j]) > a.dropout;  // P(keep) = 1 - dropout
+                    p = kp ? p * (1.0f / (1.0f - a.dropout)) : 0.0f;
+                }
+                a.out[o] = p;
+                cs[j] += p;
+                cq[j] = __fmaf_rn(p, p, cq[j]);
+            } else if (a.kind == VK_LAYER_MU) {
+                a.out[o] = y;
+                if (a.add_eps) {
+                    const float e = a.eps ? __ldg(a.eps + o) : nrm[j];
+                    a.z[o] = y + e;
+                }
+                if (a.latent_out) {
+                    const uint32_t bits = __float_as_uint(y) & ~((1u << a.mask_bits) - 1u);
+                    a.latent_out[o] = __uint_as_float(bits);
+                }
+            } else {
+                a.out[o] = y;
+            }
+        }
+    }
+    if (a.kind != VK_LAYER_HIDDEN || !a.training) return;
+
+    // ---- BatchNorm batch statistics: per-row-tile column sums, folded by the last block ----
+    const int n_rt = gridDim.y;
+    double *p0 = a.part + ((int64_t)blockIdx.y * 2 + 0) * a.N;
+    double *p1 = a.part + ((int64_t)blockIdx.y * 2 + 1) * a.N;
+    tile_colsum2<4>(cs, cq, s_red, p0, p1, n0, a.N);
+    if (!last_block_done(&a.ctl->tickets[a.layer_id], gridDim.x * gridDim.y)) return;
+    for (int n = tid; n < a.N; n += GT) {
+        double s = 0.0, q = 0.0;
+        for (int rt = 0; rt < n_rt; ++rt) {
+            s += __ldcg(a.part + ((int64_t)rt * 2 + 0) * a.N + n);
+            q += __ldcg(a.part + ((int64_t)rt * 2 + 1) * a.N + n);
+        }
+        const double mean = s / a.B;
+        double var = q / a.B - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+        const float fm = (float)mean;
+        a.bn_mean[n] = fm;
+        a.bn_rstd[n] = rstd;
+        const float sc = a.gamma[n] * rstd;
+        a.bn_a[n] = sc;
+        a.bn_c[n] = a.beta[n] - fm * sc;
+        // running statistics: momentum 0.1, unbiased variance (torch.nn.BatchNorm1d)
+        const float unb = a.B > 1 ? (float)(var * ((double)a.B / (double)(a.B - 1))) : (float)var;
+        a.running_mean[n] = 0.9f * a.running_mean[n] + 0.1f * fm;
+        a.running_var[n] = 0.9f * a.running_var[n] + 0.1f * unb;
+    }
+    if (tid == 0) *a.nbt += 1;
+}
+
+// ------------------------------------------------------------------ loss (+ dL/dR)
+struct LossArgs {
+    const float *R; const float *MU; const float *data; const int64_t *batch_rows;
+    float *dR; int B, S, ntnf, d_in, nlatent; float ce_w, ab_w, sse_w, kld_w;
+    double *part; vk_vae_ctl *ctl; int ticket_id; int write_grad;
+};
+
+__global__ void __launch_bounds__(256) loss_kernel(LossArgs a) {
+    __shared__ double s_part[8][4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 8 + warp;
+    double l_ce = 0.0, l_sse = 0.0, l_ab = 0.0, l_kld = 0.0;
+    if (b < a.B) {
+        const float *r = a.R + (int64_t)b * a.d_in;
+        const float *x = a.data + a.batch_rows[b] * (int64_t)a.d_in;
+        float *g = a.dR + (int64_t)b * a.d_in;
+        const float gsc = (float)(a.ctl->wbar / (double)a.B);
+        // softmax over the S depth outputs (encode.py:302)
+        float mx = -INFINITY;
+        for (int s = lane; s < a.S; s += 32) mx = fmaxf(mx, r[s]);
+        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.0f;
+        for (int s = lane; s < a.S; s += 32) sum += expf(r[s] - mx);
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        float ce = 0.0f, dot = 0.0f;
+        for (int s = lane; s < a.S; s += 32) {
+            const float p = expf(r[s] - mx) / sum;
+            const float pe = p + 1e-9f;
+            ce -= logf(pe) * x[s];
+            dot += p * (-gsc * a.ce_w * x[s] / pe);
+        }
+        for (int o = 16; o; o >>= 1) {
+            ce += __shfl_xor_sync(0xffffffffu, ce, o);
+            dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        }
+        if (a.write_grad)
+            for (int s = lane; s < a.S; s += 32) {
+                const float p = expf(r[s] - mx) / sum;
+                const float gs = -gsc * a.ce_w * x[s] / (p + 1e-9f);
+                g[s] = p * (gs - dot);
+            }
+        float sse = 0.0f;
+        for (int t = lane; t < a.ntnf; t += 32) {
+            const float df = r[a.S + t] - x[a.S + t];
+            sse = __fmaf_rn(df, df, sse);
+            if (a.write_grad) g[a.S + t] = gsc * a.sse_w * 2.0f * df;
+        }
+        for (int o = 16; o; o >>= 1) sse += __shfl_xor_sync(0xffffffffu, sse, o);
+        const int ia = a.S + a.ntnf;
+        const float dab = r[ia] - x[ia];
+        if (lane == 0 && a.write_grad) g[ia] = gsc * a.ab_w * 2.0f * dab;
+        float kld = 0.0f;
+        for (int k = lane; k < a.nlatent; k += 32) {
+            const float m = a.MU[(int64_t)b * a.nlatent + k];
+            kld = __fmaf_rn(m, m, kld);
+        }
+        for (int o = 16; o; o >>= 1) kld += __shfl_xor_sync(0xffffffffu, kld, o);
+        l_ce = ce; l_sse = sse; l_ab = dab * dab; l_kld = 0.5f * kld;
+    }
+    if (lane == 0) { s_part[warp][0] = l_ab; s_part[warp][1] = l_ce; s_part[warp][2] = l_sse; s_part[warp][3] = l_kld; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += s_part[w][threadIdx.x];
+        a.part[(int64_t)blockIdx.x * 4 + threadIdx.x] = t;
+    }
+    if (!last_block_done(&a.ctl->tickets[a.ticket_id], gridDim.x)) return;
+    if (threadIdx.x == 0) {
+        double t[4] = {0.0, 0.0, 0.0, 0.0};
+        for (unsigned i = 0; i < gridDim.x; ++i)
+            for (int c = 0; c < 4; ++c) t[c] += __ldcg(a.part + (int64_t)i * 4 + c);
+        const double ab = t[0] / a.B * a.ab_w, ce = t[1] / a.B * a.ce_w, sse = t[2] / a.B * a.sse_w,
+                     kld = t[3] / a.B * a.kld_w;
+        // loss.mean() over the [B, B] broadcast = mean_j(l_j) * mean_i(w_i)   (encode.py:349-352)
+        a.ctl->loss_sums[0] += ((ce + ab + sse) + kld) * a.ctl->wbar;
+        a.ctl->loss_sums[1] += ab;
+        a.ctl->loss_sums[2] += ce;
+        a.ctl->loss_sums[3] += sse;
+        a.ctl->loss_sums[4] += kld;
+        a.ctl->n_loss_steps += 1;
+    }
+}
+
+// ------------------------------------------------------------------ backward layer (wgrad + dgrad)
+struct BwdArgs {
+    LdGradOut gy;         // dL/dY [B, N]
+    LdInput in;           // layer input [B, K] (+ ones column at K for the bias gradient)
+    const float *W;       // [N, K]
+    float *gW, *gb;       // gradients [N, K], [N]
+    int B, K, N;
+    int wg_tiles_m, wg_tiles_n, dg_tiles_m, dg_tiles_n;  // dg_tiles_* == 0: no dgrad (first layer)
+    // dgrad epilogue
+    int in_kind; float *d_in;   // dL/d(input) [B, K]: dH of the previous hidden block, or dMU for z
+    const float *p_prev, *mean_prev, *rstd_prev; double *part_prev; float *m1_prev, *m2_prev; float *g_gamma, *g_beta;
+    const float *MU; float kld_w;
+    vk_vae_ctl *ctl; int ticket_id;
+};
+
+__global__ void __launch_bounds__(GT) bwd_layer_kernel(BwdArgs a) {
+    __shared__ __align__(16) float s_gemm[SMEM_GEMM_FLOATS];
+    __shared__ double s_red[2 * 16 * 64];
+    float acc[4][4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int n_wg = a.wg_tiles_m * a.wg_tiles_n;
+    if ((int)blockIdx.x < n_wg) {
+        // ---- wgrad: gW[n, k] = sum_b dY[b, n] * X[b, k];  k == K -> bias gradient ----
+        const int m0 = (blockIdx.x / a.wg_tiles_n) * 64, n0 = (blockIdx.x % a.wg_tiles_n) * 64;
+        gemm_block<64, 64, true, true>(a.B, m0, n0, a.gy, a.in, acc, s_gemm);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int m = m0 + ty * 4 + i;
+            if (m >= a.N) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + tx * 4 + j;
+                if (n < a.K) a.gW[(int64_t)m * a.K + n] = acc[i][j];
+                else if (n == a.K) a.gb[m] = acc[i][j];
+            }
+        }
+        return;
+    }
+    // ---- dgrad: dX[b, k] = sum_n dY[b, n] * W[n, k] ----
+    const int t = blockIdx.x - n_wg;
+    const int m0 = (t / a.dg_tiles_n) * 64, n0 = (t % a.dg_tiles_n) * 64;
+    LdPlain w{a.W, a.K, a.N, a.K};
+    gemm_block<64, 64, false, true>(a.N, m0, n0, a.gy, w, acc, s_gemm);
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    const float gsc = (float)(a.ctl->wbar / (double)a.B);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= a.B) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= a.K) continue;
+            const int64_t o = (int64_t)m * a.K + n;
+            float v = acc[i][j];
+            if (a.in_kind == VK_IN_Z) {
+                v = __fmaf_rn(gsc * a.kld_w, __ldg(a.MU + o), v);  // d(kld)/d(mu), encode.py:331
+            } else {
+                const float ph = (__ldg(a.p_prev + o) - __ldg(a.mean_prev + n)) * __ldg(a.rstd_prev + n);
+                s1[j] += v;
+                s2[j] = __fmaf_rn(v, ph, s2[j]);
+            }
+            a.d_in[o] = v;
+        }
+    }
+    if (a.in_kind != VK_IN_BN) return;
+    const int row_tile = t / a.dg_tiles_n;
+    double *p0 = a.part_prev + ((int64_t)row_tile * 2 + 0) * a.K;
+    double *p1 = a.part_prev + ((int64_t)row_tile * 2 + 1) * a.K;
+    tile_colsum2<4>(s1, s2, s_red, p0, p1, n0, a.K);
+    if (!last_block_done(&a.ctl->tickets[a.ticket_id], a.dg_tiles_m * a.dg_tiles_n)) return;
+    for (int n = tid; n < a.K; n += GT) {
+        double u = 0.0, v = 0.0;
+        for (int rt = 0; rt < a.dg_tiles_m; ++rt) {
+            u += __ldcg(a.part_prev + ((int64_t)rt * 2 + 0) * a.K + n);
+            v += __ldcg(a.part_prev + ((int64_t)rt * 2 + 1) * a.K + n);
+        }
+        a.g_beta[n] = (float)u;   // d/d(beta)  = sum_b dH
+        a.g_gamma[n] = (float)v;  // d/d(gamma) = sum_b dH * Phat
+        a.m1_prev[n] = (float)(u / a.B);
+        a.m2_prev[n] = (float)(v / a.B);
+    }
+}
+
+// ------------------------------------------------------------------ D-Adaptation Adam
+// One pass over the flat arenas (dadaptation.DAdaptAdam.step with lr=1, betas=(0.9, 0.999),
+// eps=1e-8, weight_decay=0, growth_rate=inf, no bias correction).  The parameter update of
+// step t uses d_t; the two global sums only feed d_{t+1}, so everything fits in one kernel.
+constexpr int OPT_BLOCKS = 296;
+
+__global__ void __launch_bounds__(256)
+dadapt_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
+              float *__restrict__ s, int64_t n, double *part, vk_vae_ctl *ctl, int ticket_id) {
+    __shared__ double s_a[256], s_b[256];
+    const double beta1 = 0.9, beta2 = 0.999, eps = 1e-8;
+    const double sqrt_beta2 = sqrt(beta2);
+    const double dlr = ctl->d;  // d * lr * bias_correction with lr = 1
+    const float f_beta1 = (float)beta1, f_beta2 = (float)beta2, f_sb2 = (float)sqrt_beta2;
+    const float a_m = (float)(dlr * (1.0 - beta1)), a_v = (float)(1.0 - beta2), a_s = (float)(dlr * (1.0 - sqrt_beta2));
+    const float f_eps = (float)eps;
+    double acc_num = 0.0, acc_l1 = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const float gi = g[i];
+        float mi = m[i], vi = v[i], si = s[i];
+        const float denom_old = sqrtf(vi) + f_eps;
+        acc_num += (double)(gi * (si / denom_old));
+        mi = __fmaf_rn(a_m, gi, mi * f_beta1);
+        vi = __fmaf_rn(a_v * gi, gi, vi * f_beta2);
+        si = __fmaf_rn(a_s, gi, si * f_sb2);
+        acc_l1 += (double)fabsf(si);
+        m[i] = mi; v[i] = vi; s[i] = si;
+        p[i] = p[i] - mi / (sqrtf(vi) + f_eps);
+    }
+    s_a[threadIdx.x] = acc_num;
+    s_b[threadIdx.x] = acc_l1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ta = 0.0, tb = 0.0;
+        for (int i = 0; i < 256; ++i) { ta += s_a[i]; tb += s_b[i]; }
+        part[2 * blockIdx.x] = ta;
+        part[2 * blockIdx.x + 1] = tb;
+    }
+    if (!last_block_done(&ctl->tickets[ticket_id], gridDim.x)) return;
+    if (threadIdx.x == 0) {
+        double num = 0.0, l1 = 0.0;
+        for (unsigned i = 0; i < gridDim.x; ++i) {
+            num += __ldcg(part + 2 * i);
+            l1 += __ldcg(part + 2 * i + 1);
+        }
+        const double numerator_acum = dlr * num;
+        const double num_w = sqrt_beta2 * ctl->num_w + (1.0 - sqrt_beta2) * numerator_acum;
+        ctl->num_w = num_w;
+        if (l1 > 0.0) {
+            const double d_hat = num_w / ((1.0 - sqrt_beta2) * l1);
+            if (d_hat > ctl->d) ctl->d = d_hat;  // d = max(d, min(d_hat, d * inf))
+        }
+        ctl->step += 1;
+    }
+}
+
+__global__ void eval_affine_kernel(float *bn_a, float *bn_c, const float *gamma, const float *beta,
+                                   const float *rm, const float *rv, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float sc = gamma[i] / sqrtf(rv[i] + 1e-5f);
+    bn_a[i] = sc;
+    bn_c[i] = beta[i] - rm[i] * sc;
+}
+
+// ------------------------------------------------------------------ host side
+extern "C" int64_t vk_vae_sizeof(int which) {
+    switch (which) {
+        case 0: return (int64_t)sizeof(vk_vae);
+        case 1: return (int64_t)sizeof(vk_vae_layer);
+        case 2: return (int64_t)sizeof(vk_vae_ctl);
+        case 3: return (int64_t)sizeof(vk_vae_inject);
+    }
+    return -1;
+}
+
+static int check_net(const vk_vae *net, int batch) {
+    if (!net || net->n_layers < 2 || net->n_layers > VK_VAE_MAX_LAYERS) {
+        vk_set_error("vk_vae: bad layer count");
+        return 1;
+    }
+    if (batch < 1 || batch > net->bmax) {
+        vk_set_error("vk_vae: batch %d outside [1, bmax=%d]", batch, net->bmax);
+        return 1;
+    }
+    return 0;
+}
+
+static LdInput make_input(const vk_vae *net, int j, int B, int ones_col) {
+    const vk_vae_layer &L = net->layers[j];
+    LdInput in;
+    in.in_kind = L.in_kind;
+    in.ones_col = ones_col;
+    in.d = LdData{net->data, net->batch_rows, net->d_in, B, L.k_in};
+    in.a = LdAffine{nullptr, nullptr, nullptr, L.k_in, B, L.k_in};
+    in.z = LdPlain{net->z, L.k_in, B, L.k_in};
+    if (L.in_kind == VK_IN_BN) {
+        const vk_vae_layer &P = net->layers[j - 1];
+        in.a = LdAffine{P.act, P.bn_a, P.bn_c, P.n_out, B, L.k_in};
+    }
+    return in;
+}
+
+static int launch_batch_rows(const vk_vae *net, int B, int mode, int64_t row0, const vk_vae_inject *inj,
+                             cudaStream_t s) {
+    const int64_t n = net->n_rows;
+    const int spe = n > B ? (int)(n / B) : 1;
+    batch_rows_kernel<<<1, 256, 0, s>>>(net->batch_rows, inj ? inj->batch_idx : nullptr, net->weights, net->ctl, B,
+                                        n, mode, row0, spe);
+    VK_LAUNCH_CHECK();
+    return 0;
+}
+
+static int launch_forward(const vk_vae *net, int B, int training, int upto /*exclusive layer index*/,
+                          const vk_vae_inject *inj, int mask_bits, float *latent_out, cudaStream_t s) {
+    for (int j = 0; j < upto; ++j) {
+        const vk_vae_layer &L = net->layers[j];
+        FwdArgs a;
+        memset(&a, 0, sizeof(a));
+        a.in = make_input(net, j, B, -1);
+        a.W = net->params + L.w_off;
+        a.bias = net->params + L.b_off;
+        a.B = B; a.K = L.k_in; a.N = L.n_out; a.kind = L.kind; a.training = training;
+        a.out = L.act;
+        a.dropout = net->dropout;
+        a.keep = (inj && L.kind == VK_LAYER_HIDDEN) ? inj->keep[j] : nullptr;
+        a.part = L.fwd_part;
+        a.bn_a = L.bn_a; a.bn_c = L.bn_c; a.bn_mean = L.bn_mean; a.bn_rstd = L.bn_rstd;
+        if (L.kind == VK_LAYER_HIDDEN) {
+            a.gamma = net->params + L.g_off;
+            a.beta = net->params + L.beta_off;
+        }
+        a.running_mean = L.running_mean; a.running_var = L.running_var; a.nbt = L.num_batches_tracked;
+        a.z = net->z;
+        a.eps = inj ? inj->eps : nullptr;
+        a.add_eps = (L.kind == VK_LAYER_MU && latent_out == nullptr) ? 1 : 0;
+        a.mask_bits = mask_bits;
+        a.latent_out = (L.kind == VK_LAYER_MU) ? latent_out : nullptr;
+        a.ctl = net->ctl; a.layer_id = j; a.slope = net->slope;
+        dim3 grid((L.n_out + 63) / 64, (B + 63) / 64);
+        fwd_layer_kernel<<<grid, GT, 0, s>>>(a);
+        VK_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+static int launch_loss(const vk_vae *net, int B, int write_grad, cudaStream_t s) {
+    const int nl = net->n_layers;
+    int mu_j = -1;
+    for (int j = 0; j < nl; ++j)
+        if (net->layers[j].kind == VK_LAYER_MU) mu_j = j;
+    LossArgs a;
+    a.R = net->layers[nl - 1].act; a.MU = net->layers[mu_j].act; a.data = net->data; a.batch_rows = net->batch_rows;
+    a.dR = net->layers[nl - 1].dact;
+    a.B = B; a.S = net->nsamples; a.ntnf = net->ntnf; a.d_in = net->d_in; a.nlatent = net->nlatent;
+    a.ce_w = net->ce_w; a.ab_w = net->ab_w; a.sse_w = net->sse_w; a.kld_w = net->kld_w;
+    a.part = net->loss_part; a.ctl = net->ctl; a.ticket_id = VK_VAE_MAX_LAYERS; a.write_grad = write_grad;
+    const int blocks = (B + 7) / 8;
+    if (blocks > 1024) {
+        vk_set_error("vk_vae: batch too large for the loss partial buffer");
+        return 1;
+    }
+    loss_kernel<<<blocks, 256, 0, s>>>(a);
+    VK_LAUNCH_CHECK();
+    return 0;
+}
+
+static int launch_backward(const vk_vae *net, int B, cudaStream_t s) {
+    const int nl = net->n_layers;
+    int mu_j = -1;
+    for (int j = 0; j < nl; ++j)
+        if (net->layers[j].kind == VK_LAYER_MU) mu_j = j;
+    for (int j = nl - 1; j >= 0; --j) {
+        const vk_vae_layer &L = net->layers[j];
+        BwdArgs a;
+        memset(&a, 0, sizeof(a));
+        a.gy.hidden = (L.kind == VK_LAYER_HIDDEN);
+        a.gy.pl = LdPlain{L.dact, L.n_out, B, L.n_out};
+        if (a.gy.hidden) {
+            a.gy.h = LdDY{L.dact, L.act, net->params + L.g_off, L.bn_mean, L.bn_rstd, L.bn_m1, L.bn_m2,
+                          L.n_out, B, L.n_out, net->dropout > 0.0f ? 1.0f / (1.0f - net->dropout) : 1.0f,
+                          net->slope, net->dropout > 0.0f ? 1 : 0};
+        }
+        a.in = make_input(net, j, B, L.k_in);
+        a.W = net->params + L.w_off;
+        a.gW = net->grads + L.w_off;
+        a.gb = net->grads + L.b_off;
+        a.B = B; a.K = L.k_in; a.N = L.n_out;
+        a.wg_tiles_m = (L.n_out + 63) / 64;
+        a.wg_tiles_n = (L.k_in + 1 + 63) / 64;
+        a.in_kind = L.in_kind;
+        a.ctl = net->ctl;
+        a.ticket_id = VK_VAE_MAX_LAYERS + 1 + j;
+        if (L.in_kind == VK_IN_DATA) {
+            a.dg_tiles_m = a.dg_tiles_n = 0;
+        } else {
+            a.dg_tiles_m = (B + 63) / 64;
+            a.dg_tiles_n = (L.k_in + 63) / 64;
+            if (L.in_kind == VK_IN_BN) {
+                const vk_vae_layer &P = net->layers[j - 1];
+                a.d_in = P.dact; a.p_prev = P.act; a.mean_prev = P.bn_mean; a.rstd_prev = P.bn_rstd;
+                a.part_prev = P.bwd_part; a.m1_prev = P.bn_m1; a.m2_prev = P.bn_m2;
+                a.g_gamma = net->grads + P.g_off; a.g_beta = net->grads + P.beta_off;
+            } else {
+                a.d_in = net->layers[mu_j].dact;
+                a.MU = net->layers[mu_j].act;
+                a.kld_w = net->kld_w;
+            }
+        }
+        const int blocks = a.wg_tiles_m * a.wg_tiles_n + a.dg_tiles_m * a.dg_tiles_n;
+        bwd_layer_kernel<<<blocks, GT, 0, s>>>(a);
+        VK_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+static int launch_dadapt(const vk_vae *net, cudaStream_t s) {
+    dadapt_kernel<<<OPT_BLOCKS, 256, 0, s>>>(net->params, net->grads, net->exp_avg, net->exp_avg_sq, net->s,
+                                             net->n_params, net->opt_part, net->ctl, 2 * VK_VAE_MAX_LAYERS + 2);
+    VK_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int vk_vae_grad_step(const vk_vae *net, int batch, const vk_vae_inject *inject, void *stream) {
+    if (check_net(net, batch)) return 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int mode = (inject && inject->batch_idx) ? 0 : 1;
+    if (launch_batch_rows(net, batch, mode, 0, inject, s)) return 1;
+    if (launch_forward(net, batch, 1, net->n_layers, inject, 0, nullptr, s)) return 1;
+    if (launch_loss(net, batch, 1, s)) return 1;
+    if (launch_backward(net, batch, s)) return 1;
+    return 0;
+}
+
+extern "C" int vk_vae_dadapt_step(const vk_vae *net, void *stream) {
+    if (check_net(net, 1)) return 1;
+    return launch_dadapt(net, (cudaStream_t)stream);
+}
+
+extern "C" int vk_vae_train_step(const vk_vae *net, int batch, const vk_vae_inject *inject, void *stream) {
+    if (vk_vae_grad_step(net, batch, inject, stream)) return 1;
+    return launch_dadapt(net, (cudaStream_t)stream);
+}
+
+extern "C" int vk_vae_forward(const vk_vae *net, int64_t row0, int batch, int training, int with_loss,
+                              const vk_vae_inject *inject, void *stream) {
+    if (check_net(net, batch)) return 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int mode = (inject && inject->batch_idx) ? 0 : 2;
+    if (launch_batch_rows(net, batch, mode, row0, inject, s)) return 1;
+    if (launch_forward(net, batch, training, net->n_layers, inject, 0, nullptr, s)) return 1;
+    if (with_loss && launch_loss(net, batch, 0, s)) return 1;
+    return 0;
+}
+
+extern "C" int vk_vae_prepare_eval(const vk_vae *net, void *stream) {
+    if (check_net(net, 1)) return 1;
+    for (int j = 0; j < net->n_layers; ++j) {
+        const vk_vae_layer &L = net->layers[j];
+        if (L.kind != VK_LAYER_HIDDEN) continue;
+        eval_affine_kernel<<<(L.n_out + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+            L.bn_a, L.bn_c, net->params + L.g_off, net->params + L.beta_off, L.running_mean, L.running_var, L.n_out);
+        VK_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" int vk_vae_encode(const vk_vae *net, int64_t row0, int64_t n, int mask_bits, float *latent_out,
+                             void *stream) {
+    if (check_net(net, 1)) return 1;
+    if (mask_bits < 0 || mask_bits > 23) {
+        vk_set_error("Must mask between 0 and 23 bits");
+        return 1;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    int mu_j = -1;
+    for (int j = 0; j < net->n_layers; ++j)
+        if (net->layers[j].kind == VK_LAYER_MU) mu_j = j;
+    if (vk_vae_prepare_eval(net, stream)) return 1;
+    for (int64_t off = 0; off < n; off += net->bmax) {
+        const int B = (int)((n - off) < net->bmax ? (n - off) : net->bmax);
+        if (launch_batch_rows(net, B, 2, row0 + off, nullptr, s)) return 1;
+        if (launch_forward(net, B, 0, mu_j + 1, nullptr, mask_bits, latent_out + off * net->nlatent, s)) return 1;
+    }
+    return 0;
+}
