@@ -1,0 +1,420 @@
+#!/usr/bin/env python
+"""bench.py -- contigs/sec of the vamb hot path (VAE train + encode + medoid clustering).
+
+Contract (one JSON line on rank 0):
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A "step" is ONE pass of the whole hot path over the synthetic workload of BASELINE.json
+configs[1]: N = 1,000,000 planted contigs x (103 TNF + 50 abundance samples), `vamb bin default`
+settings (VAE 512-512-32, 300 epochs, batch 256 doubling at epochs 25/75/150/225, then
+ClusterGenerator(windowsize=300, minsuccesses=15) run to exhaustion).
+  value  = contigs / (t_train + t_encode + t_cluster) with the normalised dataset already in HBM.
+  e2e    = the same metric through the public API (make_dataloader tensors on the HOST ->
+           VAE.trainmodel -> VAE.encode -> numpy latent -> ClusterGenerator -> numpy members),
+           host<->device copies inside the timed region.
+Warm-up steps run the same path with a shortened schedule (6 epochs covering all five batch
+sizes, clustering capped) -- they warm clocks, caches and the CUDA-graph captures.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "contigs/sec (VAE train + cluster) at N=1M, S=50"
+BATCHSTEPS = [25, 75, 150, 225]
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=1_000_000, help="contigs per GPU")
+    ap.add_argument("--nsamples", type=int, default=50)
+    ap.add_argument("--nepochs", type=int, default=300)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true", help="skip the second (host-buffer) pass")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+def schedule(n: int, nepochs: int, batch0: int = 256):
+    """[(batch, steps per epoch, epochs)] of the bin-default schedule (vamb/encode.py:383-388)."""
+    out, b, prev = [], batch0, 0
+    steps = [s for s in BATCHSTEPS if s < nepochs]
+    for s in steps + [nepochs]:
+        if s > prev:
+            out.append((b, (n // b) if n > b else 1, s - prev))
+        prev = s
+        b *= 2
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int = 0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "500",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_workload(n, nsamples, seed):
+    from vamb_b200 import synth
+
+    return synth.make_contigs(n, nsamples, seed=seed)
+
+
+def run_hot_path(tensors_dl, lengths, nsamples, nepochs, seed, resident: bool, max_clusters=None, batchsteps=None):
+    """One pass.  resident=True: dataset bound to the device before the clock starts and the latent stays
+    in HBM between encode and clustering.  Returns phase times (s) and launch counts."""
+    import vamb_b200.cluster as vc
+    import vamb_b200.encode as ve
+
+    bs = [b for b in (BATCHSTEPS if batchsteps is None else batchsteps) if b < nepochs]
+    vae = ve.VAE(nsamples, seed=seed)
+    n = len(lengths)
+    if resident:
+        vae._bind_dataset(tensors_dl.dataset.tensors)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    vae.trainmodel(tensors_dl, nepochs=nepochs, batchsteps=bs)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    if resident:
+        vae.eval()
+        latent = torch.empty((n, vae.nlatent), dtype=torch.float32, device="cuda")
+        ve._lib.check(ve._L.vk_vae_encode(ve._ct.byref(vae._net), 0, n, 12, latent.data_ptr(), vae._stream()))
+        torch.cuda.synchronize()
+    else:
+        latent = vae.encode(tensors_dl)  # numpy, D2H inside
+    t2 = time.perf_counter()
+    gen = vc.ClusterGenerator(latent, lengths, windowsize=300, minsuccesses=15, destroy=True, rng_seed=seed)
+    n_clusters = n_members = 0
+    for c in gen:
+        n_clusters += 1
+        n_members += len(c.members)
+        if max_clusters and n_clusters >= max_clusters:
+            break
+    ev1.record()
+    torch.cuda.synchronize()
+    t3 = time.perf_counter()
+    sched = schedule(n, nepochs)
+    train_steps = sum(s * e for _, s, e in sched)
+    nl = vae._net.n_layers
+    launches = train_steps * (2 * nl + 3) + ((n + vae._net.bmax - 1) // vae._net.bmax) * (nl // 2 + 1) \
+        + gen._n_probes + gen._n_evals + n_clusters + 1
+    return {
+        "t_train": t1 - t0, "t_encode": t2 - t1, "t_cluster": t3 - t2, "t_total": t3 - t0,
+        "event_ms": ev0.elapsed_time(ev1), "n_clusters": n_clusters, "n_clustered": n_members,
+        "probes": gen._n_probes, "evals": gen._n_evals, "train_steps": train_steps, "launches": launches,
+        "final_loss": vae._last_epoch_losses[0], "vae": vae, "latent_dev": latent if resident else None,
+    }
+
+
+def vae_roofline(vae, n, nepochs):
+    """Per-launch device times of one training step at every batch size of the schedule (CUDA events on
+    the launching stream) -> time share per kernel and achieved FLOP/s of the dominant one."""
+    sched = schedule(n, nepochs)
+    net = vae._net
+    nl = net.n_layers
+    dims = [(net.layers[j].k_in, net.layers[j].n_out, net.layers[j].in_kind) for j in range(nl)]
+    tot = {}
+    best = None
+    for batch, spe, epochs in sched:
+        reps = []
+        for _ in range(8):
+            reps.append(vae._profile_step(batch))
+        reps = reps[3:]
+        avg_bwd = np.mean([r["bwd"] for r in reps], axis=0)  # launch order: last layer first
+        avg_fwd = np.mean([r["fwd"] for r in reps], axis=0)
+        other = float(np.mean([r["batch_rows"] + r["loss"] + r["dadapt"] for r in reps]))
+        nsteps = spe * epochs
+        tot["fwd_layer_kernel"] = tot.get("fwd_layer_kernel", 0.0) + nsteps * float(avg_fwd.sum())
+        tot["bwd_layer_kernel"] = tot.get("bwd_layer_kernel", 0.0) + nsteps * float(avg_bwd.sum())
+        tot["other"] = tot.get("other", 0.0) + nsteps * other
+        for i, ms in enumerate(avg_bwd):
+            j = nl - 1 - i
+            k, nn, in_kind = dims[j]
+            flops = 2.0 * batch * nn * (k + 1) + (2.0 * batch * nn * k if in_kind != 0 else 0.0)
+            cand = {"kernel": f"bwd_layer_kernel[layer {j}: {k}->{nn}, B={batch}]", "ms": float(ms),
+                    "tflops": flops / (ms * 1e-3) / 1e12, "weight_ms": nsteps * float(ms)}
+            if best is None or cand["weight_ms"] > best["weight_ms"]:
+                best = cand
+    total = sum(tot.values())
+    share = {k: v / total for k, v in tot.items()}
+    return best, share, total / 1e3
+
+
+def probe_roofline(latent_dev, lengths):
+    """Cosine-distance probe at full N on the produced latent: algorithmic 133 B/contig / event time."""
+    import vamb_b200.cluster as vc
+    from vamb_b200 import _lib
+
+    gen = vc.ClusterGenerator(latent_dev, lengths, rng_seed=0)
+    n = gen._n_act
+    s = torch.cuda.current_stream().cuda_stream
+
+    def call(i):
+        _lib.check(_lib.lib.vk_probe(gen._m.data_ptr(), gen._len.data_ptr(), gen._kept.data_ptr(), n, gen._d,
+                                     (i * 7919) % n, 0.3, gen._edges.data_ptr(), gen._hdr.data_ptr(),
+                                     gen._within_over.data_ptr(), gen._nl_rows.data_ptr(), gen._nl_d.data_ptr(), s))
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for i in range(3):
+        call(i)
+    times = []
+    for i in range(10):
+        flush.zero_()  # > L2 (126 MB): the next probe reads from HBM
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        call(i + 3)
+        b.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+    ms = float(np.median(times))
+    nbytes = n * (4 * gen._d + 5)
+    return {"kernel": "probe_kernel<32>", "ms": ms, "gbs": nbytes / (ms * 1e-3) / 1e9, "bytes": nbytes}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return float(p["hbm_gbs"]), float(p["bf16_tflops_sustained"]), "measured"
+    except Exception:
+        return 6650.0, 1400.0, "fallback"
+
+
+# ---------------------------------------------------------------------------------- CPU baseline
+def cpu_baseline(abundance, tnf, lengths, nsamples, nepochs, seed, budget_s, latent=None):
+    """The oracle port (torch-CPU fp32 VAE restatement with the restated DAdaptAdam + the C/NumPy
+    clusterer) on a BOUNDED sample of the same workload, all host threads, extrapolated over the
+    bin-default schedule.  A reported baseline, not the optimisation target."""
+    from oracle import cluster_oracle as co
+    from oracle import vae_oracle as vo
+    import vamb_b200.encode as ve
+
+    n = len(lengths)
+    threads = torch.get_num_threads()
+    dl = ve.make_dataloader(abundance.copy(), tnf.copy(), lengths, batchsize=256)
+    d, t, a, w = dl.dataset.tensors
+    orc = vo.OracleVAE(nsamples, seed=seed)
+    rng = np.random.default_rng(seed)
+    per_step = {}
+    sched = schedule(n, nepochs)
+    share = budget_s * 0.5 / max(1, len(sched))
+    for batch, spe, epochs in sched:
+        b = min(batch, n)
+        times = []
+        t_start = time.perf_counter()
+        while len(times) < 3 or (time.perf_counter() - t_start < share and len(times) < 50):
+            idx = torch.from_numpy(rng.integers(0, n, size=b))
+            t0 = time.perf_counter()
+            orc.train_step(d[idx], t[idx], a[idx], w[idx])
+            times.append(time.perf_counter() - t0)
+        per_step[batch] = float(np.median(times[1:]))
+    t_train = sum(per_step[b] * spe * e for b, spe, e in sched)
+    m = min(n, 50_000)
+    t0 = time.perf_counter()
+    lat_sample, _ = orc.encode(d[:m], t[:m], a[:m])
+    t_encode = (time.perf_counter() - t0) * n / m
+    # clustering: a prefix of the clusters of the full-size latent (the reference's own max_clusters
+    # mechanism, vamb/__main__.py:1289); contigs clustered per second over the prefix
+    if latent is None:
+        from vamb_b200 import synth
+
+        latent, _ = synth.make_latent(n, 32, seed=seed, spread=0.2)
+    gen = co.OracleClusterGenerator(latent, lengths, windowsize=300, minsuccesses=15, rng_seed=seed)
+    t0 = time.perf_counter()
+    clustered = k = 0
+    for c in gen:
+        clustered += len(c.members)
+        k += 1
+        if time.perf_counter() - t0 > budget_s * 0.4:
+            break
+    dt = time.perf_counter() - t0
+    t_cluster = dt * n / max(1, clustered)
+    total = t_train + t_encode + t_cluster
+    sample = (f"oracle port, {threads} threads: train = median of >=3 steps per batch size "
+              f"{sorted(per_step)} extrapolated over {sum(s * e for _, s, e in sched)} steps; encode = {m} rows "
+              f"scaled to {n}; cluster = first {k} clusters ({clustered} contigs, {dt:.1f} s) scaled to {n}")
+    return {"value": n / total, "unit": "contigs/s", "cores": threads, "kind": "port", "sample": sample,
+            "t_train_est": t_train, "t_encode_est": t_encode, "t_cluster_est": t_cluster}
+
+
+def main():
+    args = parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        torch.set_num_threads(os.cpu_count() or 8)
+        ab, tnf, lens = make_workload(args.n, args.nsamples, args.seed)
+        vals = []
+        for _ in range(max(1, args.steps)):
+            base = cpu_baseline(ab, tnf, lens, args.nsamples, args.nepochs, args.seed, args.cpu_seconds)
+            vals.append(base["value"])
+        v = float(np.median(vals))
+        base["value"] = v
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": v, "unit": "contigs/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.n / v,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.n} contigs x (103 TNF + {args.nsamples} abundance), bin default VAE "
+                                   f"nlatent=32, {args.nepochs} epochs + medoid clustering",
+                       "note": "CPU port of the reference path (oracle/), bounded sample extrapolated"},
+            "cpu_baseline": base,
+            "e2e": {"value": v, "unit": "contigs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    import vamb_b200.encode as ve
+
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(0)
+
+    # weak scaling: every rank owns its own shard of N contigs (independent units: the hot path of a
+    # shard -- train, encode, cluster -- has no cross-shard data dependency in "replica" mode)
+    ab, tnf, lens = make_workload(args.n, args.nsamples, args.seed + rank)
+    dl = ve.make_dataloader(ab.copy(), tnf.copy(), lens, batchsize=256)
+
+    for _ in range(args.warmup):
+        run_hot_path(dl, lens, args.nsamples, 6, args.seed, resident=True, max_clusters=300,
+                     batchsteps=[1, 2, 3, 4])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    res = []
+    for _ in range(args.steps):
+        res.append(run_hot_path(dl, lens, args.nsamples, args.nepochs, args.seed, resident=True))
+    barrier()
+    clocks = sampler.stop()
+    t_step = float(np.mean([r["t_total"] for r in res]))
+    if world > 1:
+        tt = torch.tensor([t_step], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_step = float(tt.item())
+    value = world * args.n / t_step
+    last = res[-1]
+
+    e2e = None
+    if not args.no_e2e:
+        barrier()
+        r2 = run_hot_path(dl, lens, args.nsamples, args.nepochs, args.seed, resident=False)
+        barrier()
+        t2 = r2["t_total"]
+        if world > 1:
+            tt = torch.tensor([t2], device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t2 = float(tt.item())
+        d_in = args.nsamples + 104
+        h2d = args.n * (d_in + 1) * 4 + args.n * 32 * 4 + args.n * 4
+        d2h = args.n * 32 * 4 + args.n * 4 + r2["probes"] * 8700
+        e2e = {"value": world * args.n / t2, "unit": "contigs/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "t_train": r2["t_train"], "t_encode": r2["t_encode"],
+               "t_cluster": r2["t_cluster"]}
+
+    out = None
+    if rank == 0:
+        hbm_peak, tf_peak, which = measured_peaks()
+        best, share, est_train_s = vae_roofline(last["vae"], args.n, args.nepochs)
+        pr = probe_roofline(last["latent_dev"], lens)
+        roof = {"bound": "tensor", "kernel": best["kernel"], "achieved": best["tflops"], "peak": tf_peak,
+                "unit": "TFLOP/s", "frac": best["tflops"] / tf_peak, "traffic": None,
+                "peak_source": f"{which} bf16 dense sustained (MEASURED_PEAKS.json)",
+                "time_share": share, "ms_per_launch": best["ms"]}
+        roof_cluster = {"bound": "hbm", "kernel": pr["kernel"], "achieved": pr["gbs"], "peak": hbm_peak,
+                        "unit": "GB/s", "frac": pr["gbs"] / hbm_peak, "traffic": None,
+                        "algorithmic_bytes": pr["bytes"], "ms_per_launch": pr["ms"],
+                        "peak_source": f"{which} copy bandwidth (MEASURED_PEAKS.json)"}
+        base = None
+        if world == 1:
+            torch.set_num_threads(os.cpu_count() or 8)
+            lat_host = last["latent_dev"].cpu().numpy() if last["latent_dev"] is not None else None
+            base = cpu_baseline(ab, tnf, lens, args.nsamples, args.nepochs, args.seed, args.cpu_seconds, lat_host)
+        out = {
+            "metric": METRIC, "value": value, "unit": "contigs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.n} contigs/GPU x (103 TNF + {args.nsamples} abundance), bin default VAE "
+                                   f"512-512-32, {args.nepochs} epochs (batch 256 doubling at 25/75/150/225) + "
+                                   "encode + medoid clustering to exhaustion",
+                       "parallelism": f"shard-per-gpu x{world}", "l2": "inputs larger than L2 (620 MB dataset, "
+                       "128 MB latent); probe roofline flushes L2 between launches",
+                       "warmup_workload": "same path, 6 epochs covering all 5 batch sizes, clustering capped at 300"},
+            "phases_s": {"train": last["t_train"], "encode": last["t_encode"], "cluster": last["t_cluster"]},
+            "clusters": last["n_clusters"], "final_loss": last["final_loss"],
+            "roofline": roof, "roofline_cluster": roof_cluster, "cpu_baseline": base, "e2e": e2e,
+            "gpu_launches": int(last["launches"]), "clocks": clocks,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -199,6 +199,11 @@ int vk_vae_prepare_eval(const vk_vae *net, void *stream);
 /* Standalone D-Adaptation Adam step on the arenas (used after a gradient all-reduce). */
 int vk_vae_dadapt_step(const vk_vae *net, void *stream);
 
+/* vk_vae_train_step with a CUDA event before every launch; ms_out_host[i] = device time of launch i
+ * (batch_rows, forward layers, loss, backward layers from the last to the first, dadapt).  Synchronises. */
+int vk_vae_profile_step(const vk_vae *net, int batch, const vk_vae_inject *inject, float *ms_out_host,
+                        int capacity, int *n_launches, void *stream);
+
 /* Backward + gradients only (no optimiser): used by the multi-GPU path and by the tests. */
 int vk_vae_grad_step(const vk_vae *net, int batch, const vk_vae_inject *inject, void *stream);
 

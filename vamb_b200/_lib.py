@@ -79,7 +79,7 @@ _bind()
 # bound (with argtypes) in vamb_b200/encode.py next to the ctypes mirrors of their structs
 _VAE_SYMBOLS = [
     "vk_vae_sizeof", "vk_vae_train_step", "vk_vae_grad_step", "vk_vae_forward", "vk_vae_encode",
-    "vk_vae_prepare_eval", "vk_vae_dadapt_step",
+    "vk_vae_prepare_eval", "vk_vae_dadapt_step", "vk_vae_profile_step",
 ]
 for _name in _VAE_SYMBOLS:
     getattr(lib, _name)  # AttributeError = stale .so

@@ -155,7 +155,10 @@ class ClusterGenerator:
 
     # same argument checks, in the same order, as vamb/cluster.py:194-222
     def _check_params(self, matrix, lengths, maxsteps, windowsize, minsuccesses) -> None:
-        if matrix.dtype != _np.float32:
+        if isinstance(matrix, _torch.Tensor):
+            if matrix.dtype != _torch.float32 or not matrix.is_cuda:
+                raise ValueError("A tensor matrix must be a float32 CUDA tensor")
+        elif matrix.dtype != _np.float32:
             raise ValueError("Matrix must be of dtype float32")
         if maxsteps < 1:
             raise ValueError(f"maxsteps must be a positive integer, not {maxsteps}")
@@ -206,8 +209,11 @@ class ClusterGenerator:
         self._n_total = n
 
         # ---- device-resident state (HBM layout: DESIGN.md section 4) ----
-        host = _np.ascontiguousarray(matrix)
-        self._m = _torch.from_numpy(host).to(dev)
+        if isinstance(matrix, _torch.Tensor):
+            # a latent that is already resident in HBM (VAE.encode output kept on the device)
+            self._m = matrix.contiguous() if destroy else matrix.clone().contiguous()
+        else:
+            self._m = _torch.from_numpy(_np.ascontiguousarray(matrix)).to(dev)
         self._len = _torch.from_numpy(len32).to(dev)
         self._kept = _torch.ones(n, dtype=_torch.uint8, device=dev)
         self._orig = _torch.arange(n, dtype=_torch.int32, device=dev)
@@ -243,11 +249,12 @@ class ClusterGenerator:
             else:
                 self._prune_radius = float("inf")
                 self._nl_radius = float("inf")
-        if destroy and not normalized:
+        is_numpy = isinstance(matrix, _np.ndarray)
+        if destroy and not normalized and is_numpy:
             # the reference normalises the caller's array in place (vamb/cluster.py:253-258)
             if matrix.flags.c_contiguous and matrix.flags.writeable:
                 _torch.from_numpy(matrix).copy_(self._m)
-        self._user_matrix = matrix if destroy else None
+        self._user_matrix = matrix if (destroy and is_numpy) else None
 
         # ---- host-side decision state (vamb/cluster.py:266-292) ----
         self.indices = _np.arange(n, dtype=_np.int64)  # original id of every live device row

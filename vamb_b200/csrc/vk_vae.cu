@@ -604,6 +604,14 @@ __global__ void eval_affine_kernel(float *bn_a, float *bn_c, const float *gamma,
 }
 
 // ------------------------------------------------------------------ host side
+// Optional per-launch event marks (vk_vae_profile_step): one event before every launch.
+static thread_local cudaEvent_t *g_prof_events = nullptr;
+static thread_local int g_prof_n = 0, g_prof_cap = 0;
+#define PROF_MARK(s)                                                                    \
+    do {                                                                                \
+        if (g_prof_events && g_prof_n < g_prof_cap) cudaEventRecord(g_prof_events[g_prof_n++], (s)); \
+    } while (0)
+
 extern "C" int64_t vk_vae_sizeof(int which) {
     switch (which) {
         case 0: return (int64_t)sizeof(vk_vae);
@@ -645,6 +653,7 @@ static int launch_batch_rows(const vk_vae *net, int B, int mode, int64_t row0, c
                              cudaStream_t s) {
     const int64_t n = net->n_rows;
     const int spe = n > B ? (int)(n / B) : 1;
+    PROF_MARK(s);
     batch_rows_kernel<<<1, 256, 0, s>>>(net->batch_rows, inj ? inj->batch_idx : nullptr, net->weights, net->ctl, B,
                                         n, mode, row0, spe);
     VK_LAUNCH_CHECK();
@@ -678,6 +687,7 @@ static int launch_forward(const vk_vae *net, int B, int training, int upto /*exc
         a.latent_out = (L.kind == VK_LAYER_MU) ? latent_out : nullptr;
         a.ctl = net->ctl; a.layer_id = j; a.slope = net->slope;
         dim3 grid((L.n_out + 63) / 64, (B + 63) / 64);
+        PROF_MARK(s);
         fwd_layer_kernel<<<grid, GT, 0, s>>>(a);
         VK_LAUNCH_CHECK();
     }
@@ -700,6 +710,7 @@ static int launch_loss(const vk_vae *net, int B, int write_grad, cudaStream_t s)
         vk_set_error("vk_vae: batch too large for the loss partial buffer");
         return 1;
     }
+    PROF_MARK(s);
     loss_kernel<<<blocks, 256, 0, s>>>(a);
     VK_LAUNCH_CHECK();
     return 0;
@@ -748,6 +759,7 @@ static int launch_backward(const vk_vae *net, int B, cudaStream_t s) {
             }
         }
         const int blocks = a.wg_tiles_m * a.wg_tiles_n + a.dg_tiles_m * a.dg_tiles_n;
+        PROF_MARK(s);
         bwd_layer_kernel<<<blocks, GT, 0, s>>>(a);
         VK_LAUNCH_CHECK();
     }
@@ -755,6 +767,7 @@ static int launch_backward(const vk_vae *net, int B, cudaStream_t s) {
 }
 
 static int launch_dadapt(const vk_vae *net, cudaStream_t s) {
+    PROF_MARK(s);
     dadapt_kernel<<<OPT_BLOCKS, 256, 0, s>>>(net->params, net->grads, net->exp_avg, net->exp_avg_sq, net->s,
                                              net->n_params, net->opt_part, net->ctl, 2 * VK_VAE_MAX_LAYERS + 2);
     VK_LAUNCH_CHECK();
@@ -823,4 +836,33 @@ extern "C" int vk_vae_encode(const vk_vae *net, int64_t row0, int64_t n, int mas
         if (launch_forward(net, B, 0, mu_j + 1, nullptr, mask_bits, latent_out + off * net->nlatent, s)) return 1;
     }
     return 0;
+}
+
+// One training step with a CUDA event before every launch: ms_out_host[i] = device time of the
+// i-th launch (order: batch_rows, fwd x n_layers, loss, bwd x n_layers [last layer first], dadapt).
+// Returns the number of launches through *n_launches.  Synchronises the stream.
+extern "C" int vk_vae_profile_step(const vk_vae *net, int batch, const vk_vae_inject *inject, float *ms_out_host,
+                                   int capacity, int *n_launches, void *stream) {
+    if (check_net(net, batch)) return 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int cap = 2 * VK_VAE_MAX_LAYERS + 8;
+    cudaEvent_t ev[2 * VK_VAE_MAX_LAYERS + 8];
+    for (int i = 0; i < cap; ++i) VK_CUDA(cudaEventCreate(&ev[i]));
+    g_prof_events = ev; g_prof_n = 0; g_prof_cap = cap - 1;
+    int rc = vk_vae_train_step(net, batch, inject, stream);
+    const int n = g_prof_n;
+    g_prof_events = nullptr;
+    if (!rc) {
+        cudaEventRecord(ev[n], s);
+        if (cudaStreamSynchronize(s) != cudaSuccess) rc = 1;
+        for (int i = 0; i < n && i < capacity && !rc; ++i) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) != cudaSuccess) rc = 1;
+            ms_out_host[i] = ms;
+        }
+        *n_launches = n;
+    }
+    for (int i = 0; i < cap; ++i) cudaEventDestroy(ev[i]);
+    if (rc && !vk_last_error()[0]) vk_set_error("vk_vae_profile_step failed");
+    return rc;
 }

@@ -186,6 +186,8 @@ for _name, _args in {
     "vk_vae_encode": [_ct.POINTER(_VkVae), _ct.c_int64, _ct.c_int64, _ct.c_int, _ct.c_void_p, _ct.c_void_p],
     "vk_vae_prepare_eval": [_ct.POINTER(_VkVae), _ct.c_void_p],
     "vk_vae_dadapt_step": [_ct.POINTER(_VkVae), _ct.c_void_p],
+    "vk_vae_profile_step": [_ct.POINTER(_VkVae), _ct.c_int, _ct.POINTER(_VkInject), _ct.POINTER(_ct.c_float),
+                            _ct.c_int, _ct.POINTER(_ct.c_int), _ct.c_void_p],
 }.items():
     getattr(_L, _name).argtypes = _args
     getattr(_L, _name).restype = _ct.c_int
@@ -513,6 +515,17 @@ class VAE(_nn.Module):
         _torch.cuda.current_stream().synchronize()
         sums, _ = self._read_loss_sums()
         return sums
+
+    def _profile_step(self, batch: int) -> dict:
+        """Per-launch device times (ms) of one training step at ``batch`` (dataset must be bound)."""
+        cap = 2 * _MAXL + 8
+        ms = (_ct.c_float * cap)()
+        n = _ct.c_int(0)
+        _lib.check(_L.vk_vae_profile_step(_ct.byref(self._net), batch, None, ms, cap, _ct.byref(n), self._stream()))
+        nl = self._net.n_layers
+        vals = [float(ms[i]) for i in range(n.value)]
+        return {"batch_rows": vals[0], "fwd": vals[1:1 + nl], "loss": vals[1 + nl],
+                "bwd": vals[2 + nl:2 + 2 * nl], "dadapt": vals[2 + 2 * nl]}
 
     def _grad_dict(self) -> dict:
         "Gradients of the last step, keyed like ``named_parameters()``."
