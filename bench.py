@@ -103,6 +103,14 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+T_START = time.perf_counter()
+
+
+def log(msg: str) -> None:
+    """Progress on stderr (stdout carries exactly one JSON line)."""
+    print(f"[bench +{time.perf_counter() - T_START:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def make_workload(n, nsamples, seed):
     from vamb_b200 import synth
 
@@ -127,6 +135,7 @@ def run_hot_path(tensors_dl, lengths, nsamples, nepochs, seed, resident: bool, m
     vae.trainmodel(tensors_dl, nepochs=nepochs, batchsteps=bs)
     torch.cuda.synchronize()
     t1 = time.perf_counter()
+    log(f"  train {nepochs} epochs: {t1 - t0:.2f}s (loss {vae._last_epoch_losses[0]:.4f})")
     if resident:
         vae.eval()
         latent = torch.empty((n, vae.nlatent), dtype=torch.float32, device="cuda")
@@ -135,6 +144,7 @@ def run_hot_path(tensors_dl, lengths, nsamples, nepochs, seed, resident: bool, m
     else:
         latent = vae.encode(tensors_dl)  # numpy, D2H inside
     t2 = time.perf_counter()
+    log(f"  encode: {t2 - t1:.2f}s")
     gen = vc.ClusterGenerator(latent, lengths, windowsize=300, minsuccesses=15, destroy=True, rng_seed=seed)
     n_clusters = n_members = 0
     for c in gen:
@@ -145,6 +155,7 @@ def run_hot_path(tensors_dl, lengths, nsamples, nepochs, seed, resident: bool, m
     ev1.record()
     torch.cuda.synchronize()
     t3 = time.perf_counter()
+    log(f"  cluster: {t3 - t2:.2f}s, {n_clusters} clusters / {n_members} contigs, probes {gen._n_probes} evals {gen._n_evals}")
     sched = schedule(n, nepochs)
     train_steps = sum(s * e for _, s, e in sched)
     nl = vae._net.n_layers
@@ -333,7 +344,9 @@ def main():
     ab, tnf, lens = make_workload(args.n, args.nsamples, args.seed + rank)
     dl = ve.make_dataloader(ab.copy(), tnf.copy(), lens, batchsize=256)
 
+    log(f"workload ready: {args.n} contigs x {args.nsamples} samples")
     for _ in range(args.warmup):
+        log("warm-up pass")
         run_hot_path(dl, lens, args.nsamples, 6, args.seed, resident=True, max_clusters=300,
                      batchsteps=[1, 2, 3, 4])
 
@@ -347,6 +360,7 @@ def main():
     sampler.start()
     res = []
     for _ in range(args.steps):
+        log("timed pass (dataset resident in HBM)")
         res.append(run_hot_path(dl, lens, args.nsamples, args.nepochs, args.seed, resident=True))
     barrier()
     clocks = sampler.stop()
@@ -361,6 +375,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         barrier()
+        log("end-to-end pass (host buffers through the public API)")
         r2 = run_hot_path(dl, lens, args.nsamples, args.nepochs, args.seed, resident=False)
         barrier()
         t2 = r2["t_total"]
@@ -378,8 +393,10 @@ def main():
     out = None
     if rank == 0:
         hbm_peak, tf_peak, which = measured_peaks()
+        log("kernel rooflines")
         best, share, est_train_s = vae_roofline(last["vae"], args.n, args.nepochs)
         pr = probe_roofline(last["latent_dev"], lens)
+        log(f"  dominant {best['kernel']}: {best['tflops']:.1f} TFLOP/s; probe {pr['gbs']:.0f} GB/s; cpu baseline next")
         roof = {"bound": "tensor", "kernel": best["kernel"], "achieved": best["tflops"], "peak": tf_peak,
                 "unit": "TFLOP/s", "frac": best["tflops"] / tf_peak, "traffic": None,
                 "peak_source": f"{which} bf16 dense sustained (MEASURED_PEAKS.json)",

@@ -167,6 +167,11 @@ typedef struct vk_vae {
     double *loss_part;                  /* [5 * 1024] loss block partials                      */
     vk_vae_ctl *ctl;
     vk_vae_layer layers[VK_VAE_MAX_LAYERS];
+    int32_t data_ld;                    /* floats per dataset row (>= d_in; a multiple of 4 keeps rows 16-byte aligned) */
+    int32_t tc_min_batch;               /* batches >= this run the GEMMs on tcgen05 (3xTF32); 0 = never            */
+    int64_t grad_slab;                  /* floats between the split-K gradient slabs of `grads`                    */
+    int32_t n_grad_slabs;               /* slabs allocated in `grads` (>= 1)                                       */
+    int32_t reserved_;
 } vk_vae;
 
 /* Optional host-injected randomness for parity tests (all device pointers, NULL = on-device RNG). */
@@ -206,6 +211,10 @@ int vk_vae_profile_step(const vk_vae *net, int batch, const vk_vae_inject *injec
 
 /* Backward + gradients only (no optimiser): used by the multi-GPU path and by the tests. */
 int vk_vae_grad_step(const vk_vae *net, int batch, const vk_vae_inject *inject, void *stream);
+
+/* Stand-alone check of the tcgen05 3xTF32 tile GEMM: C[M,N] = A * B^T, fp32 in/out.
+ * a_mn != 0: A is stored [K][M] (else [M][K]); b_mn != 0: B is stored [K][N] (else [N][K]). */
+int vk_tc_gemm_test(const float *A, const float *B, float *C, int M, int N, int K, int a_mn, int b_mn, void *stream);
 
 #ifdef __cplusplus
 }

@@ -25,8 +25,15 @@ def unpack_keep(packed, batch, n):
     return np.unpackbits(packed)[: batch * n].reshape(batch, n)
 
 
+def set_path(vae, tc: bool):
+    """Force the tcgen05 (3xTF32) GEMM path for every batch size, or the fp32 CUDA-core path."""
+    vae._net.tc_min_batch = 1 if tc else 0
+    return vae
+
+
+@pytest.mark.parametrize("tc", [False, True], ids=["ffma", "tcgen05"])
 @pytest.mark.parametrize("case", VAE_CASES, ids=[c[0] for c in VAE_CASES])
-def test_train_steps_and_encode_match_reference_golden(case):
+def test_train_steps_and_encode_match_reference_golden(case, tc):
     import vamb_b200.encode as ve
     from oracle import vae_oracle as vo
 
@@ -34,7 +41,7 @@ def test_train_steps_and_encode_match_reference_golden(case):
     g = np.load(os.path.join(GOLDEN, f"vae_{name}.npz"))
     rpkm, tnfs, lens = vae_inputs(S, n, seed)
     dl = ve.make_dataloader(rpkm.copy(), tnfs.copy(), lens, batchsize=batch)
-    vae = ve.VAE(S, nhiddens=nh, nlatent=nl, dropout=dp, seed=seed)
+    vae = set_path(ve.VAE(S, nhiddens=nh, nlatent=nl, dropout=dp, seed=seed), tc)
     # same seed -> the reference's initial weights, bit for bit
     init = vo.init_state(S, vae.nhiddens, nl, seed)
     sd = vae.state_dict()
@@ -67,16 +74,18 @@ def test_train_steps_and_encode_match_reference_golden(case):
     assert np.all(np.abs(lat - gl) <= 1e-4 + np.abs(gl) * 2.0 ** -11)
 
 
-def test_gradients_match_oracle_default_network():
-    """One fwd+bwd at B=256 on the bin-default network (S=50, 512-512-32): every gradient tensor."""
+@pytest.mark.parametrize("tc,B", [(False, 256), (True, 256), (True, 1024), (True, 4096)],
+                         ids=["ffma-256", "tcgen05-256", "tcgen05-1024-split2", "tcgen05-4096-split8"])
+def test_gradients_match_oracle_default_network(tc, B):
+    """One fwd+bwd on the bin-default network (S=50, 512-512-32): every gradient tensor."""
     import vamb_b200.encode as ve
     from oracle import vae_oracle as vo
 
-    S, n, B = 50, 1000, 256
+    S, n = 50, 5000
     rpkm, tnfs, lens = vae_inputs(S, n, 7)
     dl = ve.make_dataloader(rpkm.copy(), tnfs.copy(), lens, batchsize=B)
     d, t, a, w = dl.dataset.tensors
-    vae = ve.VAE(S, seed=2)
+    vae = set_path(ve.VAE(S, seed=2), tc)
     o = vo.OracleVAE(S, seed=2)
     idx = torch.from_numpy(np.random.default_rng(0).choice(n, B, replace=False))
     torch.manual_seed(5)
@@ -88,7 +97,8 @@ def test_gradients_match_oracle_default_network():
         assert rel(got[k].cpu().numpy(), gref.numpy()) < 3e-5, k
 
 
-def test_odd_batch_and_many_steps_match_oracle():
+@pytest.mark.parametrize("tc", [False, True], ids=["ffma", "tcgen05"])
+def test_odd_batch_and_many_steps_match_oracle(tc):
     """B not a multiple of the tile size, 12 steps: parameters track the oracle."""
     import vamb_b200.encode as ve
     from oracle import vae_oracle as vo
@@ -97,7 +107,7 @@ def test_odd_batch_and_many_steps_match_oracle():
     rpkm, tnfs, lens = vae_inputs(S, n, 9)
     dl = ve.make_dataloader(rpkm.copy(), tnfs.copy(), lens, batchsize=B)
     d, t, a, w = dl.dataset.tensors
-    vae = ve.VAE(S, nhiddens=[96, 33], nlatent=7, seed=1)
+    vae = set_path(ve.VAE(S, nhiddens=[96, 33], nlatent=7, seed=1), tc)
     vae._reset_optimizer()
     o = vo.OracleVAE(S, nhiddens=[96, 33], nlatent=7, seed=1)
     rng = np.random.default_rng(1)

@@ -1,0 +1,260 @@
+// tcgen05 (5th-gen tensor core) building blocks for sm_100a: raw PTX wrappers, UMMA shared-memory /
+// instruction descriptors, and a 128 x BN x K tile GEMM in error-compensated 3xTF32.
+//
+// Why operands go through registers instead of TMA: every GEMM of the VAE consumes a *transformed*
+// operand (BatchNorm affine on load, or the BatchNorm/dropout/LeakyReLU backward on load) and needs
+// the tf32 hi/lo split of both operands, so the producer threads load fp32 from global (coalesced
+// float4), transform, split and write the UMMA canonical no-swizzle layouts themselves.  The matrices
+// are small and L2-resident; what matters is that the tensor pipe never waits for more than one stage.
+//
+// 3xTF32: kind::tf32 reads the top 19 bits of each fp32 operand word (low 13 mantissa bits ignored),
+// so hi = x as stored, lo = x - (x & 0xFFFFE000) (exact).  D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo leaves
+// a relative error of ~2^-21 per product, i.e. fp32-grade results from the tensor pipe.
+#pragma once
+#include "vk_common.cuh"
+
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier ----
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "LAB_WAIT%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra LAB_DONE%=;\n\t"
+        "bra LAB_WAIT%=;\n\t"
+        "LAB_DONE%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// ---- fences ----
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---- tensor memory ----
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {  // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // same warp as alloc
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// 32 lanes x 32 consecutive columns -> 32 registers per thread (thread = lane of its warp's quadrant)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- descriptors (cute/arch/mma_sm100_desc.hpp: SmemDescriptor / InstrDescriptor) ----
+// shared-memory matrix descriptor, no swizzle: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
+// version=1 [46,48) | layout_type=0 [61,64).  SBO = byte stride between core matrices along M/N,
+// LBO = byte stride between core matrices along K.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// instruction descriptor for kind::tf32, fp32 accumulate: c_format=F32 [4,6), a/b_format=TF32(2) [7,10)/[10,13),
+// a_major [15], b_major [16] (0 = K-major, 1 = MN-major), N>>3 [17,23), M>>4 [24,29)
+__device__ __forceinline__ uint32_t make_idesc_tf32(int m, int n, int a_mn_major, int b_mn_major) {
+    uint32_t d = 0;
+    d |= 1u << 4;
+    d |= 2u << 7;
+    d |= 2u << 10;
+    d |= (uint32_t)(a_mn_major & 1) << 15;
+    d |= (uint32_t)(b_mn_major & 1) << 16;
+    d |= (uint32_t)(n >> 3) << 17;
+    d |= (uint32_t)(m >> 4) << 24;
+    return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- operand tiles in shared memory (fp32 words, no swizzle) ----
+// Tile = ROWS (M or N extent, multiple of 8) x KT (=32) elements.
+//  K-major  : core matrix = 8 rows x 16 B; offset(r, k) = (r/8)*1024 + (k/4)*128 + (r%8)*16 + (k%4)*4
+//             -> SBO = 1024 (next 8 rows), LBO = 128 (next 16-byte K chunk); k8-step j starts at +256*j.
+//  MN-major : core matrix = 8 k x 16 B (4 consecutive m); offset(m, k) = (k/8)*(ROWS*32) + (m/4)*128 + (k%8)*16 + (m%4)*4
+//             -> SBO = 128 (next 4 m), LBO = ROWS*32 (next 8 k, unused by a K=8 instruction); k8-step j starts at +ROWS*32*j.
+constexpr int KT = 32;
+
+__device__ __forceinline__ uint32_t off_kmajor(int r, int k4) {  // k4 = k / 4 (one float4 per call)
+    return (uint32_t)((r >> 3) * 1024 + k4 * 128 + (r & 7) * 16);
+}
+__device__ __forceinline__ uint32_t off_mnmajor(int m4, int k, int rows) {  // m4 = m / 4
+    return (uint32_t)((k >> 3) * (rows * 32) + m4 * 128 + (k & 7) * 16);
+}
+
+__device__ __forceinline__ float4 tf32_lo(const float4 v) {
+    float4 r;
+    r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+    r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+    r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+    r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+    return r;
+}
+
+// Shared-memory plan of one CTA (dynamic smem, 1024-byte aligned by the caller):
+//   stage s in {0,1}: A_hi | A_lo (128 x KT x 4 B = 16 KB each) | B_hi | B_lo (BN x KT x 4 B each)
+constexpr int TC_BM = 128;
+constexpr int TC_THREADS = 256;
+constexpr int A_TILE_BYTES = TC_BM * KT * 4;  // 16 KB
+__host__ __device__ constexpr int b_tile_bytes(int bn) { return bn * KT * 4; }
+__host__ __device__ constexpr int stage_bytes(int bn) { return 2 * A_TILE_BYTES + 2 * b_tile_bytes(bn); }
+__host__ __device__ constexpr int tc_smem_bytes(int bn) { return 2 * stage_bytes(bn) + 1024; }
+
+struct TcShared {
+    uint64_t bar_stage[2];
+    uint64_t bar_done;
+    uint32_t tmem_base;
+};
+
+// One 128 x bn output tile: D[m, n] = sum_k A(m, k) * B(n, k), k in [0, K).
+//   LA / LB: loaders with  float4 ld4(int r, int c4)  returning 4 consecutive elements along the
+//   CONTIGUOUS dimension of the operand's storage:
+//     A_MN == false: storage [m][k] -> ld4(m, k/4)   (K-major);   A_MN == true: storage [k][m] -> ld4(k, m/4)
+//   and zeros outside the logical bounds.  bn: multiple of 16, 16 <= bn <= 128 (rows beyond the logical N
+//   must load as zeros).  The accumulator is left in TMEM (128 lanes x bn columns at sh->tmem_base);
+//   the caller runs the epilogue with tmem_ld32 and then calls tc_tile_end().
+template <bool A_MN, bool B_MN, class LA, class LB>
+__device__ __forceinline__ void tc_tile_mainloop(int K, int m0, int n0, int bn, const LA &la, const LB &lb,
+                                                 uint8_t *smem, TcShared *sh) {
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(&sh->bar_stage[0], 1);
+        mbar_init(&sh->bar_stage[1], 1);
+        mbar_init(&sh->bar_done, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(&sh->tmem_base, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = sh->tmem_base;
+    const uint32_t idesc = make_idesc_tf32(TC_BM, bn, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    const int nk = (K + KT - 1) / KT;
+    const int bbytes = b_tile_bytes(bn);
+
+    for (int kt = 0; kt < nk; ++kt) {
+        const int s = kt & 1;
+        uint8_t *st = smem + s * stage_bytes(bn);
+        uint8_t *a_hi = st, *a_lo = st + A_TILE_BYTES, *b_hi = st + 2 * A_TILE_BYTES, *b_lo = b_hi + bbytes;
+        // the MMAs that read this stage two iterations ago must have finished
+        if (kt >= 2) mbar_wait(&sh->bar_stage[s], (uint32_t)(((kt >> 1) - 1) & 1));
+        tc_fence_after();
+        const int k0 = kt * KT;
+        // ---- stage A: 128 x 32 elements = 1024 float4, 4 per thread ----
+#pragma unroll
+        for (int i = 0; i < (TC_BM * KT / 4) / TC_THREADS; ++i) {
+            const int q = tid + i * TC_THREADS;
+            float4 v;
+            uint32_t off;
+            // lanes 0-7 of a quarter-warp fill one 128-byte core matrix -> conflict-free 16-byte stores
+            if (!A_MN) {
+                const int r = ((q >> 6) << 3) | (q & 7), k4 = (q >> 3) & 7;
+                v = la.ld4(m0 + r, (k0 >> 2) + k4);
+                off = off_kmajor(r, k4);
+            } else {
+                const int k = ((q >> 8) << 3) | (q & 7), m4 = (q >> 3) & 31;
+                v = la.ld4(k0 + k, (m0 >> 2) + m4);
+                off = off_mnmajor(m4, k, TC_BM);
+            }
+            *reinterpret_cast<float4 *>(a_hi + off) = v;
+            *reinterpret_cast<float4 *>(a_lo + off) = tf32_lo(v);
+        }
+        // ---- stage B: bn x 32 elements ----
+        const int nb4 = bn * KT / 4;
+        for (int q = tid; q < nb4; q += TC_THREADS) {
+            float4 v;
+            uint32_t off;
+            if (!B_MN) {
+                const int r = ((q >> 6) << 3) | (q & 7), k4 = (q >> 3) & 7;
+                v = lb.ld4(n0 + r, (k0 >> 2) + k4);
+                off = off_kmajor(r, k4);
+            } else {
+                const int per = bn >> 2;
+                const int g = q >> 3;
+                const int k = ((g / per) << 3) | (q & 7), m4 = g % per;
+                v = lb.ld4(k0 + k, (n0 >> 2) + m4);
+                off = off_mnmajor(m4, k, bn);
+            }
+            *reinterpret_cast<float4 *>(b_hi + off) = v;
+            *reinterpret_cast<float4 *>(b_lo + off) = tf32_lo(v);
+        }
+        fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t a_lbo = A_MN ? TC_BM * 32 : 128, a_sbo = A_MN ? 128 : 1024;
+            const uint32_t b_lbo = B_MN ? (uint32_t)bn * 32 : 128, b_sbo = B_MN ? 128 : 1024;
+            const uint32_t a_step = A_MN ? TC_BM * 32 : 256, b_step = B_MN ? (uint32_t)bn * 32 : 256;
+#pragma unroll
+            for (int j = 0; j < KT / 8; ++j) {
+                const uint64_t dah = make_smem_desc(smem_u32(a_hi) + j * a_step, a_lbo, a_sbo);
+                const uint64_t dal = make_smem_desc(smem_u32(a_lo) + j * a_step, a_lbo, a_sbo);
+                const uint64_t dbh = make_smem_desc(smem_u32(b_hi) + j * b_step, b_lbo, b_sbo);
+                const uint64_t dbl = make_smem_desc(smem_u32(b_lo) + j * b_step, b_lbo, b_sbo);
+                umma_tf32(tmem_d, dal, dbh, idesc, (kt | j) ? 1u : 0u);  // small terms first
+                umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+                umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+            }
+            umma_commit(&sh->bar_stage[s]);
+            if (kt == nk - 1) umma_commit(&sh->bar_done);
+        }
+    }
+    mbar_wait(&sh->bar_done, 0);
+    tc_fence_after();
+}
+
+// Read the accumulator rows of this thread's TMEM quadrant: warp w owns lanes 32*(w%4)..+31 and
+// column half (w/4); v receives 32 consecutive columns starting at `col`.
+__device__ __forceinline__ void tc_read_acc(const TcShared *sh, int col, float (&v)[32]) {
+    const int warp = threadIdx.x >> 5;
+    const uint32_t taddr = sh->tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col;
+    tmem_ld32(taddr, v);
+}
+
+__device__ __forceinline__ void tc_tile_end(TcShared *sh) {
+    tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) tmem_dealloc(sh->tmem_base, 128);
+}
+
+}  // namespace tc

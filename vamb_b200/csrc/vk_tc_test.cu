@@ -1,0 +1,74 @@
+// Stand-alone check of the tcgen05 3xTF32 tile GEMM (vk_tc.cuh): C[M, N] = A * B^T for every
+// combination of operand storage orders.  Used by tests/test_tc_gpu.py before the core is trusted
+// inside the VAE kernels.
+#include "vk_tc.cuh"
+
+namespace {
+
+struct Ld4Plain {
+    const float *p;
+    int ld, rows, cols, aligned;
+    __device__ __forceinline__ float4 ld4(int r, int c4) const {
+        const int c = c4 * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r >= rows || c >= cols) return v;
+        const float *q = p + (int64_t)r * ld + c;
+        if (aligned && c + 3 < cols) return __ldg(reinterpret_cast<const float4 *>(q));
+        v.x = __ldg(q);
+        if (c + 1 < cols) v.y = __ldg(q + 1);
+        if (c + 2 < cols) v.z = __ldg(q + 2);
+        if (c + 3 < cols) v.w = __ldg(q + 3);
+        return v;
+    }
+};
+
+// a_mn: A stored [K][M] (else [M][K]); b_mn: B stored [K][N] (else [N][K])
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(tc::TC_THREADS, 1)
+tc_gemm_test_kernel(const float *A, const float *B, float *C, int M, int N, int K, int lda, int ldb) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ tc::TcShared sh;
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 128;
+    int bn = N - n0;
+    bn = bn > 128 ? 128 : ((bn + 15) & ~15);
+    const int al_a = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+    const int al_b = ((ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+    Ld4Plain la{A, lda, A_MN ? K : M, A_MN ? M : K, al_a};
+    Ld4Plain lb{B, ldb, B_MN ? K : N, B_MN ? N : K, al_b};
+    tc::tc_tile_mainloop<A_MN, B_MN>(K, m0, n0, bn, la, lb, smem, &sh);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m = m0 + (warp & 3) * 32 + lane;
+    for (int c = (warp >> 2) * 64; c < (warp >> 2) * 64 + 64 && c < bn; c += 32) {
+        float v[32];
+        tc::tc_read_acc(&sh, c, v);
+        if (m < M) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (n0 + c + j < N) C[(int64_t)m * N + n0 + c + j] = v[j];
+        }
+    }
+    tc::tc_tile_end(&sh);
+}
+
+}  // namespace
+
+extern "C" int vk_tc_gemm_test(const float *A, const float *B, float *C, int M, int N, int K, int a_mn, int b_mn,
+                               void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const int lda = a_mn ? M : K, ldb = b_mn ? N : K;
+    dim3 grid((N + 127) / 128, (M + 127) / 128);
+    const int smem = tc::tc_smem_bytes(128);
+#define LAUNCH(AM, BM_)                                                                                     \
+    do {                                                                                                    \
+        VK_CUDA(cudaFuncSetAttribute(tc_gemm_test_kernel<AM, BM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        tc_gemm_test_kernel<AM, BM_><<<grid, tc::TC_THREADS, smem, s>>>(A, B, C, M, N, K, lda, ldb);        \
+    } while (0)
+    if (!a_mn && !b_mn) LAUNCH(false, false);
+    else if (!a_mn && b_mn) LAUNCH(false, true);
+    else if (a_mn && !b_mn) LAUNCH(true, false);
+    else LAUNCH(true, true);
+#undef LAUNCH
+    VK_LAUNCH_CHECK();
+    return 0;
+}

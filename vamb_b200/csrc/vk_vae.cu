@@ -16,6 +16,7 @@
 // Reference lines (RasmussenLab/vamb): encode.py:259-273 _encode, :276-286 reparameterize,
 // :288-304 _decode, :316-357 calc_loss, :442-484 encode; dadaptation==3.2 DAdaptAdam.step.
 #include "vk_common.cuh"
+#include "vk_tc.cuh"
 
 // ------------------------------------------------------------------ small device helpers
 __device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
@@ -96,10 +97,22 @@ batch_rows_kernel(int64_t *batch_rows, const int64_t *batch_idx, const float *we
 
 // ------------------------------------------------------------------ operand loaders
 // at(r, c): element (row r, column c) of the logical [rows, cols] operand, 0 outside.
+// ld4(r, c4): elements (r, 4*c4 .. 4*c4+3) -- one 16-byte load per array when the row is 16-byte
+// aligned and fully inside, else four at() calls (used by the tcgen05 path, vk_tc.cuh).
+__device__ __forceinline__ bool vec_ok(const void *p, int ld) {
+    return ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
+}
+__device__ __forceinline__ float4 ldg4(const float *q) { return __ldg(reinterpret_cast<const float4 *>(q)); }
+
 struct LdPlain {
     const float *p; int ld, rows, cols;
     __device__ __forceinline__ float at(int r, int c) const {
         return (r < rows && c < cols) ? __ldg(p + (int64_t)r * ld + c) : 0.0f;
+    }
+    __device__ __forceinline__ float4 ld4(int r, int c4) const {
+        const int c = c4 << 2;
+        if (r < rows && c + 3 < cols && vec_ok(p, ld)) return ldg4(p + (int64_t)r * ld + c);
+        return make_float4(at(r, c), at(r, c + 1), at(r, c + 2), at(r, c + 3));
     }
 };
 struct LdAffine {  // BatchNorm applied on load: P * a + c
@@ -108,42 +121,86 @@ struct LdAffine {  // BatchNorm applied on load: P * a + c
         if (r >= rows || c >= cols) return 0.0f;
         return __fmaf_rn(__ldg(p + (int64_t)r * ld + c), __ldg(a + c), __ldg(sh + c));
     }
+    __device__ __forceinline__ float4 ld4(int r, int c4) const {
+        const int c = c4 << 2;
+        if (r < rows && c + 3 < cols && vec_ok(p, ld)) {
+            const float4 v = ldg4(p + (int64_t)r * ld + c), s4 = ldg4(a + c), h4 = ldg4(sh + c);
+            return make_float4(__fmaf_rn(v.x, s4.x, h4.x), __fmaf_rn(v.y, s4.y, h4.y), __fmaf_rn(v.z, s4.z, h4.z),
+                               __fmaf_rn(v.w, s4.w, h4.w));
+        }
+        return make_float4(at(r, c), at(r, c + 1), at(r, c + 2), at(r, c + 3));
+    }
 };
 struct LdData {  // gathered dataset rows
     const float *data; const int64_t *rows_idx; int ld, rows, cols;
     __device__ __forceinline__ float at(int r, int c) const {
         return (r < rows && c < cols) ? __ldg(data + rows_idx[r] * (int64_t)ld + c) : 0.0f;
     }
+    __device__ __forceinline__ float4 ld4(int r, int c4) const {
+        const int c = c4 << 2;
+        if (r < rows && c + 3 < cols && vec_ok(data, ld)) return ldg4(data + rows_idx[r] * (int64_t)ld + c);
+        return make_float4(at(r, c), at(r, c + 1), at(r, c + 2), at(r, c + 3));
+    }
 };
 struct LdDY {  // dL/dY of a hidden block from dL/dBN(P): BatchNorm, dropout and LeakyReLU backward
     const float *dh; const float *p; const float *g; const float *mean; const float *rstd;
     const float *m1; const float *m2; int ld, rows, cols; float inv_keep, slope; int has_dropout;
+    __device__ __forceinline__ float one(float pv, float dhv, float gv, float mu, float rs, float a1, float a2) const {
+        if (has_dropout && pv == 0.0f) return 0.0f;  // dropped unit
+        const float ph = (pv - mu) * rs;
+        float v = gv * rs * (dhv - a1 - ph * a2);
+        v *= inv_keep;
+        return pv > 0.0f ? v : v * slope;
+    }
     __device__ __forceinline__ float at(int r, int c) const {
         if (r >= rows || c >= cols) return 0.0f;
         const int64_t o = (int64_t)r * ld + c;
-        const float pv = __ldg(p + o);
-        if (has_dropout && pv == 0.0f) return 0.0f;  // dropped unit
-        const float rs = __ldg(rstd + c);
-        const float ph = (pv - __ldg(mean + c)) * rs;
-        float v = __ldg(g + c) * rs * (__ldg(dh + o) - __ldg(m1 + c) - ph * __ldg(m2 + c));
-        v *= inv_keep;
-        return pv > 0.0f ? v : v * slope;
+        return one(__ldg(p + o), __ldg(dh + o), __ldg(g + c), __ldg(mean + c), __ldg(rstd + c), __ldg(m1 + c),
+                   __ldg(m2 + c));
+    }
+    __device__ __forceinline__ float4 ld4(int r, int c4) const {
+        const int c = c4 << 2;
+        if (r < rows && c + 3 < cols && vec_ok(p, ld) && vec_ok(dh, ld)) {
+            const int64_t o = (int64_t)r * ld + c;
+            const float4 pv = ldg4(p + o), dv = ldg4(dh + o), gv = ldg4(g + c), mu = ldg4(mean + c),
+                         rs = ldg4(rstd + c), a1 = ldg4(m1 + c), a2 = ldg4(m2 + c);
+            return make_float4(one(pv.x, dv.x, gv.x, mu.x, rs.x, a1.x, a2.x), one(pv.y, dv.y, gv.y, mu.y, rs.y, a1.y, a2.y),
+                               one(pv.z, dv.z, gv.z, mu.z, rs.z, a1.z, a2.z), one(pv.w, dv.w, gv.w, mu.w, rs.w, a1.w, a2.w));
+        }
+        return make_float4(at(r, c), at(r, c + 1), at(r, c + 2), at(r, c + 3));
     }
 };
 // generic input activation of a layer (data / BN(P) / z) with an optional all-ones extra column
 struct LdInput {
     int in_kind; LdData d; LdAffine a; LdPlain z; int ones_col;  // ones_col < 0: none
+    __device__ __forceinline__ int nrows() const { return in_kind == VK_IN_DATA ? d.rows : in_kind == VK_IN_BN ? a.rows : z.rows; }
     __device__ __forceinline__ float at(int r, int c) const {
-        if (c == ones_col) return r < (in_kind == VK_IN_DATA ? d.rows : in_kind == VK_IN_BN ? a.rows : z.rows) ? 1.0f : 0.0f;
+        if (c == ones_col) return r < nrows() ? 1.0f : 0.0f;
         if (in_kind == VK_IN_DATA) return d.at(r, c);
         if (in_kind == VK_IN_BN) return a.at(r, c);
         return z.at(r, c);
+    }
+    __device__ __forceinline__ float4 ld4(int r, int c4) const {
+        const int c = c4 << 2;
+        if (ones_col >= c && ones_col < c + 4) return make_float4(at(r, c), at(r, c + 1), at(r, c + 2), at(r, c + 3));
+        if (in_kind == VK_IN_DATA) return d.ld4(r, c4);
+        if (in_kind == VK_IN_BN) return a.ld4(r, c4);
+        return z.ld4(r, c4);
     }
 };
 // generic dL/dY of a layer: hidden -> LdDY, mu / out -> plain
 struct LdGradOut {
     int hidden; LdDY h; LdPlain pl;
     __device__ __forceinline__ float at(int r, int c) const { return hidden ? h.at(r, c) : pl.at(r, c); }
+    __device__ __forceinline__ float4 ld4(int r, int c4) const { return hidden ? h.ld4(r, c4) : pl.ld4(r, c4); }
+};
+// rows [off, off + n) of another loader (split-K slices of the batch dimension)
+template <class L>
+struct LdRowSlice {
+    L inner; int off, n;
+    __device__ __forceinline__ float4 ld4(int r, int c4) const {
+        return r < n ? inner.ld4(r + off, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 };
 
 // ------------------------------------------------------------------ 64x64x16 fp32 GEMM tile
@@ -273,6 +330,33 @@ struct FwdArgs {
     vk_vae_ctl *ctl; int layer_id; float slope;
 };
 
+// Fold the per-row-tile column sums of P and P^2 into the BatchNorm affine, the saved batch statistics
+// and the running statistics (torch.nn.BatchNorm1d, momentum 0.1, unbiased running variance).  Run by
+// every thread of the last block to finish.
+__device__ __forceinline__ void bn_forward_finalize(const FwdArgs &a, int n_rt) {
+    for (int n = threadIdx.x; n < a.N; n += blockDim.x) {
+        double s = 0.0, q = 0.0;
+        for (int rt = 0; rt < n_rt; ++rt) {
+            s += __ldcg(a.part + ((int64_t)rt * 2 + 0) * a.N + n);
+            q += __ldcg(a.part + ((int64_t)rt * 2 + 1) * a.N + n);
+        }
+        const double mean = s / a.B;
+        double var = q / a.B - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+        const float fm = (float)mean;
+        a.bn_mean[n] = fm;
+        a.bn_rstd[n] = rstd;
+        const float sc = a.gamma[n] * rstd;
+        a.bn_a[n] = sc;
+        a.bn_c[n] = a.beta[n] - fm * sc;
+        const float unb = a.B > 1 ? (float)(var * ((double)a.B / (double)(a.B - 1))) : (float)var;
+        a.running_mean[n] = 0.9f * a.running_mean[n] + 0.1f * fm;
+        a.running_var[n] = 0.9f * a.running_var[n] + 0.1f * unb;
+    }
+    if (threadIdx.x == 0) *a.nbt += 1;
+}
+
 __global__ void __launch_bounds__(GT) fwd_layer_kernel(FwdArgs a) {
     __shared__ __align__(16) float s_gemm[SMEM_GEMM_FLOATS];
     __shared__ double s_red[2 * 16 * 64];
@@ -347,34 +431,13 @@ __global__ void __launch_bounds__(GT) fwd_layer_kernel(FwdArgs a) {
     double *p1 = a.part + ((int64_t)blockIdx.y * 2 + 1) * a.N;
     tile_colsum2<4>(cs, cq, s_red, p0, p1, n0, a.N);
     if (!last_block_done(&a.ctl->tickets[a.layer_id], gridDim.x * gridDim.y)) return;
-    for (int n = tid; n < a.N; n += GT) {
-        double s = 0.0, q = 0.0;
-        for (int rt = 0; rt < n_rt; ++rt) {
-            s += __ldcg(a.part + ((int64_t)rt * 2 + 0) * a.N + n);
-            q += __ldcg(a.part + ((int64_t)rt * 2 + 1) * a.N + n);
-        }
-        const double mean = s / a.B;
-        double var = q / a.B - mean * mean;
-        if (var < 0.0) var = 0.0;
-        const float rstd = (float)(1.0 / sqrt(var + 1e-5));
-        const float fm = (float)mean;
-        a.bn_mean[n] = fm;
-        a.bn_rstd[n] = rstd;
-        const float sc = a.gamma[n] * rstd;
-        a.bn_a[n] = sc;
-        a.bn_c[n] = a.beta[n] - fm * sc;
-        // running statistics: momentum 0.1, unbiased variance (torch.nn.BatchNorm1d)
-        const float unb = a.B > 1 ? (float)(var * ((double)a.B / (double)(a.B - 1))) : (float)var;
-        a.running_mean[n] = 0.9f * a.running_mean[n] + 0.1f * fm;
-        a.running_var[n] = 0.9f * a.running_var[n] + 0.1f * unb;
-    }
-    if (tid == 0) *a.nbt += 1;
+    bn_forward_finalize(a, n_rt);
 }
 
 // ------------------------------------------------------------------ loss (+ dL/dR)
 struct LossArgs {
     const float *R; const float *MU; const float *data; const int64_t *batch_rows;
-    float *dR; int B, S, ntnf, d_in, nlatent; float ce_w, ab_w, sse_w, kld_w;
+    float *dR; int B, S, ntnf, d_in, nlatent, data_ld; float ce_w, ab_w, sse_w, kld_w;
     double *part; vk_vae_ctl *ctl; int ticket_id; int write_grad;
 };
 
@@ -385,7 +448,7 @@ __global__ void __launch_bounds__(256) loss_kernel(LossArgs a) {
     double l_ce = 0.0, l_sse = 0.0, l_ab = 0.0, l_kld = 0.0;
     if (b < a.B) {
         const float *r = a.R + (int64_t)b * a.d_in;
-        const float *x = a.data + a.batch_rows[b] * (int64_t)a.d_in;
+        const float *x = a.data + a.batch_rows[b] * (int64_t)a.data_ld;
         float *g = a.dR + (int64_t)b * a.d_in;
         const float gsc = (float)(a.ctl->wbar / (double)a.B);
         // softmax over the S depth outputs (encode.py:302)
@@ -469,6 +532,22 @@ struct BwdArgs {
     vk_vae_ctl *ctl; int ticket_id;
 };
 
+// Fold the per-row-tile column sums of dH and dH*Phat: BatchNorm weight/bias gradients and the two
+// batch means the consumer needs (last block to finish).
+__device__ __forceinline__ void bn_backward_finalize(const BwdArgs &a) {
+    for (int n = threadIdx.x; n < a.K; n += blockDim.x) {
+        double u = 0.0, v = 0.0;
+        for (int rt = 0; rt < a.dg_tiles_m; ++rt) {
+            u += __ldcg(a.part_prev + ((int64_t)rt * 2 + 0) * a.K + n);
+            v += __ldcg(a.part_prev + ((int64_t)rt * 2 + 1) * a.K + n);
+        }
+        a.g_beta[n] = (float)u;   // d/d(beta)  = sum_b dH
+        a.g_gamma[n] = (float)v;  // d/d(gamma) = sum_b dH * Phat
+        a.m1_prev[n] = (float)(u / a.B);
+        a.m2_prev[n] = (float)(v / a.B);
+    }
+}
+
 __global__ void __launch_bounds__(GT) bwd_layer_kernel(BwdArgs a) {
     __shared__ __align__(16) float s_gemm[SMEM_GEMM_FLOATS];
     __shared__ double s_red[2 * 16 * 64];
@@ -525,17 +604,224 @@ __global__ void __launch_bounds__(GT) bwd_layer_kernel(BwdArgs a) {
     double *p1 = a.part_prev + ((int64_t)row_tile * 2 + 1) * a.K;
     tile_colsum2<4>(s1, s2, s_red, p0, p1, n0, a.K);
     if (!last_block_done(&a.ctl->tickets[a.ticket_id], a.dg_tiles_m * a.dg_tiles_n)) return;
-    for (int n = tid; n < a.K; n += GT) {
-        double u = 0.0, v = 0.0;
-        for (int rt = 0; rt < a.dg_tiles_m; ++rt) {
-            u += __ldcg(a.part_prev + ((int64_t)rt * 2 + 0) * a.K + n);
-            v += __ldcg(a.part_prev + ((int64_t)rt * 2 + 1) * a.K + n);
+    bn_backward_finalize(a);
+}
+
+// ------------------------------------------------------------------ tcgen05 (3xTF32) layer kernels
+// Same arguments and results as fwd_layer_kernel / bwd_layer_kernel; the GEMM core is the 128 x bn
+// tensor-core tile of vk_tc.cuh and the epilogue goes TMEM -> registers -> shared tile -> global.
+constexpr int TS = 132;  // padded row stride (floats) of the shared epilogue tile: conflict-free float4 rows
+
+__device__ __forceinline__ uint8_t *align1024(uint8_t *p) {
+    return reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
+}
+
+// Column sums of two per-element quantities over the 128 rows of the shared tile(s), fixed order.
+// f(r, c) -> (v0, v1).  Writes out0/out1[n0 + c] for c < bn with n0 + c < N.
+template <class F>
+__device__ __forceinline__ void tc_colsum2(int bn, int n0, int N, double (*s_cs)[2][128], double *out0, double *out1,
+                                           const F &f) {
+    const int tid = threadIdx.x, col = tid & 127, half = tid >> 7;
+    if (col < bn) {
+        double a0 = 0.0, a1 = 0.0;
+        for (int r = half * 64; r < half * 64 + 64; ++r) {
+            float v0, v1;
+            f(r, col, v0, v1);
+            a0 += (double)v0;
+            a1 += (double)v1;
         }
-        a.g_beta[n] = (float)u;   // d/d(beta)  = sum_b dH
-        a.g_gamma[n] = (float)v;  // d/d(gamma) = sum_b dH * Phat
-        a.m1_prev[n] = (float)(u / a.B);
-        a.m2_prev[n] = (float)(v / a.B);
+        s_cs[half][0][col] = a0;
+        s_cs[half][1][col] = a1;
     }
+    __syncthreads();
+    if (tid < bn && n0 + tid < N) {
+        out0[n0 + tid] = s_cs[0][0][tid] + s_cs[1][0][tid];
+        out1[n0 + tid] = s_cs[0][1][tid] + s_cs[1][1][tid];
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(tc::TC_THREADS, 1) fwd_layer_tc_kernel(FwdArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ tc::TcShared sh;
+    __shared__ double s_cs[2][2][128];
+    uint8_t *smem = align1024(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 128;
+    int bn = a.N - n0;
+    bn = bn > 128 ? 128 : ((bn + 15) & ~15);
+    LdPlain w{a.W, a.K, a.N, a.K};
+    tc::tc_tile_mainloop<false, false>(a.K, m0, n0, bn, a.in, w, smem, &sh);
+
+    float *tile = reinterpret_cast<float *>(smem);  // [128][TS]; the operand stages are dead now
+    const uint32_t k0 = (uint32_t)a.ctl->seed, k1 = (uint32_t)(a.ctl->seed >> 32);
+    const uint32_t step_lo = (uint32_t)a.ctl->step, step_hi = (uint32_t)(a.ctl->step >> 32);
+    const int row = (warp & 3) * 32 + lane, m = m0 + row;
+    const bool hidden = a.kind == VK_LAYER_HIDDEN;
+    const bool drop = hidden && a.training && a.dropout > 0.0f;
+    const float keep_scale = 1.0f / (1.0f - a.dropout);
+    for (int c = (warp >> 2) * 64; c < (warp >> 2) * 64 + 64 && c < bn; c += 32) {
+        float v[32];
+        tc::tc_read_acc(&sh, c, v);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+            uint32_t rnd[4] = {0u, 0u, 0u, 0u};
+            const int nb = n0 + c + 4 * j4;
+            if (drop && a.keep == nullptr && m < a.B)
+                philox4x32((uint32_t)m, (uint32_t)(nb >> 2), step_lo, step_hi ^ ((uint32_t)(a.layer_id + 1) << 24), k0, k1, rnd);
+            float o4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = nb + j;
+                float p = 0.0f;
+                if (m < a.B && n < a.N) {
+                    const float y = v[4 * j4 + j] + __ldg(a.bias + n);
+                    if (hidden) {
+                        p = y > 0.0f ? y : y * a.slope;
+                        if (drop) {
+                            const bool kp = a.keep ? (a.keep[(int64_t)m * a.N + n] != 0) : (u32_to_unit(rnd[j]) > a.dropout);
+                            p = kp ? p * keep_scale : 0.0f;
+                        }
+                    } else {
+                        p = y;
+                    }
+                }
+                o4[j] = p;
+            }
+            *reinterpret_cast<float4 *>(tile + row * TS + c + 4 * j4) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        }
+    }
+    tc::tc_tile_end(&sh);  // fence + __syncthreads + TMEM dealloc: the tile is complete for everyone
+    // coalesced store of the tile
+    const bool vec = ((a.N & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
+    const int q_per_row = bn >> 2;
+    for (int q = tid; q < 128 * q_per_row; q += tc::TC_THREADS) {
+        const int r = q / q_per_row, c = (q % q_per_row) << 2;
+        if (m0 + r >= a.B) continue;
+        const float4 t = *reinterpret_cast<const float4 *>(tile + r * TS + c);
+        float *dst = a.out + (int64_t)(m0 + r) * a.N + n0 + c;
+        if (vec && n0 + c + 3 < a.N) *reinterpret_cast<float4 *>(dst) = t;
+        else {
+            if (n0 + c < a.N) dst[0] = t.x;
+            if (n0 + c + 1 < a.N) dst[1] = t.y;
+            if (n0 + c + 2 < a.N) dst[2] = t.z;
+            if (n0 + c + 3 < a.N) dst[3] = t.w;
+        }
+    }
+    if (!hidden || !a.training) return;
+    double *p0 = a.part + ((int64_t)blockIdx.y * 2 + 0) * a.N;
+    double *p1 = a.part + ((int64_t)blockIdx.y * 2 + 1) * a.N;
+    tc_colsum2(bn, n0, a.N, s_cs, p0, p1, [&](int r, int c, float &v0, float &v1) {
+        const float p = tile[r * TS + c];  // rows >= B and columns >= N hold zeros
+        v0 = p;
+        v1 = p * p;
+    });
+    if (!last_block_done(&a.ctl->tickets[a.layer_id], gridDim.x * gridDim.y)) return;
+    bn_forward_finalize(a, gridDim.y);
+}
+
+// grid: [wgrad tiles (tiles_m x tiles_n x nsplit)] + [dgrad tiles (dg_tiles_m x dg_tiles_n)], 128-row tiles
+struct BwdTcExtra {
+    int nsplit, k_per_split;   // split-K over the batch for wgrad
+    int64_t slab;              // floats between gradient slabs
+};
+
+__global__ void __launch_bounds__(tc::TC_THREADS, 1) bwd_layer_tc_kernel(BwdArgs a, BwdTcExtra x) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ tc::TcShared sh;
+    __shared__ double s_cs[2][2][128];
+    uint8_t *smem = align1024(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_wg = a.wg_tiles_m * a.wg_tiles_n * x.nsplit;
+    if ((int)blockIdx.x < n_wg) {
+        // ---- wgrad slice: gW[n, k] (+ bias column) over batch rows [b0, b0 + nb) ----
+        const int split = blockIdx.x / (a.wg_tiles_m * a.wg_tiles_n);
+        const int t = blockIdx.x % (a.wg_tiles_m * a.wg_tiles_n);
+        const int m0 = (t / a.wg_tiles_n) * 128, n0 = (t % a.wg_tiles_n) * 128;
+        int bn = a.K + 1 - n0;
+        bn = bn > 128 ? 128 : ((bn + 15) & ~15);
+        const int b0 = split * x.k_per_split;
+        int nb = a.B - b0;
+        nb = nb < 0 ? 0 : (nb > x.k_per_split ? x.k_per_split : nb);
+        LdRowSlice<LdGradOut> la{a.gy, b0, nb};
+        LdRowSlice<LdInput> lb{a.in, b0, nb};
+        tc::tc_tile_mainloop<true, true>(nb > 0 ? nb : 1, m0, n0, bn, la, lb, smem, &sh);
+        const int m = m0 + (warp & 3) * 32 + lane;
+        float *gW = a.gW + (int64_t)split * x.slab, *gb = a.gb + (int64_t)split * x.slab;
+        for (int c = (warp >> 2) * 64; c < (warp >> 2) * 64 + 64 && c < bn; c += 32) {
+            float v[32];
+            tc::tc_read_acc(&sh, c, v);
+            if (m < a.N) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = n0 + c + j;
+                    if (n < a.K) gW[(int64_t)m * a.K + n] = v[j];
+                    else if (n == a.K) gb[m] = v[j];
+                }
+            }
+        }
+        tc::tc_tile_end(&sh);
+        return;
+    }
+    // ---- dgrad: dX[b, k] = sum_n dY[b, n] * W[n, k] ----
+    const int t = blockIdx.x - n_wg;
+    const int m0 = (t / a.dg_tiles_n) * 128, n0 = (t % a.dg_tiles_n) * 128;
+    int bn = a.K - n0;
+    bn = bn > 128 ? 128 : ((bn + 15) & ~15);
+    LdPlain w{a.W, a.K, a.N, a.K};
+    tc::tc_tile_mainloop<false, true>(a.N, m0, n0, bn, a.gy, w, smem, &sh);
+    float *tile = reinterpret_cast<float *>(smem);
+    const int row = (warp & 3) * 32 + lane, m = m0 + row;
+    const float gsc = (float)(a.ctl->wbar / (double)a.B);
+    for (int c = (warp >> 2) * 64; c < (warp >> 2) * 64 + 64 && c < bn; c += 32) {
+        float v[32];
+        tc::tc_read_acc(&sh, c, v);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+            float o4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + c + 4 * j4 + j;
+                float val = 0.0f;
+                if (m < a.B && n < a.K) {
+                    val = v[4 * j4 + j];
+                    if (a.in_kind == VK_IN_Z) val = __fmaf_rn(gsc * a.kld_w, __ldg(a.MU + (int64_t)m * a.K + n), val);
+                }
+                o4[j] = val;
+            }
+            *reinterpret_cast<float4 *>(tile + row * TS + c + 4 * j4) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        }
+    }
+    tc::tc_tile_end(&sh);
+    const bool vec = ((a.K & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.d_in) & 15) == 0);
+    const int q_per_row = bn >> 2;
+    for (int q = tid; q < 128 * q_per_row; q += tc::TC_THREADS) {
+        const int r = q / q_per_row, c = (q % q_per_row) << 2;
+        if (m0 + r >= a.B) continue;
+        const float4 tv = *reinterpret_cast<const float4 *>(tile + r * TS + c);
+        float *dst = a.d_in + (int64_t)(m0 + r) * a.K + n0 + c;
+        if (vec && n0 + c + 3 < a.K) *reinterpret_cast<float4 *>(dst) = tv;
+        else {
+            if (n0 + c < a.K) dst[0] = tv.x;
+            if (n0 + c + 1 < a.K) dst[1] = tv.y;
+            if (n0 + c + 2 < a.K) dst[2] = tv.z;
+            if (n0 + c + 3 < a.K) dst[3] = tv.w;
+        }
+    }
+    if (a.in_kind != VK_IN_BN) return;
+    const int row_tile = t / a.dg_tiles_n;
+    double *p0 = a.part_prev + ((int64_t)row_tile * 2 + 0) * a.K;
+    double *p1 = a.part_prev + ((int64_t)row_tile * 2 + 1) * a.K;
+    tc_colsum2(bn, n0, a.K, s_cs, p0, p1, [&](int r, int c, float &v0, float &v1) {
+        const float dv = tile[r * TS + c];
+        float ph = 0.0f;
+        if (m0 + r < a.B && n0 + c < a.K)
+            ph = (__ldg(a.p_prev + (int64_t)(m0 + r) * a.K + n0 + c) - __ldg(a.mean_prev + n0 + c)) * __ldg(a.rstd_prev + n0 + c);
+        v0 = dv;
+        v1 = dv * ph;
+    });
+    if (!last_block_done(&a.ctl->tickets[a.ticket_id], a.dg_tiles_m * a.dg_tiles_n)) return;
+    bn_backward_finalize(a);
 }
 
 // ------------------------------------------------------------------ D-Adaptation Adam
@@ -546,7 +832,7 @@ constexpr int OPT_BLOCKS = 296;
 
 __global__ void __launch_bounds__(256)
 dadapt_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
-              float *__restrict__ s, int64_t n, double *part, vk_vae_ctl *ctl, int ticket_id) {
+              float *__restrict__ s, int64_t n, double *part, vk_vae_ctl *ctl, int ticket_id, int nslab, int64_t slab) {
     __shared__ double s_a[256], s_b[256];
     const double beta1 = 0.9, beta2 = 0.999, eps = 1e-8;
     const double sqrt_beta2 = sqrt(beta2);
@@ -556,7 +842,8 @@ dadapt_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restr
     const float f_eps = (float)eps;
     double acc_num = 0.0, acc_l1 = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
-        const float gi = g[i];
+        float gi = g[i];
+        for (int sl = 1; sl < nslab; ++sl) gi += g[(int64_t)sl * slab + i];  // split-K partial gradients, fixed order
         float mi = m[i], vi = v[i], si = s[i];
         const float denom_old = sqrtf(vi) + f_eps;
         acc_num += (double)(gi * (si / denom_old));
@@ -634,12 +921,31 @@ static int check_net(const vk_vae *net, int batch) {
     return 0;
 }
 
+static bool use_tc(const vk_vae *net, int B) { return net->tc_min_batch > 0 && B >= net->tc_min_batch; }
+
+static int tc_nsplit(const vk_vae *net, int B) {
+    int ns = B / 512;
+    if (ns < 1) ns = 1;
+    if (ns > net->n_grad_slabs) ns = net->n_grad_slabs;
+    return ns;
+}
+
+static int tc_prepare() {
+    static bool done = false;
+    if (done) return 0;
+    const int smem = tc::tc_smem_bytes(128);
+    VK_CUDA(cudaFuncSetAttribute(fwd_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VK_CUDA(cudaFuncSetAttribute(bwd_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    done = true;
+    return 0;
+}
+
 static LdInput make_input(const vk_vae *net, int j, int B, int ones_col) {
     const vk_vae_layer &L = net->layers[j];
     LdInput in;
     in.in_kind = L.in_kind;
     in.ones_col = ones_col;
-    in.d = LdData{net->data, net->batch_rows, net->d_in, B, L.k_in};
+    in.d = LdData{net->data, net->batch_rows, net->data_ld, B, L.k_in};
     in.a = LdAffine{nullptr, nullptr, nullptr, L.k_in, B, L.k_in};
     in.z = LdPlain{net->z, L.k_in, B, L.k_in};
     if (L.in_kind == VK_IN_BN) {
@@ -686,9 +992,15 @@ static int launch_forward(const vk_vae *net, int B, int training, int upto /*exc
         a.mask_bits = mask_bits;
         a.latent_out = (L.kind == VK_LAYER_MU) ? latent_out : nullptr;
         a.ctl = net->ctl; a.layer_id = j; a.slope = net->slope;
-        dim3 grid((L.n_out + 63) / 64, (B + 63) / 64);
         PROF_MARK(s);
-        fwd_layer_kernel<<<grid, GT, 0, s>>>(a);
+        if (use_tc(net, B) && L.kind != VK_LAYER_MU) {
+            if (tc_prepare()) return 1;
+            dim3 grid((L.n_out + 127) / 128, (B + 127) / 128);
+            fwd_layer_tc_kernel<<<grid, tc::TC_THREADS, tc::tc_smem_bytes(128), s>>>(a);
+        } else {
+            dim3 grid((L.n_out + 63) / 64, (B + 63) / 64);
+            fwd_layer_kernel<<<grid, GT, 0, s>>>(a);
+        }
         VK_LAUNCH_CHECK();
     }
     return 0;
@@ -703,6 +1015,7 @@ static int launch_loss(const vk_vae *net, int B, int write_grad, cudaStream_t s)
     a.R = net->layers[nl - 1].act; a.MU = net->layers[mu_j].act; a.data = net->data; a.batch_rows = net->batch_rows;
     a.dR = net->layers[nl - 1].dact;
     a.B = B; a.S = net->nsamples; a.ntnf = net->ntnf; a.d_in = net->d_in; a.nlatent = net->nlatent;
+    a.data_ld = net->data_ld;
     a.ce_w = net->ce_w; a.ab_w = net->ab_w; a.sse_w = net->sse_w; a.kld_w = net->kld_w;
     a.part = net->loss_part; a.ctl = net->ctl; a.ticket_id = VK_VAE_MAX_LAYERS; a.write_grad = write_grad;
     const int blocks = (B + 7) / 8;
@@ -758,23 +1071,48 @@ static int launch_backward(const vk_vae *net, int B, cudaStream_t s) {
                 a.kld_w = net->kld_w;
             }
         }
-        const int blocks = a.wg_tiles_m * a.wg_tiles_n + a.dg_tiles_m * a.dg_tiles_n;
         PROF_MARK(s);
-        bwd_layer_kernel<<<blocks, GT, 0, s>>>(a);
+        if (use_tc(net, B)) {
+            if (tc_prepare()) return 1;
+            BwdTcExtra x;
+            x.nsplit = tc_nsplit(net, B);
+            x.k_per_split = (((B + x.nsplit - 1) / x.nsplit) + 31) & ~31;
+            x.slab = net->grad_slab;
+            a.wg_tiles_m = (L.n_out + 127) / 128;
+            a.wg_tiles_n = (L.k_in + 1 + 127) / 128;
+            if (a.dg_tiles_m) {
+                a.dg_tiles_m = (B + 127) / 128;
+                a.dg_tiles_n = (L.k_in + 127) / 128;
+            }
+            const int blocks = a.wg_tiles_m * a.wg_tiles_n * x.nsplit + a.dg_tiles_m * a.dg_tiles_n;
+            bwd_layer_tc_kernel<<<blocks, tc::TC_THREADS, tc::tc_smem_bytes(128), s>>>(a, x);
+        } else {
+            const int blocks = a.wg_tiles_m * a.wg_tiles_n + a.dg_tiles_m * a.dg_tiles_n;
+            bwd_layer_kernel<<<blocks, GT, 0, s>>>(a);
+        }
         VK_LAUNCH_CHECK();
     }
     return 0;
 }
 
-static int launch_dadapt(const vk_vae *net, cudaStream_t s) {
+__global__ void reduce_slabs_kernel(float *g, int64_t n, int nslab, int64_t slab) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float t = g[i];
+        for (int sl = 1; sl < nslab; ++sl) t += g[(int64_t)sl * slab + i];
+        g[i] = t;
+    }
+}
+
+static int launch_dadapt(const vk_vae *net, int nslab, cudaStream_t s) {
     PROF_MARK(s);
     dadapt_kernel<<<OPT_BLOCKS, 256, 0, s>>>(net->params, net->grads, net->exp_avg, net->exp_avg_sq, net->s,
-                                             net->n_params, net->opt_part, net->ctl, 2 * VK_VAE_MAX_LAYERS + 2);
+                                             net->n_params, net->opt_part, net->ctl, 2 * VK_VAE_MAX_LAYERS + 2,
+                                             nslab, net->grad_slab);
     VK_LAUNCH_CHECK();
     return 0;
 }
 
-extern "C" int vk_vae_grad_step(const vk_vae *net, int batch, const vk_vae_inject *inject, void *stream) {
+static int grad_step_impl(const vk_vae *net, int batch, const vk_vae_inject *inject, void *stream) {
     if (check_net(net, batch)) return 1;
     cudaStream_t s = (cudaStream_t)stream;
     const int mode = (inject && inject->batch_idx) ? 0 : 1;
@@ -785,14 +1123,25 @@ extern "C" int vk_vae_grad_step(const vk_vae *net, int batch, const vk_vae_injec
     return 0;
 }
 
+extern "C" int vk_vae_grad_step(const vk_vae *net, int batch, const vk_vae_inject *inject, void *stream) {
+    if (grad_step_impl(net, batch, inject, stream)) return 1;
+    if (use_tc(net, batch) && tc_nsplit(net, batch) > 1) {
+        // leave the complete gradient in slab 0 (all-reduce / inspection read only that slab)
+        reduce_slabs_kernel<<<OPT_BLOCKS, 256, 0, (cudaStream_t)stream>>>(net->grads, net->n_params,
+                                                                          tc_nsplit(net, batch), net->grad_slab);
+        VK_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
 extern "C" int vk_vae_dadapt_step(const vk_vae *net, void *stream) {
     if (check_net(net, 1)) return 1;
-    return launch_dadapt(net, (cudaStream_t)stream);
+    return launch_dadapt(net, 1, (cudaStream_t)stream);
 }
 
 extern "C" int vk_vae_train_step(const vk_vae *net, int batch, const vk_vae_inject *inject, void *stream) {
-    if (vk_vae_grad_step(net, batch, inject, stream)) return 1;
-    return launch_dadapt(net, (cudaStream_t)stream);
+    if (grad_step_impl(net, batch, inject, stream)) return 1;
+    return launch_dadapt(net, use_tc(net, batch) ? tc_nsplit(net, batch) : 1, (cudaStream_t)stream);
 }
 
 extern "C" int vk_vae_forward(const vk_vae *net, int64_t row0, int batch, int training, int with_loss,

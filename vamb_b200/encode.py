@@ -45,6 +45,7 @@ except ImportError:  # pragma: no cover
 
 _MAX_BATCH = 8192  # rows of the activation workspaces (training batches double up to 4096)
 _GRAPH_CHUNK = 128  # optimiser steps per captured CUDA graph
+_TC_MIN_BATCH = 512  # batches >= this run their GEMMs on the tcgen05 tensor-core path (0 = never)
 
 
 def set_batchsize(data_loader: _DataLoader, batch_size: int, n_obs: int, encode=False) -> _DataLoader:
@@ -171,6 +172,8 @@ class _VkVae(_ct.Structure):
         ("z", _ct.c_void_p), ("batch_rows", _ct.c_void_p), ("opt_part", _ct.c_void_p), ("loss_part", _ct.c_void_p),
         ("ctl", _ct.c_void_p),
         ("layers", _VkLayer * _MAXL),
+        ("data_ld", _ct.c_int32), ("tc_min_batch", _ct.c_int32), ("grad_slab", _ct.c_int64),
+        ("n_grad_slabs", _ct.c_int32), ("reserved_", _ct.c_int32),
     ]
 
 
@@ -314,7 +317,9 @@ class VAE(_nn.Module):
             p.data = view
         self._arena = arena
         self._offsets = offsets
-        self._grads = _torch.zeros(total, **f32)
+        self._n_slabs = 8  # split-K partial-gradient slabs of the tensor-core wgrad (slab 0 = the gradient)
+        self._grads_all = _torch.zeros(self._n_slabs * total, **f32)
+        self._grads = self._grads_all[:total]
         self._exp_avg = _torch.zeros(total, **f32)
         self._exp_avg_sq = _torch.zeros(total, **f32)
         self._s = _torch.zeros(total, **f32)
@@ -332,6 +337,9 @@ class VAE(_nn.Module):
         net.ce_w, net.ab_w = ce_w, (1 - self.alpha) * (1 / self.nsamples)
         net.sse_w, net.kld_w = self.alpha / self.ntnf, 1 / (self.nlatent * self.beta)
         net.n_params = total
+        net.grad_slab, net.n_grad_slabs = total, self._n_slabs
+        net.data_ld = (net.d_in + 3) // 4 * 4
+        net.tc_min_batch = _TC_MIN_BATCH
         for field, t in (("params", arena), ("grads", self._grads), ("exp_avg", self._exp_avg),
                          ("exp_avg_sq", self._exp_avg_sq), ("s", self._s)):
             setattr(net, field, t.data_ptr())
@@ -419,11 +427,11 @@ class VAE(_nn.Module):
             return len(depths)
         dev = self._arena.device
         n = len(depths)
-        data = _torch.empty((n, self._net.d_in), dtype=_torch.float32, device=dev)
+        data = _torch.zeros((n, self._net.data_ld), dtype=_torch.float32, device=dev)
         s = self.nsamples
         data[:, :s] = depths.to(dev, non_blocking=True)
         data[:, s:s + self.ntnf] = tnf.to(dev, non_blocking=True)
-        data[:, s + self.ntnf:] = ab.reshape(n, 1).to(dev, non_blocking=True)
+        data[:, s + self.ntnf:s + self.ntnf + 1] = ab.reshape(n, 1).to(dev, non_blocking=True)
         weights = w.reshape(n).to(dev).contiguous()
         self._dataset = (key, data, weights)
         self._net.data, self._net.weights, self._net.n_rows = data.data_ptr(), weights.data_ptr(), n
@@ -449,7 +457,8 @@ class VAE(_nn.Module):
         if b > self._net.bmax:
             raise ValueError(f"at most {self._net.bmax} rows per forward call")
         src_dev = depths.device
-        data = _torch.cat((depths.to(dev), tnf.to(dev), abundance.reshape(b, -1).to(dev)), 1).float().contiguous()
+        pad = _torch.zeros((b, self._net.data_ld - self._net.d_in), dtype=_torch.float32, device=dev)
+        data = _torch.cat((depths.to(dev), tnf.to(dev), abundance.reshape(b, -1).to(dev), pad), 1).float().contiguous()
         weights = _torch.ones(b, dtype=_torch.float32, device=dev)
         tmp = _VkVae.from_buffer_copy(self._net)
         tmp.data, tmp.weights, tmp.n_rows = data.data_ptr(), weights.data_ptr(), b
