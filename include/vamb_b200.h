@@ -113,6 +113,57 @@ int vk_compact_rows_sync(const float *matrix, const float *lengths, const int32_
 int vk_distances(const float *matrix, int64_t n, int d, int64_t medoid_row, float *dists, void *stream);
 
 
+/* ------------------------------------------------------------------ native clusterer driver
+ * The decision logic of vamb/cluster.py (ClusterGenerator.__next__ :298-316 and everything it
+ * calls) in C++ on top of the kernels above: one foreign call per emitted cluster.  All device and
+ * pinned buffers are owned by the caller; sizes as in vamb_b200/cluster.py. */
+typedef struct vk_cluster_config {
+    int64_t n;                 /* observations                                                          */
+    int32_t d;                 /* latent width                                                          */
+    int32_t maxsteps, windowsize, minsuccesses;
+    float nl_radius, prune_radius;
+    double pack_fraction;      /* compact the device arrays when live rows < pack_fraction * physical   */
+    /* double-buffered device state (set 2 is the compaction target) */
+    float *matrix, *matrix2;   /* [n, d] normalised rows                                                */
+    float *lengths, *lengths2; /* [n]                                                                   */
+    uint8_t *kept, *kept2;     /* [n]                                                                   */
+    int32_t *orig, *orig2;     /* [n] original ids                                                      */
+    int32_t *nl_rows;          /* [n]                                                                   */
+    float *nl_dists;           /* [n]                                                                   */
+    vk_probe_header *hdr;      /* device                                                                */
+    int32_t *within_overflow;  /* [n]                                                                   */
+    const float *edges;        /* [61] device                                                           */
+    uint64_t *cand_out;        /* [3 * VK_MAX_CAND] device                                              */
+    int32_t *members;          /* [n + 1] device                                                        */
+    int32_t *tile_scratch;     /* [2 + ceil(n / 1024)] device                                           */
+    vk_probe_header *hdr_host; /* pinned                                                                */
+    uint64_t *cand_out_host;   /* pinned [3 * VK_MAX_CAND]                                              */
+    int32_t *members_host;     /* pinned [members_host_cap]                                             */
+    int32_t members_host_cap;
+    int32_t seed_key_len;      /* 32-bit words of |rng_seed| (CPython random.seed(int)), >= 1           */
+    const uint32_t *seed_key;  /* host                                                                  */
+    const int64_t *order_host; /* host [n]: np.argsort(lengths)[::-1] (vamb/cluster.py:275)             */
+    const float *normalpdf_host; /* host [31]: the smoothing kernel (vamb/cluster.py:39-73)             */
+    void *stream;
+} vk_cluster_config;
+
+typedef struct vk_cluster_result {
+    int64_t medoid, seed, n_members, n_remaining;
+    const int64_t *members_host; /* ascending original ids; valid until the next call                  */
+    double maximal_pvr, observed_pvr, radius, peak_valley_ratio; /* NaN = None                         */
+    int32_t kind;                /* 0 loner, 1 fallback, 2 normal                                      */
+    int32_t successes, attempts;
+} vk_cluster_result;
+
+int vk_cluster_create(void **handle, const vk_cluster_config *cfg);
+int vk_cluster_next(void *handle, vk_cluster_result *out); /* 0 = cluster, 2 = exhausted, 1 = error */
+int vk_cluster_stats(void *handle, int64_t *out4);         /* probes, evals, packs, physical rows   */
+void vk_cluster_destroy(void *handle);
+int64_t vk_cluster_sizeof(int which);                      /* 0: vk_cluster_config, 1: vk_cluster_result */
+/* CPython-compatible random.Random(seed).sample(range(n_i), min(n_i, k)) for each i: writes k slots per
+ * call into out (unused slots = -1).  Host only; used by the CPU test-suite. */
+int vk_cluster_rng_selftest(const uint32_t *key, int key_len, const int32_t *ns, int n_calls, int k, int32_t *out);
+
 /* ------------------------------------------------------------------ VAE (vamb/encode.py) */
 
 #define VK_VAE_MAX_LAYERS 10 /* linear layers: len(nhiddens) encoder + mu + len(nhiddens) decoder + output */

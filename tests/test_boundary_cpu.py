@@ -74,3 +74,18 @@ class TestClusterBadParams:
 
         assert np.array_equal(vc._histogram_edges(), co.linspace_edges())
         assert np.array_equal(vc._NORMALPDF, co.NORMALPDF)
+
+
+def test_native_rng_matches_cpython_sample():
+    """The C++ driver restates random.Random(seed).sample(): MT19937 + init_by_array + rejection
+    _randbelow + the pool / set switch.  Must match CPython call for call."""
+    import random
+
+    from vamb_b200 import _cluster_native as cn
+
+    for seed in (0, 1, 5, 2 ** 40 + 17, 12345678901234567890, -7):
+        for k in (25, 10, 3, 40):
+            ns = [0, 1, 2, 5, 24, 25, 26, 100, 277, 278, 300, 5000, 100000, 7, 1]
+            got = cn.rng_selftest(seed, ns, k)
+            r = random.Random(seed)
+            assert got == [r.sample(list(range(n)), min(n, k)) for n in ns], (seed, k)

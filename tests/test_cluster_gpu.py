@@ -97,12 +97,13 @@ def test_probe_header_matches_oracle(vk, d, n):
         assert np.array_equal(got, sel[dist <= np.float32(0.3)])
 
 
+@pytest.mark.parametrize("driver", ["native", "python"])
 @pytest.mark.parametrize("name", list(_util.CLUSTER_CASES))
-def test_cuda_clusterer_matches_reference_golden(name):
+def test_cuda_clusterer_matches_reference_golden(name, driver):
     import vamb_b200.cluster as vc
 
     g, lat, lens, rng_seed = _util.load_cluster_golden(name)
-    clusters = list(vc.ClusterGenerator(lat, lens, rng_seed=rng_seed, **_util.CLUSTER_CASES[name]))
+    clusters = list(vc.ClusterGenerator(lat, lens, rng_seed=rng_seed, _driver=driver, **_util.CLUSTER_CASES[name]))
     _util.assert_clusters_equal_golden(clusters, g)
 
 
@@ -116,6 +117,8 @@ def test_cuda_clusterer_matches_oracle_larger(n, d, spread, seed):
     oc = list(co.OracleClusterGenerator(lat, lens, rng_seed=seed))
     gc = list(vc.ClusterGenerator(lat, lens, rng_seed=seed))
     _util.assert_clusters_equal(gc, oc)
+    gp = list(vc.ClusterGenerator(lat, lens, rng_seed=seed, _driver="python"))
+    _util.assert_clusters_equal(gp, oc)
 
 
 def test_forced_packing_and_unpruned_paths_agree():
@@ -125,10 +128,11 @@ def test_forced_packing_and_unpruned_paths_agree():
 
     lat, lens = synth.make_latent(6000, 32, 31, 0.3)
     base = list(vc.ClusterGenerator(lat, lens, rng_seed=1))
-    gen = vc.ClusterGenerator(lat, lens, rng_seed=1)
-    gen._pack_fraction = 2.0  # pack after every emitted cluster, like the reference's CPU path
-    _util.assert_clusters_equal(list(gen), base)
-    gen = vc.ClusterGenerator(lat, lens, rng_seed=1)
+    for driver in ("native", "python"):
+        # pack after every emitted cluster, like the reference's CPU path
+        gen = vc.ClusterGenerator(lat, lens, rng_seed=1, _driver=driver, _pack_fraction=2.0)
+        _util.assert_clusters_equal(list(gen), base)
+    gen = vc.ClusterGenerator(lat, lens, rng_seed=1, _driver="python")
     gen._prune_radius = float("inf")
     gen._nl_radius = float("inf")
     _util.assert_clusters_equal(list(gen), base)

@@ -16,7 +16,7 @@ OUT = os.path.join(HERE, "_vk.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-fPIC,-ffp-contract=off",
     "--expt-relaxed-constexpr",
     "-shared",
 ]

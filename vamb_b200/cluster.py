@@ -23,6 +23,7 @@ oracle/cluster_oracle.py.  There is no CPU fallback: without the CUDA extension 
 sm_100 device construction raises.
 """
 
+import os as _os
 import random as _random
 from collections import deque as _deque
 from math import ceil as _ceil
@@ -139,6 +140,7 @@ class ClusterGenerator:
         "_orig2", "_nl_rows", "_nl_d", "_hdr", "_hdr_host", "_hdr_np", "_within_over", "_edges",
         "_cand_out", "_cand_out_host", "_members", "_members_host", "_tile_scratch", "_row_of_orig",
         "_user_matrix", "_prune_radius", "_nl_radius", "_n_probes", "_n_evals", "_pack_fraction",
+        "_native", "_native_cfg", "_native_keep", "_result",
     ]
 
     def __repr__(self) -> str:
@@ -182,6 +184,8 @@ class ClusterGenerator:
         normalized: bool = False,
         cuda: bool = False,
         rng_seed: int = 0,
+        _driver: Optional[str] = None,
+        _pack_fraction: float = 0.5,
     ):
         self._check_params(matrix, lengths, maxsteps, windowsize, minsuccesses)
         if matrix.ndim != 2:
@@ -233,7 +237,8 @@ class ClusterGenerator:
         self._edges = _torch.from_numpy(self.histogram_edges).to(dev)
         self._n_probes = 0
         self._n_evals = 0
-        self._pack_fraction = 0.5
+        self._pack_fraction = _pack_fraction
+        self._native = None
 
         if not normalized:
             _lib.check(_lib.lib.vk_normalize_rows(self._m.data_ptr(), n, d, self._stream))
@@ -268,6 +273,84 @@ class ClusterGenerator:
         self.attempts = _deque(maxlen=windowsize)
         self.successes = 0
         self.histogram = _np.empty(_NBINS, dtype=_np.float32)
+
+        driver = _driver or _os.environ.get("VAMB_B200_CLUSTER_DRIVER", "native")
+        if driver not in ("native", "python"):
+            raise ValueError(f"unknown cluster driver {driver!r}")
+        if driver == "native":
+            self._create_native(windowsize, rng_seed)
+
+    def _create_native(self, windowsize: int, rng_seed: int) -> None:
+        """Hand the decision loop to the C++ driver (vk_cluster_next): same logic, same clusters."""
+        from . import _cluster_native as _cn
+
+        n = self._n_total
+        self._m2 = _torch.empty_like(self._m)
+        self._len2 = _torch.empty_like(self._len)
+        self._kept2 = _torch.empty_like(self._kept)
+        self._orig2 = _torch.empty_like(self._orig)
+        cfg = _cn.VkClusterConfig()
+        cfg.n, cfg.d = n, self._d
+        cfg.maxsteps, cfg.windowsize, cfg.minsuccesses = self.maxsteps, windowsize, self.minsuccesses
+        cfg.nl_radius, cfg.prune_radius = self._nl_radius, self._prune_radius
+        cfg.pack_fraction = self._pack_fraction
+        for name, t in (("matrix", self._m), ("matrix2", self._m2), ("lengths", self._len), ("lengths2", self._len2),
+                        ("kept", self._kept), ("kept2", self._kept2), ("orig", self._orig), ("orig2", self._orig2),
+                        ("nl_rows", self._nl_rows), ("nl_dists", self._nl_d), ("hdr", self._hdr),
+                        ("within_overflow", self._within_over), ("edges", self._edges), ("cand_out", self._cand_out),
+                        ("members", self._members), ("tile_scratch", self._tile_scratch),
+                        ("hdr_host", self._hdr_host), ("cand_out_host", self._cand_out_host),
+                        ("members_host", self._members_host)):
+            setattr(cfg, name, t.data_ptr())
+        cfg.members_host_cap = self._members_host.numel()
+        key = _cn.seed_key(rng_seed)
+        order = _np.ascontiguousarray(self.order, dtype=_np.int64)
+        pdf = _np.ascontiguousarray(_NORMALPDF, dtype=_np.float32)
+        cfg.seed_key_len = len(key)
+        cfg.seed_key = _lib.ctypes.cast(key, _lib.ctypes.c_void_p)
+        cfg.order_host = order.ctypes.data
+        cfg.normalpdf_host = pdf.ctypes.data
+        cfg.stream = self._stream
+        handle = _lib.ctypes.c_void_p()
+        _lib.check(_cn._L.vk_cluster_create(_lib.ctypes.byref(handle), _lib.ctypes.byref(cfg)))
+        self._native = handle
+        self._native_cfg = cfg
+        self._native_keep = (key, order, pdf)
+        self._result = _cn.VkClusterResult()
+
+    def __del__(self):
+        try:
+            if self._native is not None:
+                from . import _cluster_native as _cn
+
+                _cn._L.vk_cluster_destroy(self._native)
+                self._native = None
+        except Exception:
+            pass
+
+    def _next_native(self) -> Cluster:
+        from . import _cluster_native as _cn
+
+        res = self._result
+        rc = _cn._L.vk_cluster_next(self._native, _lib.ctypes.byref(res))
+        if rc == 2:
+            raise StopIteration
+        _lib.check(rc)
+        members = _np.ctypeslib.as_array(res.members_host, shape=(res.n_members,)).copy()
+        kind = res.kind
+        cluster = Cluster(
+            int(res.medoid), int(res.seed), members, res.maximal_pvr,
+            res.observed_pvr if kind == 2 else None,
+            None if kind == 0 else res.radius,
+            int(res.successes), int(res.attempts),
+        )
+        self.n_emitted_clusters += 1
+        self.n_remaining_points = int(res.n_remaining)
+        self.peak_valley_ratio = res.peak_valley_ratio
+        stats = (_lib.ctypes.c_int64 * 4)()
+        _cn._L.vk_cluster_stats(self._native, stats)
+        self._n_probes, self._n_evals, self._n_act = int(stats[0]), int(stats[1]), int(stats[3])
+        return cluster
 
     # ------------------------------------------------------------------ API extras
     @property
@@ -507,6 +590,8 @@ class ClusterGenerator:
             return cluster
 
     def __next__(self) -> Cluster:
+        if self._native is not None:
+            return self._next_native()
         if self.n_remaining_points == 0:
             raise StopIteration
         assert self.n_remaining_points > 0

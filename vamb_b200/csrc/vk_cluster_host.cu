@@ -1,0 +1,436 @@
+// Native host driver of the medoid clusterer: the decision logic of vamb/cluster.py
+// (ClusterGenerator.__next__ :298-316, find_cluster :545-604, wander_medoid :415-450,
+// find_threshold :452-543, get_next_seed :342-384, update_successes :386-413) in C++, so that one
+// emitted cluster costs one foreign call instead of ~10 Python round trips.  The device work is the
+// same set of kernels (vk_probe_sync, vk_eval_candidates_sync, vk_select_members_sync,
+// vk_compact_rows_sync); vamb_b200/cluster.py keeps the line-by-line Python rendition of this logic
+// and the two are tested to emit identical clusters.
+//
+// The reference samples medoid candidates with Python's random.Random(rng_seed).sample(); to emit the
+// same clusters this file restates CPython's generator: MT19937 seeded by init_by_array over the
+// 32-bit words of |seed|, getrandbits(k) = genrand_uint32() >> (32 - k), _randbelow by rejection,
+// and sample() with its pool / set-rejection switch at n <= 21 + 4^ceil(log4(3k)).
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <deque>
+#include <new>
+#include <unordered_set>
+#include <vector>
+
+#include "vk_common.cuh"
+
+namespace {
+
+struct MT19937 {
+    uint32_t mt[624];
+    int idx;
+    void init_genrand(uint32_t s) {
+        mt[0] = s;
+        for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+        idx = 624;
+    }
+    void init_by_array(const uint32_t *key, int len) {
+        init_genrand(19650218u);
+        int i = 1, j = 0;
+        for (int k = (624 > len ? 624 : len); k; --k) {
+            mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
+            ++i; ++j;
+            if (i >= 624) { mt[0] = mt[623]; i = 1; }
+            if (j >= len) j = 0;
+        }
+        for (int k = 623; k; --k) {
+            mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1566083941u)) - (uint32_t)i;
+            ++i;
+            if (i >= 624) { mt[0] = mt[623]; i = 1; }
+        }
+        mt[0] = 0x80000000u;
+    }
+    uint32_t next() {
+        if (idx >= 624) {
+            for (int k = 0; k < 624; ++k) {
+                const uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
+                mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            idx = 0;
+        }
+        uint32_t y = mt[idx++];
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        return y;
+    }
+    // random.Random._randbelow_with_getrandbits for 0 < n < 2^32
+    uint32_t randbelow(uint32_t n) {
+        int k = 0;
+        for (uint32_t t = n; t; t >>= 1) ++k;
+        uint32_t r = next() >> (32 - k);
+        while (r >= n) r = next() >> (32 - k);
+        return r;
+    }
+    // random.Random.sample(population, k)
+    void sample(const std::vector<int32_t> &population, int k, std::vector<int32_t> &result) {
+        const int n = (int)population.size();
+        result.assign(k, 0);
+        double setsize = 21.0;
+        if (k > 5) setsize += pow(4.0, ceil(log((double)k * 3.0) / log(4.0)));
+        if ((double)n <= setsize) {
+            std::vector<int32_t> pool(population);
+            for (int i = 0; i < k; ++i) {
+                const uint32_t j = randbelow((uint32_t)(n - i));
+                result[i] = pool[j];
+                pool[j] = pool[n - i - 1];
+            }
+        } else {
+            std::unordered_set<uint32_t> selected;
+            for (int i = 0; i < k; ++i) {
+                uint32_t j = randbelow((uint32_t)n);
+                while (selected.count(j)) j = randbelow((uint32_t)n);
+                selected.insert(j);
+                result[i] = population[j];
+            }
+        }
+    }
+};
+
+struct Probe {
+    int32_t medoid;
+    unsigned __int128 density;
+    uint64_t hist[VK_NBINS];
+    int32_t n_within, n_lt, n_nl, rank;
+    std::vector<int32_t> within;  // ascending rows
+};
+
+struct State {
+    vk_cluster_config c;
+    int cur;  // which of the two buffer sets is live
+    int64_t n_act;
+    std::vector<int32_t> indices;    // original id of every live device row (ascending)
+    std::vector<uint8_t> kept_host;  // host mirror of the device mask
+    std::vector<int64_t> order;
+    int64_t order_index;
+    double pvr;
+    std::deque<uint8_t> attempts;
+    int successes;
+    int64_t n_emitted, n_remaining;
+    MT19937 rng;
+    float pdf[31];
+    float edges[VK_NBINS + 1];
+    std::vector<int64_t> members;
+    int64_t n_probes, n_evals, n_packs;
+
+    float *M() const { return cur ? c.matrix2 : c.matrix; }
+    float *LEN() const { return cur ? c.lengths2 : c.lengths; }
+    uint8_t *KEPT() const { return cur ? c.kept2 : c.kept; }
+    int32_t *ORIG() const { return cur ? c.orig2 : c.orig; }
+};
+
+int do_probe(State &st, int32_t row, Probe &p) {
+    ++st.n_probes;
+    const vk_cluster_config &c = st.c;
+    if (vk_probe_sync(st.M(), st.LEN(), st.KEPT(), st.n_act, c.d, row, c.nl_radius, c.edges, c.hdr, c.within_overflow,
+                      c.nl_rows, c.nl_dists, c.hdr_host, c.stream))
+        return 1;
+    const vk_probe_header *h = c.hdr_host;
+    p.medoid = row;
+    p.density = ((unsigned __int128)h->density_hi << 12) + h->density_lo;
+    memcpy(p.hist, h->hist, sizeof(p.hist));
+    p.n_within = h->n_within; p.n_lt = h->n_lt; p.n_nl = h->n_nl; p.rank = h->rank;
+    const int inl = p.n_within < VK_PROBE_INLINE ? p.n_within : VK_PROBE_INLINE;
+    p.within.assign(h->within, h->within + inl);
+    if (p.n_within > VK_PROBE_INLINE) {
+        const size_t extra = (size_t)(p.n_within - VK_PROBE_INLINE);
+        p.within.resize((size_t)p.n_within);
+        VK_CUDA(cudaMemcpyAsync(p.within.data() + VK_PROBE_INLINE, c.within_overflow + VK_PROBE_INLINE,
+                                extra * sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)c.stream));
+        VK_CUDA(cudaStreamSynchronize((cudaStream_t)c.stream));
+    }
+    std::sort(p.within.begin(), p.within.end());
+    return 0;
+}
+
+int do_eval(State &st, const Probe &p, const std::vector<int32_t> &rows, std::vector<unsigned __int128> &dens) {
+    const vk_cluster_config &c = st.c;
+    dens.clear();
+    for (size_t i = 0; i < rows.size(); i += VK_MAX_CAND) {
+        const int n = (int)std::min<size_t>(VK_MAX_CAND, rows.size() - i);
+        ++st.n_evals;
+        if (vk_eval_candidates_sync(st.M(), st.LEN(), c.d, c.nl_rows, c.nl_dists, p.n_nl, c.prune_radius,
+                                    rows.data() + i, n, c.cand_out, c.cand_out_host, c.stream))
+            return 1;
+        for (int k = 0; k < n; ++k)
+            dens.push_back(((unsigned __int128)c.cand_out_host[VK_MAX_CAND + k] << 12) + c.cand_out_host[k]);
+    }
+    return 0;
+}
+
+int do_select(State &st, const Probe &p, float threshold) {
+    const vk_cluster_config &c = st.c;
+    if (vk_select_members_sync(c.nl_rows, c.nl_dists, p.n_nl, threshold, st.ORIG(), st.KEPT(), c.members,
+                               c.members_host, c.members_host_cap, c.stream))
+        return 1;
+    const int cnt = c.members_host[0];
+    st.members.resize((size_t)cnt);
+    if (cnt + 1 <= c.members_host_cap) {
+        for (int i = 0; i < cnt; ++i) st.members[i] = c.members_host[1 + i];
+    } else {
+        std::vector<int32_t> tmp((size_t)cnt);
+        VK_CUDA(cudaMemcpyAsync(tmp.data(), c.members + 1, sizeof(int32_t) * (size_t)cnt, cudaMemcpyDeviceToHost,
+                                (cudaStream_t)c.stream));
+        VK_CUDA(cudaStreamSynchronize((cudaStream_t)c.stream));
+        for (int i = 0; i < cnt; ++i) st.members[i] = tmp[i];
+    }
+    std::sort(st.members.begin(), st.members.end());
+    return 0;
+}
+
+int do_pack(State &st) {
+    const vk_cluster_config &c = st.c;
+    ++st.n_packs;
+    int64_t n_out = 0;
+    const int nxt = st.cur ^ 1;
+    if (vk_compact_rows_sync(st.M(), st.LEN(), st.ORIG(), st.KEPT(), st.n_act, c.d, nxt ? c.matrix2 : c.matrix,
+                             nxt ? c.lengths2 : c.lengths, nxt ? c.orig2 : c.orig, nxt ? c.kept2 : c.kept,
+                             c.tile_scratch, &n_out, c.stream))
+        return 1;
+    st.cur = nxt;
+    size_t w = 0;
+    for (size_t i = 0; i < (size_t)st.n_act; ++i)
+        if (st.kept_host[i]) st.indices[w++] = st.indices[i];
+    st.indices.resize(w);
+    st.kept_host.assign(w, 1);
+    if ((int64_t)w != n_out) {
+        vk_set_error("vk_cluster: host/device live-row counts disagree (%lld vs %lld)", (long long)w, (long long)n_out);
+        return 1;
+    }
+    st.n_act = n_out;
+    return 0;
+}
+
+// vamb/cluster.py:342-384
+int32_t next_seed(State &st) {
+    int64_t n_orig = (int64_t)st.order.size();
+    int64_t i = st.order_index - 1;
+    for (;;) {
+        i = (i + 1) % n_orig;
+        if (i == 0 && st.n_emitted > 0) {
+            size_t w = 0;
+            for (size_t k = 0; k < st.order.size(); ++k)
+                if (st.order[k] > -1) st.order[w++] = st.order[k];
+            st.order.resize(w);
+            n_orig = (int64_t)w;
+        }
+        const int64_t o = st.order[(size_t)i];
+        if (o == -1) continue;
+        const auto it = std::lower_bound(st.indices.begin(), st.indices.end(), (int32_t)o);
+        const size_t row = (size_t)(it - st.indices.begin());
+        if (it == st.indices.end() || *it != (int32_t)o || !st.kept_host[row]) {
+            st.order[(size_t)i] = -1;
+            continue;
+        }
+        st.order_index = i + 1;
+        return (int32_t)row;
+    }
+}
+
+// vamb/cluster.py:386-413
+void update_successes(State &st, bool success) {
+    if ((int)st.attempts.size() == st.c.windowsize) {
+        st.successes -= st.attempts.front();
+        st.attempts.pop_front();
+    }
+    st.successes += success ? 1 : 0;
+    st.attempts.push_back(success ? 1 : 0);
+    if ((int)st.attempts.size() == st.c.windowsize && st.successes < st.c.minsuccesses) {
+        st.pvr += 0.1;
+        st.attempts.clear();
+        st.successes = 0;
+        st.order_index = 0;
+    }
+}
+
+// vamb/cluster.py:415-450 with one device pass per round of candidates
+int wander(State &st, int32_t seed, Probe &probe, int32_t &seed_rank) {
+    std::unordered_set<int32_t> tried;
+    tried.insert(seed);
+    if (do_probe(st, seed, probe)) return 1;
+    seed_rank = probe.rank;
+    unsigned __int128 local = probe.density;
+    std::vector<int32_t> cand, sampled;
+    std::vector<unsigned __int128> dens;
+    for (;;) {
+        cand.clear();
+        for (int32_t r : probe.within)
+            if (!tried.count(r)) cand.push_back(r);
+        const int k = (int)std::min<size_t>(cand.size(), (size_t)st.c.maxsteps);
+        st.rng.sample(cand, k, sampled);
+        if (sampled.empty()) break;
+        if (do_eval(st, probe, sampled, dens)) return 1;
+        int winner = -1;
+        for (size_t i = 0; i < sampled.size(); ++i) {
+            tried.insert(sampled[i]);
+            if (dens[i] > local) { winner = (int)i; break; }
+        }
+        if (winner < 0) break;
+        const unsigned __int128 want = dens[(size_t)winner];
+        if (do_probe(st, sampled[(size_t)winner], probe)) return 1;
+        if (probe.density != want) {
+            vk_set_error("vk_cluster: probe and candidate densities disagree");
+            return 1;
+        }
+        local = probe.density;
+    }
+    return 0;
+}
+
+// vamb/cluster.py:452-543.  Returns 0 = loner, 1 = no threshold, 2 = (threshold, observed_pvr)
+int find_threshold(State &st, const Probe &p, double &threshold, double &observed_pvr) {
+    if (p.n_lt == 1) return 0;
+    float hist[VK_NBINS];
+    for (int i = 0; i < VK_NBINS; ++i) hist[i] = (float)p.hist[i];  // exact sums, rounded once
+    float dens[VK_NBINS + 30];
+    for (int i = 0; i < VK_NBINS + 30; ++i) dens[i] = 0.0f;
+    for (int i = 0; i < VK_NBINS; ++i)
+        for (int j = 0; j < 31; ++j) {
+            const float prod = st.pdf[j] * hist[i];  // two roundings, as in the reference (no fma)
+            dens[i + j] = dens[i + j] + prod;
+        }
+    double peak_density = 0.0, minimum_x = 0.0, density_at_minimum = 0.0, x = 0.0;
+    bool peak_over = false, have_threshold = false;
+    const double delta_x = 0.3 / (double)VK_NBINS;
+    for (int i = 0; i < VK_NBINS; ++i) {
+        const double density = (double)dens[15 + i];
+        if (!peak_over && density > peak_density) {
+            if (x > 0.1) return 1;
+            peak_density = density;
+        }
+        if (!peak_over && density < 0.6 * peak_density) {
+            peak_over = true;
+            density_at_minimum = density;
+        }
+        if (peak_over && density > 1.5 * density_at_minimum) break;
+        if (peak_over && density < density_at_minimum) {
+            minimum_x = x;
+            density_at_minimum = density;
+            if (density < st.pvr * peak_density) {
+                threshold = minimum_x;
+                have_threshold = true;
+            }
+        }
+        x += delta_x;
+    }
+    if (!have_threshold) return 1;
+    if (threshold > 0.2 + st.pvr) return 1;
+    observed_pvr = density_at_minimum / peak_density;
+    return 2;
+}
+
+}  // namespace
+
+extern "C" int vk_cluster_create(void **handle, const vk_cluster_config *cfg) {
+    State *st = new (std::nothrow) State();
+    if (!st) {
+        vk_set_error("vk_cluster_create: out of memory");
+        return 1;
+    }
+    st->c = *cfg;
+    st->cur = 0;
+    st->n_act = cfg->n;
+    st->indices.resize((size_t)cfg->n);
+    for (int64_t i = 0; i < cfg->n; ++i) st->indices[(size_t)i] = (int32_t)i;
+    st->kept_host.assign((size_t)cfg->n, 1);
+    st->order.assign(cfg->order_host, cfg->order_host + cfg->n);
+    st->order_index = 0;
+    st->pvr = 0.1;
+    st->successes = 0;
+    st->n_emitted = 0;
+    st->n_remaining = cfg->n;
+    st->n_probes = st->n_evals = st->n_packs = 0;
+    st->rng.init_by_array(cfg->seed_key, cfg->seed_key_len);
+    memcpy(st->pdf, cfg->normalpdf_host, sizeof(st->pdf));
+    *handle = st;
+    return 0;
+}
+
+extern "C" void vk_cluster_destroy(void *handle) { delete static_cast<State *>(handle); }
+
+extern "C" int vk_cluster_stats(void *handle, int64_t *out4) {
+    State *st = static_cast<State *>(handle);
+    out4[0] = st->n_probes; out4[1] = st->n_evals; out4[2] = st->n_packs; out4[3] = st->n_act;
+    return 0;
+}
+
+// One ClusterGenerator.__next__ (vamb/cluster.py:298-316).  Returns 0 = a cluster, 2 = exhausted, 1 = error.
+extern "C" int vk_cluster_next(void *handle, vk_cluster_result *out) {
+    State &st = *static_cast<State *>(handle);
+    if (st.n_remaining == 0) return 2;
+    Probe probe;
+    for (;;) {  // find_cluster, vamb/cluster.py:545-604
+        const int32_t seed = next_seed(st);
+        int32_t seed_rank = 0;
+        if (wander(st, seed, probe, seed_rank)) return 1;
+        double threshold = 0.0, observed = 0.0;
+        const int kind = find_threshold(st, probe, threshold, observed);
+        out->medoid = st.indices[(size_t)probe.medoid];
+        out->seed = seed_rank;
+        out->maximal_pvr = st.pvr;
+        out->successes = st.successes;
+        out->attempts = (int32_t)st.attempts.size();
+        if (kind == 0) {
+            if (do_select(st, probe, 0.0f)) return 1;
+            if (st.members.size() != 1 || st.members[0] != out->medoid) {
+                vk_set_error("vk_cluster: loner selection returned %zu members", st.members.size());
+                return 1;
+            }
+            out->kind = 0; out->radius = NAN; out->observed_pvr = NAN;
+            break;
+        }
+        if (kind == 1) {
+            if (st.pvr > 0.55) {
+                if (do_select(st, probe, (float)0.06)) return 1;
+                out->kind = 1; out->radius = 0.06; out->observed_pvr = NAN;
+                break;
+            }
+            update_successes(st, false);
+            continue;
+        }
+        if (do_select(st, probe, (float)threshold)) return 1;
+        out->kind = 2; out->radius = threshold; out->observed_pvr = observed;
+        if (st.pvr < 0.55) update_successes(st, true);
+        break;
+    }
+    st.n_emitted += 1;
+    st.n_remaining -= (int64_t)st.members.size();
+    for (int64_t m : st.members) {
+        const auto it = std::lower_bound(st.indices.begin(), st.indices.end(), (int32_t)m);
+        st.kept_host[(size_t)(it - st.indices.begin())] = 0;
+    }
+    out->members_host = st.members.data();
+    out->n_members = (int64_t)st.members.size();
+    out->peak_valley_ratio = st.pvr;
+    out->n_remaining = st.n_remaining;
+    if (st.n_remaining && (double)st.n_remaining < st.c.pack_fraction * (double)st.n_act)
+        if (do_pack(st)) return 1;
+    return 0;
+}
+
+extern "C" int vk_cluster_rng_selftest(const uint32_t *key, int key_len, const int32_t *ns, int n_calls, int k,
+                                       int32_t *out) {
+    MT19937 rng;
+    rng.init_by_array(key, key_len);
+    std::vector<int32_t> pop, res;
+    for (int i = 0; i < n_calls; ++i) {
+        pop.resize((size_t)ns[i]);
+        for (int j = 0; j < ns[i]; ++j) pop[(size_t)j] = j;
+        const int kk = ns[i] < k ? ns[i] : k;
+        rng.sample(pop, kk, res);
+        for (int j = 0; j < k; ++j) out[(size_t)i * k + j] = j < kk ? res[(size_t)j] : -1;
+    }
+    return 0;
+}
+
+extern "C" int64_t vk_cluster_sizeof(int which) {
+    return which == 0 ? (int64_t)sizeof(vk_cluster_config) : (int64_t)sizeof(vk_cluster_result);
+}

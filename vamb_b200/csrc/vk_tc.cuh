@@ -134,6 +134,9 @@ __device__ __forceinline__ float4 tf32_lo(const float4 v) {
 // Shared-memory plan of one CTA (dynamic smem, 1024-byte aligned by the caller):
 //   stage s in {0,1}: A_hi | A_lo (128 x KT x 4 B = 16 KB each) | B_hi | B_lo (BN x KT x 4 B each)
 constexpr int TC_BM = 128;
+#ifndef TC_MN_SWAP
+#define TC_MN_SWAP 0  // which descriptor field carries the M/N-group stride of an MN-major no-swizzle operand
+#endif
 constexpr int TC_THREADS = 256;
 constexpr int A_TILE_BYTES = TC_BM * KT * 4;  // 16 KB
 __host__ __device__ constexpr int b_tile_bytes(int bn) { return bn * KT * 4; }
@@ -145,6 +148,54 @@ struct TcShared {
     uint64_t bar_done;
     uint32_t tmem_base;
 };
+
+__device__ __forceinline__ float f4_get(const float4 &v, int e) {
+    return e == 0 ? v.x : (e == 1 ? v.y : (e == 2 ? v.z : v.w));
+}
+
+// Stage one operand tile (rows x KT) into the K-major no-swizzle layout, as hi (fp32 words, the tensor
+// core reads their top 19 bits) and lo (tf32 remainder).
+//  MN == false: source [row][k], k contiguous.  Lane l of a quarter-warp fills one 128-byte core matrix
+//               -> conflict-free 16-byte stores.
+//  MN == true : source [k][row], row contiguous (MN-major operands measured to produce zeros with the
+//               no-swizzle descriptor, so they are transposed on the fly instead).  A warp loads 4 k x 32
+//               rows as float4 and scatters the 4 row-elements with a lane-dependent rotation so that the
+//               32 scalar stores of each instruction hit 32 different banks (bank = (row%8)*4 + k%4).
+template <bool MN, class L>
+__device__ __forceinline__ void stage_operand(const L &ld, int r0, int k0, int rows, uint8_t *hi, uint8_t *lo) {
+    const int tid = threadIdx.x;
+    if (!MN) {
+        const int n4 = rows * (KT / 4);
+        for (int q = tid; q < n4; q += TC_THREADS) {
+            const int r = ((q >> 6) << 3) | (q & 7), k4 = (q >> 3) & 7;
+            const float4 v = ld.ld4(r0 + r, (k0 >> 2) + k4);
+            const uint32_t off = off_kmajor(r, k4);
+            *reinterpret_cast<float4 *>(hi + off) = v;
+            *reinterpret_cast<float4 *>(lo + off) = tf32_lo(v);
+        }
+    } else {
+        const int lane = tid & 31, warp = tid >> 5;
+        const int row_blocks = (rows + 31) >> 5;          // 32-row blocks
+        const int units = row_blocks * (KT / 4);          // one unit = 4 k x 32 rows = one warp load
+        const int kq = lane & 3, rot = (lane >> 3) & 3;
+        for (int u = warp; u < units; u += TC_THREADS / 32) {
+            const int rb = u % row_blocks, kb = u / row_blocks;
+            const int k = kb * 4 + kq;
+            const int r4 = rb * 8 + (lane >> 2);           // row / 4
+            if (r4 * 4 >= rows) continue;
+            const float4 v = ld.ld4(k0 + k, (r0 >> 2) + r4);
+            const float4 w = tf32_lo(v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int ee = (e + rot) & 3;
+                const int r = r4 * 4 + ee;
+                const uint32_t off = (uint32_t)((r >> 3) * 1024 + (k >> 2) * 128 + (r & 7) * 16 + (k & 3) * 4);
+                *reinterpret_cast<float *>(hi + off) = f4_get(v, ee);
+                *reinterpret_cast<float *>(lo + off) = f4_get(w, ee);
+            }
+        }
+    }
+}
 
 // One 128 x bn output tile: D[m, n] = sum_k A(m, k) * B(n, k), k in [0, K).
 //   LA / LB: loaders with  float4 ld4(int r, int c4)  returning 4 consecutive elements along the
@@ -168,7 +219,7 @@ __device__ __forceinline__ void tc_tile_mainloop(int K, int m0, int n0, int bn, 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = sh->tmem_base;
-    const uint32_t idesc = make_idesc_tf32(TC_BM, bn, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    const uint32_t idesc = make_idesc_tf32(TC_BM, bn, 0, 0);  // both operand tiles are K-major in shared memory
     const int nk = (K + KT - 1) / KT;
     const int bbytes = b_tile_bytes(bn);
 
@@ -180,51 +231,14 @@ __device__ __forceinline__ void tc_tile_mainloop(int K, int m0, int n0, int bn, 
         if (kt >= 2) mbar_wait(&sh->bar_stage[s], (uint32_t)(((kt >> 1) - 1) & 1));
         tc_fence_after();
         const int k0 = kt * KT;
-        // ---- stage A: 128 x 32 elements = 1024 float4, 4 per thread ----
-#pragma unroll
-        for (int i = 0; i < (TC_BM * KT / 4) / TC_THREADS; ++i) {
-            const int q = tid + i * TC_THREADS;
-            float4 v;
-            uint32_t off;
-            // lanes 0-7 of a quarter-warp fill one 128-byte core matrix -> conflict-free 16-byte stores
-            if (!A_MN) {
-                const int r = ((q >> 6) << 3) | (q & 7), k4 = (q >> 3) & 7;
-                v = la.ld4(m0 + r, (k0 >> 2) + k4);
-                off = off_kmajor(r, k4);
-            } else {
-                const int k = ((q >> 8) << 3) | (q & 7), m4 = (q >> 3) & 31;
-                v = la.ld4(k0 + k, (m0 >> 2) + m4);
-                off = off_mnmajor(m4, k, TC_BM);
-            }
-            *reinterpret_cast<float4 *>(a_hi + off) = v;
-            *reinterpret_cast<float4 *>(a_lo + off) = tf32_lo(v);
-        }
-        // ---- stage B: bn x 32 elements ----
-        const int nb4 = bn * KT / 4;
-        for (int q = tid; q < nb4; q += TC_THREADS) {
-            float4 v;
-            uint32_t off;
-            if (!B_MN) {
-                const int r = ((q >> 6) << 3) | (q & 7), k4 = (q >> 3) & 7;
-                v = lb.ld4(n0 + r, (k0 >> 2) + k4);
-                off = off_kmajor(r, k4);
-            } else {
-                const int per = bn >> 2;
-                const int g = q >> 3;
-                const int k = ((g / per) << 3) | (q & 7), m4 = g % per;
-                v = lb.ld4(k0 + k, (n0 >> 2) + m4);
-                off = off_mnmajor(m4, k, bn);
-            }
-            *reinterpret_cast<float4 *>(b_hi + off) = v;
-            *reinterpret_cast<float4 *>(b_lo + off) = tf32_lo(v);
-        }
+        // ---- stage A (128 rows) and B (bn rows), 32 k each, into K-major core-matrix tiles ----
+        stage_operand<A_MN>(la, m0, k0, TC_BM, a_hi, a_lo);
+        stage_operand<B_MN>(lb, n0, k0, bn, b_hi, b_lo);
         fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
-            const uint32_t a_lbo = A_MN ? TC_BM * 32 : 128, a_sbo = A_MN ? 128 : 1024;
-            const uint32_t b_lbo = B_MN ? (uint32_t)bn * 32 : 128, b_sbo = B_MN ? 128 : 1024;
-            const uint32_t a_step = A_MN ? TC_BM * 32 : 256, b_step = B_MN ? (uint32_t)bn * 32 : 256;
+            const uint32_t a_lbo = 128, a_sbo = 1024, b_lbo = 128, b_sbo = 1024, a_step = 256, b_step = 256;
 #pragma unroll
             for (int j = 0; j < KT / 8; ++j) {
                 const uint64_t dah = make_smem_desc(smem_u32(a_hi) + j * a_step, a_lbo, a_sbo);

@@ -25,7 +25,7 @@ struct Ld4Plain {
 // a_mn: A stored [K][M] (else [M][K]); b_mn: B stored [K][N] (else [N][K])
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(tc::TC_THREADS, 1)
-tc_gemm_test_kernel(const float *A, const float *B, float *C, int M, int N, int K, int lda, int ldb) {
+tc_gemm_test_kernel(const float *A, const float *B, float *C, int M, int N, int K, int lda, int ldb, int variant) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ tc::TcShared sh;
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -53,6 +53,9 @@ tc_gemm_test_kernel(const float *A, const float *B, float *C, int M, int N, int 
 
 }  // namespace
 
+static int g_variant = -1;
+extern "C" void vk_tc_set_variant(int v) { g_variant = v; }
+
 extern "C" int vk_tc_gemm_test(const float *A, const float *B, float *C, int M, int N, int K, int a_mn, int b_mn,
                                void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
@@ -62,7 +65,7 @@ extern "C" int vk_tc_gemm_test(const float *A, const float *B, float *C, int M, 
 #define LAUNCH(AM, BM_)                                                                                     \
     do {                                                                                                    \
         VK_CUDA(cudaFuncSetAttribute(tc_gemm_test_kernel<AM, BM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        tc_gemm_test_kernel<AM, BM_><<<grid, tc::TC_THREADS, smem, s>>>(A, B, C, M, N, K, lda, ldb);        \
+        tc_gemm_test_kernel<AM, BM_><<<grid, tc::TC_THREADS, smem, s>>>(A, B, C, M, N, K, lda, ldb, g_variant);        \
     } while (0)
     if (!a_mn && !b_mn) LAUNCH(false, false);
     else if (!a_mn && b_mn) LAUNCH(false, true);

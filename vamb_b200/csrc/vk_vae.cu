@@ -15,6 +15,8 @@
 //
 // Reference lines (RasmussenLab/vamb): encode.py:259-273 _encode, :276-286 reparameterize,
 // :288-304 _decode, :316-357 calc_loss, :442-484 encode; dadaptation==3.2 DAdaptAdam.step.
+#include <stdlib.h>
+
 #include "vk_common.cuh"
 #include "vk_tc.cuh"
 
@@ -328,6 +330,7 @@ struct FwdArgs {
     // mu
     float *z; const float *eps; int add_eps; int mask_bits; float *latent_out;
     vk_vae_ctl *ctl; int layer_id; float slope;
+    int tile_n;           // tensor-core path: output columns per CTA (multiple of 16, <= 128)
 };
 
 // Fold the per-row-tile column sums of P and P^2 into the BatchNorm affine, the saved batch statistics
@@ -530,6 +533,7 @@ struct BwdArgs {
     const float *p_prev, *mean_prev, *rstd_prev; double *part_prev; float *m1_prev, *m2_prev; float *g_gamma, *g_beta;
     const float *MU; float kld_w;
     vk_vae_ctl *ctl; int ticket_id;
+    int tile_n;           // tensor-core path: output columns per CTA
 };
 
 // Fold the per-row-tile column sums of dH and dH*Phat: BatchNorm weight/bias gradients and the two
@@ -647,9 +651,9 @@ __global__ void __launch_bounds__(tc::TC_THREADS, 1) fwd_layer_tc_kernel(FwdArgs
     __shared__ double s_cs[2][2][128];
     uint8_t *smem = align1024(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 128;
+    const int m0 = blockIdx.y * 128, n0 = blockIdx.x * a.tile_n;
     int bn = a.N - n0;
-    bn = bn > 128 ? 128 : ((bn + 15) & ~15);
+    bn = bn > a.tile_n ? a.tile_n : ((bn + 15) & ~15);
     LdPlain w{a.W, a.K, a.N, a.K};
     tc::tc_tile_mainloop<false, false>(a.K, m0, n0, bn, a.in, w, smem, &sh);
 
@@ -737,9 +741,9 @@ __global__ void __launch_bounds__(tc::TC_THREADS, 1) bwd_layer_tc_kernel(BwdArgs
         // ---- wgrad slice: gW[n, k] (+ bias column) over batch rows [b0, b0 + nb) ----
         const int split = blockIdx.x / (a.wg_tiles_m * a.wg_tiles_n);
         const int t = blockIdx.x % (a.wg_tiles_m * a.wg_tiles_n);
-        const int m0 = (t / a.wg_tiles_n) * 128, n0 = (t % a.wg_tiles_n) * 128;
+        const int m0 = (t / a.wg_tiles_n) * 128, n0 = (t % a.wg_tiles_n) * a.tile_n;
         int bn = a.K + 1 - n0;
-        bn = bn > 128 ? 128 : ((bn + 15) & ~15);
+        bn = bn > a.tile_n ? a.tile_n : ((bn + 15) & ~15);
         const int b0 = split * x.k_per_split;
         int nb = a.B - b0;
         nb = nb < 0 ? 0 : (nb > x.k_per_split ? x.k_per_split : nb);
@@ -765,9 +769,9 @@ __global__ void __launch_bounds__(tc::TC_THREADS, 1) bwd_layer_tc_kernel(BwdArgs
     }
     // ---- dgrad: dX[b, k] = sum_n dY[b, n] * W[n, k] ----
     const int t = blockIdx.x - n_wg;
-    const int m0 = (t / a.dg_tiles_n) * 128, n0 = (t % a.dg_tiles_n) * 128;
+    const int m0 = (t / a.dg_tiles_n) * 128, n0 = (t % a.dg_tiles_n) * a.tile_n;
     int bn = a.K - n0;
-    bn = bn > 128 ? 128 : ((bn + 15) & ~15);
+    bn = bn > a.tile_n ? a.tile_n : ((bn + 15) & ~15);
     LdPlain w{a.W, a.K, a.N, a.K};
     tc::tc_tile_mainloop<false, true>(a.N, m0, n0, bn, a.gy, w, smem, &sh);
     float *tile = reinterpret_cast<float *>(smem);
@@ -923,11 +927,25 @@ static int check_net(const vk_vae *net, int batch) {
 
 static bool use_tc(const vk_vae *net, int B) { return net->tc_min_batch > 0 && B >= net->tc_min_batch; }
 
+static int env_int(const char *name) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : 0;
+}
+
 static int tc_nsplit(const vk_vae *net, int B) {
+    static const int forced = env_int("VK_TC_NSPLIT");  // tuning / debugging override
+    if (forced > 0) return forced > net->n_grad_slabs ? net->n_grad_slabs : forced;
     int ns = B / 512;
     if (ns < 1) ns = 1;
     if (ns > net->n_grad_slabs) ns = net->n_grad_slabs;
     return ns;
+}
+
+// output columns per CTA: narrower tiles for small batches so that enough CTAs exist
+static int tc_tile_n(int B) {
+    static const int forced = env_int("VK_TC_TILE_N");  // tuning / debugging override
+    if (forced >= 16 && forced <= 128 && (forced & 15) == 0) return forced;
+    return B <= 512 ? 32 : (B <= 2048 ? 64 : 128);
 }
 
 static int tc_prepare() {
@@ -995,7 +1013,8 @@ static int launch_forward(const vk_vae *net, int B, int training, int upto /*exc
         PROF_MARK(s);
         if (use_tc(net, B) && L.kind != VK_LAYER_MU) {
             if (tc_prepare()) return 1;
-            dim3 grid((L.n_out + 127) / 128, (B + 127) / 128);
+            a.tile_n = tc_tile_n(B);
+            dim3 grid((L.n_out + a.tile_n - 1) / a.tile_n, (B + 127) / 128);
             fwd_layer_tc_kernel<<<grid, tc::TC_THREADS, tc::tc_smem_bytes(128), s>>>(a);
         } else {
             dim3 grid((L.n_out + 63) / 64, (B + 63) / 64);
@@ -1078,11 +1097,12 @@ static int launch_backward(const vk_vae *net, int B, cudaStream_t s) {
             x.nsplit = tc_nsplit(net, B);
             x.k_per_split = (((B + x.nsplit - 1) / x.nsplit) + 31) & ~31;
             x.slab = net->grad_slab;
+            a.tile_n = tc_tile_n(B);
             a.wg_tiles_m = (L.n_out + 127) / 128;
-            a.wg_tiles_n = (L.k_in + 1 + 127) / 128;
+            a.wg_tiles_n = (L.k_in + 1 + a.tile_n - 1) / a.tile_n;
             if (a.dg_tiles_m) {
                 a.dg_tiles_m = (B + 127) / 128;
-                a.dg_tiles_n = (L.k_in + 127) / 128;
+                a.dg_tiles_n = (L.k_in + a.tile_n - 1) / a.tile_n;
             }
             const int blocks = a.wg_tiles_m * a.wg_tiles_n * x.nsplit + a.dg_tiles_m * a.dg_tiles_n;
             bwd_layer_tc_kernel<<<blocks, tc::TC_THREADS, tc::tc_smem_bytes(128), s>>>(a, x);
