@@ -127,6 +127,12 @@ struct ProbeAcc {
     unsigned rank;
 };
 
+// One pass over the live rows.  The hot loop is load + 4 fma + 3 shuffles per lane; everything else
+// (mask lookup, length load, histogram / density / list bookkeeping) happens only for the few rows whose
+// distance is small enough to matter.  Neighbour-list entries are staged per WARP (ballot-compacted,
+// no block barrier) and flushed with one global reservation per ~48 entries.
+constexpr int PB_WBUF = 64;  // staged entries per warp (<= 16 appended per iteration)
+
 template <int DFIX>
 __global__ void __launch_bounds__(PB_THREADS, 4)
 probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths,
@@ -136,21 +142,21 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
     const int d = DFIX ? DFIX : d_rt;
     __shared__ float s_edges[VK_NBINS + 1];
     __shared__ u64 s_hist[VK_NBINS];
-    __shared__ int32_t s_nl_rows[PB_TILE];
-    __shared__ float s_nl_d[PB_TILE];
-    __shared__ int s_nl_cnt, s_nl_base;
+    __shared__ int32_t s_wrows[PB_THREADS / 32][PB_WBUF];
+    __shared__ float s_wd[PB_THREADS / 32][PB_WBUF];
     __shared__ ProbeAcc s_acc;
     __shared__ __align__(16) float s_q[DFIX ? DFIX : PB_MAX_D];
 
     const int tid = threadIdx.x;
-    const int lane8 = tid & 7;
+    const int lane8 = tid & 7, lane = tid & 31, warp = tid >> 5;
     const int g = tid >> 3;
     const unsigned gmask = group8_mask();
+    const unsigned lt_mask = (1u << lane) - 1u;
     const bool vec4 = (d & 3) == 0;
 
     if (tid <= VK_NBINS) s_edges[tid] = edges_g[tid];
     if (tid < VK_NBINS) s_hist[tid] = 0ull;
-    if (tid == 0) { s_nl_cnt = 0; s_acc.dens = 0ull; s_acc.dens_hi = 0ull; s_acc.nlt = 0u; s_acc.rank = 0u; }
+    if (tid == 0) { s_acc.dens = 0ull; s_acc.dens_hi = 0ull; s_acc.nlt = 0u; s_acc.rank = 0u; }
     for (int k = tid; k < d; k += PB_THREADS) s_q[k] = matrix[mrow * (int64_t)d + k];
     __syncthreads();
 
@@ -158,9 +164,24 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
     if (DFIX == 32) qv = *reinterpret_cast<const float4 *>(s_q + 4 * lane8);
     const float e_lo = s_edges[0], e_hi = s_edges[VK_NBINS];
     const float rad = 0.05f;
+    const float lim = fmaxf(fmaxf(nl_radius, e_hi), rad);  // rows beyond this distance need no bookkeeping
 
     u64 t_dens = 0ull, t_dens_hi = 0ull;
-    unsigned t_nlt = 0u, t_rank = 0u;
+    unsigned t_nlt = 0u;
+    int wcnt = 0;  // entries staged by this warp (warp-uniform)
+
+    auto flush_warp = [&]() {
+        __syncwarp();
+        int base = 0;
+        if (lane == 0 && wcnt) base = atomicAdd(&hdr->n_nl, wcnt);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int i = lane; i < wcnt; i += 32) {
+            nl_rows[base + i] = s_wrows[warp][i];
+            nl_dists[base + i] = s_wd[warp][i];
+        }
+        __syncwarp();
+        wcnt = 0;
+    };
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t row0 = (int64_t)tile * PB_TILE;
@@ -189,57 +210,48 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
 #pragma unroll
             for (int k = 0; k < PB_R; ++k) acc[k] = group8_sum(acc[k], gmask);
 
-            if (lane8 == 0) {
 #pragma unroll
-                for (int k = 0; k < PB_R; ++k) {
-                    const int64_t row = rows[k];
-                    if (row >= n) continue;
-                    if (!kept[row]) continue;
-                    float dd = __fsub_rn(0.5f, acc[k]);
-                    if (row == mrow) dd = 0.0f;
-                    if (row < mrow) ++t_rank;
+            for (int k = 0; k < PB_R; ++k) {
+                const int64_t row = rows[k];
+                float dd = __fsub_rn(0.5f, acc[k]);
+                if (row == mrow) dd = 0.0f;
+                bool cand = (lane8 == 0) && (row < n) && (dd <= lim);
+                if (cand) cand = kept[row] != 0;  // rare: the mask is only consulted for near rows
+                const bool nl_hit = cand && (dd <= nl_radius);
+                const unsigned ballot = __ballot_sync(0xffffffffu, nl_hit);
+                if (ballot) {
+                    if (nl_hit) {
+                        const int pos = wcnt + __popc(ballot & lt_mask);
+                        s_wrows[warp][pos] = (int32_t)row;
+                        s_wd[warp][pos] = dd;
+                    }
+                    wcnt += __popc(ballot);
+                }
+                if (cand) {
                     if (dd < rad) ++t_nlt;
                     const bool in_hist = (dd >= e_lo) && (dd <= e_hi);
                     const bool within = dd <= rad;
-                    float len = 0.0f;
-                    if (in_hist || within) len = __ldg(lengths + row);
-                    if (within) {
-                        density_add(t_dens, t_dens_hi, __float2ull_rz(len), closeness_fx(rad, dd));
-                        const int pos = atomicAdd(&hdr->n_within, 1);
-                        if (pos < VK_PROBE_INLINE) hdr->within[pos] = (int32_t)row;
-                        else within_overflow[pos] = (int32_t)row;
-                    }
-                    if (in_hist) atomicAdd(&s_hist[hist_bin(dd, s_edges)], __float2ull_rz(len));
-                    if (dd <= nl_radius) {
-                        const int slot = atomicAdd(&s_nl_cnt, 1);
-                        s_nl_rows[slot] = (int32_t)row;
-                        s_nl_d[slot] = dd;
+                    if (in_hist || within) {
+                        const u64 len = __float2ull_rz(__ldg(lengths + row));
+                        if (within) {
+                            density_add(t_dens, t_dens_hi, len, closeness_fx(rad, dd));
+                            const int pos = atomicAdd(&hdr->n_within, 1);
+                            if (pos < VK_PROBE_INLINE) hdr->within[pos] = (int32_t)row;
+                            else within_overflow[pos] = (int32_t)row;
+                        }
+                        if (in_hist) atomicAdd(&s_hist[hist_bin(dd, s_edges)], len);
                     }
                 }
             }
-        }
-        // flush this tile's neighbour-list entries: one global reservation per tile
-        __syncthreads();
-        const int cnt = s_nl_cnt;
-        if (cnt > 0) {
-            if (tid == 0) s_nl_base = atomicAdd(&hdr->n_nl, cnt);
-            __syncthreads();
-            const int base = s_nl_base;
-            for (int i = tid; i < cnt; i += PB_THREADS) {
-                nl_rows[base + i] = s_nl_rows[i];
-                nl_dists[base + i] = s_nl_d[i];
-            }
-            __syncthreads();
-            if (tid == 0) s_nl_cnt = 0;
-            __syncthreads();
+            if (wcnt > PB_WBUF - PB_GROUPS / 8 * PB_R) flush_warp();
         }
     }
+    flush_warp();
 
-    if (lane8 == 0 && (t_dens | t_dens_hi | t_nlt | t_rank)) {
+    if (lane8 == 0 && (t_dens | t_dens_hi | t_nlt)) {
         if (t_dens) atomicAdd(&s_acc.dens, t_dens);
         if (t_dens_hi) atomicAdd(&s_acc.dens_hi, t_dens_hi);
         if (t_nlt) atomicAdd(&s_acc.nlt, t_nlt);
-        if (t_rank) atomicAdd(&s_acc.rank, t_rank);
     }
     __syncthreads();
     if (tid < VK_NBINS) {
@@ -250,8 +262,16 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
         if (s_acc.dens) atomicAdd(reinterpret_cast<u64 *>(&hdr->density_lo), s_acc.dens);
         if (s_acc.dens_hi) atomicAdd(reinterpret_cast<u64 *>(&hdr->density_hi), s_acc.dens_hi);
         if (s_acc.nlt) atomicAdd(&hdr->n_lt, (int)s_acc.nlt);
-        if (s_acc.rank) atomicAdd(&hdr->rank, (int)s_acc.rank);
     }
+}
+
+// rank = number of kept rows before the medoid row (the reference's packed index of the seed,
+// vamb/cluster.py:370); only the seed probe of a cluster asks for it.
+__global__ void __launch_bounds__(256) rank_kernel(const uint8_t *__restrict__ kept, int64_t mrow, vk_probe_header *hdr) {
+    unsigned cnt = 0;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < mrow; i += (int64_t)gridDim.x * 256) cnt += kept[i] != 0;
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&hdr->rank, (int)cnt);
 }
 
 static int probe_grid(int n_tiles) {
@@ -286,6 +306,12 @@ extern "C" int vk_probe(const float *matrix, const float *lengths, const uint8_t
         probe_kernel<0><<<grid, PB_THREADS, 0, s>>>(matrix, lengths, kept, n, d, medoid_row, nl_radius, edges,
                                                     hdr, within_overflow, nl_rows, nl_dists, n_tiles);
     VK_LAUNCH_CHECK();
+    if (medoid_row > 0) {
+        int rb = (int)((medoid_row + 256 * 64 - 1) / (256 * 64));
+        if (rb > 2 * vk_num_sms()) rb = 2 * vk_num_sms();
+        rank_kernel<<<rb, 256, 0, s>>>(kept, medoid_row, hdr);
+        VK_LAUNCH_CHECK();
+    }
     return 0;
 }
 

@@ -153,44 +153,65 @@ __device__ __forceinline__ float f4_get(const float4 &v, int e) {
     return e == 0 ? v.x : (e == 1 ? v.y : (e == 2 ? v.z : v.w));
 }
 
-// Stage one operand tile (rows x KT) into the K-major no-swizzle layout, as hi (fp32 words, the tensor
-// core reads their top 19 bits) and lo (tf32 remainder).
+// Per-thread slice of one operand tile (rows x KT): up to TC_ITEMS float4, fetched in ONE batch of
+// independent global loads (so a k-tile costs one memory round trip, not one per item) and written to
+// shared memory later, which lets the loads of tile kt+1 fly while the tensor core works on tile kt.
 //  MN == false: source [row][k], k contiguous.  Lane l of a quarter-warp fills one 128-byte core matrix
 //               -> conflict-free 16-byte stores.
-//  MN == true : source [k][row], row contiguous (MN-major operands measured to produce zeros with the
-//               no-swizzle descriptor, so they are transposed on the fly instead).  A warp loads 4 k x 32
-//               rows as float4 and scatters the 4 row-elements with a lane-dependent rotation so that the
-//               32 scalar stores of each instruction hit 32 different banks (bank = (row%8)*4 + k%4).
-template <bool MN, class L>
-__device__ __forceinline__ void stage_operand(const L &ld, int r0, int k0, int rows, uint8_t *hi, uint8_t *lo) {
+//  MN == true : source [k][row], row contiguous (MN-major UMMA operands measured to produce zeros with
+//               the no-swizzle descriptor, so they are transposed on the fly instead).  A warp loads
+//               4 k x 32 rows as float4 and scatters the 4 row-elements with a lane-dependent rotation so
+//               that the 32 scalar stores of each instruction hit 32 different banks
+//               (bank = (row%8)*4 + k%4).
+constexpr int TC_ITEMS = 4;  // 128 rows x 32 k / 4 / 256 threads
+
+template <bool MN>
+__device__ __forceinline__ bool item_coords(int i, int rows, int &r, int &c) {
     const int tid = threadIdx.x;
     if (!MN) {
-        const int n4 = rows * (KT / 4);
-        for (int q = tid; q < n4; q += TC_THREADS) {
-            const int r = ((q >> 6) << 3) | (q & 7), k4 = (q >> 3) & 7;
-            const float4 v = ld.ld4(r0 + r, (k0 >> 2) + k4);
-            const uint32_t off = off_kmajor(r, k4);
-            *reinterpret_cast<float4 *>(hi + off) = v;
-            *reinterpret_cast<float4 *>(lo + off) = tf32_lo(v);
-        }
+        const int q = tid + i * TC_THREADS;
+        r = ((q >> 6) << 3) | (q & 7);  // row
+        c = (q >> 3) & 7;               // k / 4
+        return q < rows * (KT / 4);
     } else {
-        const int lane = tid & 31, warp = tid >> 5;
-        const int row_blocks = (rows + 31) >> 5;          // 32-row blocks
-        const int units = row_blocks * (KT / 4);          // one unit = 4 k x 32 rows = one warp load
-        const int kq = lane & 3, rot = (lane >> 3) & 3;
-        for (int u = warp; u < units; u += TC_THREADS / 32) {
-            const int rb = u % row_blocks, kb = u / row_blocks;
-            const int k = kb * 4 + kq;
-            const int r4 = rb * 8 + (lane >> 2);           // row / 4
-            if (r4 * 4 >= rows) continue;
-            const float4 v = ld.ld4(k0 + k, (r0 >> 2) + r4);
-            const float4 w = tf32_lo(v);
+        const int lane = tid & 31, u = (tid >> 5) + i * (TC_THREADS / 32);
+        const int row_blocks = (rows + 31) >> 5;
+        const int rb = u % row_blocks, kb = u / row_blocks;
+        r = kb * 4 + (lane & 3);        // k
+        c = rb * 8 + (lane >> 2);       // row / 4
+        return kb < KT / 4 && c * 4 < rows;
+    }
+}
+
+template <bool MN, class L>
+__device__ __forceinline__ void load_items(const L &ld, int r0, int k0, int rows, float4 (&v)[TC_ITEMS]) {
+#pragma unroll
+    for (int i = 0; i < TC_ITEMS; ++i) {
+        int r, c;
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (item_coords<MN>(i, rows, r, c)) v[i] = MN ? ld.ld4(k0 + r, (r0 >> 2) + c) : ld.ld4(r0 + r, (k0 >> 2) + c);
+    }
+}
+
+template <bool MN>
+__device__ __forceinline__ void store_items(const float4 (&v)[TC_ITEMS], int rows, uint8_t *hi, uint8_t *lo) {
+#pragma unroll
+    for (int i = 0; i < TC_ITEMS; ++i) {
+        int r, c;
+        if (!item_coords<MN>(i, rows, r, c)) continue;
+        const float4 w = tf32_lo(v[i]);
+        if (!MN) {
+            const uint32_t off = off_kmajor(r, c);
+            *reinterpret_cast<float4 *>(hi + off) = v[i];
+            *reinterpret_cast<float4 *>(lo + off) = w;
+        } else {
+            const int k = r, rot = ((threadIdx.x & 31) >> 3) & 3;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int ee = (e + rot) & 3;
-                const int r = r4 * 4 + ee;
-                const uint32_t off = (uint32_t)((r >> 3) * 1024 + (k >> 2) * 128 + (r & 7) * 16 + (k & 3) * 4);
-                *reinterpret_cast<float *>(hi + off) = f4_get(v, ee);
+                const int row = c * 4 + ee;
+                const uint32_t off = (uint32_t)((row >> 3) * 1024 + (k >> 2) * 128 + (row & 7) * 16 + (k & 3) * 4);
+                *reinterpret_cast<float *>(hi + off) = f4_get(v[i], ee);
                 *reinterpret_cast<float *>(lo + off) = f4_get(w, ee);
             }
         }
@@ -200,14 +221,19 @@ __device__ __forceinline__ void stage_operand(const L &ld, int r0, int k0, int r
 // One 128 x bn output tile: D[m, n] = sum_k A(m, k) * B(n, k), k in [0, K).
 //   LA / LB: loaders with  float4 ld4(int r, int c4)  returning 4 consecutive elements along the
 //   CONTIGUOUS dimension of the operand's storage:
-//     A_MN == false: storage [m][k] -> ld4(m, k/4)   (K-major);   A_MN == true: storage [k][m] -> ld4(k, m/4)
-//   and zeros outside the logical bounds.  bn: multiple of 16, 16 <= bn <= 128 (rows beyond the logical N
-//   must load as zeros).  The accumulator is left in TMEM (128 lanes x bn columns at sh->tmem_base);
-//   the caller runs the epilogue with tmem_ld32 and then calls tc_tile_end().
+//     A_MN == false: storage [m][k] -> ld4(m, k/4);   A_MN == true: storage [k][m] -> ld4(k, m/4)
+//   and zeros outside the logical bounds.  bn: multiple of 16, 16 <= bn <= 128.  The accumulator is left
+//   in TMEM (128 lanes x bn columns at sh->tmem_base); the caller runs the epilogue with tc_read_acc and
+//   then calls tc_tile_end().
 template <bool A_MN, bool B_MN, class LA, class LB>
 __device__ __forceinline__ void tc_tile_mainloop(int K, int m0, int n0, int bn, const LA &la, const LB &lb,
                                                  uint8_t *smem, TcShared *sh) {
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int nk = (K + KT - 1) / KT;
+    // the first tile's loads are in flight while the barriers / tensor memory are set up
+    float4 ra[TC_ITEMS], rb[TC_ITEMS];
+    load_items<A_MN>(la, m0, 0, TC_BM, ra);
+    load_items<B_MN>(lb, n0, 0, bn, rb);
     if (tid == 0) {
         mbar_init(&sh->bar_stage[0], 1);
         mbar_init(&sh->bar_stage[1], 1);
@@ -220,7 +246,6 @@ __device__ __forceinline__ void tc_tile_mainloop(int K, int m0, int n0, int bn, 
     tc_fence_after();
     const uint32_t tmem_d = sh->tmem_base;
     const uint32_t idesc = make_idesc_tf32(TC_BM, bn, 0, 0);  // both operand tiles are K-major in shared memory
-    const int nk = (K + KT - 1) / KT;
     const int bbytes = b_tile_bytes(bn);
 
     for (int kt = 0; kt < nk; ++kt) {
@@ -230,21 +255,23 @@ __device__ __forceinline__ void tc_tile_mainloop(int K, int m0, int n0, int bn, 
         // the MMAs that read this stage two iterations ago must have finished
         if (kt >= 2) mbar_wait(&sh->bar_stage[s], (uint32_t)(((kt >> 1) - 1) & 1));
         tc_fence_after();
-        const int k0 = kt * KT;
-        // ---- stage A (128 rows) and B (bn rows), 32 k each, into K-major core-matrix tiles ----
-        stage_operand<A_MN>(la, m0, k0, TC_BM, a_hi, a_lo);
-        stage_operand<B_MN>(lb, n0, k0, bn, b_hi, b_lo);
+        store_items<A_MN>(ra, TC_BM, a_hi, a_lo);
+        store_items<B_MN>(rb, bn, b_hi, b_lo);
         fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncthreads();
+        if (kt + 1 < nk) {  // next tile's global loads overlap the MMAs issued below
+            load_items<A_MN>(la, m0, (kt + 1) * KT, TC_BM, ra);
+            load_items<B_MN>(lb, n0, (kt + 1) * KT, bn, rb);
+        }
         if (tid == 0) {
             tc_fence_after();
-            const uint32_t a_lbo = 128, a_sbo = 1024, b_lbo = 128, b_sbo = 1024, a_step = 256, b_step = 256;
+            const uint32_t lbo = 128, sbo = 1024, step = 256;
 #pragma unroll
             for (int j = 0; j < KT / 8; ++j) {
-                const uint64_t dah = make_smem_desc(smem_u32(a_hi) + j * a_step, a_lbo, a_sbo);
-                const uint64_t dal = make_smem_desc(smem_u32(a_lo) + j * a_step, a_lbo, a_sbo);
-                const uint64_t dbh = make_smem_desc(smem_u32(b_hi) + j * b_step, b_lbo, b_sbo);
-                const uint64_t dbl = make_smem_desc(smem_u32(b_lo) + j * b_step, b_lbo, b_sbo);
+                const uint64_t dah = make_smem_desc(smem_u32(a_hi) + j * step, lbo, sbo);
+                const uint64_t dal = make_smem_desc(smem_u32(a_lo) + j * step, lbo, sbo);
+                const uint64_t dbh = make_smem_desc(smem_u32(b_hi) + j * step, lbo, sbo);
+                const uint64_t dbl = make_smem_desc(smem_u32(b_lo) + j * step, lbo, sbo);
                 umma_tf32(tmem_d, dal, dbh, idesc, (kt | j) ? 1u : 0u);  // small terms first
                 umma_tf32(tmem_d, dah, dbl, idesc, 1u);
                 umma_tf32(tmem_d, dah, dbh, idesc, 1u);

@@ -27,6 +27,7 @@ from typing import IO, Optional, Union
 
 import numpy as _np
 import torch as _torch
+import torch.distributed as _dist
 from torch import Tensor
 from torch import nn as _nn
 from torch.nn.functional import softmax as _softmax
@@ -391,6 +392,8 @@ class VAE(_nn.Module):
         seed64 = (self._seed * 0x9E3779B97F4A7C15 + 0x1234567) & 0x7FFFFFFFFFFFFFFF
         self._ctl_i64[_VkCtl.seed.offset // 8] = seed64
         self._graphs = {}
+        self._dp_group = None
+        self._use_graphs = True
 
     def _stream(self) -> int:
         return _torch.cuda.current_stream().cuda_stream
@@ -554,27 +557,66 @@ class VAE(_nn.Module):
         stream = _torch.cuda.current_stream()
         done = 0
 
+        def one_step():
+            if self._dp_group is None:
+                _lib.check(_L.vk_vae_train_step(_ct.byref(self._net), batch, None, self._stream()))
+            else:
+                # row-sharded data parallelism: local gradients, ONE all-reduce (average) of the
+                # packed gradient arena over NCCL / NVLink, then the identical optimiser step on every rank
+                _lib.check(_L.vk_vae_grad_step(_ct.byref(self._net), batch, None, self._stream()))
+                _dist.all_reduce(self._grads, op=_dist.ReduceOp.AVG, group=self._dp_group)
+                _lib.check(_L.vk_vae_dadapt_step(_ct.byref(self._net), self._stream()))
+
         def eager(k):
             for _ in range(k):
-                _lib.check(_L.vk_vae_train_step(_ct.byref(self._net), batch, None, self._stream()))
+                one_step()
 
-        if nsteps >= 2 * _GRAPH_CHUNK:
+        if nsteps >= 2 * _GRAPH_CHUNK and self._use_graphs:
             key = (batch, _GRAPH_CHUNK)
             if key not in self._graphs:
                 eager(1)  # warm-up outside capture (also advances training by one step)
                 done += 1
                 stream.synchronize()
                 g = _torch.cuda.CUDAGraph()
-                with _torch.cuda.graph(g):
-                    # NB: capture executes nothing; the graph's steps run at replay
-                    for _ in range(_GRAPH_CHUNK):
-                        _lib.check(_L.vk_vae_train_step(_ct.byref(self._net), batch, None, self._stream()))
-                self._graphs[key] = g
-            g = self._graphs[key]
-            while nsteps - done >= _GRAPH_CHUNK:
+                try:
+                    with _torch.cuda.graph(g):
+                        # NB: capture executes nothing; the graph's steps run at replay
+                        for _ in range(_GRAPH_CHUNK):
+                            one_step()
+                    self._graphs[key] = g
+                except Exception:
+                    if self._dp_group is None:
+                        raise
+                    self._use_graphs = False  # this NCCL build cannot be captured: run the steps eagerly
+                    _torch.cuda.synchronize()
+            g = self._graphs.get(key)
+            while g is not None and nsteps - done >= _GRAPH_CHUNK:
                 g.replay()
                 done += _GRAPH_CHUNK
         eager(nsteps - done)
+
+    # ------------------------------------------------------------------ multi-GPU (row-sharded data parallel)
+    def enable_data_parallel(self, group=None) -> None:
+        """Train this replica as one rank of a data-parallel group: every rank binds its own row shard of
+        the dataset; each optimiser step all-reduces (averages) the gradient arena once.  Parameters start
+        identical (same CPU seed) and stay identical; dropout / noise / shuffling streams are per rank;
+        BatchNorm batch statistics are per GPU and the running statistics are averaged before
+        ``encode`` / ``save`` (``sync_running_stats``).  ``torch.distributed`` must be initialised (NCCL)."""
+        if not _dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self._dp_group = group if group is not None else _dist.group.WORLD
+        rank = _dist.get_rank(self._dp_group)
+        so = _VkCtl.seed.offset // 8
+        self._ctl_i64[so] = int(self._ctl_i64[so].item()) ^ ((rank + 1) * 0x2545F4914F6CDD1D & 0x7FFFFFFFFFFFFFFF)
+        self._graphs = {}
+
+    def sync_running_stats(self) -> None:
+        "Average the BatchNorm running statistics over the data-parallel group."
+        if self._dp_group is None:
+            return
+        for bn in list(self.encodernorms) + list(self.decodernorms):
+            _dist.all_reduce(bn.running_mean, op=_dist.ReduceOp.AVG, group=self._dp_group)
+            _dist.all_reduce(bn.running_var, op=_dist.ReduceOp.AVG, group=self._dp_group)
 
     def trainepoch(self, data_loader: _DataLoader, epoch: int, optimizer, batchsteps: list[int]) -> _DataLoader:
         """One pass over the data (vamb/encode.py:359-440).  ``optimizer`` is accepted for
@@ -595,6 +637,10 @@ class VAE(_nn.Module):
         if batch > self._net.bmax:
             raise ValueError(f"batch size {batch} exceeds the workspace limit {self._net.bmax}")
         nsteps = len(data_loader)  # N // batch with drop_last, else 1
+        if self._dp_group is not None:
+            t = _torch.tensor([nsteps], device=self._arena.device)
+            _dist.all_reduce(t, op=_dist.ReduceOp.MIN, group=self._dp_group)  # every rank takes the same steps
+            nsteps = int(t.item())
 
         self._ctl_i32[_VkCtl.epoch.offset // 4] = int(epoch)
         so = _VkCtl.step.offset // 8
@@ -620,6 +666,7 @@ class VAE(_nn.Module):
         Output: A (n_contigs x n_latent) Numpy array of latent repr.
         """
         self.eval()
+        self.sync_running_stats()
         n = self._bind_dataset(data_loader.dataset.tensors)
         dev = self._arena.device
         out = _torch.empty((n, self.nlatent), dtype=_torch.float32, device=dev)
