@@ -185,7 +185,7 @@ def vae_roofline(vae, n, nepochs):
         reps = reps[3:]
         avg_bwd = np.mean([r["bwd"] for r in reps], axis=0)  # launch order: last layer first
         avg_fwd = np.mean([r["fwd"] for r in reps], axis=0)
-        other = float(np.mean([r["batch_rows"] + r["loss"] + r["dadapt"] for r in reps]))
+        other = float(np.mean([r["batch_rows"] + r["loss"] + r["dadapt"] + r["prep"] for r in reps]))
         nsteps = spe * epochs
         tot["fwd_layer_kernel"] = tot.get("fwd_layer_kernel", 0.0) + nsteps * float(avg_fwd.sum())
         tot["bwd_layer_kernel"] = tot.get("bwd_layer_kernel", 0.0) + nsteps * float(avg_bwd.sum())

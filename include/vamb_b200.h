@@ -201,6 +201,15 @@ typedef struct vk_vae_layer {
     float *bn_a, *bn_c;         /* BN(P) = P * bn_a + bn_c  (batch statistics in training, running in eval)         */
     float *bn_mean, *bn_rstd;   /* batch mean and 1/sqrt(var + eps) of the current step                             */
     float *bn_m1, *bn_m2;       /* mean_b dH and mean_b dH*Phat of the current step                                 */
+    float *bn_bA, *bn_bB, *bn_bC; /* dL/dY = sgn * (bA*dH + bB*P + bC): folded BatchNorm/dropout backward constants  */
+    /* Tensor-core operand staging: plain K-major arrays, zero padded (rows to 128, K to 32); `hi` is
+     * the fp32 value (the tensor core reads its top 19 bits), `lo` the tf32 remainder. */
+    float *xop_hi, *xop_lo;     /* layer input            [bmax, ld = round32(k_in)]       A of the forward GEMM    */
+    float *xt_hi, *xt_lo;       /* its transpose + a row of ones [round128(k_in + 1), bmax] B of wgrad              */
+    float *dy_hi, *dy_lo;       /* dL/dY                  [bmax, ld = round32(n_out)]      A of dgrad               */
+    float *dyt_hi, *dyt_lo;     /* its transpose          [round128(n_out), bmax]          A of wgrad               */
+    float *w_hi, *w_lo;         /* W                      [round128(n_out), round32(k_in)] B of the forward GEMM    */
+    float *wt_hi, *wt_lo;       /* W^T                    [round128(k_in), round32(n_out)] B of dgrad               */
 } vk_vae_layer;
 
 typedef struct vk_vae {
@@ -255,10 +264,11 @@ int vk_vae_prepare_eval(const vk_vae *net, void *stream);
 /* Standalone D-Adaptation Adam step on the arenas (used after a gradient all-reduce). */
 int vk_vae_dadapt_step(const vk_vae *net, void *stream);
 
-/* vk_vae_train_step with a CUDA event before every launch; ms_out_host[i] = device time of launch i
- * (batch_rows, forward layers, loss, backward layers from the last to the first, dadapt).  Synchronises. */
+/* vk_vae_train_step with a CUDA event before every launch: ms_out_host[i] = device time of launch i,
+ * kinds_out_host[i] = 0 batch rows | 1 forward layer | 2 loss | 3 backward layer | 4 optimiser |
+ * 5 operand staging.  Synchronises. */
 int vk_vae_profile_step(const vk_vae *net, int batch, const vk_vae_inject *inject, float *ms_out_host,
-                        int capacity, int *n_launches, void *stream);
+                        int *kinds_out_host, int capacity, int *n_launches, void *stream);
 
 /* Backward + gradients only (no optimiser): used by the multi-GPU path and by the tests. */
 int vk_vae_grad_step(const vk_vae *net, int batch, const vk_vae_inject *inject, void *stream);

@@ -19,7 +19,7 @@ for B in (256, 512, 1024, 2048, 4096):
     reps = [vae._profile_step(B) for _ in range(5)]
     fwd = np.mean([r["fwd"] for r in reps], axis=0) * 1e3
     bwd = np.mean([r["bwd"] for r in reps], axis=0) * 1e3
-    oth = np.mean([[r["batch_rows"], r["loss"], r["dadapt"]] for r in reps], axis=0) * 1e3
+    oth = np.mean([[r["batch_rows"], r["loss"], r["dadapt"], r["prep"]] for r in reps], axis=0) * 1e3
     nsteps = 640
     torch.cuda.synchronize()
     vae._run_steps(B, nsteps)  # includes capture the first time
@@ -29,4 +29,4 @@ for B in (256, 512, 1024, 2048, 4096):
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / nsteps * 1e6
     print(f"B={B:5d} tc_min={tcmin}: {dt:7.1f} us/step (graph) | sum of launches {fwd.sum()+bwd.sum()+oth.sum():7.1f} us | "
-          f"fwd {np.round(fwd,1).tolist()} bwd {np.round(bwd,1).tolist()} rows/loss/opt {np.round(oth,1).tolist()}")
+          f"fwd {np.round(fwd,1).tolist()} bwd {np.round(bwd,1).tolist()} rows/loss/opt/prep {np.round(oth,1).tolist()} launches {reps[0]['n_launches']}")

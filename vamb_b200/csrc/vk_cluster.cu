@@ -183,68 +183,79 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
         wcnt = 0;
     };
 
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t row0 = (int64_t)tile * PB_TILE;
+    // chunks of 128 consecutive rows (4 per lane group), grid-strided; for D = 32 the next chunk's loads
+    // are issued before the current chunk is processed (register double buffering) so that every resident
+    // warp keeps 128 bytes per lane in flight.
+    constexpr int CHUNK = PB_GROUPS * PB_R;
+    const int n32 = (int)n;
+    const int n_chunks = (n32 + CHUNK - 1) / CHUNK;
+    float4 vnext[PB_R];
+    auto load_chunk = [&](int c, float4 (&v)[PB_R]) {
+#pragma unroll
+        for (int k = 0; k < PB_R; ++k) {
+            const int row = c * CHUNK + k * PB_GROUPS + g;
+            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < n32) v[k] = ldg_stream4(matrix + (int64_t)row * 32 + 4 * lane8);
+        }
+    };
+    if (DFIX == 32 && (int)blockIdx.x < n_chunks) load_chunk(blockIdx.x, vnext);
 #pragma unroll 1
-        for (int it = 0; it < PB_TILE / (PB_GROUPS * PB_R); ++it) {
-            float acc[PB_R];
-            int64_t rows[PB_R];
-            if (DFIX == 32) {
-                float4 v[PB_R];
+    for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        float acc[PB_R];
+        int rows[PB_R];
 #pragma unroll
-                for (int k = 0; k < PB_R; ++k) {
-                    rows[k] = row0 + (int64_t)(it * PB_R + k) * PB_GROUPS + g;
-                    v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (rows[k] < n) v[k] = ldg_stream4(matrix + rows[k] * 32 + 4 * lane8);
-                }
+        for (int k = 0; k < PB_R; ++k) rows[k] = c * CHUNK + k * PB_GROUPS + g;
+        if (DFIX == 32) {
+            float4 v[PB_R];
 #pragma unroll
-                for (int k = 0; k < PB_R; ++k) acc[k] = chain4(v[k], qv);
-            } else {
+            for (int k = 0; k < PB_R; ++k) v[k] = vnext[k];
+            if (c + (int)gridDim.x < n_chunks) load_chunk(c + gridDim.x, vnext);
 #pragma unroll
-                for (int k = 0; k < PB_R; ++k) {
-                    rows[k] = row0 + (int64_t)(it * PB_R + k) * PB_GROUPS + g;
-                    acc[k] = 0.0f;
-                    if (rows[k] < n) acc[k] = lane_chain_generic(matrix + rows[k] * (int64_t)d, s_q, d, lane8, vec4);
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < PB_R; ++k) acc[k] = group8_sum(acc[k], gmask);
-
+            for (int k = 0; k < PB_R; ++k) acc[k] = chain4(v[k], qv);
+        } else {
 #pragma unroll
             for (int k = 0; k < PB_R; ++k) {
-                const int64_t row = rows[k];
-                float dd = __fsub_rn(0.5f, acc[k]);
-                if (row == mrow) dd = 0.0f;
-                bool cand = (lane8 == 0) && (row < n) && (dd <= lim);
-                if (cand) cand = kept[row] != 0;  // rare: the mask is only consulted for near rows
-                const bool nl_hit = cand && (dd <= nl_radius);
-                const unsigned ballot = __ballot_sync(0xffffffffu, nl_hit);
-                if (ballot) {
-                    if (nl_hit) {
-                        const int pos = wcnt + __popc(ballot & lt_mask);
-                        s_wrows[warp][pos] = (int32_t)row;
-                        s_wd[warp][pos] = dd;
-                    }
-                    wcnt += __popc(ballot);
+                acc[k] = 0.0f;
+                if (rows[k] < n32) acc[k] = lane_chain_generic(matrix + rows[k] * (int64_t)d, s_q, d, lane8, vec4);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < PB_R; ++k) acc[k] = group8_sum(acc[k], gmask);
+
+#pragma unroll
+        for (int k = 0; k < PB_R; ++k) {
+            const int row = rows[k];
+            float dd = __fsub_rn(0.5f, acc[k]);
+            if (row == (int)mrow) dd = 0.0f;
+            bool cand = (lane8 == 0) && (row < n32) && (dd <= lim);
+            if (cand) cand = kept[row] != 0;  // rare: the mask is only consulted for near rows
+            const bool nl_hit = cand && (dd <= nl_radius);
+            const unsigned ballot = __ballot_sync(0xffffffffu, nl_hit);
+            if (ballot) {
+                if (nl_hit) {
+                    const int pos = wcnt + __popc(ballot & lt_mask);
+                    s_wrows[warp][pos] = row;
+                    s_wd[warp][pos] = dd;
                 }
-                if (cand) {
-                    if (dd < rad) ++t_nlt;
-                    const bool in_hist = (dd >= e_lo) && (dd <= e_hi);
-                    const bool within = dd <= rad;
-                    if (in_hist || within) {
-                        const u64 len = __float2ull_rz(__ldg(lengths + row));
-                        if (within) {
-                            density_add(t_dens, t_dens_hi, len, closeness_fx(rad, dd));
-                            const int pos = atomicAdd(&hdr->n_within, 1);
-                            if (pos < VK_PROBE_INLINE) hdr->within[pos] = (int32_t)row;
-                            else within_overflow[pos] = (int32_t)row;
-                        }
-                        if (in_hist) atomicAdd(&s_hist[hist_bin(dd, s_edges)], len);
+                wcnt += __popc(ballot);
+            }
+            if (cand) {
+                if (dd < rad) ++t_nlt;
+                const bool in_hist = (dd >= e_lo) && (dd <= e_hi);
+                const bool within = dd <= rad;
+                if (in_hist || within) {
+                    const u64 len = __float2ull_rz(__ldg(lengths + row));
+                    if (within) {
+                        density_add(t_dens, t_dens_hi, len, closeness_fx(rad, dd));
+                        const int pos = atomicAdd(&hdr->n_within, 1);
+                        if (pos < VK_PROBE_INLINE) hdr->within[pos] = row;
+                        else within_overflow[pos] = row;
                     }
+                    if (in_hist) atomicAdd(&s_hist[hist_bin(dd, s_edges)], len);
                 }
             }
-            if (wcnt > PB_WBUF - PB_GROUPS / 8 * PB_R) flush_warp();
         }
+        if (wcnt > PB_WBUF - PB_GROUPS / 8 * PB_R) flush_warp();
     }
     flush_warp();
 

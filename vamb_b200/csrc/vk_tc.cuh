@@ -299,3 +299,131 @@ __device__ __forceinline__ void tc_tile_end(TcShared *sh) {
 }
 
 }  // namespace tc
+
+// =====================================================================================================
+// v2 main loop: operands are PLAIN K-major arrays in global memory -- `hi` (fp32 value) and `lo` (tf32
+// remainder), zero padded to 128 rows / 32 columns, 16-byte aligned rows -- produced once per layer by the
+// prep kernels (vk_vae.cu).  No transform, no bounds checks: a multi-stage cp.async pipeline copies the
+// 16-byte chunks straight into the no-swizzle core-matrix tiles and the elected thread issues the three
+// 3xTF32 MMAs per k8-step.  Global loads of tile kt+D are in flight while the tensor core works on tile kt.
+namespace tc {
+
+struct OpRef {
+    const float *hi, *lo;
+    int ld;  // floats per row (multiple of 4)
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *gptr) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__host__ __device__ constexpr int tc2_smem_bytes(int bn, int stages) { return stages * stage_bytes(bn) + 1024; }
+
+struct Tc2Shared {
+    uint64_t bar_stage[4];
+    uint64_t bar_done;
+    uint32_t tmem_base;
+};
+
+// D[128 x bn] = sum over k-tiles [kt0, kt0 + nk) of A[m0.., k] * B[n0.., k]^T.  STAGES in {3, 4}.
+template <int STAGES>
+__device__ __forceinline__ void tc2_mainloop(const OpRef A, int m0, const OpRef B, int n0, int bn, int kt0, int nk,
+                                             uint8_t *smem, Tc2Shared *sh) {
+    constexpr int D = STAGES - 2;  // prefetch distance (tiles in flight beyond the one being multiplied)
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int sbytes = stage_bytes(bn), bbytes = b_tile_bytes(bn);
+    const uint32_t smem_base = smem_u32(smem);
+    // per-thread copy items: row r = ((q >> 6) << 3) | (q & 7), 16-byte chunk k4 = (q >> 3) & 7
+    const int nb_items = (bn * (KT / 4)) / TC_THREADS;  // 1, 2 or 4 (bn = 32, 64, 128); 0 when bn < 32
+    const int nb4 = bn * (KT / 4);
+    auto issue_tile = [&](int kt, int stage) {
+        const int k0 = (kt0 + kt) * KT;
+        const uint32_t st = smem_base + stage * sbytes;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int q = tid + i * TC_THREADS;
+            const int r = ((q >> 6) << 3) | (q & 7), k4 = (q >> 3) & 7;
+            const size_t g = (size_t)(m0 + r) * A.ld + k0 + k4 * 4;
+            const uint32_t off = off_kmajor(r, k4);
+            cp_async16(st + off, A.hi + g);
+            cp_async16(st + A_TILE_BYTES + off, A.lo + g);
+        }
+        for (int q = tid; q < nb4; q += TC_THREADS) {
+            const int r = ((q >> 6) << 3) | (q & 7), k4 = (q >> 3) & 7;
+            const size_t g = (size_t)(n0 + r) * B.ld + k0 + k4 * 4;
+            const uint32_t off = off_kmajor(r, k4);
+            cp_async16(st + 2 * A_TILE_BYTES + off, B.hi + g);
+            cp_async16(st + 2 * A_TILE_BYTES + bbytes + off, B.lo + g);
+        }
+        (void)nb_items;
+    };
+    // prologue: the first D tiles are in flight while barriers / tensor memory are set up
+#pragma unroll
+    for (int t = 0; t < D; ++t) {
+        if (t < nk) issue_tile(t, t % STAGES);
+        cp_async_commit();
+    }
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(&sh->bar_stage[s], 1);
+        mbar_init(&sh->bar_done, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc(&sh->tmem_base, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = sh->tmem_base;
+    const uint32_t idesc = make_idesc_tf32(TC_BM, bn, 0, 0);
+    const uint64_t desc0 = make_smem_desc(smem_base, 128, 1024);
+
+    for (int kt = 0; kt < nk; ++kt) {
+        // refill: tile kt+D goes to the stage that held tile kt+D-STAGES = kt-2 (its MMAs are long done)
+        if (kt + D < nk) {
+            const int s2 = (kt + D) % STAGES;
+            if (kt >= 2) mbar_wait(&sh->bar_stage[s2], (uint32_t)(((kt - 2) / STAGES) & 1));
+            issue_tile(kt + D, s2);
+        }
+        cp_async_commit();
+        cp_async_wait<D>();   // this thread's copies of tile kt have landed
+        fence_async_smem();   // ... and are visible to the tensor core (async proxy)
+        __syncthreads();      // ... for every thread
+        if (tid == 0) {
+            tc_fence_after();
+            const int s = kt % STAGES;
+            // descriptors differ only in the 14-bit start-address field: add (byte offset >> 4)
+            const uint64_t d0 = desc0 + (uint64_t)((uint32_t)(s * sbytes) >> 4);
+#pragma unroll
+            for (int j = 0; j < KT / 8; ++j) {
+                const uint64_t dah = d0 + 16u * j, dal = dah + (A_TILE_BYTES >> 4);
+                const uint64_t dbh = dah + (2 * A_TILE_BYTES >> 4), dbl = dbh + (uint32_t)(bbytes >> 4);
+                umma_tf32(tmem_d, dal, dbh, idesc, (kt | j) ? 1u : 0u);  // small terms first
+                umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+                umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+            }
+            umma_commit(&sh->bar_stage[s]);
+            if (kt == nk - 1) umma_commit(&sh->bar_done);
+        }
+    }
+    if (nk > 0) mbar_wait(&sh->bar_done, 0);
+    tc_fence_after();
+}
+
+__device__ __forceinline__ void tc2_read_acc(const Tc2Shared *sh, int col, float (&v)[32]) {
+    const int warp = threadIdx.x >> 5;
+    const uint32_t taddr = sh->tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col;
+    tmem_ld32(taddr, v);
+}
+
+__device__ __forceinline__ void tc2_tile_end(Tc2Shared *sh) {
+    tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) tmem_dealloc(sh->tmem_base, 128);
+}
+
+}  // namespace tc

@@ -79,31 +79,52 @@ __device__ __forceinline__ double block_sum256(double v, double *s8) {
 
 // ------------------------------------------------------------------ batch rows + mean weight
 // mode 0: rows from inject->batch_idx; 1: epoch permutation; 2: contiguous [row0, row0+B)
+// "last block done": returns true in every thread of the block that finishes last.
+__device__ __forceinline__ bool last_block_done(int32_t *ticket, int total) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int t = atomicAdd(ticket, 1);
+        s_last = (t == total - 1);
+        if (s_last) *ticket = 0;  // self-reset for the next launch
+    }
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last != 0;
+}
+
+// One thread per batch row (grid = ceil(B / 256) blocks); the batch-mean weight is folded by the last
+// block from per-block partial sums in block order (fixed order -> reproducible).
 __global__ void __launch_bounds__(256)
 batch_rows_kernel(int64_t *batch_rows, const int64_t *batch_idx, const float *weights, vk_vae_ctl *ctl, int B,
-                  int64_t n_rows, int mode, int64_t row0, int steps_per_epoch) {
-    __shared__ double s_w[256];
+                  int64_t n_rows, int mode, int64_t row0, int steps_per_epoch, double *part, int ticket_id) {
+    __shared__ double s_w[16];
     const int tid = threadIdx.x;
+    const int b = blockIdx.x * 256 + tid;
     double acc = 0.0;
-    int half_bits = 1;
-    while ((1ull << (2 * half_bits)) < (uint64_t)n_rows) ++half_bits;
-    const uint64_t key = mix64(ctl->seed ^ (0x5851F42D4C957F2Dull * (uint64_t)(ctl->epoch + 1)));
-    int64_t pos0 = 0;
-    if (mode == 1) {
-        int64_t t = ctl->step - ctl->epoch_step0;
-        if (steps_per_epoch > 0) t %= steps_per_epoch;
-        pos0 = t * (int64_t)B;
-    }
-    for (int b = tid; b < B; b += 256) {
+    if (b < B) {
         int64_t r;
         if (mode == 0) r = batch_idx[b];
-        else if (mode == 1) r = (int64_t)feistel_perm((uint64_t)(pos0 + b), (uint64_t)n_rows, half_bits, key);
-        else r = row0 + b;
+        else if (mode == 1) {
+            int half_bits = 1;
+            while ((1ull << (2 * half_bits)) < (uint64_t)n_rows) ++half_bits;
+            const uint64_t key = mix64(ctl->seed ^ (0x5851F42D4C957F2Dull * (uint64_t)(ctl->epoch + 1)));
+            int64_t t = ctl->step - ctl->epoch_step0;
+            if (steps_per_epoch > 0) t %= steps_per_epoch;
+            r = (int64_t)feistel_perm((uint64_t)(t * (int64_t)B + b), (uint64_t)n_rows, half_bits, key);
+        } else r = row0 + b;
         batch_rows[b] = r;
-        acc += (double)weights[r];
+        acc = (double)weights[r];
     }
     const double t = block_sum256(acc, s_w);
-    if (tid == 0) ctl->wbar = t / (double)B;
+    if (tid == 0) part[blockIdx.x] = t;
+    if (!last_block_done(&ctl->tickets[ticket_id], gridDim.x)) return;
+    if (tid == 0) {
+        double tot = 0.0;
+        for (unsigned i = 0; i < gridDim.x; ++i) tot += __ldcg(part + i);
+        ctl->wbar = tot / (double)B;
+    }
 }
 
 // ------------------------------------------------------------------ operand loaders
@@ -311,21 +332,6 @@ __device__ __forceinline__ void tile_colsum2(const float (&v0)[TN], const float 
     __syncthreads();
 }
 
-// "last block done": returns true in every thread of the block that finishes last.
-__device__ __forceinline__ bool last_block_done(int32_t *ticket, int total) {
-    __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int t = atomicAdd(ticket, 1);
-        s_last = (t == total - 1);
-        if (s_last) *ticket = 0;  // self-reset for the next launch
-    }
-    __syncthreads();
-    if (s_last) __threadfence();
-    return s_last != 0;
-}
-
 // ------------------------------------------------------------------ forward layer
 struct FwdArgs {
     LdInput in;           // input activation [B, K]
@@ -340,6 +346,7 @@ struct FwdArgs {
     float *z; const float *eps; int add_eps; int mask_bits; float *latent_out;
     vk_vae_ctl *ctl; int layer_id; float slope;
     int tile_n;           // tensor-core path: output columns per CTA (multiple of 16, <= 128)
+    tc::OpRef a_op, b_op; // v2: staged operands (layer input, W)
 };
 
 // Fold the per-row-tile column sums of P and P^2 into the BatchNorm affine, the saved batch statistics
@@ -553,6 +560,8 @@ struct BwdArgs {
     const float *MU; float kld_w;
     vk_vae_ctl *ctl; int ticket_id;
     int tile_n;           // tensor-core path: output columns per CTA
+    tc::OpRef wg_a, wg_b, dg_a, dg_b;  // v2: dY^T, X^T(+ones) | dY, W^T
+    float *bA_prev, *bB_prev, *bC_prev; const float *gamma_prev; float inv_keep;
 };
 
 // Fold the per-row-tile column sums of dH and dH*Phat: BatchNorm weight/bias gradients and the two
@@ -569,6 +578,16 @@ __device__ __forceinline__ void bn_backward_finalize(const BwdArgs &a) {
         a.g_gamma[n] = (float)v;  // d/d(gamma) = sum_b dH * Phat
         a.m1_prev[n] = (float)(u / a.B);
         a.m2_prev[n] = (float)(v / a.B);
+        if (a.bA_prev) {
+            // dL/dY = sgn * inv_keep * gamma * rstd * (dH - m1 - (P - mean) * rstd * m2) = sgn * (bA*dH + bB*P + bC)
+            const float rs = a.rstd_prev[n], mu = a.mean_prev[n];
+            const float m1 = (float)(u / a.B), m2 = (float)(v / a.B);
+            const float bA = a.inv_keep * a.gamma_prev[n] * rs;
+            const float bB = -bA * rs * m2;
+            a.bA_prev[n] = bA;
+            a.bB_prev[n] = bB;
+            a.bC_prev[n] = -bA * m1 - bB * mu;
+        }
     }
 }
 
@@ -848,6 +867,272 @@ __global__ void __launch_bounds__(tc::TC_THREADS, 1) bwd_layer_tc_kernel(BwdArgs
     bn_backward_finalize(a);
 }
 
+// ---- v2: the same epilogues fed by the cp.async main loop over staged operands
+template <int STAGES>
+__global__ void __launch_bounds__(tc::TC_THREADS, 1) fwd_layer_tc2_kernel(FwdArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ tc::Tc2Shared sh;
+    __shared__ double s_cs[2][2][128];
+    uint8_t *smem = align1024(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.y * 128, n0 = blockIdx.x * a.tile_n;
+    int bn = a.N - n0;
+    bn = bn > a.tile_n ? a.tile_n : ((bn + 15) & ~15);
+    tc::tc2_mainloop<STAGES>(a.a_op, m0, a.b_op, n0, bn, 0, (a.K + tc::KT - 1) / tc::KT, smem, &sh);
+
+    float *tile = reinterpret_cast<float *>(smem);  // [128][TS]; the operand stages are dead now
+    const uint32_t k0 = (uint32_t)a.ctl->seed, k1 = (uint32_t)(a.ctl->seed >> 32);
+    const uint32_t step_lo = (uint32_t)a.ctl->step, step_hi = (uint32_t)(a.ctl->step >> 32);
+    const int row = (warp & 3) * 32 + lane, m = m0 + row;
+    const bool hidden = a.kind == VK_LAYER_HIDDEN;
+    const bool drop = hidden && a.training && a.dropout > 0.0f;
+    const float keep_scale = 1.0f / (1.0f - a.dropout);
+    for (int c = (warp >> 2) * 64; c < (warp >> 2) * 64 + 64 && c < bn; c += 32) {
+        float v[32];
+        tc::tc2_read_acc(&sh, c, v);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+            uint32_t rnd[4] = {0u, 0u, 0u, 0u};
+            const int nb = n0 + c + 4 * j4;
+            if (drop && a.keep == nullptr && m < a.B)
+                philox4x32((uint32_t)m, (uint32_t)(nb >> 2), step_lo, step_hi ^ ((uint32_t)(a.layer_id + 1) << 24), k0, k1, rnd);
+            float o4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = nb + j;
+                float p = 0.0f;
+                if (m < a.B && n < a.N) {
+                    const float y = v[4 * j4 + j] + __ldg(a.bias + n);
+                    if (hidden) {
+                        p = y > 0.0f ? y : y * a.slope;
+                        if (drop) {
+                            const bool kp = a.keep ? (a.keep[(int64_t)m * a.N + n] != 0) : (u32_to_unit(rnd[j]) > a.dropout);
+                            p = kp ? p * keep_scale : 0.0f;
+                        }
+                    } else {
+                        p = y;
+                    }
+                }
+                o4[j] = p;
+            }
+            *reinterpret_cast<float4 *>(tile + row * TS + c + 4 * j4) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        }
+    }
+    tc::tc2_tile_end(&sh);  // fence + __syncthreads + TMEM dealloc: the tile is complete for everyone
+    // coalesced store of the tile
+    const bool vec = ((a.N & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
+    const int q_per_row = bn >> 2;
+    for (int q = tid; q < 128 * q_per_row; q += tc::TC_THREADS) {
+        const int r = q / q_per_row, c = (q % q_per_row) << 2;
+        if (m0 + r >= a.B) continue;
+        const float4 t = *reinterpret_cast<const float4 *>(tile + r * TS + c);
+        float *dst = a.out + (int64_t)(m0 + r) * a.N + n0 + c;
+        if (vec && n0 + c + 3 < a.N) *reinterpret_cast<float4 *>(dst) = t;
+        else {
+            if (n0 + c < a.N) dst[0] = t.x;
+            if (n0 + c + 1 < a.N) dst[1] = t.y;
+            if (n0 + c + 2 < a.N) dst[2] = t.z;
+            if (n0 + c + 3 < a.N) dst[3] = t.w;
+        }
+    }
+    if (!hidden || !a.training) return;
+    double *p0 = a.part + ((int64_t)blockIdx.y * 2 + 0) * a.N;
+    double *p1 = a.part + ((int64_t)blockIdx.y * 2 + 1) * a.N;
+    tc_colsum2(bn, n0, a.N, s_cs, p0, p1, [&](int r, int c, float &v0, float &v1) {
+        const float p = tile[r * TS + c];  // rows >= B and columns >= N hold zeros
+        v0 = p;
+        v1 = p * p;
+    });
+    if (!last_block_done(&a.ctl->tickets[a.layer_id], gridDim.x * gridDim.y)) return;
+    bn_forward_finalize(a, gridDim.y);
+}
+
+
+template <int STAGES>
+__global__ void __launch_bounds__(tc::TC_THREADS, 1) bwd_layer_tc2_kernel(BwdArgs a, BwdTcExtra x) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ tc::Tc2Shared sh;
+    __shared__ double s_cs[2][2][128];
+    uint8_t *smem = align1024(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_wg = a.wg_tiles_m * a.wg_tiles_n * x.nsplit;
+    if ((int)blockIdx.x < n_wg) {
+        // ---- wgrad slice: gW[n, k] (+ bias column) over batch rows [b0, b0 + nb) ----
+        const int split = blockIdx.x / (a.wg_tiles_m * a.wg_tiles_n);
+        const int t = blockIdx.x % (a.wg_tiles_m * a.wg_tiles_n);
+        const int m0 = (t / a.wg_tiles_n) * 128, n0 = (t % a.wg_tiles_n) * a.tile_n;
+        int bn = a.K + 1 - n0;
+        bn = bn > a.tile_n ? a.tile_n : ((bn + 15) & ~15);
+        const int b0 = split * x.k_per_split;
+        int nb = a.B - b0;
+        nb = nb < 0 ? 0 : (nb > x.k_per_split ? x.k_per_split : nb);
+        const int nk = (nb + tc::KT - 1) / tc::KT;  // b0 is a multiple of 32; the staged operands are zero padded
+        tc::tc2_mainloop<STAGES>(a.wg_a, m0, a.wg_b, n0, bn, b0 / tc::KT, nk, smem, &sh);
+        const int m = m0 + (warp & 3) * 32 + lane;
+        float *gW = a.gW + (int64_t)split * x.slab, *gb = a.gb + (int64_t)split * x.slab;
+        for (int c = (warp >> 2) * 64; c < (warp >> 2) * 64 + 64 && c < bn; c += 32) {
+            float v[32];
+            if (nk > 0) tc::tc2_read_acc(&sh, c, v);
+            else
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+            if (m < a.N) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = n0 + c + j;
+                    if (n < a.K) gW[(int64_t)m * a.K + n] = v[j];
+                    else if (n == a.K) gb[m] = v[j];
+                }
+            }
+        }
+        tc::tc2_tile_end(&sh);
+        return;
+    }
+    // ---- dgrad: dX[b, k] = sum_n dY[b, n] * W[n, k] ----
+    const int t = blockIdx.x - n_wg;
+    const int m0 = (t / a.dg_tiles_n) * 128, n0 = (t % a.dg_tiles_n) * a.tile_n;
+    int bn = a.K - n0;
+    bn = bn > a.tile_n ? a.tile_n : ((bn + 15) & ~15);
+    tc::tc2_mainloop<STAGES>(a.dg_a, m0, a.dg_b, n0, bn, 0, (a.N + tc::KT - 1) / tc::KT, smem, &sh);
+    float *tile = reinterpret_cast<float *>(smem);
+    const int row = (warp & 3) * 32 + lane, m = m0 + row;
+    const float gsc = (float)(a.ctl->wbar / (double)a.B);
+    for (int c = (warp >> 2) * 64; c < (warp >> 2) * 64 + 64 && c < bn; c += 32) {
+        float v[32];
+        tc::tc2_read_acc(&sh, c, v);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+            float o4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + c + 4 * j4 + j;
+                float val = 0.0f;
+                if (m < a.B && n < a.K) {
+                    val = v[4 * j4 + j];
+                    if (a.in_kind == VK_IN_Z) val = __fmaf_rn(gsc * a.kld_w, __ldg(a.MU + (int64_t)m * a.K + n), val);
+                }
+                o4[j] = val;
+            }
+            *reinterpret_cast<float4 *>(tile + row * TS + c + 4 * j4) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        }
+    }
+    tc::tc2_tile_end(&sh);
+    const bool vec = ((a.K & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.d_in) & 15) == 0);
+    const int q_per_row = bn >> 2;
+    for (int q = tid; q < 128 * q_per_row; q += tc::TC_THREADS) {
+        const int r = q / q_per_row, c = (q % q_per_row) << 2;
+        if (m0 + r >= a.B) continue;
+        const float4 tv = *reinterpret_cast<const float4 *>(tile + r * TS + c);
+        float *dst = a.d_in + (int64_t)(m0 + r) * a.K + n0 + c;
+        if (vec && n0 + c + 3 < a.K) *reinterpret_cast<float4 *>(dst) = tv;
+        else {
+            if (n0 + c < a.K) dst[0] = tv.x;
+            if (n0 + c + 1 < a.K) dst[1] = tv.y;
+            if (n0 + c + 2 < a.K) dst[2] = tv.z;
+            if (n0 + c + 3 < a.K) dst[3] = tv.w;
+        }
+    }
+    if (a.in_kind != VK_IN_BN) return;
+    const int row_tile = t / a.dg_tiles_n;
+    double *p0 = a.part_prev + ((int64_t)row_tile * 2 + 0) * a.K;
+    double *p1 = a.part_prev + ((int64_t)row_tile * 2 + 1) * a.K;
+    tc_colsum2(bn, n0, a.K, s_cs, p0, p1, [&](int r, int c, float &v0, float &v1) {
+        const float dv = tile[r * TS + c];
+        float ph = 0.0f;
+        if (m0 + r < a.B && n0 + c < a.K)
+            ph = (__ldg(a.p_prev + (int64_t)(m0 + r) * a.K + n0 + c) - __ldg(a.mean_prev + n0 + c)) * __ldg(a.rstd_prev + n0 + c);
+        v0 = dv;
+        v1 = dv * ph;
+    });
+    if (!last_block_done(&a.ctl->tickets[a.ticket_id], a.dg_tiles_m * a.dg_tiles_n)) return;
+    bn_backward_finalize(a);
+}
+
+
+// ------------------------------------------------------------------ operand staging ("prep") kernels
+// Materialise a transformed operand ONCE per layer as the plain K-major hi/lo arrays the v2 GEMM
+// consumes, plus its transpose (the wgrad operands reduce over the batch, so they need the batch as
+// their contiguous K dimension).  32 x 32 tiles through shared memory keep both writes coalesced.
+//   mode 0: plain copy of src[rows, cols]            (weights, z, dL/dR, dL/dmu)
+//   mode 1: BatchNorm on load  src * c0[col] + c1[col]
+//   mode 2: dL/dY = sgn(P) * (c0*dH + c1*P + c2), 0 for dropped units   (src = dH, p = P)
+//   mode 3: gathered dataset rows
+struct PrepArgs {
+    int mode;
+    const float *src; int ld_src;
+    const float *p;
+    const float *c0, *c1, *c2;
+    const float *data; const int64_t *rows_idx; int data_ld;
+    float slope; int has_dropout;
+    int rows, cols;            // logical extent
+    int rows_w, cols_w;        // extent written (zeros outside the logical extent): rows_w >= rows, multiple of 32
+    float *hi, *lo; int ld;    // [row][col]  (nullable)
+    float *hiT, *loT; int ldT; // [col][row]  (nullable)
+    int ones_row;              // transposed row `cols` = 1 for row < rows (bias-gradient column), 0 = off
+};
+
+__device__ __forceinline__ float prep_value(const PrepArgs &a, int r, int c) {
+    if (r >= a.rows || c >= a.cols) return 0.0f;
+    switch (a.mode) {
+        case 0: return __ldg(a.src + (int64_t)r * a.ld_src + c);
+        case 1: return __fmaf_rn(__ldg(a.src + (int64_t)r * a.ld_src + c), __ldg(a.c0 + c), __ldg(a.c1 + c));
+        case 2: {
+            const float pv = __ldg(a.p + (int64_t)r * a.ld_src + c);
+            if (a.has_dropout && pv == 0.0f) return 0.0f;
+            const float v = __fmaf_rn(__ldg(a.c0 + c), __ldg(a.src + (int64_t)r * a.ld_src + c),
+                                      __fmaf_rn(__ldg(a.c1 + c), pv, __ldg(a.c2 + c)));
+            return pv > 0.0f ? v : v * a.slope;
+        }
+        default: return __ldg(a.data + a.rows_idx[r] * (int64_t)a.data_ld + c);
+    }
+}
+
+__device__ __forceinline__ void prep_tile(const PrepArgs &a, int r0, int c0, float (*tile)[33]) {
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = r0 + ty * 4 + i, c = c0 + tx;
+        float v = prep_value(a, r, c);
+        if (a.hi && r < a.rows_w && c < a.cols_w) {
+            a.hi[(int64_t)r * a.ld + c] = v;
+            a.lo[(int64_t)r * a.ld + c] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        }
+        if (a.ones_row && c == a.cols) v = r < a.rows ? 1.0f : 0.0f;
+        tile[ty * 4 + i][tx] = v;
+    }
+    __syncthreads();
+    if (a.hiT) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = c0 + ty * 4 + i, r = r0 + tx;  // transposed element (c, r)
+            if (c < a.cols + (a.ones_row ? 1 : 0) && r < a.rows_w) {
+                const float v = tile[tx][ty * 4 + i];
+                a.hiT[(int64_t)c * a.ldT + r] = v;
+                a.loT[(int64_t)c * a.ldT + r] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) prep_kernel(PrepArgs a) {
+    __shared__ float tile[32][33];
+    prep_tile(a, blockIdx.y * 32, blockIdx.x * 32, tile);
+}
+
+struct PrepMulti {
+    PrepArgs l[VK_VAE_MAX_LAYERS];
+    int n;
+};
+
+// every layer's weights in one launch (blockIdx.z = layer)
+__global__ void __launch_bounds__(256) prep_weights_kernel(PrepMulti m) {
+    __shared__ float tile[32][33];
+    const PrepArgs &a = m.l[blockIdx.z];
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    if (r0 >= a.rows_w || c0 >= a.cols + 1) return;
+    prep_tile(a, r0, c0, tile);
+}
+
 // ------------------------------------------------------------------ D-Adaptation Adam
 // One pass over the flat arenas (dadaptation.DAdaptAdam.step with lr=1, betas=(0.9, 0.999),
 // eps=1e-8, weight_decay=0, growth_rate=inf, no bias correction).  The parameter update of
@@ -921,10 +1206,15 @@ __global__ void eval_affine_kernel(float *bn_a, float *bn_c, const float *gamma,
 // ------------------------------------------------------------------ host side
 // Optional per-launch event marks (vk_vae_profile_step): one event before every launch.
 static thread_local cudaEvent_t *g_prof_events = nullptr;
+static thread_local int *g_prof_kinds = nullptr;
 static thread_local int g_prof_n = 0, g_prof_cap = 0;
-#define PROF_MARK(s)                                                                    \
+enum { PK_ROWS = 0, PK_FWD = 1, PK_LOSS = 2, PK_BWD = 3, PK_OPT = 4, PK_PREP = 5 };
+#define PROF_MARK_K(s, kind)                                                            \
     do {                                                                                \
-        if (g_prof_events && g_prof_n < g_prof_cap) cudaEventRecord(g_prof_events[g_prof_n++], (s)); \
+        if (g_prof_events && g_prof_n < g_prof_cap) {                                   \
+            g_prof_kinds[g_prof_n] = (kind);                                            \
+            cudaEventRecord(g_prof_events[g_prof_n++], (s));                            \
+        }                                                                               \
     } while (0)
 
 extern "C" int64_t vk_vae_sizeof(int which) {
@@ -988,6 +1278,92 @@ static int tc_prepare() {
     return 0;
 }
 
+
+// ---- v2 tensor-core path: operand staging + cp.async GEMMs ------------------------------------------
+static inline int r32(int v) { return (v + 31) & ~31; }
+static inline int r128(int v) { return (v + 127) & ~127; }
+
+static int tc2_prepare() {
+    static bool done = false;
+    if (done) return 0;
+    VK_CUDA(cudaFuncSetAttribute(fwd_layer_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::tc2_smem_bytes(128, 3)));
+    VK_CUDA(cudaFuncSetAttribute(fwd_layer_tc2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::tc2_smem_bytes(64, 4)));
+    VK_CUDA(cudaFuncSetAttribute(bwd_layer_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::tc2_smem_bytes(128, 3)));
+    VK_CUDA(cudaFuncSetAttribute(bwd_layer_tc2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::tc2_smem_bytes(64, 4)));
+    done = true;
+    return 0;
+}
+
+static int tc2_smem_for(int tile_n, int stages) {
+    const int need = tc::tc2_smem_bytes(tile_n, stages), epi = 128 * TS * 4 + 1024;
+    return need > epi ? need : epi;
+}
+
+static int launch_prep(const PrepArgs &a, cudaStream_t s) {
+    const int cx = a.cols + (a.ones_row ? 1 : 0);
+    dim3 grid((cx + 31) / 32, (a.rows_w + 31) / 32);
+    PROF_MARK_K(s, PK_PREP);
+    prep_kernel<<<grid, 256, 0, s>>>(a);
+    VK_LAUNCH_CHECK();
+    return 0;
+}
+
+// stage the input of layer j (A of its forward GEMM; its transpose is B of its wgrad)
+static int launch_prep_input(const vk_vae *net, int j, int B, int training, cudaStream_t s) {
+    const vk_vae_layer &L = net->layers[j];
+    PrepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.rows = B; a.cols = L.k_in; a.rows_w = r128(B); a.cols_w = L.k_in;
+    a.hi = L.xop_hi; a.lo = L.xop_lo; a.ld = r32(L.k_in);
+    if (training) { a.hiT = L.xt_hi; a.loT = L.xt_lo; a.ldT = net->bmax; a.ones_row = 1; }
+    if (L.in_kind == VK_IN_DATA) {
+        a.mode = 3; a.data = net->data; a.rows_idx = net->batch_rows; a.data_ld = net->data_ld;
+    } else if (L.in_kind == VK_IN_BN) {
+        const vk_vae_layer &P = net->layers[j - 1];
+        a.mode = 1; a.src = P.act; a.ld_src = P.n_out; a.c0 = P.bn_a; a.c1 = P.bn_c;
+    } else {
+        a.mode = 0; a.src = net->z; a.ld_src = L.k_in;
+    }
+    return launch_prep(a, s);
+}
+
+// stage dL/dY of layer j (A of its dgrad; its transpose is A of its wgrad)
+static int launch_prep_grad(const vk_vae *net, int j, int B, cudaStream_t s) {
+    const vk_vae_layer &L = net->layers[j];
+    PrepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.rows = B; a.cols = L.n_out; a.rows_w = r128(B); a.cols_w = L.n_out;
+    a.hi = L.dy_hi; a.lo = L.dy_lo; a.ld = r32(L.n_out);
+    a.hiT = L.dyt_hi; a.loT = L.dyt_lo; a.ldT = net->bmax;
+    a.src = L.dact; a.ld_src = L.n_out;
+    if (L.kind == VK_LAYER_HIDDEN) {
+        a.mode = 2; a.p = L.act; a.c0 = L.bn_bA; a.c1 = L.bn_bB; a.c2 = L.bn_bC;
+        a.slope = net->slope; a.has_dropout = net->dropout > 0.0f ? 1 : 0;
+    }
+    return launch_prep(a, s);
+}
+
+static int launch_prep_weights(const vk_vae *net, cudaStream_t s) {
+    PrepMulti m;
+    memset(&m, 0, sizeof(m));
+    m.n = net->n_layers;
+    int gx = 1, gy = 1;
+    for (int j = 0; j < net->n_layers; ++j) {
+        const vk_vae_layer &L = net->layers[j];
+        PrepArgs &a = m.l[j];
+        a.mode = 0; a.src = net->params + L.w_off; a.ld_src = L.k_in;
+        a.rows = L.n_out; a.cols = L.k_in; a.rows_w = r32(L.n_out); a.cols_w = L.k_in;
+        a.hi = L.w_hi; a.lo = L.w_lo; a.ld = r32(L.k_in);
+        a.hiT = L.wt_hi; a.loT = L.wt_lo; a.ldT = r32(L.n_out);
+        gx = gx > (L.k_in + 32) / 32 ? gx : (L.k_in + 32) / 32;
+        gy = gy > a.rows_w / 32 ? gy : a.rows_w / 32;
+    }
+    PROF_MARK_K(s, PK_PREP);
+    prep_weights_kernel<<<dim3(gx, gy, net->n_layers), 256, 0, s>>>(m);
+    VK_LAUNCH_CHECK();
+    return 0;
+}
+
 static LdInput make_input(const vk_vae *net, int j, int B, int ones_col) {
     const vk_vae_layer &L = net->layers[j];
     LdInput in;
@@ -1007,9 +1383,10 @@ static int launch_batch_rows(const vk_vae *net, int B, int mode, int64_t row0, c
                              cudaStream_t s) {
     const int64_t n = net->n_rows;
     const int spe = n > B ? (int)(n / B) : 1;
-    PROF_MARK(s);
-    batch_rows_kernel<<<1, 256, 0, s>>>(net->batch_rows, inj ? inj->batch_idx : nullptr, net->weights, net->ctl, B,
-                                        n, mode, row0, spe);
+    PROF_MARK_K(s, PK_ROWS);
+    batch_rows_kernel<<<(B + 255) / 256, 256, 0, s>>>(net->batch_rows, inj ? inj->batch_idx : nullptr, net->weights,
+                                                       net->ctl, B, n, mode, row0, spe, net->opt_part + 1024,
+                                                       2 * VK_VAE_MAX_LAYERS + 3);
     VK_LAUNCH_CHECK();
     return 0;
 }
@@ -1040,12 +1417,18 @@ static int launch_forward(const vk_vae *net, int B, int training, int upto /*exc
         a.mask_bits = mask_bits;
         a.latent_out = (L.kind == VK_LAYER_MU) ? latent_out : nullptr;
         a.ctl = net->ctl; a.layer_id = j; a.slope = net->slope;
-        PROF_MARK(s);
-        if (use_tc(net, B) && L.kind != VK_LAYER_MU) {
-            if (tc_prepare()) return 1;
+        const bool tcp = use_tc(net, B);
+        if (tcp && (training || L.kind != VK_LAYER_MU))
+            if (launch_prep_input(net, j, B, training, s)) return 1;
+        PROF_MARK_K(s, PK_FWD);
+        if (tcp && L.kind != VK_LAYER_MU) {
+            if (tc2_prepare()) return 1;
             a.tile_n = tc_tile_n(B);
+            a.a_op = tc::OpRef{L.xop_hi, L.xop_lo, r32(L.k_in)};
+            a.b_op = tc::OpRef{L.w_hi, L.w_lo, r32(L.k_in)};
             dim3 grid((L.n_out + a.tile_n - 1) / a.tile_n, (B + 127) / 128);
-            fwd_layer_tc_kernel<<<grid, tc::TC_THREADS, tc_smem_for(a.tile_n), s>>>(a);
+            if (a.tile_n > 64) fwd_layer_tc2_kernel<3><<<grid, tc::TC_THREADS, tc2_smem_for(a.tile_n, 3), s>>>(a);
+            else fwd_layer_tc2_kernel<4><<<grid, tc::TC_THREADS, tc2_smem_for(a.tile_n, 4), s>>>(a);
         } else {
             dim3 grid((L.n_out + 63) / 64, (B + 63) / 64);
             fwd_layer_kernel<<<grid, GT, 0, s>>>(a);
@@ -1072,7 +1455,7 @@ static int launch_loss(const vk_vae *net, int B, int write_grad, cudaStream_t s)
         vk_set_error("vk_vae: batch too large for the loss partial buffer");
         return 1;
     }
-    PROF_MARK(s);
+    PROF_MARK_K(s, PK_LOSS);
     loss_kernel<<<blocks, 256, 0, s>>>(a);
     VK_LAUNCH_CHECK();
     return 0;
@@ -1114,15 +1497,20 @@ static int launch_backward(const vk_vae *net, int B, cudaStream_t s) {
                 a.d_in = P.dact; a.p_prev = P.act; a.mean_prev = P.bn_mean; a.rstd_prev = P.bn_rstd;
                 a.part_prev = P.bwd_part; a.m1_prev = P.bn_m1; a.m2_prev = P.bn_m2;
                 a.g_gamma = net->grads + P.g_off; a.g_beta = net->grads + P.beta_off;
+                a.bA_prev = P.bn_bA; a.bB_prev = P.bn_bB; a.bC_prev = P.bn_bC;
+                a.gamma_prev = net->params + P.g_off;
+                a.inv_keep = net->dropout > 0.0f ? 1.0f / (1.0f - net->dropout) : 1.0f;
             } else {
                 a.d_in = net->layers[mu_j].dact;
                 a.MU = net->layers[mu_j].act;
                 a.kld_w = net->kld_w;
             }
         }
-        PROF_MARK(s);
+        if (use_tc(net, B))
+            if (launch_prep_grad(net, j, B, s)) return 1;
+        PROF_MARK_K(s, PK_BWD);
         if (use_tc(net, B)) {
-            if (tc_prepare()) return 1;
+            if (tc2_prepare()) return 1;
             BwdTcExtra x;
             x.nsplit = tc_nsplit(net, B);
             x.k_per_split = (((B + x.nsplit - 1) / x.nsplit) + 31) & ~31;
@@ -1134,8 +1522,13 @@ static int launch_backward(const vk_vae *net, int B, cudaStream_t s) {
                 a.dg_tiles_m = (B + 127) / 128;
                 a.dg_tiles_n = (L.k_in + a.tile_n - 1) / a.tile_n;
             }
+            a.wg_a = tc::OpRef{L.dyt_hi, L.dyt_lo, net->bmax};
+            a.wg_b = tc::OpRef{L.xt_hi, L.xt_lo, net->bmax};
+            a.dg_a = tc::OpRef{L.dy_hi, L.dy_lo, r32(L.n_out)};
+            a.dg_b = tc::OpRef{L.wt_hi, L.wt_lo, r32(L.n_out)};
             const int blocks = a.wg_tiles_m * a.wg_tiles_n * x.nsplit + a.dg_tiles_m * a.dg_tiles_n;
-            bwd_layer_tc_kernel<<<blocks, tc::TC_THREADS, tc_smem_for(a.tile_n), s>>>(a, x);
+            if (a.tile_n > 64) bwd_layer_tc2_kernel<3><<<blocks, tc::TC_THREADS, tc2_smem_for(a.tile_n, 3), s>>>(a, x);
+            else bwd_layer_tc2_kernel<4><<<blocks, tc::TC_THREADS, tc2_smem_for(a.tile_n, 4), s>>>(a, x);
         } else {
             const int blocks = a.wg_tiles_m * a.wg_tiles_n + a.dg_tiles_m * a.dg_tiles_n;
             bwd_layer_kernel<<<blocks, GT, 0, s>>>(a);
@@ -1154,7 +1547,7 @@ __global__ void reduce_slabs_kernel(float *g, int64_t n, int nslab, int64_t slab
 }
 
 static int launch_dadapt(const vk_vae *net, int nslab, cudaStream_t s) {
-    PROF_MARK(s);
+    PROF_MARK_K(s, PK_OPT);
     dadapt_kernel<<<OPT_BLOCKS, 256, 0, s>>>(net->params, net->grads, net->exp_avg, net->exp_avg_sq, net->s,
                                              net->n_params, net->opt_part, net->ctl, 2 * VK_VAE_MAX_LAYERS + 2,
                                              nslab, net->grad_slab);
@@ -1167,6 +1560,7 @@ static int grad_step_impl(const vk_vae *net, int batch, const vk_vae_inject *inj
     cudaStream_t s = (cudaStream_t)stream;
     const int mode = (inject && inject->batch_idx) ? 0 : 1;
     if (launch_batch_rows(net, batch, mode, 0, inject, s)) return 1;
+    if (use_tc(net, batch) && launch_prep_weights(net, s)) return 1;
     if (launch_forward(net, batch, 1, net->n_layers, inject, 0, nullptr, s)) return 1;
     if (launch_loss(net, batch, 1, s)) return 1;
     if (launch_backward(net, batch, s)) return 1;
@@ -1200,6 +1594,7 @@ extern "C" int vk_vae_forward(const vk_vae *net, int64_t row0, int batch, int tr
     cudaStream_t s = (cudaStream_t)stream;
     const int mode = (inject && inject->batch_idx) ? 0 : 2;
     if (launch_batch_rows(net, batch, mode, row0, inject, s)) return 1;
+    if (use_tc(net, batch) && launch_prep_weights(net, s)) return 1;
     if (launch_forward(net, batch, training, net->n_layers, inject, 0, nullptr, s)) return 1;
     if (with_loss && launch_loss(net, batch, 0, s)) return 1;
     return 0;
@@ -1229,6 +1624,7 @@ extern "C" int vk_vae_encode(const vk_vae *net, int64_t row0, int64_t n, int mas
     for (int j = 0; j < net->n_layers; ++j)
         if (net->layers[j].kind == VK_LAYER_MU) mu_j = j;
     if (vk_vae_prepare_eval(net, stream)) return 1;
+    if (use_tc(net, (int)(n < net->bmax ? n : net->bmax)) && launch_prep_weights(net, s)) return 1;
     for (int64_t off = 0; off < n; off += net->bmax) {
         const int B = (int)((n - off) < net->bmax ? (n - off) : net->bmax);
         if (launch_batch_rows(net, B, 2, row0 + off, nullptr, s)) return 1;
@@ -1237,17 +1633,18 @@ extern "C" int vk_vae_encode(const vk_vae *net, int64_t row0, int64_t n, int mas
     return 0;
 }
 
-// One training step with a CUDA event before every launch: ms_out_host[i] = device time of the
-// i-th launch (order: batch_rows, fwd x n_layers, loss, bwd x n_layers [last layer first], dadapt).
-// Returns the number of launches through *n_launches.  Synchronises the stream.
+// One training step with a CUDA event before every launch: ms_out_host[i] = device time of the i-th
+// launch, kinds_out_host[i] = what it was (0 batch rows, 1 forward layer, 2 loss, 3 backward layer,
+// 4 optimiser, 5 operand staging).  Returns the number of launches through *n_launches.  Synchronises.
 extern "C" int vk_vae_profile_step(const vk_vae *net, int batch, const vk_vae_inject *inject, float *ms_out_host,
-                                   int capacity, int *n_launches, void *stream) {
+                                   int *kinds_out_host, int capacity, int *n_launches, void *stream) {
     if (check_net(net, batch)) return 1;
     cudaStream_t s = (cudaStream_t)stream;
-    const int cap = 2 * VK_VAE_MAX_LAYERS + 8;
-    cudaEvent_t ev[2 * VK_VAE_MAX_LAYERS + 8];
+    const int cap = 96;
+    cudaEvent_t ev[96];
+    int kinds[96];
     for (int i = 0; i < cap; ++i) VK_CUDA(cudaEventCreate(&ev[i]));
-    g_prof_events = ev; g_prof_n = 0; g_prof_cap = cap - 1;
+    g_prof_events = ev; g_prof_kinds = kinds; g_prof_n = 0; g_prof_cap = cap - 1;
     int rc = vk_vae_train_step(net, batch, inject, stream);
     const int n = g_prof_n;
     g_prof_events = nullptr;
@@ -1258,8 +1655,9 @@ extern "C" int vk_vae_profile_step(const vk_vae *net, int batch, const vk_vae_in
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) != cudaSuccess) rc = 1;
             ms_out_host[i] = ms;
+            kinds_out_host[i] = kinds[i];
         }
-        *n_launches = n;
+        *n_launches = n < capacity ? n : capacity;
     }
     for (int i = 0; i < cap; ++i) cudaEventDestroy(ev[i]);
     if (rc && !vk_last_error()[0]) vk_set_error("vk_vae_profile_step failed");

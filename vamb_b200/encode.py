@@ -35,6 +35,7 @@ from torch.utils.data import DataLoader as _DataLoader
 from torch.utils.data.dataset import TensorDataset as _TensorDataset
 
 from . import _lib
+from . import parallel as _par
 from . import vambtools as _vambtools
 
 try:  # the reference logs through loguru; fall back to the std logger when it is absent
@@ -157,6 +158,10 @@ class _VkLayer(_ct.Structure):
         ("act", _ct.c_void_p), ("dact", _ct.c_void_p), ("fwd_part", _ct.c_void_p), ("bwd_part", _ct.c_void_p),
         ("bn_a", _ct.c_void_p), ("bn_c", _ct.c_void_p), ("bn_mean", _ct.c_void_p), ("bn_rstd", _ct.c_void_p),
         ("bn_m1", _ct.c_void_p), ("bn_m2", _ct.c_void_p),
+        ("bn_bA", _ct.c_void_p), ("bn_bB", _ct.c_void_p), ("bn_bC", _ct.c_void_p),
+        ("xop_hi", _ct.c_void_p), ("xop_lo", _ct.c_void_p), ("xt_hi", _ct.c_void_p), ("xt_lo", _ct.c_void_p),
+        ("dy_hi", _ct.c_void_p), ("dy_lo", _ct.c_void_p), ("dyt_hi", _ct.c_void_p), ("dyt_lo", _ct.c_void_p),
+        ("w_hi", _ct.c_void_p), ("w_lo", _ct.c_void_p), ("wt_hi", _ct.c_void_p), ("wt_lo", _ct.c_void_p),
     ]
 
 
@@ -191,7 +196,7 @@ for _name, _args in {
     "vk_vae_prepare_eval": [_ct.POINTER(_VkVae), _ct.c_void_p],
     "vk_vae_dadapt_step": [_ct.POINTER(_VkVae), _ct.c_void_p],
     "vk_vae_profile_step": [_ct.POINTER(_VkVae), _ct.c_int, _ct.POINTER(_VkInject), _ct.POINTER(_ct.c_float),
-                            _ct.c_int, _ct.POINTER(_ct.c_int), _ct.c_void_p],
+                            _ct.POINTER(_ct.c_int), _ct.c_int, _ct.POINTER(_ct.c_int), _ct.c_void_p],
 }.items():
     getattr(_L, _name).argtypes = _args
     getattr(_L, _name).restype = _ct.c_int
@@ -381,8 +386,16 @@ class VAE(_nn.Module):
                 ly.num_batches_tracked = bn.num_batches_tracked.data_ptr()
                 ly.fwd_part = buf(f"fp{j}", n_rt * 2 * n, dtype=_torch.float64)
                 ly.bwd_part = buf(f"bp{j}", n_rt * 2 * n, dtype=_torch.float64)
-                for f in ("bn_a", "bn_c", "bn_mean", "bn_rstd", "bn_m1", "bn_m2"):
+                for f in ("bn_a", "bn_c", "bn_mean", "bn_rstd", "bn_m1", "bn_m2", "bn_bA", "bn_bB", "bn_bC"):
                     setattr(ly, f, buf(f"{f}{j}", n))
+            # tensor-core operand staging (see include/vamb_b200.h): zero-initialised, padded
+            k = lin.in_features
+            r32 = lambda v: (v + 31) // 32 * 32
+            r128 = lambda v: (v + 127) // 128 * 128
+            for name, rows, cols in (("xop", bmax, r32(k)), ("xt", r128(k + 1), bmax), ("dy", bmax, r32(n)),
+                                     ("dyt", r128(n), bmax), ("w", r128(n), r32(k)), ("wt", r128(k), r32(n))):
+                setattr(ly, f"{name}_hi", buf(f"{name}_hi{j}", rows, cols))
+                setattr(ly, f"{name}_lo", buf(f"{name}_lo{j}", rows, cols))
         self._net = net
         self._dataset = None  # (data [N, d_in], weights [N]) resident on the device
         self._ctl_f64 = self._ctl[: (_ct.sizeof(_VkCtl) // 8) * 8].view(_torch.float64)
@@ -529,15 +542,23 @@ class VAE(_nn.Module):
         return sums
 
     def _profile_step(self, batch: int) -> dict:
-        """Per-launch device times (ms) of one training step at ``batch`` (dataset must be bound)."""
-        cap = 2 * _MAXL + 8
+        """Per-launch device times (ms) of one training step at ``batch`` (dataset must be bound).
+        ``fwd`` / ``bwd`` are per layer (backward: last layer first); ``prep`` = operand staging."""
+        cap = 96
         ms = (_ct.c_float * cap)()
+        kinds = (_ct.c_int * cap)()
         n = _ct.c_int(0)
-        _lib.check(_L.vk_vae_profile_step(_ct.byref(self._net), batch, None, ms, cap, _ct.byref(n), self._stream()))
-        nl = self._net.n_layers
-        vals = [float(ms[i]) for i in range(n.value)]
-        return {"batch_rows": vals[0], "fwd": vals[1:1 + nl], "loss": vals[1 + nl],
-                "bwd": vals[2 + nl:2 + 2 * nl], "dadapt": vals[2 + 2 * nl]}
+        _lib.check(_L.vk_vae_profile_step(_ct.byref(self._net), batch, None, ms, kinds, cap, _ct.byref(n), self._stream()))
+        out = {"batch_rows": 0.0, "fwd": [], "loss": 0.0, "bwd": [], "dadapt": 0.0, "prep": 0.0, "n_launches": n.value}
+        for i in range(n.value):
+            k, v = kinds[i], float(ms[i])
+            if k == 1:
+                out["fwd"].append(v)
+            elif k == 3:
+                out["bwd"].append(v)
+            else:
+                out[{0: "batch_rows", 2: "loss", 4: "dadapt", 5: "prep"}[k]] += v
+        return out
 
     def _grad_dict(self) -> dict:
         "Gradients of the last step, keyed like ``named_parameters()``."
@@ -564,7 +585,7 @@ class VAE(_nn.Module):
                 # row-sharded data parallelism: local gradients, ONE all-reduce (average) of the
                 # packed gradient arena over NCCL / NVLink, then the identical optimiser step on every rank
                 _lib.check(_L.vk_vae_grad_step(_ct.byref(self._net), batch, None, self._stream()))
-                _dist.all_reduce(self._grads, op=_dist.ReduceOp.AVG, group=self._dp_group)
+                _par.allreduce_mean_(self._grads, self._dp_group)
                 _lib.check(_L.vk_vae_dadapt_step(_ct.byref(self._net), self._stream()))
 
         def eager(k):
@@ -614,9 +635,7 @@ class VAE(_nn.Module):
         "Average the BatchNorm running statistics over the data-parallel group."
         if self._dp_group is None:
             return
-        for bn in list(self.encodernorms) + list(self.decodernorms):
-            _dist.all_reduce(bn.running_mean, op=_dist.ReduceOp.AVG, group=self._dp_group)
-            _dist.all_reduce(bn.running_var, op=_dist.ReduceOp.AVG, group=self._dp_group)
+        _par.average_running_stats_(list(self.encodernorms) + list(self.decodernorms), self._dp_group)
 
     def trainepoch(self, data_loader: _DataLoader, epoch: int, optimizer, batchsteps: list[int]) -> _DataLoader:
         """One pass over the data (vamb/encode.py:359-440).  ``optimizer`` is accepted for
@@ -638,9 +657,7 @@ class VAE(_nn.Module):
             raise ValueError(f"batch size {batch} exceeds the workspace limit {self._net.bmax}")
         nsteps = len(data_loader)  # N // batch with drop_last, else 1
         if self._dp_group is not None:
-            t = _torch.tensor([nsteps], device=self._arena.device)
-            _dist.all_reduce(t, op=_dist.ReduceOp.MIN, group=self._dp_group)  # every rank takes the same steps
-            nsteps = int(t.item())
+            nsteps = _par.agree_min(nsteps, self._dp_group, self._arena.device)  # every rank takes the same steps
 
         self._ctl_i32[_VkCtl.epoch.offset // 4] = int(epoch)
         so = _VkCtl.step.offset // 8
