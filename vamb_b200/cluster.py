@@ -15,7 +15,7 @@ include/vamb_b200.h:
     find_threshold (head)     :457-481  /        set, exact density, histogram, neighbour list)
     wander_medoid candidates  :427-448    ->   vk_eval_candidates_sync (<= maxsteps medoids / pass)
     _smaller_indices + mask   :640-650,308 ->  vk_select_members_sync
-    pack / overwrite_matrix   :318-335    ->   vk_compact_rows_sync (only when < half is left)
+    pack / overwrite_matrix   :318-335    ->   vk_compact_rows_sync (when < 90 % of the rows are live)
 
 Results follow the reference's CPU semantics (``cuda=False`` path, where emitted rows
 no longer exist) under "vk arithmetic v1" (DESIGN.md section 3) and are bit-identical to
@@ -185,7 +185,7 @@ class ClusterGenerator:
         cuda: bool = False,
         rng_seed: int = 0,
         _driver: Optional[str] = None,
-        _pack_fraction: float = 0.5,
+        _pack_fraction: float = 0.9,
     ):
         self._check_params(matrix, lengths, maxsteps, windowsize, minsuccesses)
         if matrix.ndim != 2:

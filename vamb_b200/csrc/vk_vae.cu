@@ -884,7 +884,7 @@ __global__ void __launch_bounds__(tc::TC_THREADS, 1) fwd_layer_tc2_kernel(FwdArg
     const uint32_t k0 = (uint32_t)a.ctl->seed, k1 = (uint32_t)(a.ctl->seed >> 32);
     const uint32_t step_lo = (uint32_t)a.ctl->step, step_hi = (uint32_t)(a.ctl->step >> 32);
     const int row = (warp & 3) * 32 + lane, m = m0 + row;
-    const bool hidden = a.kind == VK_LAYER_HIDDEN;
+    const bool hidden = a.kind == VK_LAYER_HIDDEN, is_mu = a.kind == VK_LAYER_MU;
     const bool drop = hidden && a.training && a.dropout > 0.0f;
     const float keep_scale = 1.0f / (1.0f - a.dropout);
     for (int c = (warp >> 2) * 64; c < (warp >> 2) * 64 + 64 && c < bn; c += 32) {
@@ -896,6 +896,19 @@ __global__ void __launch_bounds__(tc::TC_THREADS, 1) fwd_layer_tc2_kernel(FwdArg
             const int nb = n0 + c + 4 * j4;
             if (drop && a.keep == nullptr && m < a.B)
                 philox4x32((uint32_t)m, (uint32_t)(nb >> 2), step_lo, step_hi ^ ((uint32_t)(a.layer_id + 1) << 24), k0, k1, rnd);
+            float nrm[4] = {0.f, 0.f, 0.f, 0.f};
+            if (is_mu && a.add_eps && a.eps == nullptr && m < a.B) {  // reparameterisation noise (encode.py:277)
+                philox4x32((uint32_t)m, (uint32_t)(nb >> 2), step_lo, step_hi ^ 0x7F000000u, k0, k1, rnd);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float u1 = u32_to_unit(rnd[2 * h]), u2 = u32_to_unit(rnd[2 * h + 1]);
+                    const float rr = sqrtf(-2.0f * logf(u1));
+                    float sn, cn;
+                    sincosf(6.28318530717958647692f * u2, &sn, &cn);
+                    nrm[2 * h] = rr * cn;
+                    nrm[2 * h + 1] = rr * sn;
+                }
+            }
             float o4[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -911,6 +924,12 @@ __global__ void __launch_bounds__(tc::TC_THREADS, 1) fwd_layer_tc2_kernel(FwdArg
                         }
                     } else {
                         p = y;
+                        if (is_mu) {
+                            const int64_t o = (int64_t)m * a.N + n;
+                            if (a.add_eps) a.z[o] = y + (a.eps ? __ldg(a.eps + o) : nrm[j]);
+                            if (a.latent_out)
+                                a.latent_out[o] = __uint_as_float(__float_as_uint(y) & ~((1u << a.mask_bits) - 1u));
+                        }
                     }
                 }
                 o4[j] = p;
@@ -1095,7 +1114,7 @@ __device__ __forceinline__ void prep_tile(const PrepArgs &a, int r0, int c0, flo
         float v = prep_value(a, r, c);
         if (a.hi && r < a.rows_w && c < a.cols_w) {
             a.hi[(int64_t)r * a.ld + c] = v;
-            a.lo[(int64_t)r * a.ld + c] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+            if (a.lo) a.lo[(int64_t)r * a.ld + c] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
         }
         if (a.ones_row && c == a.cols) v = r < a.rows ? 1.0f : 0.0f;
         tile[ty * 4 + i][tx] = v;
@@ -1108,7 +1127,7 @@ __device__ __forceinline__ void prep_tile(const PrepArgs &a, int r0, int c0, flo
             if (c < a.cols + (a.ones_row ? 1 : 0) && r < a.rows_w) {
                 const float v = tile[tx][ty * 4 + i];
                 a.hiT[(int64_t)c * a.ldT + r] = v;
-                a.loT[(int64_t)c * a.ldT + r] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+                if (a.loT) a.loT[(int64_t)c * a.ldT + r] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
             }
         }
     }
@@ -1137,7 +1156,7 @@ __global__ void __launch_bounds__(256) prep_weights_kernel(PrepMulti m) {
 // One pass over the flat arenas (dadaptation.DAdaptAdam.step with lr=1, betas=(0.9, 0.999),
 // eps=1e-8, weight_decay=0, growth_rate=inf, no bias correction).  The parameter update of
 // step t uses d_t; the two global sums only feed d_{t+1}, so everything fits in one kernel.
-constexpr int OPT_BLOCKS = 296;
+constexpr int OPT_ELEMS = 1024;  // elements per block
 
 __global__ void __launch_bounds__(256)
 dadapt_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
@@ -1150,10 +1169,15 @@ dadapt_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restr
     const float a_m = (float)(dlr * (1.0 - beta1)), a_v = (float)(1.0 - beta2), a_s = (float)(dlr * (1.0 - sqrt_beta2));
     const float f_eps = (float)eps;
     double acc_num = 0.0, acc_l1 = 0.0;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    // 4 independent elements per thread (their loads are issued together), 1024 elements per block
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int64_t i = (int64_t)blockIdx.x * 1024 + u * 256 + threadIdx.x;
+        if (i >= n) continue;
         float gi = g[i];
         for (int sl = 1; sl < nslab; ++sl) gi += g[(int64_t)sl * slab + i];  // split-K partial gradients, fixed order
         float mi = m[i], vi = v[i], si = s[i];
+        const float pi = p[i];
         const float denom_old = sqrtf(vi) + f_eps;
         acc_num += (double)(gi * (si / denom_old));
         mi = __fmaf_rn(a_m, gi, mi * f_beta1);
@@ -1161,7 +1185,7 @@ dadapt_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restr
         si = __fmaf_rn(a_s, gi, si * f_sb2);
         acc_l1 += (double)fabsf(si);
         m[i] = mi; v[i] = vi; s[i] = si;
-        p[i] = p[i] - mi / (sqrtf(vi) + f_eps);
+        p[i] = pi - mi / (sqrtf(vi) + f_eps);
     }
     {
         const double ta = block_sum256(acc_num, s_a), tb = block_sum256(acc_l1, s_b);
@@ -1314,8 +1338,8 @@ static int launch_prep_input(const vk_vae *net, int j, int B, int training, cuda
     PrepArgs a;
     memset(&a, 0, sizeof(a));
     a.rows = B; a.cols = L.k_in; a.rows_w = r128(B); a.cols_w = L.k_in;
-    a.hi = L.xop_hi; a.lo = L.xop_lo; a.ld = r32(L.k_in);
-    if (training) { a.hiT = L.xt_hi; a.loT = L.xt_lo; a.ldT = net->bmax; a.ones_row = 1; }
+    a.hi = L.xop_hi; a.lo = nullptr; a.ld = r32(L.k_in);  // the GEMM derives the tf32 remainders in shared memory
+    if (training) { a.hiT = L.xt_hi; a.loT = nullptr; a.ldT = net->bmax; a.ones_row = 1; }
     if (L.in_kind == VK_IN_DATA) {
         a.mode = 3; a.data = net->data; a.rows_idx = net->batch_rows; a.data_ld = net->data_ld;
     } else if (L.in_kind == VK_IN_BN) {
@@ -1333,8 +1357,8 @@ static int launch_prep_grad(const vk_vae *net, int j, int B, cudaStream_t s) {
     PrepArgs a;
     memset(&a, 0, sizeof(a));
     a.rows = B; a.cols = L.n_out; a.rows_w = r128(B); a.cols_w = L.n_out;
-    a.hi = L.dy_hi; a.lo = L.dy_lo; a.ld = r32(L.n_out);
-    a.hiT = L.dyt_hi; a.loT = L.dyt_lo; a.ldT = net->bmax;
+    a.hi = L.dy_hi; a.lo = nullptr; a.ld = r32(L.n_out);
+    a.hiT = L.dyt_hi; a.loT = nullptr; a.ldT = net->bmax;
     a.src = L.dact; a.ld_src = L.n_out;
     if (L.kind == VK_LAYER_HIDDEN) {
         a.mode = 2; a.p = L.act; a.c0 = L.bn_bA; a.c1 = L.bn_bB; a.c2 = L.bn_bC;
@@ -1353,8 +1377,8 @@ static int launch_prep_weights(const vk_vae *net, cudaStream_t s) {
         PrepArgs &a = m.l[j];
         a.mode = 0; a.src = net->params + L.w_off; a.ld_src = L.k_in;
         a.rows = L.n_out; a.cols = L.k_in; a.rows_w = r32(L.n_out); a.cols_w = L.k_in;
-        a.hi = L.w_hi; a.lo = L.w_lo; a.ld = r32(L.k_in);
-        a.hiT = L.wt_hi; a.loT = L.wt_lo; a.ldT = r32(L.n_out);
+        a.hi = L.w_hi; a.lo = nullptr; a.ld = r32(L.k_in);
+        a.hiT = L.wt_hi; a.loT = nullptr; a.ldT = r32(L.n_out);
         gx = gx > (L.k_in + 32) / 32 ? gx : (L.k_in + 32) / 32;
         gy = gy > a.rows_w / 32 ? gy : a.rows_w / 32;
     }
@@ -1418,10 +1442,10 @@ static int launch_forward(const vk_vae *net, int B, int training, int upto /*exc
         a.latent_out = (L.kind == VK_LAYER_MU) ? latent_out : nullptr;
         a.ctl = net->ctl; a.layer_id = j; a.slope = net->slope;
         const bool tcp = use_tc(net, B);
-        if (tcp && (training || L.kind != VK_LAYER_MU))
+        if (tcp)
             if (launch_prep_input(net, j, B, training, s)) return 1;
         PROF_MARK_K(s, PK_FWD);
-        if (tcp && L.kind != VK_LAYER_MU) {
+        if (tcp) {
             if (tc2_prepare()) return 1;
             a.tile_n = tc_tile_n(B);
             a.a_op = tc::OpRef{L.xop_hi, L.xop_lo, r32(L.k_in)};
@@ -1548,7 +1572,12 @@ __global__ void reduce_slabs_kernel(float *g, int64_t n, int nslab, int64_t slab
 
 static int launch_dadapt(const vk_vae *net, int nslab, cudaStream_t s) {
     PROF_MARK_K(s, PK_OPT);
-    dadapt_kernel<<<OPT_BLOCKS, 256, 0, s>>>(net->params, net->grads, net->exp_avg, net->exp_avg_sq, net->s,
+    const int opt_blocks = (int)((net->n_params + OPT_ELEMS - 1) / OPT_ELEMS);
+    if (opt_blocks > 1024) {
+        vk_set_error("vk_vae: parameter arena too large for the optimiser partial buffer");
+        return 1;
+    }
+    dadapt_kernel<<<opt_blocks, 256, 0, s>>>(net->params, net->grads, net->exp_avg, net->exp_avg_sq, net->s,
                                              net->n_params, net->opt_part, net->ctl, 2 * VK_VAE_MAX_LAYERS + 2,
                                              nslab, net->grad_slab);
     VK_LAUNCH_CHECK();
@@ -1571,7 +1600,7 @@ extern "C" int vk_vae_grad_step(const vk_vae *net, int batch, const vk_vae_injec
     if (grad_step_impl(net, batch, inject, stream)) return 1;
     if (use_tc(net, batch) && tc_nsplit(net, batch) > 1) {
         // leave the complete gradient in slab 0 (all-reduce / inspection read only that slab)
-        reduce_slabs_kernel<<<OPT_BLOCKS, 256, 0, (cudaStream_t)stream>>>(net->grads, net->n_params,
+        reduce_slabs_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(net->grads, net->n_params,
                                                                           tc_nsplit(net, batch), net->grad_slab);
         VK_LAUNCH_CHECK();
     }

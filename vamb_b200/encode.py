@@ -47,7 +47,7 @@ except ImportError:  # pragma: no cover
 
 _MAX_BATCH = 8192  # rows of the activation workspaces (training batches double up to 4096)
 _GRAPH_CHUNK = 128  # optimiser steps per captured CUDA graph
-_TC_MIN_BATCH = 512  # batches >= this run their GEMMs on the tcgen05 tensor-core path (0 = never)
+_TC_MIN_BATCH = 128  # batches >= this run their GEMMs on the tcgen05 tensor-core path (0 = never)
 
 
 def set_batchsize(data_loader: _DataLoader, batch_size: int, n_obs: int, encode=False) -> _DataLoader:
@@ -395,7 +395,7 @@ class VAE(_nn.Module):
             for name, rows, cols in (("xop", bmax, r32(k)), ("xt", r128(k + 1), bmax), ("dy", bmax, r32(n)),
                                      ("dyt", r128(n), bmax), ("w", r128(n), r32(k)), ("wt", r128(k), r32(n))):
                 setattr(ly, f"{name}_hi", buf(f"{name}_hi{j}", rows, cols))
-                setattr(ly, f"{name}_lo", buf(f"{name}_lo{j}", rows, cols))
+                setattr(ly, f"{name}_lo", None)  # the GEMM derives the tf32 remainders in shared memory
         self._net = net
         self._dataset = None  # (data [N, d_in], weights [N]) resident on the device
         self._ctl_f64 = self._ctl[: (_ct.sizeof(_VkCtl) // 8) * 8].view(_torch.float64)
