@@ -1,0 +1,22 @@
+"""Fixed cost vs per-k-tile cost of the tcgen05 tile kernel (v1 main loop, plain epilogue)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from vamb_b200 import _lib
+_lib.require_device()
+s = torch.cuda.current_stream().cuda_stream
+def timeit(fn, iters=50):
+    for _ in range(5): fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters): fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters * 1e3
+x = torch.zeros(1, device="cuda")
+print(f"empty torch kernel (x.add_): {timeit(lambda: x.add_(1)):.1f} us per launch")
+for M, N in ((256, 512), (4096, 512)):
+    for K in (32, 64, 128, 256, 512, 1024):
+        A = torch.randn(M, K, device="cuda"); B = torch.randn(N, K, device="cuda"); C = torch.empty(M, N, device="cuda")
+        t = timeit(lambda: _lib.check(_lib.lib.vk_tc_gemm_test(A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, 0, 0, s)))
+        print(f"tc_gemm_test M={M} N={N} K={K}: {t:.1f} us per launch (back-to-back)")
