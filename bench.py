@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=1_000_000, help="contigs per GPU")
+    ap.add_argument("--contigs", dest="n", type=int, default=1_000_000, help="contigs per GPU")
     ap.add_argument("--nsamples", type=int, default=50)
     ap.add_argument("--nepochs", type=int, default=300)
     ap.add_argument("--seed", type=int, default=0)
@@ -238,6 +238,12 @@ def probe_roofline(latent_dev, lengths):
     return {"kernel": "probe_kernel<32>", "ms": ms, "gbs": nbytes / (ms * 1e-3) / 1e9, "bytes": nbytes}
 
 
+def reference_threads() -> int:
+    """The reference caps its BLAS/OpenMP threads at min(ncpu, 8) (vamb/__main__.py:27-40, 2221-2228); more threads
+    oversubscribe these small kernels (the 128-thread run on the GPU box was far slower per step)."""
+    return min(os.cpu_count() or 8, 8)
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -297,7 +303,7 @@ def cpu_baseline(abundance, tnf, lengths, nsamples, nepochs, seed, budget_s, lat
     dt = time.perf_counter() - t0
     t_cluster = dt * n / max(1, clustered)
     total = t_train + t_encode + t_cluster
-    sample = (f"oracle port, {threads} threads: train = median of >=3 steps per batch size "
+    sample = (f"oracle port, {threads} threads (the reference's own cap min(ncpu, 8)): train = median of >=3 steps per batch size "
               f"{sorted(per_step)} extrapolated over {sum(s * e for _, s, e in sched)} steps; encode = {m} rows "
               f"scaled to {n}; cluster = first {k} clusters ({clustered} contigs, {dt:.1f} s) scaled to {n}")
     return {"value": n / total, "unit": "contigs/s", "cores": threads, "kind": "port", "sample": sample,
@@ -313,7 +319,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        torch.set_num_threads(os.cpu_count() or 8)
+        torch.set_num_threads(reference_threads())
         ab, tnf, lens = make_workload(args.n, args.nsamples, args.seed)
         vals = []
         for _ in range(max(1, args.steps)):
@@ -412,7 +418,7 @@ def main():
                         "peak_source": f"{which} copy bandwidth (MEASURED_PEAKS.json)"}
         base = None
         if world == 1:
-            torch.set_num_threads(os.cpu_count() or 8)
+            torch.set_num_threads(reference_threads())
             lat_host = last["latent_dev"].cpu().numpy() if last["latent_dev"] is not None else None
             base = cpu_baseline(ab, tnf, lens, args.nsamples, args.nepochs, args.seed, args.cpu_seconds, lat_host)
         out = {

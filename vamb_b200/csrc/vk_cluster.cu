@@ -13,6 +13,7 @@
 //   select_members_kernel   vamb/cluster.py:640-650, 308-309   _smaller_indices + kept_mask update
 //   compact_*_kernel        vamb/cluster.py:318-335   pack (vambcore.overwrite_matrix)
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "vk_common.cuh"
@@ -28,6 +29,14 @@ void vk_set_error(const char *fmt, ...) {
 }
 
 extern "C" const char *vk_last_error(void) { return g_err; }
+
+bool vk_pdl_enabled() {
+    static const bool on = [] {
+        const char *v = getenv("VK_PDL");
+        return v ? atoi(v) != 0 : true;
+    }();
+    return on;
+}
 extern "C" int vk_abi_version(void) { return VK_ABI_VERSION; }
 
 int vk_num_sms() {
@@ -134,7 +143,7 @@ struct ProbeAcc {
 constexpr int PB_WBUF = 64;  // staged entries per warp (<= 16 appended per iteration)
 
 template <int DFIX>
-__global__ void __launch_bounds__(PB_THREADS, 4)
+__global__ void __launch_bounds__(PB_THREADS, 5)
 probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths,
              const uint8_t *__restrict__ kept, int64_t n, int d_rt, int64_t mrow, float nl_radius,
              const float *__restrict__ edges_g, vk_probe_header *hdr, int32_t *within_overflow,
@@ -286,7 +295,7 @@ __global__ void __launch_bounds__(256) rank_kernel(const uint8_t *__restrict__ k
 }
 
 static int probe_grid(int n_tiles) {
-    const int cap = vk_num_sms() * 4;
+    const int cap = vk_num_sms() * 5;
     return n_tiles < cap ? n_tiles : cap;
 }
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/vamb_b200.h"
 
@@ -94,4 +95,33 @@ __device__ __forceinline__ u64 closeness_fx(float radius, float d) {
 __device__ __forceinline__ void density_add(u64 &lo, u64 &hi, u64 len, u64 cq) {
     lo += len * (cq & 4095ull);
     hi += len * (cq >> 12);
+}
+
+// ---- programmatic dependent launch (PDL): the next kernel of the stream may be scheduled while this one
+// is still running; it blocks in pdl_wait() until this grid has completed and its memory is visible.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// every kernel of the VAE step starts with this pair (before any global-memory access)
+__device__ __forceinline__ void pdl_entry() {
+    pdl_launch_dependents();
+    pdl_wait();
+}
+
+bool vk_pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t vk_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                    Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = vk_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }

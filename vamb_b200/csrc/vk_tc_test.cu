@@ -75,3 +75,56 @@ extern "C" int vk_tc_gemm_test(const float *A, const float *B, float *C, int M, 
     VK_LAUNCH_CHECK();
     return 0;
 }
+
+// ---- launch / prologue overhead probes (tools/tc_fixed_cost.py) ----
+namespace {
+// mode 0: nothing; 1: + barrier init + TMEM alloc/dealloc; 2: + one MMA + commit + wait; 3: + __threadfence + atomic
+__global__ void __launch_bounds__(tc::TC_THREADS, 1) tc_overhead_kernel(int mode, int *counter) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ tc::Tc2Shared sh;
+    if (mode == 0) return;
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) {
+        tc::mbar_init(&sh.bar_done, 1);
+        tc::mbar_fence_init();
+    }
+    if (warp == 0) tc::tmem_alloc(&sh.tmem_base, 128);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    if (mode >= 2) {
+        for (int i = tid; i < 16384; i += tc::TC_THREADS) reinterpret_cast<float *>(smem)[i] = 1.0f;
+        tc::fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            const uint64_t d = tc::make_smem_desc(tc::smem_u32(smem), 128, 1024);
+            tc::umma_tf32(sh.tmem_base, d, d + (32768 >> 4), tc::make_idesc_tf32(128, 32, 0, 0), 0u);
+            tc::umma_commit(&sh.bar_done);
+        }
+        tc::mbar_wait(&sh.bar_done, 0);
+        tc::tc_fence_after();
+    }
+    if (mode >= 3) {
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(counter, 1);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(sh.tmem_base, 128);
+}
+}  // namespace
+
+extern "C" int vk_tc_overhead_test(int mode, int grid, int smem_bytes, int *counter, void *stream) {
+    static bool attr = false;
+    if (!attr) {
+        VK_CUDA(cudaFuncSetAttribute(tc_overhead_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = true;
+    }
+    tc_overhead_kernel<<<grid, tc::TC_THREADS, smem_bytes, (cudaStream_t)stream>>>(mode, counter);
+    VK_LAUNCH_CHECK();
+    return 0;
+}

@@ -99,6 +99,7 @@ __device__ __forceinline__ bool last_block_done(int32_t *ticket, int total) {
 __global__ void __launch_bounds__(256)
 batch_rows_kernel(int64_t *batch_rows, const int64_t *batch_idx, const float *weights, vk_vae_ctl *ctl, int B,
                   int64_t n_rows, int mode, int64_t row0, int steps_per_epoch, double *part, int ticket_id) {
+    pdl_entry();
     __shared__ double s_w[16];
     const int tid = threadIdx.x;
     const int b = blockIdx.x * 256 + tid;
@@ -378,6 +379,7 @@ __device__ __forceinline__ void bn_forward_finalize(const FwdArgs &a, int n_rt) 
 }
 
 __global__ void __launch_bounds__(GT) fwd_layer_kernel(FwdArgs a) {
+    pdl_entry();
     __shared__ __align__(16) float s_gemm[SMEM_GEMM_FLOATS];
     __shared__ double s_red[2 * 16 * 64];
     float acc[4][4];
@@ -462,6 +464,7 @@ struct LossArgs {
 };
 
 __global__ void __launch_bounds__(256) loss_kernel(LossArgs a) {
+    pdl_entry();
     __shared__ double s_part[8][4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * 8 + warp;
@@ -592,6 +595,7 @@ __device__ __forceinline__ void bn_backward_finalize(const BwdArgs &a) {
 }
 
 __global__ void __launch_bounds__(GT) bwd_layer_kernel(BwdArgs a) {
+    pdl_entry();
     __shared__ __align__(16) float s_gemm[SMEM_GEMM_FLOATS];
     __shared__ double s_red[2 * 16 * 64];
     float acc[4][4];
@@ -870,6 +874,7 @@ __global__ void __launch_bounds__(tc::TC_THREADS, 1) bwd_layer_tc_kernel(BwdArgs
 // ---- v2: the same epilogues fed by the cp.async main loop over staged operands
 template <int STAGES>
 __global__ void __launch_bounds__(tc::TC_THREADS, 1) fwd_layer_tc2_kernel(FwdArgs a) {
+    pdl_entry();
     extern __shared__ uint8_t smem_raw[];
     __shared__ tc::Tc2Shared sh;
     __shared__ double s_cs[2][2][128];
@@ -969,6 +974,7 @@ __global__ void __launch_bounds__(tc::TC_THREADS, 1) fwd_layer_tc2_kernel(FwdArg
 
 template <int STAGES>
 __global__ void __launch_bounds__(tc::TC_THREADS, 1) bwd_layer_tc2_kernel(BwdArgs a, BwdTcExtra x) {
+    pdl_entry();
     extern __shared__ uint8_t smem_raw[];
     __shared__ tc::Tc2Shared sh;
     __shared__ double s_cs[2][2][128];
@@ -1134,6 +1140,7 @@ __device__ __forceinline__ void prep_tile(const PrepArgs &a, int r0, int c0, flo
 }
 
 __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a) {
+    pdl_entry();
     __shared__ float tile[32][33];
     prep_tile(a, blockIdx.y * 32, blockIdx.x * 32, tile);
 }
@@ -1145,6 +1152,7 @@ struct PrepMulti {
 
 // every layer's weights in one launch (blockIdx.z = layer)
 __global__ void __launch_bounds__(256) prep_weights_kernel(PrepMulti m) {
+    pdl_entry();
     __shared__ float tile[32][33];
     const PrepArgs &a = m.l[blockIdx.z];
     const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
@@ -1161,6 +1169,7 @@ constexpr int OPT_ELEMS = 1024;  // elements per block
 __global__ void __launch_bounds__(256)
 dadapt_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
               float *__restrict__ s, int64_t n, double *part, vk_vae_ctl *ctl, int ticket_id, int nslab, int64_t slab) {
+    pdl_entry();
     __shared__ double s_a[256], s_b[256];
     const double beta1 = 0.9, beta2 = 0.999, eps = 1e-8;
     const double sqrt_beta2 = sqrt(beta2);
@@ -1327,7 +1336,7 @@ static int launch_prep(const PrepArgs &a, cudaStream_t s) {
     const int cx = a.cols + (a.ones_row ? 1 : 0);
     dim3 grid((cx + 31) / 32, (a.rows_w + 31) / 32);
     PROF_MARK_K(s, PK_PREP);
-    prep_kernel<<<grid, 256, 0, s>>>(a);
+    VK_CUDA(vk_launch(prep_kernel, dim3(grid), dim3(256), (size_t)(0), s, a));
     VK_LAUNCH_CHECK();
     return 0;
 }
@@ -1383,7 +1392,7 @@ static int launch_prep_weights(const vk_vae *net, cudaStream_t s) {
         gy = gy > a.rows_w / 32 ? gy : a.rows_w / 32;
     }
     PROF_MARK_K(s, PK_PREP);
-    prep_weights_kernel<<<dim3(gx, gy, net->n_layers), 256, 0, s>>>(m);
+    VK_CUDA(vk_launch(prep_weights_kernel, dim3(dim3(gx, gy, net->n_layers)), dim3(256), (size_t)(0), s, m));
     VK_LAUNCH_CHECK();
     return 0;
 }
@@ -1408,9 +1417,9 @@ static int launch_batch_rows(const vk_vae *net, int B, int mode, int64_t row0, c
     const int64_t n = net->n_rows;
     const int spe = n > B ? (int)(n / B) : 1;
     PROF_MARK_K(s, PK_ROWS);
-    batch_rows_kernel<<<(B + 255) / 256, 256, 0, s>>>(net->batch_rows, inj ? inj->batch_idx : nullptr, net->weights,
+    VK_CUDA(vk_launch(batch_rows_kernel, dim3((B + 255) / 256), dim3(256), (size_t)(0), s, net->batch_rows, inj ? inj->batch_idx : nullptr, net->weights,
                                                        net->ctl, B, n, mode, row0, spe, net->opt_part + 1024,
-                                                       2 * VK_VAE_MAX_LAYERS + 3);
+                                                       2 * VK_VAE_MAX_LAYERS + 3));
     VK_LAUNCH_CHECK();
     return 0;
 }
@@ -1451,11 +1460,11 @@ static int launch_forward(const vk_vae *net, int B, int training, int upto /*exc
             a.a_op = tc::OpRef{L.xop_hi, L.xop_lo, r32(L.k_in)};
             a.b_op = tc::OpRef{L.w_hi, L.w_lo, r32(L.k_in)};
             dim3 grid((L.n_out + a.tile_n - 1) / a.tile_n, (B + 127) / 128);
-            if (a.tile_n > 64) fwd_layer_tc2_kernel<3><<<grid, tc::TC_THREADS, tc2_smem_for(a.tile_n, 3), s>>>(a);
-            else fwd_layer_tc2_kernel<4><<<grid, tc::TC_THREADS, tc2_smem_for(a.tile_n, 4), s>>>(a);
+            if (a.tile_n > 64) VK_CUDA(vk_launch(fwd_layer_tc2_kernel<3>, dim3(grid), dim3(tc::TC_THREADS), (size_t)(tc2_smem_for(a.tile_n, 3)), s, a));
+            else VK_CUDA(vk_launch(fwd_layer_tc2_kernel<4>, dim3(grid), dim3(tc::TC_THREADS), (size_t)(tc2_smem_for(a.tile_n, 4)), s, a));
         } else {
             dim3 grid((L.n_out + 63) / 64, (B + 63) / 64);
-            fwd_layer_kernel<<<grid, GT, 0, s>>>(a);
+            VK_CUDA(vk_launch(fwd_layer_kernel, dim3(grid), dim3(GT), (size_t)(0), s, a));
         }
         VK_LAUNCH_CHECK();
     }
@@ -1480,7 +1489,7 @@ static int launch_loss(const vk_vae *net, int B, int write_grad, cudaStream_t s)
         return 1;
     }
     PROF_MARK_K(s, PK_LOSS);
-    loss_kernel<<<blocks, 256, 0, s>>>(a);
+    VK_CUDA(vk_launch(loss_kernel, dim3(blocks), dim3(256), (size_t)(0), s, a));
     VK_LAUNCH_CHECK();
     return 0;
 }
@@ -1551,11 +1560,11 @@ static int launch_backward(const vk_vae *net, int B, cudaStream_t s) {
             a.dg_a = tc::OpRef{L.dy_hi, L.dy_lo, r32(L.n_out)};
             a.dg_b = tc::OpRef{L.wt_hi, L.wt_lo, r32(L.n_out)};
             const int blocks = a.wg_tiles_m * a.wg_tiles_n * x.nsplit + a.dg_tiles_m * a.dg_tiles_n;
-            if (a.tile_n > 64) bwd_layer_tc2_kernel<3><<<blocks, tc::TC_THREADS, tc2_smem_for(a.tile_n, 3), s>>>(a, x);
-            else bwd_layer_tc2_kernel<4><<<blocks, tc::TC_THREADS, tc2_smem_for(a.tile_n, 4), s>>>(a, x);
+            if (a.tile_n > 64) VK_CUDA(vk_launch(bwd_layer_tc2_kernel<3>, dim3(blocks), dim3(tc::TC_THREADS), (size_t)(tc2_smem_for(a.tile_n, 3)), s, a, x));
+            else VK_CUDA(vk_launch(bwd_layer_tc2_kernel<4>, dim3(blocks), dim3(tc::TC_THREADS), (size_t)(tc2_smem_for(a.tile_n, 4)), s, a, x));
         } else {
             const int blocks = a.wg_tiles_m * a.wg_tiles_n + a.dg_tiles_m * a.dg_tiles_n;
-            bwd_layer_kernel<<<blocks, GT, 0, s>>>(a);
+            VK_CUDA(vk_launch(bwd_layer_kernel, dim3(blocks), dim3(GT), (size_t)(0), s, a));
         }
         VK_LAUNCH_CHECK();
     }
@@ -1563,6 +1572,7 @@ static int launch_backward(const vk_vae *net, int B, cudaStream_t s) {
 }
 
 __global__ void reduce_slabs_kernel(float *g, int64_t n, int nslab, int64_t slab) {
+    pdl_entry();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float t = g[i];
         for (int sl = 1; sl < nslab; ++sl) t += g[(int64_t)sl * slab + i];
@@ -1577,9 +1587,9 @@ static int launch_dadapt(const vk_vae *net, int nslab, cudaStream_t s) {
         vk_set_error("vk_vae: parameter arena too large for the optimiser partial buffer");
         return 1;
     }
-    dadapt_kernel<<<opt_blocks, 256, 0, s>>>(net->params, net->grads, net->exp_avg, net->exp_avg_sq, net->s,
+    VK_CUDA(vk_launch(dadapt_kernel, dim3(opt_blocks), dim3(256), (size_t)(0), s, net->params, net->grads, net->exp_avg, net->exp_avg_sq, net->s,
                                              net->n_params, net->opt_part, net->ctl, 2 * VK_VAE_MAX_LAYERS + 2,
-                                             nslab, net->grad_slab);
+                                             nslab, net->grad_slab));
     VK_LAUNCH_CHECK();
     return 0;
 }
@@ -1600,8 +1610,8 @@ extern "C" int vk_vae_grad_step(const vk_vae *net, int batch, const vk_vae_injec
     if (grad_step_impl(net, batch, inject, stream)) return 1;
     if (use_tc(net, batch) && tc_nsplit(net, batch) > 1) {
         // leave the complete gradient in slab 0 (all-reduce / inspection read only that slab)
-        reduce_slabs_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(net->grads, net->n_params,
-                                                                          tc_nsplit(net, batch), net->grad_slab);
+        VK_CUDA(vk_launch(reduce_slabs_kernel, dim3(296), dim3(256), (size_t)(0), (cudaStream_t)stream, net->grads, net->n_params,
+                                                                          tc_nsplit(net, batch), net->grad_slab));
         VK_LAUNCH_CHECK();
     }
     return 0;
