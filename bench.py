@@ -436,12 +436,17 @@ def main():
             "roofline": roof, "roofline_cluster": roof_cluster, "cpu_baseline": base, "e2e": e2e,
             "gpu_launches": int(last["launches"]), "clocks": clocks,
         }
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
         import torch.distributed as dist
 
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        # The replayed CUDA graphs hold captured NCCL kernels; tearing the communicator down underneath them
+        # can block at interpreter exit, and all work is done: leave without the teardown.
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -20,13 +20,25 @@ for M, N in ((256, 512), (4096, 512)):
         A = torch.randn(M, K, device="cuda"); B = torch.randn(N, K, device="cuda"); C = torch.empty(M, N, device="cuda")
         t = timeit(lambda: _lib.check(_lib.lib.vk_tc_gemm_test(A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, 0, 0, s)))
         print(f"tc_gemm_test M={M} N={N} K={K}: {t:.1f} us per launch (back-to-back)")
-cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+lib = _lib.lib
+import ctypes
+lib.vk_tc_mma_rate_test.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+out = torch.zeros(2, dtype=torch.int64, device="cuda")
+for sw in (0, 1):
+    for n in (32, 64, 128):
+        for n_mma in (1, 12, 48, 192, 768):
+            _lib.check(lib.vk_tc_mma_rate_test(n_mma, n, sw, out.data_ptr(), s)); torch.cuda.synchronize()
+            _lib.check(lib.vk_tc_mma_rate_test(n_mma, n, sw, out.data_ptr(), s)); torch.cuda.synchronize()
+            o = out.tolist()
+            print(f"mma rate swizzle={sw} N={n} n_mma={n_mma}: issue {o[0]} cyc ({o[0]/n_mma:.1f}/mma), complete {o[1]} cyc ({o[1]/n_mma:.1f}/mma)")
+if os.environ.get("MMA_ONLY"): sys.exit(0)
+cnt = torch.zeros(4, dtype=torch.int32, device="cuda")
 lib = _lib.lib
 import ctypes
 lib.vk_tc_overhead_test.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
 lib.vk_tc_overhead_test.restype = ctypes.c_int
-for smem in (1024, 70 * 1024, 197 * 1024):
-    for mode in (0, 1, 2, 3):
+for smem in (70 * 1024, 197 * 1024):
+    for mode in (0, 1, 2, 3, 4, 5):
         for grid in (32, 128):
             t = timeit(lambda: _lib.check(lib.vk_tc_overhead_test(mode, grid, smem, cnt.data_ptr(), s)))
             print(f"overhead kernel smem={smem//1024}KB mode={mode} grid={grid}: {t:.1f} us per launch")

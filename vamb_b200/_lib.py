@@ -10,7 +10,8 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint8, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "_vk.so")
+# VAMB_B200_SO selects another build of the same library (tools/kernel_timeline.py uses the stamped one)
+_SO = os.environ.get("VAMB_B200_SO") or os.path.join(_HERE, "_vk.so")
 
 VK_ABI_VERSION = 1
 VK_NBINS = 60

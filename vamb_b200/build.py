@@ -13,6 +13,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "_vk.so")
+OUT_TIMELINE = os.path.join(HERE, "_vk_timeline.so")  # diagnostic build with in-kernel time stamps
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -36,18 +37,22 @@ def needs_build() -> bool:
     return any(os.path.getmtime(p) > t for p in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, timeline: bool = False) -> str:
+    if timeline:
+        force = True
     if not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + sources() + ["-lcuda"]
+    out = OUT_TIMELINE if timeline else OUT
+    cmd = ([nvcc] + NVCC_FLAGS + (["-DVK_TIMELINE"] if timeline else []) + (["-Xptxas", "-v"] if verbose else [])
+           + ["-o", out] + sources() + ["-lcuda"])
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building vamb_b200/_vk.so")
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force=True, verbose="-v" in sys.argv))
+    print(build(force=True, verbose="-v" in sys.argv, timeline="--timeline" in sys.argv))

@@ -143,7 +143,7 @@ struct ProbeAcc {
 constexpr int PB_WBUF = 64;  // staged entries per warp (<= 16 appended per iteration)
 
 template <int DFIX>
-__global__ void __launch_bounds__(PB_THREADS, 5)
+__global__ void __launch_bounds__(PB_THREADS, 4)
 probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths,
              const uint8_t *__restrict__ kept, int64_t n, int d_rt, int64_t mrow, float nl_radius,
              const float *__restrict__ edges_g, vk_probe_header *hdr, int32_t *within_overflow,
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(256) rank_kernel(const uint8_t *__restrict__ k
 }
 
 static int probe_grid(int n_tiles) {
-    const int cap = vk_num_sms() * 5;
+    const int cap = vk_num_sms() * 4;
     return n_tiles < cap ? n_tiles : cap;
 }
 

@@ -102,6 +102,27 @@ __device__ __forceinline__ void density_add(u64 &lo, u64 &hi, u64 len, u64 cq) {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 // every kernel of the VAE step starts with this pair (before any global-memory access)
+// ---- optional in-kernel timeline (build with -DVK_TIMELINE; tools/kernel_timeline.py) ----
+#ifdef VK_TIMELINE
+static __device__ unsigned long long vk_tl[4096];  // per translation unit; vk_vae.cu reads its own
+static __device__ int vk_tl_base;
+__device__ __forceinline__ void tl_mark(int slot) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        vk_tl[(vk_tl_base + slot) & 4095] = t;
+        vk_tl[((vk_tl_base + slot) & 4095) ^ 2048] = (unsigned long long)clock64();
+    }
+}
+__device__ __forceinline__ void tl_begin(int kernel_id) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) vk_tl_base = kernel_id * 64;
+    tl_mark(0);
+}
+#else
+#define tl_mark(slot) ((void)0)
+#define tl_begin(id) ((void)0)
+#endif
+
 __device__ __forceinline__ void pdl_entry() {
     pdl_launch_dependents();
     pdl_wait();

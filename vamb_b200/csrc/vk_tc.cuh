@@ -301,11 +301,9 @@ __device__ __forceinline__ void tc_tile_end(TcShared *sh) {
 }  // namespace tc
 
 // =====================================================================================================
-// v2 main loop: operands are PLAIN K-major arrays in global memory -- `hi` (fp32 value) and `lo` (tf32
-// remainder), zero padded to 128 rows / 32 columns, 16-byte aligned rows -- produced once per layer by the
-// prep kernels (vk_vae.cu).  No transform, no bounds checks: a multi-stage cp.async pipeline copies the
-// 16-byte chunks straight into the no-swizzle core-matrix tiles and the elected thread issues the three
-// 3xTF32 MMAs per k8-step.  Global loads of tile kt+D are in flight while the tensor core works on tile kt.
+// Layer GEMM main loop: operands are PLAIN K-major fp32 arrays in global memory, zero padded to 128 rows /
+// 32 columns with 16-byte aligned rows -- produced once per layer by the prep kernels (vk_vae.cu).  No
+// transform and no bounds checks on the way in; the tf32 remainders are derived in shared memory.
 namespace tc {
 
 struct OpRef {
@@ -322,116 +320,177 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-__host__ __device__ constexpr int tc2_smem_bytes(int bn, int stages) { return stages * stage_bytes(bn) + 1024; }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 16 consecutive columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
 
-struct Tc2Shared {
-    uint64_t bar_stage[4];
-    uint64_t bar_done;
+// Warp-specialised pipeline.  A CTA is 8 producer/epilogue warps + 1 MMA warp (WS_THREADS = 288).
+// Shared-memory ring of S stages, each  A_hi 16 KB | B_hi bn*128 B | A_lo | B_lo :
+//   producers : cp.async the fp32 ("hi") chunks of tile kt+P straight into the no-swizzle core-matrix
+//               layout, wait for their OWN copies of tile kt, derive the tf32 remainders ("lo") of exactly
+//               those chunks, proxy-fence and arrive on full[stage] (one arrival per warp);
+//   MMA warp  : one lane waits full[stage], issues the 12 tcgen05.mma of the k-tile (3xTF32, small terms
+//               first) back to back and commits them to empty[stage] -- so the tensor pipe stays busy
+//               (a tf32 MMA with M = 128 issues every ~48 cycles for N <= 64, 64 cycles for N = 128;
+//               tools/tc_fixed_cost.py) while the producers run ahead.
+// A stage is refilled once the MMAs that read it two k-tiles ago have completed (P = S - 2 tiles in flight).
+constexpr int WS_THREADS = 288;
+constexpr int WS_EPI_THREADS = 256;
+__host__ __device__ constexpr int ws_hi_bytes(int bn) { return A_TILE_BYTES + b_tile_bytes(bn); }
+__host__ __device__ constexpr int ws_smem_bytes(int bn, int stages) { return stages * 2 * ws_hi_bytes(bn) + 1024; }
+
+struct WsShared {
+    uint64_t full[4], empty[4], done;
     uint32_t tmem_base;
 };
 
-// D[128 x bn] = sum over k-tiles [kt0, kt0 + nk) of A[m0.., k] * B[n0.., k]^T.  STAGES in {3, 4}.
-template <int STAGES>
-__device__ __forceinline__ void tc2_mainloop(const OpRef A, int m0, const OpRef B, int n0, int bn, int kt0, int nk,
-                                             uint8_t *smem, Tc2Shared *sh) {
-    constexpr int D = STAGES - 2;  // prefetch distance (tiles in flight beyond the one being multiplied)
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int sbytes = stage_bytes(bn), bbytes = b_tile_bytes(bn);
+// D[128 x bn] = sum over k-tiles [kt0, kt0 + nk) of A[m0.., k] * B[n0.., k]^T with A, B plain K-major fp32
+// arrays, zero padded to 128 rows / 32 columns (ld = floats per row, multiple of 4).
+// Returns true for the 256 epilogue threads (accumulator complete), false for the MMA warp (which is done).
+template <int S>
+__device__ __forceinline__ bool ws_mainloop(const float *A, int lda, int m0, const float *B, int ldb, int n0, int bn,
+                                            int kt0, int nk, uint8_t *smem, WsShared *sh) {
+    static_assert(S >= 3 && S <= 4, "ring depth");
+    constexpr int P = S - 2;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int hbytes = ws_hi_bytes(bn), sbytes = 2 * hbytes;
     const uint32_t smem_base = smem_u32(smem);
-    // per-thread copy items: row r = ((q >> 6) << 3) | (q & 7), 16-byte chunk k4 = (q >> 3) & 7
-    const int nb_items = (bn * (KT / 4)) / TC_THREADS;  // 1, 2 or 4 (bn = 32, 64, 128); 0 when bn < 32
-    const int nb4 = bn * (KT / 4);
-    // Only the fp32 values travel (cp.async of `hi`); each thread derives the tf32 remainder of exactly the
-    // chunks it copied itself once its own copies have landed, so no extra barrier and half the L2 traffic.
-    auto issue_tile = [&](int kt, int stage) {
-        const int k0 = (kt0 + kt) * KT;
-        const uint32_t st = smem_base + stage * sbytes;
+    // chunk q = tid + 256 i of a tile: row ((q >> 6) << 3) | (q & 7) = r0 + 32 i, 16-byte column k4, at byte q * 16
+    const int r0 = ((tid >> 6) << 3) | (tid & 7), k4 = (tid >> 3) & 7;
+    const float *pa = A + (size_t)(m0 + r0) * lda + (size_t)kt0 * KT + k4 * 4;
+    const float *pb = B + (size_t)(n0 + r0) * ldb + (size_t)kt0 * KT + k4 * 4;
+    const size_t a_step = (size_t)32 * lda, b_step = (size_t)32 * ldb;
+    const int nbi = bn >> 5;                                // whole 32-row groups of the B tile
+    const bool b_tail = tid < (bn & 31) * 8;                // + 16 rows when bn is an odd multiple of 16
+    const uint32_t soff = (uint32_t)tid * 16u;
+    auto issue_tile = [&](int kt, int slot) {
+        const uint32_t st = smem_base + slot * sbytes + soff;
+        const float *ga = pa + (size_t)kt * KT, *gb = pb + (size_t)kt * KT;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int q = tid + i * TC_THREADS;
-            const int r = ((q >> 6) << 3) | (q & 7), k4 = (q >> 3) & 7;
-            cp_async16(st + off_kmajor(r, k4), A.hi + (size_t)(m0 + r) * A.ld + k0 + k4 * 4);
-        }
-        for (int q = tid; q < nb4; q += TC_THREADS) {
-            const int r = ((q >> 6) << 3) | (q & 7), k4 = (q >> 3) & 7;
-            cp_async16(st + 2 * A_TILE_BYTES + off_kmajor(r, k4), B.hi + (size_t)(n0 + r) * B.ld + k0 + k4 * 4);
-        }
-        (void)nb_items;
+        for (int i = 0; i < 4; ++i) cp_async16(st + i * 4096, ga + i * a_step);
+        for (int i = 0; i < nbi; ++i) cp_async16(st + A_TILE_BYTES + i * 4096, gb + i * b_step);
+        if (b_tail) cp_async16(st + A_TILE_BYTES + nbi * 4096, gb + nbi * b_step);
     };
-    auto split_tile = [&](int stage) {
-        uint8_t *st = smem + stage * sbytes;
+    auto split_tile = [&](int slot) {
+        uint8_t *st = smem + slot * sbytes + soff;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int q = tid + i * TC_THREADS;
-            const uint32_t off = off_kmajor(((q >> 6) << 3) | (q & 7), (q >> 3) & 7);
-            *reinterpret_cast<float4 *>(st + A_TILE_BYTES + off) = tf32_lo(*reinterpret_cast<const float4 *>(st + off));
-        }
-        for (int q = tid; q < nb4; q += TC_THREADS) {
-            const uint32_t off = off_kmajor(((q >> 6) << 3) | (q & 7), (q >> 3) & 7);
-            *reinterpret_cast<float4 *>(st + 2 * A_TILE_BYTES + bbytes + off) =
-                tf32_lo(*reinterpret_cast<const float4 *>(st + 2 * A_TILE_BYTES + off));
-        }
+        for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<float4 *>(st + hbytes + i * 4096) = tf32_lo(*reinterpret_cast<const float4 *>(st + i * 4096));
+        for (int i = 0; i < nbi; ++i)
+            *reinterpret_cast<float4 *>(st + hbytes + A_TILE_BYTES + i * 4096) =
+                tf32_lo(*reinterpret_cast<const float4 *>(st + A_TILE_BYTES + i * 4096));
+        if (b_tail)
+            *reinterpret_cast<float4 *>(st + hbytes + A_TILE_BYTES + nbi * 4096) =
+                tf32_lo(*reinterpret_cast<const float4 *>(st + A_TILE_BYTES + nbi * 4096));
     };
-    // prologue: the first D tiles are in flight while barriers / tensor memory are set up
+    // the first P tiles are in flight while barriers / tensor memory are set up
+    if (warp < 8) {
 #pragma unroll
-    for (int t = 0; t < D; ++t) {
-        if (t < nk) issue_tile(t, t % STAGES);
-        cp_async_commit();
+        for (int t = 0; t < P; ++t) {
+            if (t < nk) issue_tile(t, t);
+            cp_async_commit();
+        }
     }
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) mbar_init(&sh->bar_stage[s], 1);
-        mbar_init(&sh->bar_done, 1);
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&sh->full[s], 8);
+            mbar_init(&sh->empty[s], 1);
+        }
+        mbar_init(&sh->done, 1);
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc(&sh->tmem_base, 128);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_d = sh->tmem_base;
-    const uint32_t idesc = make_idesc_tf32(TC_BM, bn, 0, 0);
-    const uint64_t desc0 = make_smem_desc(smem_base, 128, 1024);
-
+    tl_mark(8);
+    if (warp == 8) {
+        if (lane == 0) {
+            const uint32_t tmem_d = sh->tmem_base;
+            const uint32_t idesc = make_idesc_tf32(TC_BM, bn, 0, 0);
+            const uint64_t desc0 = make_smem_desc(smem_base, 128, 1024);
+            int slot = 0;
+            uint32_t phase = 0;
+            for (int kt = 0; kt < nk; ++kt) {
+                mbar_wait(&sh->full[slot], phase);
+                tc_fence_after();
+                // descriptors differ only in the 14-bit start-address field: add (byte offset >> 4)
+                const uint64_t dh = desc0 + (uint64_t)((uint32_t)(slot * sbytes) >> 4);
+                const uint64_t dl = dh + (uint64_t)((uint32_t)hbytes >> 4);
+#pragma unroll
+                for (int j = 0; j < KT / 8; ++j) {
+                    const uint64_t dah = dh + 16u * j, dbh = dah + (A_TILE_BYTES >> 4);
+                    const uint64_t dal = dl + 16u * j, dbl = dal + (A_TILE_BYTES >> 4);
+                    umma_tf32(tmem_d, dal, dbh, idesc, (kt | j) ? 1u : 0u);  // small terms first
+                    umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+                    umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+                }
+                umma_commit(&sh->empty[slot]);
+                if (kt == nk - 1) umma_commit(&sh->done);
+                if (++slot == S) {
+                    slot = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+        return false;
+    }
     for (int kt = 0; kt < nk; ++kt) {
-        // refill: tile kt+D goes to the stage that held tile kt+D-STAGES = kt-2 (its MMAs are long done)
-        if (kt + D < nk) {
-            const int s2 = (kt + D) % STAGES;
-            if (kt >= 2) mbar_wait(&sh->bar_stage[s2], (uint32_t)(((kt - 2) / STAGES) & 1));
-            issue_tile(kt + D, s2);
+        const int nt = kt + P;
+        if (nt < nk) {
+            // the MMAs of tile nt - S read this stage; they were issued two k-tiles ago
+            if (nt >= S) mbar_wait(&sh->empty[nt % S], (uint32_t)(((nt / S) - 1) & 1));
+            issue_tile(nt, nt % S);
         }
         cp_async_commit();
-        cp_async_wait<D>();   // this thread's copies of tile kt have landed
-        split_tile(kt % STAGES);
-        fence_async_smem();   // ... and are visible to the tensor core (async proxy)
-        __syncthreads();      // ... for every thread
-        if (tid == 0) {
-            tc_fence_after();
-            const int s = kt % STAGES;
-            // descriptors differ only in the 14-bit start-address field: add (byte offset >> 4)
-            const uint64_t d0 = desc0 + (uint64_t)((uint32_t)(s * sbytes) >> 4);
-#pragma unroll
-            for (int j = 0; j < KT / 8; ++j) {
-                const uint64_t dah = d0 + 16u * j, dal = dah + (A_TILE_BYTES >> 4);
-                const uint64_t dbh = dah + (2 * A_TILE_BYTES >> 4), dbl = dbh + (uint32_t)(bbytes >> 4);
-                umma_tf32(tmem_d, dal, dbh, idesc, (kt | j) ? 1u : 0u);  // small terms first
-                umma_tf32(tmem_d, dah, dbl, idesc, 1u);
-                umma_tf32(tmem_d, dah, dbh, idesc, 1u);
-            }
-            umma_commit(&sh->bar_stage[s]);
-            if (kt == nk - 1) umma_commit(&sh->bar_done);
-        }
+        cp_async_wait<P>();      // this thread's copies of tile kt have landed
+        split_tile(kt % S);
+        fence_async_smem();      // visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh->full[kt % S]);
+        if (kt < 20) tl_mark(10 + kt);
     }
-    if (nk > 0) mbar_wait(&sh->bar_done, 0);
+    tl_mark(9);
+    if (nk > 0) mbar_wait(&sh->done, 0);
     tc_fence_after();
+    return true;
 }
 
-__device__ __forceinline__ void tc2_read_acc(const Tc2Shared *sh, int col, float (&v)[32]) {
-    const int warp = threadIdx.x >> 5;
-    const uint32_t taddr = sh->tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col;
-    tmem_ld32(taddr, v);
+// Accumulator -> shared tile [128][ts] (raw values): warp w owns TMEM lanes 32*(w%4)..+31, the two warp
+// groups take alternate 16-column chunks.  nk == 0 (an empty split) yields zeros.
+__device__ __forceinline__ void ws_acc_to_tile(const WsShared *sh, int bn, int nk, float *tile, int ts) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = (warp & 3) * 32 + lane;
+    for (int c = (warp >> 2) * 16; c < bn; c += 32) {
+        float v[16];
+        if (nk > 0) tmem_ld16(sh->tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c, v);
+        else
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0.0f;
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4)
+            *reinterpret_cast<float4 *>(tile + row * ts + c + 4 * j4) =
+                make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+    }
 }
 
-__device__ __forceinline__ void tc2_tile_end(Tc2Shared *sh) {
+// all epilogue threads: tile complete for everyone, tensor memory released
+__device__ __forceinline__ void ws_tile_end(WsShared *sh) {
     tc_fence_before();
     __syncthreads();
     if ((threadIdx.x >> 5) == 0) tmem_dealloc(sh->tmem_base, 128);

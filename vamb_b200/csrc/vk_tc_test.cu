@@ -81,7 +81,7 @@ namespace {
 // mode 0: nothing; 1: + barrier init + TMEM alloc/dealloc; 2: + one MMA + commit + wait; 3: + __threadfence + atomic
 __global__ void __launch_bounds__(tc::TC_THREADS, 1) tc_overhead_kernel(int mode, int *counter) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ tc::Tc2Shared sh;
+    __shared__ tc::TcShared sh;
     if (mode == 0) return;
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -105,11 +105,30 @@ __global__ void __launch_bounds__(tc::TC_THREADS, 1) tc_overhead_kernel(int mode
         tc::mbar_wait(&sh.bar_done, 0);
         tc::tc_fence_after();
     }
-    if (mode >= 3) {
+    if (mode == 3) {
         __syncthreads();
         if (tid == 0) {
             __threadfence();
             atomicAdd(counter, 1);
+        }
+    }
+    if (mode == 4) {  // + accumulator read-back and a global store
+        float v[32];
+        tc::tc_read_acc(&sh, 0, v);
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) t += v[j];
+        if (t == 123.456f) counter[1] = 1;
+    }
+    if (mode == 5) {  // sixteen dependent MMA+commit+wait round trips instead of one
+        for (int it = 1; it < 16; ++it) {
+            if (tid == 0) {
+                const uint64_t d = tc::make_smem_desc(tc::smem_u32(smem), 128, 1024);
+                tc::umma_tf32(sh.tmem_base, d, d + (32768 >> 4), tc::make_idesc_tf32(128, 32, 0, 0), 1u);
+                tc::umma_commit(&sh.bar_done);
+            }
+            tc::mbar_wait(&sh.bar_done, (uint32_t)(it & 1));
+            tc::tc_fence_after();
         }
     }
     tc::tc_fence_before();
@@ -125,6 +144,50 @@ extern "C" int vk_tc_overhead_test(int mode, int grid, int smem_bytes, int *coun
         attr = true;
     }
     tc_overhead_kernel<<<grid, tc::TC_THREADS, smem_bytes, (cudaStream_t)stream>>>(mode, counter);
+    VK_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- issue / execution rate of back-to-back tcgen05.mma (tools/tc_fixed_cost.py) ----
+namespace {
+__global__ void __launch_bounds__(tc::TC_THREADS, 1) tc_mma_rate_kernel(int n_mma, int n, int swizzle, long long *out) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ tc::TcShared sh;
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) {
+        tc::mbar_init(&sh.bar_done, 1);
+        tc::mbar_fence_init();
+    }
+    if (warp == 0) tc::tmem_alloc(&sh.tmem_base, 128);
+    for (int i = tid; i < 16384; i += tc::TC_THREADS) reinterpret_cast<float *>(smem)[i] = 1.0f;
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    if (tid == 0) {
+        uint64_t d = tc::make_smem_desc(tc::smem_u32(smem), swizzle ? 16 : 128, 1024);
+        if (swizzle) d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+        const uint64_t da = d, db = d + (32768 >> 4);
+        const uint32_t idesc = tc::make_idesc_tf32(128, n, 0, 0);
+        const long long t0 = clock64();
+        for (int i = 0; i < n_mma; ++i) tc::umma_tf32(sh.tmem_base, da + (uint64_t)((i & 3) * (swizzle ? 2 : 16)), db, idesc, 1u);
+        tc::umma_commit(&sh.bar_done);
+        const long long t1 = clock64();
+        tc::mbar_wait(&sh.bar_done, 0);
+        const long long t2 = clock64();
+        out[0] = t1 - t0;
+        out[1] = t2 - t0;
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(sh.tmem_base, 128);
+}
+}  // namespace
+
+extern "C" int vk_tc_mma_rate_test(int n_mma, int n, int swizzle, long long *out_dev, void *stream) {
+    VK_CUDA(cudaFuncSetAttribute(tc_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    tc_mma_rate_kernel<<<1, tc::TC_THREADS, 100 * 1024, (cudaStream_t)stream>>>(n_mma, n, swizzle, out_dev);
     VK_LAUNCH_CHECK();
     return 0;
 }

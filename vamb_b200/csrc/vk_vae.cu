@@ -353,8 +353,8 @@ struct FwdArgs {
 // Fold the per-row-tile column sums of P and P^2 into the BatchNorm affine, the saved batch statistics
 // and the running statistics (torch.nn.BatchNorm1d, momentum 0.1, unbiased running variance).  Run by
 // every thread of the last block to finish.
-__device__ __forceinline__ void bn_forward_finalize(const FwdArgs &a, int n_rt) {
-    for (int n = threadIdx.x; n < a.N; n += blockDim.x) {
+__device__ __forceinline__ void bn_forward_finalize(const FwdArgs &a, int n_rt, int nthreads) {
+    for (int n = threadIdx.x; n < a.N; n += nthreads) {
         double s = 0.0, q = 0.0;
 #pragma unroll 8
         for (int rt = 0; rt < n_rt; ++rt) {
@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(GT) fwd_layer_kernel(FwdArgs a) {
     double *p1 = a.part + ((int64_t)blockIdx.y * 2 + 1) * a.N;
     tile_colsum2<4>(cs, cq, s_red, p0, p1, n0, a.N);
     if (!last_block_done(&a.ctl->tickets[a.layer_id], gridDim.x * gridDim.y)) return;
-    bn_forward_finalize(a, n_rt);
+    bn_forward_finalize(a, n_rt, blockDim.x);
 }
 
 // ------------------------------------------------------------------ loss (+ dL/dR)
@@ -569,8 +569,8 @@ struct BwdArgs {
 
 // Fold the per-row-tile column sums of dH and dH*Phat: BatchNorm weight/bias gradients and the two
 // batch means the consumer needs (last block to finish).
-__device__ __forceinline__ void bn_backward_finalize(const BwdArgs &a) {
-    for (int n = threadIdx.x; n < a.K; n += blockDim.x) {
+__device__ __forceinline__ void bn_backward_finalize(const BwdArgs &a, int nthreads) {
+    for (int n = threadIdx.x; n < a.K; n += nthreads) {
         double u = 0.0, v = 0.0;
 #pragma unroll 8
         for (int rt = 0; rt < a.dg_tiles_m; ++rt) {
@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(GT) bwd_layer_kernel(BwdArgs a) {
     double *p1 = a.part_prev + ((int64_t)row_tile * 2 + 1) * a.K;
     tile_colsum2<4>(s1, s2, s_red, p0, p1, n0, a.K);
     if (!last_block_done(&a.ctl->tickets[a.ticket_id], a.dg_tiles_m * a.dg_tiles_n)) return;
-    bn_backward_finalize(a);
+    bn_backward_finalize(a, blockDim.x);
 }
 
 // ------------------------------------------------------------------ tcgen05 (3xTF32) layer kernels
@@ -688,278 +688,103 @@ __device__ __forceinline__ void tc_colsum2(int bn, int n0, int N, double (*s_cs)
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(tc::TC_THREADS, 1) fwd_layer_tc_kernel(FwdArgs a) {
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ tc::TcShared sh;
-    __shared__ double s_cs[2][2][128];
-    uint8_t *smem = align1024(smem_raw);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = blockIdx.y * 128, n0 = blockIdx.x * a.tile_n;
-    int bn = a.N - n0;
-    bn = bn > a.tile_n ? a.tile_n : ((bn + 15) & ~15);
-    LdPlain w{a.W, a.K, a.N, a.K};
-    tc::tc_tile_mainloop<false, false>(a.K, m0, n0, bn, a.in, w, smem, &sh);
-
-    float *tile = reinterpret_cast<float *>(smem);  // [128][TS]; the operand stages are dead now
-    const uint32_t k0 = (uint32_t)a.ctl->seed, k1 = (uint32_t)(a.ctl->seed >> 32);
-    const uint32_t step_lo = (uint32_t)a.ctl->step, step_hi = (uint32_t)(a.ctl->step >> 32);
-    const int row = (warp & 3) * 32 + lane, m = m0 + row;
-    const bool hidden = a.kind == VK_LAYER_HIDDEN;
-    const bool drop = hidden && a.training && a.dropout > 0.0f;
-    const float keep_scale = 1.0f / (1.0f - a.dropout);
-    for (int c = (warp >> 2) * 64; c < (warp >> 2) * 64 + 64 && c < bn; c += 32) {
-        float v[32];
-        tc::tc_read_acc(&sh, c, v);
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-            uint32_t rnd[4] = {0u, 0u, 0u, 0u};
-            const int nb = n0 + c + 4 * j4;
-            if (drop && a.keep == nullptr && m < a.B)
-                philox4x32((uint32_t)m, (uint32_t)(nb >> 2), step_lo, step_hi ^ ((uint32_t)(a.layer_id + 1) << 24), k0, k1, rnd);
-            float o4[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int n = nb + j;
-                float p = 0.0f;
-                if (m < a.B && n < a.N) {
-                    const float y = v[4 * j4 + j] + __ldg(a.bias + n);
-                    if (hidden) {
-                        p = y > 0.0f ? y : y * a.slope;
-                        if (drop) {
-                            const bool kp = a.keep ? (a.keep[(int64_t)m * a.N + n] != 0) : (u32_to_unit(rnd[j]) > a.dropout);
-                            p = kp ? p * keep_scale : 0.0f;
-                        }
-                    } else {
-                        p = y;
-                    }
-                }
-                o4[j] = p;
-            }
-            *reinterpret_cast<float4 *>(tile + row * TS + c + 4 * j4) = make_float4(o4[0], o4[1], o4[2], o4[3]);
-        }
-    }
-    tc::tc_tile_end(&sh);  // fence + __syncthreads + TMEM dealloc: the tile is complete for everyone
-    // coalesced store of the tile
-    const bool vec = ((a.N & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
-    const int q_per_row = bn >> 2;
-    for (int q = tid; q < 128 * q_per_row; q += tc::TC_THREADS) {
-        const int r = q / q_per_row, c = (q % q_per_row) << 2;
-        if (m0 + r >= a.B) continue;
-        const float4 t = *reinterpret_cast<const float4 *>(tile + r * TS + c);
-        float *dst = a.out + (int64_t)(m0 + r) * a.N + n0 + c;
-        if (vec && n0 + c + 3 < a.N) *reinterpret_cast<float4 *>(dst) = t;
-        else {
-            if (n0 + c < a.N) dst[0] = t.x;
-            if (n0 + c + 1 < a.N) dst[1] = t.y;
-            if (n0 + c + 2 < a.N) dst[2] = t.z;
-            if (n0 + c + 3 < a.N) dst[3] = t.w;
-        }
-    }
-    if (!hidden || !a.training) return;
-    double *p0 = a.part + ((int64_t)blockIdx.y * 2 + 0) * a.N;
-    double *p1 = a.part + ((int64_t)blockIdx.y * 2 + 1) * a.N;
-    tc_colsum2(bn, n0, a.N, s_cs, p0, p1, [&](int r, int c, float &v0, float &v1) {
-        const float p = tile[r * TS + c];  // rows >= B and columns >= N hold zeros
-        v0 = p;
-        v1 = p * p;
-    });
-    if (!last_block_done(&a.ctl->tickets[a.layer_id], gridDim.x * gridDim.y)) return;
-    bn_forward_finalize(a, gridDim.y);
-}
-
 // grid: [wgrad tiles (tiles_m x tiles_n x nsplit)] + [dgrad tiles (dg_tiles_m x dg_tiles_n)], 128-row tiles
 struct BwdTcExtra {
     int nsplit, k_per_split;   // split-K over the batch for wgrad
     int64_t slab;              // floats between gradient slabs
 };
 
-__global__ void __launch_bounds__(tc::TC_THREADS, 1) bwd_layer_tc_kernel(BwdArgs a, BwdTcExtra x) {
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ tc::TcShared sh;
-    __shared__ double s_cs[2][2][128];
-    uint8_t *smem = align1024(smem_raw);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n_wg = a.wg_tiles_m * a.wg_tiles_n * x.nsplit;
-    if ((int)blockIdx.x < n_wg) {
-        // ---- wgrad slice: gW[n, k] (+ bias column) over batch rows [b0, b0 + nb) ----
-        const int split = blockIdx.x / (a.wg_tiles_m * a.wg_tiles_n);
-        const int t = blockIdx.x % (a.wg_tiles_m * a.wg_tiles_n);
-        const int m0 = (t / a.wg_tiles_n) * 128, n0 = (t % a.wg_tiles_n) * a.tile_n;
-        int bn = a.K + 1 - n0;
-        bn = bn > a.tile_n ? a.tile_n : ((bn + 15) & ~15);
-        const int b0 = split * x.k_per_split;
-        int nb = a.B - b0;
-        nb = nb < 0 ? 0 : (nb > x.k_per_split ? x.k_per_split : nb);
-        LdRowSlice<LdGradOut> la{a.gy, b0, nb};
-        LdRowSlice<LdInput> lb{a.in, b0, nb};
-        tc::tc_tile_mainloop<true, true>(nb > 0 ? nb : 1, m0, n0, bn, la, lb, smem, &sh);
-        const int m = m0 + (warp & 3) * 32 + lane;
-        float *gW = a.gW + (int64_t)split * x.slab, *gb = a.gb + (int64_t)split * x.slab;
-        for (int c = (warp >> 2) * 64; c < (warp >> 2) * 64 + 64 && c < bn; c += 32) {
-            float v[32];
-            tc::tc_read_acc(&sh, c, v);
-            if (m < a.N) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int n = n0 + c + j;
-                    if (n < a.K) gW[(int64_t)m * a.K + n] = v[j];
-                    else if (n == a.K) gb[m] = v[j];
-                }
-            }
-        }
-        tc::tc_tile_end(&sh);
-        return;
-    }
-    // ---- dgrad: dX[b, k] = sum_n dY[b, n] * W[n, k] ----
-    const int t = blockIdx.x - n_wg;
-    const int m0 = (t / a.dg_tiles_n) * 128, n0 = (t % a.dg_tiles_n) * a.tile_n;
-    int bn = a.K - n0;
-    bn = bn > a.tile_n ? a.tile_n : ((bn + 15) & ~15);
-    LdPlain w{a.W, a.K, a.N, a.K};
-    tc::tc_tile_mainloop<false, true>(a.N, m0, n0, bn, a.gy, w, smem, &sh);
-    float *tile = reinterpret_cast<float *>(smem);
-    const int row = (warp & 3) * 32 + lane, m = m0 + row;
-    const float gsc = (float)(a.ctl->wbar / (double)a.B);
-    for (int c = (warp >> 2) * 64; c < (warp >> 2) * 64 + 64 && c < bn; c += 32) {
-        float v[32];
-        tc::tc_read_acc(&sh, c, v);
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-            float o4[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int n = n0 + c + 4 * j4 + j;
-                float val = 0.0f;
-                if (m < a.B && n < a.K) {
-                    val = v[4 * j4 + j];
-                    if (a.in_kind == VK_IN_Z) val = __fmaf_rn(gsc * a.kld_w, __ldg(a.MU + (int64_t)m * a.K + n), val);
-                }
-                o4[j] = val;
-            }
-            *reinterpret_cast<float4 *>(tile + row * TS + c + 4 * j4) = make_float4(o4[0], o4[1], o4[2], o4[3]);
-        }
-    }
-    tc::tc_tile_end(&sh);
-    const bool vec = ((a.K & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.d_in) & 15) == 0);
-    const int q_per_row = bn >> 2;
-    for (int q = tid; q < 128 * q_per_row; q += tc::TC_THREADS) {
-        const int r = q / q_per_row, c = (q % q_per_row) << 2;
-        if (m0 + r >= a.B) continue;
-        const float4 tv = *reinterpret_cast<const float4 *>(tile + r * TS + c);
-        float *dst = a.d_in + (int64_t)(m0 + r) * a.K + n0 + c;
-        if (vec && n0 + c + 3 < a.K) *reinterpret_cast<float4 *>(dst) = tv;
-        else {
-            if (n0 + c < a.K) dst[0] = tv.x;
-            if (n0 + c + 1 < a.K) dst[1] = tv.y;
-            if (n0 + c + 2 < a.K) dst[2] = tv.z;
-            if (n0 + c + 3 < a.K) dst[3] = tv.w;
-        }
-    }
-    if (a.in_kind != VK_IN_BN) return;
-    const int row_tile = t / a.dg_tiles_n;
-    double *p0 = a.part_prev + ((int64_t)row_tile * 2 + 0) * a.K;
-    double *p1 = a.part_prev + ((int64_t)row_tile * 2 + 1) * a.K;
-    tc_colsum2(bn, n0, a.K, s_cs, p0, p1, [&](int r, int c, float &v0, float &v1) {
-        const float dv = tile[r * TS + c];
-        float ph = 0.0f;
-        if (m0 + r < a.B && n0 + c < a.K)
-            ph = (__ldg(a.p_prev + (int64_t)(m0 + r) * a.K + n0 + c) - __ldg(a.mean_prev + n0 + c)) * __ldg(a.rstd_prev + n0 + c);
-        v0 = dv;
-        v1 = dv * ph;
-    });
-    if (!last_block_done(&a.ctl->tickets[a.ticket_id], a.dg_tiles_m * a.dg_tiles_n)) return;
-    bn_backward_finalize(a);
-}
-
-// ---- v2: the same epilogues fed by the cp.async main loop over staged operands
-template <int STAGES>
-__global__ void __launch_bounds__(tc::TC_THREADS, 1) fwd_layer_tc2_kernel(FwdArgs a) {
+// Forward layer: D = X' W^T on the tensor core, then one coalesced pass over the shared tile does bias,
+// LeakyReLU, dropout (one Philox call per four outputs) / the reparameterisation, and the global stores;
+// hidden layers in training add the BatchNorm column sums and the last CTA folds them.
+template <int S>
+__global__ void __launch_bounds__(tc::WS_THREADS, 1) fwd_layer_tc_kernel(FwdArgs a) {
+    tl_begin(a.layer_id);
     pdl_entry();
+    tl_mark(1);
     extern __shared__ uint8_t smem_raw[];
-    __shared__ tc::Tc2Shared sh;
+    __shared__ tc::WsShared sh;
     __shared__ double s_cs[2][2][128];
+    __shared__ __align__(16) float s_bias[128];
     uint8_t *smem = align1024(smem_raw);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x;
     const int m0 = blockIdx.y * 128, n0 = blockIdx.x * a.tile_n;
     int bn = a.N - n0;
     bn = bn > a.tile_n ? a.tile_n : ((bn + 15) & ~15);
-    tc::tc2_mainloop<STAGES>(a.a_op, m0, a.b_op, n0, bn, 0, (a.K + tc::KT - 1) / tc::KT, smem, &sh);
-
-    float *tile = reinterpret_cast<float *>(smem);  // [128][TS]; the operand stages are dead now
+    if (tid < bn) s_bias[tid] = n0 + tid < a.N ? __ldg(a.bias + n0 + tid) : 0.0f;
     const uint32_t k0 = (uint32_t)a.ctl->seed, k1 = (uint32_t)(a.ctl->seed >> 32);
     const uint32_t step_lo = (uint32_t)a.ctl->step, step_hi = (uint32_t)(a.ctl->step >> 32);
-    const int row = (warp & 3) * 32 + lane, m = m0 + row;
+    const int nk = (a.K + tc::KT - 1) / tc::KT;
+    if (!tc::ws_mainloop<S>(a.a_op.hi, a.a_op.ld, m0, a.b_op.hi, a.b_op.ld, n0, bn, 0, nk, smem, &sh)) return;
+    tl_mark(2);
+    float *tile = reinterpret_cast<float *>(smem);  // [128][TS]; the operand stages are dead now
+    tc::ws_acc_to_tile(&sh, bn, nk, tile, TS);
+    tl_mark(3);
+    tc::ws_tile_end(&sh);
+
     const bool hidden = a.kind == VK_LAYER_HIDDEN, is_mu = a.kind == VK_LAYER_MU;
     const bool drop = hidden && a.training && a.dropout > 0.0f;
+    const bool philox_drop = drop && a.keep == nullptr;
+    const bool philox_eps = is_mu && a.add_eps && a.eps == nullptr;
     const float keep_scale = 1.0f / (1.0f - a.dropout);
-    for (int c = (warp >> 2) * 64; c < (warp >> 2) * 64 + 64 && c < bn; c += 32) {
-        float v[32];
-        tc::tc2_read_acc(&sh, c, v);
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-            uint32_t rnd[4] = {0u, 0u, 0u, 0u};
-            const int nb = n0 + c + 4 * j4;
-            if (drop && a.keep == nullptr && m < a.B)
-                philox4x32((uint32_t)m, (uint32_t)(nb >> 2), step_lo, step_hi ^ ((uint32_t)(a.layer_id + 1) << 24), k0, k1, rnd);
-            float nrm[4] = {0.f, 0.f, 0.f, 0.f};
-            if (is_mu && a.add_eps && a.eps == nullptr && m < a.B) {  // reparameterisation noise (encode.py:277)
-                philox4x32((uint32_t)m, (uint32_t)(nb >> 2), step_lo, step_hi ^ 0x7F000000u, k0, k1, rnd);
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const float u1 = u32_to_unit(rnd[2 * h]), u2 = u32_to_unit(rnd[2 * h + 1]);
-                    const float rr = sqrtf(-2.0f * logf(u1));
-                    float sn, cn;
-                    sincosf(6.28318530717958647692f * u2, &sn, &cn);
-                    nrm[2 * h] = rr * cn;
-                    nrm[2 * h + 1] = rr * sn;
-                }
-            }
-            float o4[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int n = nb + j;
-                float p = 0.0f;
-                if (m < a.B && n < a.N) {
-                    const float y = v[4 * j4 + j] + __ldg(a.bias + n);
-                    if (hidden) {
-                        p = y > 0.0f ? y : y * a.slope;
-                        if (drop) {
-                            const bool kp = a.keep ? (a.keep[(int64_t)m * a.N + n] != 0) : (u32_to_unit(rnd[j]) > a.dropout);
-                            p = kp ? p * keep_scale : 0.0f;
-                        }
-                    } else {
-                        p = y;
-                        if (is_mu) {
-                            const int64_t o = (int64_t)m * a.N + n;
-                            if (a.add_eps) a.z[o] = y + (a.eps ? __ldg(a.eps + o) : nrm[j]);
-                            if (a.latent_out)
-                                a.latent_out[o] = __uint_as_float(__float_as_uint(y) & ~((1u << a.mask_bits) - 1u));
-                        }
-                    }
-                }
-                o4[j] = p;
-            }
-            *reinterpret_cast<float4 *>(tile + row * TS + c + 4 * j4) = make_float4(o4[0], o4[1], o4[2], o4[3]);
-        }
-    }
-    tc::tc2_tile_end(&sh);  // fence + __syncthreads + TMEM dealloc: the tile is complete for everyone
-    // coalesced store of the tile
     const bool vec = ((a.N & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
     const int q_per_row = bn >> 2;
-    for (int q = tid; q < 128 * q_per_row; q += tc::TC_THREADS) {
-        const int r = q / q_per_row, c = (q % q_per_row) << 2;
-        if (m0 + r >= a.B) continue;
+    for (int q = tid; q < 128 * q_per_row; q += tc::WS_EPI_THREADS) {
+        const int r = q / q_per_row, c = (q - r * q_per_row) << 2;
+        const int m = m0 + r, nb = n0 + c;
         const float4 t = *reinterpret_cast<const float4 *>(tile + r * TS + c);
-        float *dst = a.out + (int64_t)(m0 + r) * a.N + n0 + c;
-        if (vec && n0 + c + 3 < a.N) *reinterpret_cast<float4 *>(dst) = t;
-        else {
-            if (n0 + c < a.N) dst[0] = t.x;
-            if (n0 + c + 1 < a.N) dst[1] = t.y;
-            if (n0 + c + 2 < a.N) dst[2] = t.z;
-            if (n0 + c + 3 < a.N) dst[3] = t.w;
+        const float4 bz = *reinterpret_cast<const float4 *>(s_bias + c);
+        const float y[4] = {t.x + bz.x, t.y + bz.y, t.z + bz.z, t.w + bz.w};
+        float o[4];
+        uint32_t rnd[4] = {0u, 0u, 0u, 0u};
+        if (philox_drop)
+            philox4x32((uint32_t)m, (uint32_t)(nb >> 2), step_lo, step_hi ^ ((uint32_t)(a.layer_id + 1) << 24), k0, k1, rnd);
+        float nrm[4] = {0.f, 0.f, 0.f, 0.f};
+        if (philox_eps) {  // reparameterisation noise (encode.py:277)
+            philox4x32((uint32_t)m, (uint32_t)(nb >> 2), step_lo, step_hi ^ 0x7F000000u, k0, k1, rnd);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float u1 = u32_to_unit(rnd[2 * h]), u2 = u32_to_unit(rnd[2 * h + 1]);
+                const float rr = sqrtf(-2.0f * logf(u1));
+                float sn, cn;
+                sincosf(6.28318530717958647692f * u2, &sn, &cn);
+                nrm[2 * h] = rr * cn;
+                nrm[2 * h + 1] = rr * sn;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool inside = m < a.B && nb + j < a.N;
+            float p = y[j];
+            if (hidden) {
+                p = p > 0.0f ? p : p * a.slope;
+                if (drop) {
+                    bool kp;
+                    if (a.keep) kp = inside && a.keep[(int64_t)m * a.N + nb + j] != 0;
+                    else kp = u32_to_unit(rnd[j]) > a.dropout;
+                    p = kp ? p * keep_scale : 0.0f;
+                }
+            } else if (is_mu && inside) {
+                const int64_t oi = (int64_t)m * a.N + nb + j;
+                if (a.add_eps) a.z[oi] = p + (a.eps ? __ldg(a.eps + oi) : nrm[j]);
+                if (a.latent_out) a.latent_out[oi] = __uint_as_float(__float_as_uint(p) & ~((1u << a.mask_bits) - 1u));
+            }
+            o[j] = inside ? p : 0.0f;
+        }
+        *reinterpret_cast<float4 *>(tile + r * TS + c) = make_float4(o[0], o[1], o[2], o[3]);
+        if (m < a.B) {
+            float *dst = a.out + (int64_t)m * a.N + nb;
+            if (vec && nb + 3 < a.N) *reinterpret_cast<float4 *>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+            else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (nb + j < a.N) dst[j] = o[j];
+            }
         }
     }
+    tl_mark(4);
     if (!hidden || !a.training) return;
+    __syncthreads();
     double *p0 = a.part + ((int64_t)blockIdx.y * 2 + 0) * a.N;
     double *p1 = a.part + ((int64_t)blockIdx.y * 2 + 1) * a.N;
     tc_colsum2(bn, n0, a.N, s_cs, p0, p1, [&](int r, int c, float &v0, float &v1) {
@@ -967,19 +792,26 @@ __global__ void __launch_bounds__(tc::TC_THREADS, 1) fwd_layer_tc2_kernel(FwdArg
         v0 = p;
         v1 = p * p;
     });
+    tl_mark(5);
     if (!last_block_done(&a.ctl->tickets[a.layer_id], gridDim.x * gridDim.y)) return;
-    bn_forward_finalize(a, gridDim.y);
+    tl_mark(6);
+    bn_forward_finalize(a, gridDim.y, tc::WS_EPI_THREADS);
+    tl_mark(7);
 }
 
-
-template <int STAGES>
-__global__ void __launch_bounds__(tc::TC_THREADS, 1) bwd_layer_tc2_kernel(BwdArgs a, BwdTcExtra x) {
+// Backward layer: wgrad slices (split-K over the batch, one gradient slab per split) and dgrad tiles in
+// one launch.
+template <int S>
+__global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(BwdArgs a, BwdTcExtra x) {
+    tl_begin(8 + a.ticket_id);
     pdl_entry();
+    tl_mark(1);
     extern __shared__ uint8_t smem_raw[];
-    __shared__ tc::Tc2Shared sh;
+    __shared__ tc::WsShared sh;
     __shared__ double s_cs[2][2][128];
     uint8_t *smem = align1024(smem_raw);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x;
+    float *tile = reinterpret_cast<float *>(smem);
     const int n_wg = a.wg_tiles_m * a.wg_tiles_n * x.nsplit;
     if ((int)blockIdx.x < n_wg) {
         // ---- wgrad slice: gW[n, k] (+ bias column) over batch rows [b0, b0 + nb) ----
@@ -992,25 +824,21 @@ __global__ void __launch_bounds__(tc::TC_THREADS, 1) bwd_layer_tc2_kernel(BwdArg
         int nb = a.B - b0;
         nb = nb < 0 ? 0 : (nb > x.k_per_split ? x.k_per_split : nb);
         const int nk = (nb + tc::KT - 1) / tc::KT;  // b0 is a multiple of 32; the staged operands are zero padded
-        tc::tc2_mainloop<STAGES>(a.wg_a, m0, a.wg_b, n0, bn, b0 / tc::KT, nk, smem, &sh);
-        const int m = m0 + (warp & 3) * 32 + lane;
+        if (!tc::ws_mainloop<S>(a.wg_a.hi, a.wg_a.ld, m0, a.wg_b.hi, a.wg_b.ld, n0, bn, b0 / tc::KT, nk, smem, &sh)) return;
+        tl_mark(2);
+        tc::ws_acc_to_tile(&sh, bn, nk, tile, TS);
+        tl_mark(3);
+        tc::ws_tile_end(&sh);
         float *gW = a.gW + (int64_t)split * x.slab, *gb = a.gb + (int64_t)split * x.slab;
-        for (int c = (warp >> 2) * 64; c < (warp >> 2) * 64 + 64 && c < bn; c += 32) {
-            float v[32];
-            if (nk > 0) tc::tc2_read_acc(&sh, c, v);
-            else
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = 0.0f;
-            if (m < a.N) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int n = n0 + c + j;
-                    if (n < a.K) gW[(int64_t)m * a.K + n] = v[j];
-                    else if (n == a.K) gb[m] = v[j];
-                }
-            }
+        for (int q = tid; q < 128 * bn; q += tc::WS_EPI_THREADS) {
+            const int r = q / bn, c = q - r * bn;
+            const int m = m0 + r, n = n0 + c;
+            if (m >= a.N) continue;
+            const float val = tile[r * TS + c];
+            if (n < a.K) gW[(int64_t)m * a.K + n] = val;
+            else if (n == a.K) gb[m] = val;
         }
-        tc::tc2_tile_end(&sh);
+        tl_mark(4);
         return;
     }
     // ---- dgrad: dX[b, k] = sum_n dY[b, n] * W[n, k] ----
@@ -1018,46 +846,38 @@ __global__ void __launch_bounds__(tc::TC_THREADS, 1) bwd_layer_tc2_kernel(BwdArg
     const int m0 = (t / a.dg_tiles_n) * 128, n0 = (t % a.dg_tiles_n) * a.tile_n;
     int bn = a.K - n0;
     bn = bn > a.tile_n ? a.tile_n : ((bn + 15) & ~15);
-    tc::tc2_mainloop<STAGES>(a.dg_a, m0, a.dg_b, n0, bn, 0, (a.N + tc::KT - 1) / tc::KT, smem, &sh);
-    float *tile = reinterpret_cast<float *>(smem);
-    const int row = (warp & 3) * 32 + lane, m = m0 + row;
     const float gsc = (float)(a.ctl->wbar / (double)a.B);
-    for (int c = (warp >> 2) * 64; c < (warp >> 2) * 64 + 64 && c < bn; c += 32) {
-        float v[32];
-        tc::tc2_read_acc(&sh, c, v);
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-            float o4[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int n = n0 + c + 4 * j4 + j;
-                float val = 0.0f;
-                if (m < a.B && n < a.K) {
-                    val = v[4 * j4 + j];
-                    if (a.in_kind == VK_IN_Z) val = __fmaf_rn(gsc * a.kld_w, __ldg(a.MU + (int64_t)m * a.K + n), val);
-                }
-                o4[j] = val;
-            }
-            *reinterpret_cast<float4 *>(tile + row * TS + c + 4 * j4) = make_float4(o4[0], o4[1], o4[2], o4[3]);
-        }
-    }
-    tc::tc2_tile_end(&sh);
+    const int nk = (a.N + tc::KT - 1) / tc::KT;
+    if (!tc::ws_mainloop<S>(a.dg_a.hi, a.dg_a.ld, m0, a.dg_b.hi, a.dg_b.ld, n0, bn, 0, nk, smem, &sh)) return;
+    tc::ws_acc_to_tile(&sh, bn, nk, tile, TS);
+    tc::ws_tile_end(&sh);
     const bool vec = ((a.K & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.d_in) & 15) == 0);
+    const bool add_kld = a.in_kind == VK_IN_Z;
     const int q_per_row = bn >> 2;
-    for (int q = tid; q < 128 * q_per_row; q += tc::TC_THREADS) {
-        const int r = q / q_per_row, c = (q % q_per_row) << 2;
-        if (m0 + r >= a.B) continue;
+    for (int q = tid; q < 128 * q_per_row; q += tc::WS_EPI_THREADS) {
+        const int r = q / q_per_row, c = (q - r * q_per_row) << 2;
+        const int m = m0 + r, nb = n0 + c;
         const float4 tv = *reinterpret_cast<const float4 *>(tile + r * TS + c);
-        float *dst = a.d_in + (int64_t)(m0 + r) * a.K + n0 + c;
-        if (vec && n0 + c + 3 < a.K) *reinterpret_cast<float4 *>(dst) = tv;
-        else {
-            if (n0 + c < a.K) dst[0] = tv.x;
-            if (n0 + c + 1 < a.K) dst[1] = tv.y;
-            if (n0 + c + 2 < a.K) dst[2] = tv.z;
-            if (n0 + c + 3 < a.K) dst[3] = tv.w;
+        float o[4] = {tv.x, tv.y, tv.z, tv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool inside = m < a.B && nb + j < a.K;
+            if (add_kld && inside) o[j] = __fmaf_rn(gsc * a.kld_w, __ldg(a.MU + (int64_t)m * a.K + nb + j), o[j]);
+            o[j] = inside ? o[j] : 0.0f;
+        }
+        *reinterpret_cast<float4 *>(tile + r * TS + c) = make_float4(o[0], o[1], o[2], o[3]);
+        if (m < a.B) {
+            float *dst = a.d_in + (int64_t)m * a.K + nb;
+            if (vec && nb + 3 < a.K) *reinterpret_cast<float4 *>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+            else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (nb + j < a.K) dst[j] = o[j];
+            }
         }
     }
     if (a.in_kind != VK_IN_BN) return;
+    __syncthreads();
     const int row_tile = t / a.dg_tiles_n;
     double *p0 = a.part_prev + ((int64_t)row_tile * 2 + 0) * a.K;
     double *p1 = a.part_prev + ((int64_t)row_tile * 2 + 1) * a.K;
@@ -1070,7 +890,7 @@ __global__ void __launch_bounds__(tc::TC_THREADS, 1) bwd_layer_tc2_kernel(BwdArg
         v1 = dv * ph;
     });
     if (!last_block_done(&a.ctl->tickets[a.ticket_id], a.dg_tiles_m * a.dg_tiles_n)) return;
-    bn_backward_finalize(a);
+    bn_backward_finalize(a, tc::WS_EPI_THREADS);
 }
 
 
@@ -1295,41 +1115,26 @@ static int tc_tile_n(int B) {
     return B <= 512 ? 32 : (B <= 2048 ? 64 : 128);
 }
 
-// dynamic shared memory: two operand stages, and never less than the 128 x TS epilogue tile
+// ---- tensor-core path: operand staging + warp-specialised GEMMs ------------------------------------
+static inline int r32(int v) { return (v + 31) & ~31; }
+static inline int r128(int v) { return (v + 127) & ~127; }
+
+// ring depth: 4 stages while two operand tiles (hi + lo) of a stage fit, 3 for the 128-column tile
+static inline int tc_stages(int tile_n) { return tile_n > 64 ? 3 : 4; }
 static int tc_smem_for(int tile_n) {
-    const int need = tc::tc_smem_bytes(tile_n), epi = 128 * TS * 4 + 1024;
+    const int need = tc::ws_smem_bytes(tile_n, tc_stages(tile_n)), epi = 128 * TS * 4 + 1024;
     return need > epi ? need : epi;
 }
 
 static int tc_prepare() {
     static bool done = false;
     if (done) return 0;
-    const int smem = tc::tc_smem_bytes(128);
-    VK_CUDA(cudaFuncSetAttribute(fwd_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    VK_CUDA(cudaFuncSetAttribute(bwd_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VK_CUDA(cudaFuncSetAttribute(fwd_layer_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::ws_smem_bytes(128, 3)));
+    VK_CUDA(cudaFuncSetAttribute(fwd_layer_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::ws_smem_bytes(64, 4)));
+    VK_CUDA(cudaFuncSetAttribute(bwd_layer_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::ws_smem_bytes(128, 3)));
+    VK_CUDA(cudaFuncSetAttribute(bwd_layer_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::ws_smem_bytes(64, 4)));
     done = true;
     return 0;
-}
-
-
-// ---- v2 tensor-core path: operand staging + cp.async GEMMs ------------------------------------------
-static inline int r32(int v) { return (v + 31) & ~31; }
-static inline int r128(int v) { return (v + 127) & ~127; }
-
-static int tc2_prepare() {
-    static bool done = false;
-    if (done) return 0;
-    VK_CUDA(cudaFuncSetAttribute(fwd_layer_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::tc2_smem_bytes(128, 3)));
-    VK_CUDA(cudaFuncSetAttribute(fwd_layer_tc2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::tc2_smem_bytes(64, 4)));
-    VK_CUDA(cudaFuncSetAttribute(bwd_layer_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::tc2_smem_bytes(128, 3)));
-    VK_CUDA(cudaFuncSetAttribute(bwd_layer_tc2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::tc2_smem_bytes(64, 4)));
-    done = true;
-    return 0;
-}
-
-static int tc2_smem_for(int tile_n, int stages) {
-    const int need = tc::tc2_smem_bytes(tile_n, stages), epi = 128 * TS * 4 + 1024;
-    return need > epi ? need : epi;
 }
 
 static int launch_prep(const PrepArgs &a, cudaStream_t s) {
@@ -1455,13 +1260,13 @@ static int launch_forward(const vk_vae *net, int B, int training, int upto /*exc
             if (launch_prep_input(net, j, B, training, s)) return 1;
         PROF_MARK_K(s, PK_FWD);
         if (tcp) {
-            if (tc2_prepare()) return 1;
+            if (tc_prepare()) return 1;
             a.tile_n = tc_tile_n(B);
             a.a_op = tc::OpRef{L.xop_hi, L.xop_lo, r32(L.k_in)};
             a.b_op = tc::OpRef{L.w_hi, L.w_lo, r32(L.k_in)};
             dim3 grid((L.n_out + a.tile_n - 1) / a.tile_n, (B + 127) / 128);
-            if (a.tile_n > 64) VK_CUDA(vk_launch(fwd_layer_tc2_kernel<3>, dim3(grid), dim3(tc::TC_THREADS), (size_t)(tc2_smem_for(a.tile_n, 3)), s, a));
-            else VK_CUDA(vk_launch(fwd_layer_tc2_kernel<4>, dim3(grid), dim3(tc::TC_THREADS), (size_t)(tc2_smem_for(a.tile_n, 4)), s, a));
+            if (a.tile_n > 64) VK_CUDA(vk_launch(fwd_layer_tc_kernel<3>, dim3(grid), dim3(tc::WS_THREADS), (size_t)tc_smem_for(a.tile_n), s, a));
+            else VK_CUDA(vk_launch(fwd_layer_tc_kernel<4>, dim3(grid), dim3(tc::WS_THREADS), (size_t)tc_smem_for(a.tile_n), s, a));
         } else {
             dim3 grid((L.n_out + 63) / 64, (B + 63) / 64);
             VK_CUDA(vk_launch(fwd_layer_kernel, dim3(grid), dim3(GT), (size_t)(0), s, a));
@@ -1543,7 +1348,7 @@ static int launch_backward(const vk_vae *net, int B, cudaStream_t s) {
             if (launch_prep_grad(net, j, B, s)) return 1;
         PROF_MARK_K(s, PK_BWD);
         if (use_tc(net, B)) {
-            if (tc2_prepare()) return 1;
+            if (tc_prepare()) return 1;
             BwdTcExtra x;
             x.nsplit = tc_nsplit(net, B);
             x.k_per_split = (((B + x.nsplit - 1) / x.nsplit) + 31) & ~31;
@@ -1560,8 +1365,8 @@ static int launch_backward(const vk_vae *net, int B, cudaStream_t s) {
             a.dg_a = tc::OpRef{L.dy_hi, L.dy_lo, r32(L.n_out)};
             a.dg_b = tc::OpRef{L.wt_hi, L.wt_lo, r32(L.n_out)};
             const int blocks = a.wg_tiles_m * a.wg_tiles_n * x.nsplit + a.dg_tiles_m * a.dg_tiles_n;
-            if (a.tile_n > 64) VK_CUDA(vk_launch(bwd_layer_tc2_kernel<3>, dim3(blocks), dim3(tc::TC_THREADS), (size_t)(tc2_smem_for(a.tile_n, 3)), s, a, x));
-            else VK_CUDA(vk_launch(bwd_layer_tc2_kernel<4>, dim3(blocks), dim3(tc::TC_THREADS), (size_t)(tc2_smem_for(a.tile_n, 4)), s, a, x));
+            if (a.tile_n > 64) VK_CUDA(vk_launch(bwd_layer_tc_kernel<3>, dim3(blocks), dim3(tc::WS_THREADS), (size_t)tc_smem_for(a.tile_n), s, a, x));
+            else VK_CUDA(vk_launch(bwd_layer_tc_kernel<4>, dim3(blocks), dim3(tc::WS_THREADS), (size_t)tc_smem_for(a.tile_n), s, a, x));
         } else {
             const int blocks = a.wg_tiles_m * a.wg_tiles_n + a.dg_tiles_m * a.dg_tiles_n;
             VK_CUDA(vk_launch(bwd_layer_kernel, dim3(blocks), dim3(GT), (size_t)(0), s, a));
@@ -1702,3 +1507,11 @@ extern "C" int vk_vae_profile_step(const vk_vae *net, int batch, const vk_vae_in
     if (rc && !vk_last_error()[0]) vk_set_error("vk_vae_profile_step failed");
     return rc;
 }
+
+#ifdef VK_TIMELINE
+extern "C" int vk_timeline_read(unsigned long long *out_host) {
+    VK_CUDA(cudaDeviceSynchronize());
+    VK_CUDA(cudaMemcpyFromSymbol(out_host, vk_tl, sizeof(unsigned long long) * 4096));
+    return 0;
+}
+#endif
