@@ -118,9 +118,32 @@ __device__ __forceinline__ void tl_begin(int kernel_id) {
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) vk_tl_base = kernel_id * 64;
     tl_mark(0);
 }
+// one record per launch, in launch order: [kind, start of block 0, end of block 0, 0]
+static __device__ unsigned long long vk_tk[4096 * 4];
+static __device__ unsigned int vk_tk_seq;
+__device__ __forceinline__ int tk_begin(int kind) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) {
+        const int idx = (int)(atomicAdd(&vk_tk_seq, 1u) & 4095u);
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        vk_tk[idx * 4] = (unsigned long long)kind;
+        vk_tk[idx * 4 + 1] = t;
+        return idx;
+    }
+    return -1;
+}
+__device__ __forceinline__ void tk_end(int idx) {
+    if (idx >= 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        vk_tk[idx * 4 + 2] = t;
+    }
+}
 #else
 #define tl_mark(slot) ((void)0)
 #define tl_begin(id) ((void)0)
+#define tk_begin(kind) (-1)
+#define tk_end(idx) ((void)(idx))
 #endif
 
 __device__ __forceinline__ void pdl_entry() {

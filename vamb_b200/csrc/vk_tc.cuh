@@ -338,70 +338,107 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 lanes x 16 consecutive columns, registers -> tensor memory
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem, 128 lanes x 8 columns] * B[smem descriptor]^T
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// "Lane-major" storage of an A-role operand (the 128-row side of the GEMM): 128-row panels of an
+// [rows][ld] array, each k-tile of a panel is one 16 KB block  [k / 4 (8)][row (128)][k % 4 (4)]  so that
+// the 32 lanes of a warp read / write consecutive float4.  Same footprint as the row-major array.
+__host__ __device__ __forceinline__ size_t lane_major_index(int r, int k, int ld) {
+    return (size_t)(r >> 7) * 128 * ld + (size_t)(k >> 5) * 4096 + (size_t)((k & 31) >> 2) * 512 + (size_t)(r & 127) * 4 + (k & 3);
+}
+
 // Warp-specialised pipeline.  A CTA is 8 producer/epilogue warps + 1 MMA warp (WS_THREADS = 288).
-// Shared-memory ring of S stages, each  A_hi 16 KB | B_hi bn*128 B | A_lo | B_lo :
-//   producers : cp.async the fp32 ("hi") chunks of tile kt+P straight into the no-swizzle core-matrix
-//               layout, wait for their OWN copies of tile kt, derive the tf32 remainders ("lo") of exactly
-//               those chunks, proxy-fence and arrive on full[stage] (one arrival per warp);
-//   MMA warp  : one lane waits full[stage], issues the 12 tcgen05.mma of the k-tile (3xTF32, small terms
-//               first) back to back and commits them to empty[stage] -- so the tensor pipe stays busy
-//               (a tf32 MMA with M = 128 issues every ~48 cycles for N <= 64, 64 cycles for N = 128;
-//               tools/tc_fixed_cost.py) while the producers run ahead.
-// A stage is refilled once the MMAs that read it two k-tiles ago have completed (P = S - 2 tiles in flight).
+// Shared memory bandwidth (128 B/clk) is what bounds a 3xTF32 tile loop that keeps both operands in shared
+// memory (each k-tile: copy in, read + write for the split, and twelve MMA reads of the 128-row operand), so
+// the 128-row operand A never touches shared memory:
+//   producers : warp w owns TMEM lanes 32 (w % 4).. and the k-half (w / 4) of each k-tile: it loads its 16
+//               values per row from the lane-major array (coalesced float4), splits them into the tf32 value
+//               ("hi" = the fp32 word, the MMA ignores the low mantissa bits) and the remainder ("lo") in
+//               registers and writes both to the A stage in TENSOR memory (tcgen05.st); the narrow operand
+//               B goes global -> shared with cp.async, each thread deriving "lo" of the chunk it copied;
+//               then proxy/tcgen05 fences and one arrival per warp on full[stage];
+//   MMA warp  : one lane waits full[stage], issues the 12 tcgen05.mma (A from tensor memory, B from shared
+//               memory; small terms first) of the k-tile and commits them to empty[stage].
+// Tensor memory: columns [0, 128) accumulator, then S stages of 64 columns (A_hi 32 | A_lo 32).
+// A stage is refilled once the MMAs that read it have completed; two tiles are in flight.
 constexpr int WS_THREADS = 288;
 constexpr int WS_EPI_THREADS = 256;
-__host__ __device__ constexpr int ws_hi_bytes(int bn) { return A_TILE_BYTES + b_tile_bytes(bn); }
-__host__ __device__ constexpr int ws_smem_bytes(int bn, int stages) { return stages * 2 * ws_hi_bytes(bn) + 1024; }
+constexpr int WS_STAGES = 4;
+constexpr uint32_t WS_TMEM_COLS = 512;  // 128 + 4 * 64 rounded up to a power of two
+__host__ __device__ constexpr int ws_smem_bytes(int bn) { return WS_STAGES * 2 * b_tile_bytes(bn) + 1024; }
 
 struct WsShared {
-    uint64_t full[4], empty[4], done;
+    uint64_t full[WS_STAGES], empty[WS_STAGES], done;
     uint32_t tmem_base;
 };
 
-// D[128 x bn] = sum over k-tiles [kt0, kt0 + nk) of A[m0.., k] * B[n0.., k]^T with A, B plain K-major fp32
-// arrays, zero padded to 128 rows / 32 columns (ld = floats per row, multiple of 4).
+// D[128 x bn] = sum over k-tiles [kt0, kt0 + nk) of A[m0.., k] * B[n0.., k]^T.  A: lane-major (m0 a multiple
+// of 128), B: plain K-major; both fp32, zero padded to whole tiles (ld = floats per row, multiple of 32).
 // Returns true for the 256 epilogue threads (accumulator complete), false for the MMA warp (which is done).
-template <int S>
 __device__ __forceinline__ bool ws_mainloop(const float *A, int lda, int m0, const float *B, int ldb, int n0, int bn,
                                             int kt0, int nk, uint8_t *smem, WsShared *sh) {
-    static_assert(S >= 3 && S <= 4, "ring depth");
-    constexpr int P = S - 2;
+    constexpr int S = WS_STAGES, P = 2;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int hbytes = ws_hi_bytes(bn), sbytes = 2 * hbytes;
+    const int bbytes = b_tile_bytes(bn), sbytes = 2 * bbytes;
     const uint32_t smem_base = smem_u32(smem);
-    // chunk q = tid + 256 i of a tile: row ((q >> 6) << 3) | (q & 7) = r0 + 32 i, 16-byte column k4, at byte q * 16
+    // B chunk q = tid + 256 i of a tile: row ((q >> 6) << 3) | (q & 7) = r0 + 32 i, 16-byte column k4, at byte q * 16
     const int r0 = ((tid >> 6) << 3) | (tid & 7), k4 = (tid >> 3) & 7;
-    const float *pa = A + (size_t)(m0 + r0) * lda + (size_t)kt0 * KT + k4 * 4;
     const float *pb = B + (size_t)(n0 + r0) * ldb + (size_t)kt0 * KT + k4 * 4;
-    const size_t a_step = (size_t)32 * lda, b_step = (size_t)32 * ldb;
+    const size_t b_step = (size_t)32 * ldb;
     const int nbi = bn >> 5;                                // whole 32-row groups of the B tile
     const bool b_tail = tid < (bn & 31) * 8;                // + 16 rows when bn is an odd multiple of 16
     const uint32_t soff = (uint32_t)tid * 16u;
-    auto issue_tile = [&](int kt, int slot) {
+    // A: row 32 (warp % 4) + lane of the panel, float4 groups 4 (warp / 4) .. + 3 of each k-tile
+    const float4 *pa = reinterpret_cast<const float4 *>(A + (size_t)(m0 >> 7) * 128 * lda + (size_t)kt0 * 4096) +
+                       (warp >> 2) * 4 * 128 + (warp & 3) * 32 + lane;
+    auto issue_b = [&](int kt, int slot) {
         const uint32_t st = smem_base + slot * sbytes + soff;
-        const float *ga = pa + (size_t)kt * KT, *gb = pb + (size_t)kt * KT;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) cp_async16(st + i * 4096, ga + i * a_step);
-        for (int i = 0; i < nbi; ++i) cp_async16(st + A_TILE_BYTES + i * 4096, gb + i * b_step);
-        if (b_tail) cp_async16(st + A_TILE_BYTES + nbi * 4096, gb + nbi * b_step);
+        const float *gb = pb + (size_t)kt * KT;
+        for (int i = 0; i < nbi; ++i) cp_async16(st + i * 4096, gb + i * b_step);
+        if (b_tail) cp_async16(st + nbi * 4096, gb + nbi * b_step);
     };
-    auto split_tile = [&](int slot) {
+    auto split_b = [&](int slot) {
         uint8_t *st = smem + slot * sbytes + soff;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<float4 *>(st + hbytes + i * 4096) = tf32_lo(*reinterpret_cast<const float4 *>(st + i * 4096));
         for (int i = 0; i < nbi; ++i)
-            *reinterpret_cast<float4 *>(st + hbytes + A_TILE_BYTES + i * 4096) =
-                tf32_lo(*reinterpret_cast<const float4 *>(st + A_TILE_BYTES + i * 4096));
+            *reinterpret_cast<float4 *>(st + bbytes + i * 4096) = tf32_lo(*reinterpret_cast<const float4 *>(st + i * 4096));
         if (b_tail)
-            *reinterpret_cast<float4 *>(st + hbytes + A_TILE_BYTES + nbi * 4096) =
-                tf32_lo(*reinterpret_cast<const float4 *>(st + A_TILE_BYTES + nbi * 4096));
+            *reinterpret_cast<float4 *>(st + bbytes + nbi * 4096) = tf32_lo(*reinterpret_cast<const float4 *>(st + nbi * 4096));
     };
-    // the first P tiles are in flight while barriers / tensor memory are set up
+    auto load_a = [&](int kt, float4 (&v)[4]) {
+        const float4 *g = pa + (size_t)kt * 1024;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = __ldg(g + j * 128);
+    };
+    // the first two tiles are in flight while barriers / tensor memory are set up
+    float4 ra[2][4];
     if (warp < 8) {
 #pragma unroll
         for (int t = 0; t < P; ++t) {
-            if (t < nk) issue_tile(t, t);
+            if (t < nk) {
+                issue_b(t, t);
+                load_a(t, ra[t]);
+            }
             cp_async_commit();
         }
     }
@@ -414,14 +451,14 @@ __device__ __forceinline__ bool ws_mainloop(const float *A, int lda, int m0, con
         mbar_init(&sh->done, 1);
         mbar_fence_init();
     }
-    if (warp == 0) tmem_alloc(&sh->tmem_base, 128);
+    if (warp == 0) tmem_alloc(&sh->tmem_base, WS_TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     tl_mark(8);
+    const uint32_t tmem_d = sh->tmem_base;
     if (warp == 8) {
         if (lane == 0) {
-            const uint32_t tmem_d = sh->tmem_base;
             const uint32_t idesc = make_idesc_tf32(TC_BM, bn, 0, 0);
             const uint64_t desc0 = make_smem_desc(smem_base, 128, 1024);
             int slot = 0;
@@ -429,16 +466,15 @@ __device__ __forceinline__ bool ws_mainloop(const float *A, int lda, int m0, con
             for (int kt = 0; kt < nk; ++kt) {
                 mbar_wait(&sh->full[slot], phase);
                 tc_fence_after();
+                const uint32_t ah = tmem_d + 128u + 64u * slot, al = ah + 32u;
                 // descriptors differ only in the 14-bit start-address field: add (byte offset >> 4)
-                const uint64_t dh = desc0 + (uint64_t)((uint32_t)(slot * sbytes) >> 4);
-                const uint64_t dl = dh + (uint64_t)((uint32_t)hbytes >> 4);
+                const uint64_t bh = desc0 + (uint64_t)((uint32_t)(slot * sbytes) >> 4);
+                const uint64_t bl = bh + (uint64_t)((uint32_t)bbytes >> 4);
 #pragma unroll
                 for (int j = 0; j < KT / 8; ++j) {
-                    const uint64_t dah = dh + 16u * j, dbh = dah + (A_TILE_BYTES >> 4);
-                    const uint64_t dal = dl + 16u * j, dbl = dal + (A_TILE_BYTES >> 4);
-                    umma_tf32(tmem_d, dal, dbh, idesc, (kt | j) ? 1u : 0u);  // small terms first
-                    umma_tf32(tmem_d, dah, dbl, idesc, 1u);
-                    umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+                    umma_tf32_ts(tmem_d, al + 8u * j, bh + 16u * j, idesc, (kt | j) ? 1u : 0u);  // small terms first
+                    umma_tf32_ts(tmem_d, ah + 8u * j, bl + 16u * j, idesc, 1u);
+                    umma_tf32_ts(tmem_d, ah + 8u * j, bh + 16u * j, idesc, 1u);
                 }
                 umma_commit(&sh->empty[slot]);
                 if (kt == nk - 1) umma_commit(&sh->done);
@@ -450,20 +486,39 @@ __device__ __forceinline__ bool ws_mainloop(const float *A, int lda, int m0, con
         }
         return false;
     }
-    for (int kt = 0; kt < nk; ++kt) {
-        const int nt = kt + P;
+    const uint32_t a_lane = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + 128u + (uint32_t)(warp >> 2) * 16u;
+    auto produce = [&](int kt, float4(&v)[4]) {
+        const int nt = kt + P, slot = kt % S;
         if (nt < nk) {
-            // the MMAs of tile nt - S read this stage; they were issued two k-tiles ago
+            // stage nt % S was read by the MMAs of tile nt - S (issued two k-tiles ago)
             if (nt >= S) mbar_wait(&sh->empty[nt % S], (uint32_t)(((nt / S) - 1) & 1));
-            issue_tile(nt, nt % S);
+            issue_b(nt, nt % S);
         }
         cp_async_commit();
-        cp_async_wait<P>();      // this thread's copies of tile kt have landed
-        split_tile(kt % S);
-        fence_async_smem();      // visible to the tensor core (async proxy)
+        // A tile kt: registers -> tensor memory (its stage was released before B of this tile was issued)
+        float hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 l4 = tf32_lo(v[j]);
+            hi[4 * j] = v[j].x; hi[4 * j + 1] = v[j].y; hi[4 * j + 2] = v[j].z; hi[4 * j + 3] = v[j].w;
+            lo[4 * j] = l4.x; lo[4 * j + 1] = l4.y; lo[4 * j + 2] = l4.z; lo[4 * j + 3] = l4.w;
+        }
+        tc_fence_after();
+        tmem_st16(a_lane + 64u * slot, hi);
+        tmem_st16(a_lane + 64u * slot + 32u, lo);
+        if (nt < nk) load_a(nt, v);  // v's registers are free again: next-but-one tile
+        cp_async_wait<P>();          // this thread's B copies of tile kt have landed
+        split_b(slot);
+        tmem_wait_st();
+        fence_async_smem();          // shared-memory writes visible to the tensor core (async proxy)
+        tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sh->full[kt % S]);
+        if (lane == 0) mbar_arrive(&sh->full[slot]);
         if (kt < 20) tl_mark(10 + kt);
+    };
+    for (int kt = 0; kt < nk; kt += 2) {
+        produce(kt, ra[0]);
+        if (kt + 1 < nk) produce(kt + 1, ra[1]);
     }
     tl_mark(9);
     if (nk > 0) mbar_wait(&sh->done, 0);
@@ -493,7 +548,7 @@ __device__ __forceinline__ void ws_acc_to_tile(const WsShared *sh, int bn, int n
 __device__ __forceinline__ void ws_tile_end(WsShared *sh) {
     tc_fence_before();
     __syncthreads();
-    if ((threadIdx.x >> 5) == 0) tmem_dealloc(sh->tmem_base, 128);
+    if ((threadIdx.x >> 5) == 0) tmem_dealloc(sh->tmem_base, WS_TMEM_COLS);
 }
 
 }  // namespace tc

@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(tc::TC_THREADS, 1) tc_mma_rate_kernel(int n_mm
         tc::mbar_init(&sh.bar_done, 1);
         tc::mbar_fence_init();
     }
-    if (warp == 0) tc::tmem_alloc(&sh.tmem_base, 128);
+    if (warp == 0) tc::tmem_alloc(&sh.tmem_base, 256);
     for (int i = tid; i < 16384; i += tc::TC_THREADS) reinterpret_cast<float *>(smem)[i] = 1.0f;
     tc::fence_async_smem();
     tc::tc_fence_before();
@@ -171,7 +171,10 @@ __global__ void __launch_bounds__(tc::TC_THREADS, 1) tc_mma_rate_kernel(int n_mm
         const uint64_t da = d, db = d + (32768 >> 4);
         const uint32_t idesc = tc::make_idesc_tf32(128, n, 0, 0);
         const long long t0 = clock64();
-        for (int i = 0; i < n_mma; ++i) tc::umma_tf32(sh.tmem_base, da + (uint64_t)((i & 3) * (swizzle ? 2 : 16)), db, idesc, 1u);
+        if (swizzle == 2)  // A operand from tensor memory (columns 128..), B from shared memory
+            for (int i = 0; i < n_mma; ++i) tc::umma_tf32_ts(sh.tmem_base, sh.tmem_base + 128u + 8u * (i & 3), db, idesc, 1u);
+        else
+            for (int i = 0; i < n_mma; ++i) tc::umma_tf32(sh.tmem_base, da + (uint64_t)((i & 3) * (swizzle ? 2 : 16)), db, idesc, 1u);
         tc::umma_commit(&sh.bar_done);
         const long long t1 = clock64();
         tc::mbar_wait(&sh.bar_done, 0);
@@ -181,7 +184,7 @@ __global__ void __launch_bounds__(tc::TC_THREADS, 1) tc_mma_rate_kernel(int n_mm
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(sh.tmem_base, 128);
+    if (warp == 0) tc::tmem_dealloc(sh.tmem_base, 256);
 }
 }  // namespace
 

@@ -99,6 +99,7 @@ __device__ __forceinline__ bool last_block_done(int32_t *ticket, int total) {
 __global__ void __launch_bounds__(256)
 batch_rows_kernel(int64_t *batch_rows, const int64_t *batch_idx, const float *weights, vk_vae_ctl *ctl, int B,
                   int64_t n_rows, int mode, int64_t row0, int steps_per_epoch, double *part, int ticket_id) {
+    const int tk = tk_begin(1);
     pdl_entry();
     __shared__ double s_w[16];
     const int tid = threadIdx.x;
@@ -120,12 +121,14 @@ batch_rows_kernel(int64_t *batch_rows, const int64_t *batch_idx, const float *we
     }
     const double t = block_sum256(acc, s_w);
     if (tid == 0) part[blockIdx.x] = t;
+    tk_end(tk);
     if (!last_block_done(&ctl->tickets[ticket_id], gridDim.x)) return;
     if (tid == 0) {
         double tot = 0.0;
         for (unsigned i = 0; i < gridDim.x; ++i) tot += __ldcg(part + i);
         ctl->wbar = tot / (double)B;
     }
+    tk_end(tk);
 }
 
 // ------------------------------------------------------------------ operand loaders
@@ -464,6 +467,7 @@ struct LossArgs {
 };
 
 __global__ void __launch_bounds__(256) loss_kernel(LossArgs a) {
+    const int tk = tk_begin(30);
     pdl_entry();
     __shared__ double s_part[8][4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -523,6 +527,7 @@ __global__ void __launch_bounds__(256) loss_kernel(LossArgs a) {
         for (int w = 0; w < 8; ++w) t += s_part[w][threadIdx.x];
         a.part[(int64_t)blockIdx.x * 4 + threadIdx.x] = t;
     }
+    tk_end(tk);
     if (!last_block_done(&a.ctl->tickets[a.ticket_id], gridDim.x)) return;
     // fixed-order parallel fold of the block partials: thread t sums blocks t, t+256, ...; then a serial
     // fold of the 256 thread sums (same order every run)
@@ -697,9 +702,9 @@ struct BwdTcExtra {
 // Forward layer: D = X' W^T on the tensor core, then one coalesced pass over the shared tile does bias,
 // LeakyReLU, dropout (one Philox call per four outputs) / the reparameterisation, and the global stores;
 // hidden layers in training add the BatchNorm column sums and the last CTA folds them.
-template <int S>
 __global__ void __launch_bounds__(tc::WS_THREADS, 1) fwd_layer_tc_kernel(FwdArgs a) {
     tl_begin(a.layer_id);
+    const int tk = tk_begin(20 + a.layer_id);
     pdl_entry();
     tl_mark(1);
     extern __shared__ uint8_t smem_raw[];
@@ -715,12 +720,13 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) fwd_layer_tc_kernel(FwdArgs
     const uint32_t k0 = (uint32_t)a.ctl->seed, k1 = (uint32_t)(a.ctl->seed >> 32);
     const uint32_t step_lo = (uint32_t)a.ctl->step, step_hi = (uint32_t)(a.ctl->step >> 32);
     const int nk = (a.K + tc::KT - 1) / tc::KT;
-    if (!tc::ws_mainloop<S>(a.a_op.hi, a.a_op.ld, m0, a.b_op.hi, a.b_op.ld, n0, bn, 0, nk, smem, &sh)) return;
+    if (!tc::ws_mainloop(a.a_op.hi, a.a_op.ld, m0, a.b_op.hi, a.b_op.ld, n0, bn, 0, nk, smem, &sh)) return;
     tl_mark(2);
     float *tile = reinterpret_cast<float *>(smem);  // [128][TS]; the operand stages are dead now
     tc::ws_acc_to_tile(&sh, bn, nk, tile, TS);
     tl_mark(3);
     tc::ws_tile_end(&sh);
+    tl_mark(44);
 
     const bool hidden = a.kind == VK_LAYER_HIDDEN, is_mu = a.kind == VK_LAYER_MU;
     const bool drop = hidden && a.training && a.dropout > 0.0f;
@@ -783,6 +789,7 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) fwd_layer_tc_kernel(FwdArgs
         }
     }
     tl_mark(4);
+    tk_end(tk);
     if (!hidden || !a.training) return;
     __syncthreads();
     double *p0 = a.part + ((int64_t)blockIdx.y * 2 + 0) * a.N;
@@ -792,18 +799,15 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) fwd_layer_tc_kernel(FwdArgs
         v0 = p;
         v1 = p * p;
     });
-    tl_mark(5);
-    if (!last_block_done(&a.ctl->tickets[a.layer_id], gridDim.x * gridDim.y)) return;
-    tl_mark(6);
-    bn_forward_finalize(a, gridDim.y, tc::WS_EPI_THREADS);
-    tl_mark(7);
+    tl_mark(5);  // the consumer (prep_kernel of the next layer) folds the column sums
+    tk_end(tk);
 }
 
 // Backward layer: wgrad slices (split-K over the batch, one gradient slab per split) and dgrad tiles in
 // one launch.
-template <int S>
 __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(BwdArgs a, BwdTcExtra x) {
     tl_begin(8 + a.ticket_id);
+    const int tk = tk_begin(40 + a.ticket_id);
     pdl_entry();
     tl_mark(1);
     extern __shared__ uint8_t smem_raw[];
@@ -824,7 +828,7 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(BwdArgs
         int nb = a.B - b0;
         nb = nb < 0 ? 0 : (nb > x.k_per_split ? x.k_per_split : nb);
         const int nk = (nb + tc::KT - 1) / tc::KT;  // b0 is a multiple of 32; the staged operands are zero padded
-        if (!tc::ws_mainloop<S>(a.wg_a.hi, a.wg_a.ld, m0, a.wg_b.hi, a.wg_b.ld, n0, bn, b0 / tc::KT, nk, smem, &sh)) return;
+        if (!tc::ws_mainloop(a.wg_a.hi, a.wg_a.ld, m0, a.wg_b.hi, a.wg_b.ld, n0, bn, b0 / tc::KT, nk, smem, &sh)) return;
         tl_mark(2);
         tc::ws_acc_to_tile(&sh, bn, nk, tile, TS);
         tl_mark(3);
@@ -839,6 +843,7 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(BwdArgs
             else if (n == a.K) gb[m] = val;
         }
         tl_mark(4);
+        tk_end(tk);
         return;
     }
     // ---- dgrad: dX[b, k] = sum_n dY[b, n] * W[n, k] ----
@@ -848,7 +853,7 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(BwdArgs
     bn = bn > a.tile_n ? a.tile_n : ((bn + 15) & ~15);
     const float gsc = (float)(a.ctl->wbar / (double)a.B);
     const int nk = (a.N + tc::KT - 1) / tc::KT;
-    if (!tc::ws_mainloop<S>(a.dg_a.hi, a.dg_a.ld, m0, a.dg_b.hi, a.dg_b.ld, n0, bn, 0, nk, smem, &sh)) return;
+    if (!tc::ws_mainloop(a.dg_a.hi, a.dg_a.ld, m0, a.dg_b.hi, a.dg_b.ld, n0, bn, 0, nk, smem, &sh)) return;
     tc::ws_acc_to_tile(&sh, bn, nk, tile, TS);
     tc::ws_tile_end(&sh);
     const bool vec = ((a.K & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.d_in) & 15) == 0);
@@ -889,8 +894,7 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(BwdArgs
         v0 = dv;
         v1 = dv * ph;
     });
-    if (!last_block_done(&a.ctl->tickets[a.ticket_id], a.dg_tiles_m * a.dg_tiles_n)) return;
-    bn_backward_finalize(a, tc::WS_EPI_THREADS);
+    // the consumer (prep_kernel staging dL/dY of the previous layer) folds the column sums
 }
 
 
@@ -914,44 +918,142 @@ struct PrepArgs {
     float *hi, *lo; int ld;    // [row][col]  (nullable)
     float *hiT, *loT; int ldT; // [col][row]  (nullable)
     int ones_row;              // transposed row `cols` = 1 for row < rows (bias-gradient column), 0 = off
+    int hi_lane, hiT_lane;     // store in the lane-major layout of an A-role operand (vk_tc.cuh)
+    // BatchNorm folding in the consumer: the producing GEMM leaves per-row-tile column sums in `fin_part`;
+    // every block folds them for its own 32 columns (c0/c1/c2 then come from shared memory) and the first
+    // row of blocks also stores what later kernels need.  fin = 0: off, 1: forward statistics (mode 1),
+    // 2: backward sums (mode 2).
+    int fin, fin_rt, fin_batch;
+    const double *fin_part;
+    const float *gamma, *beta, *mean_in, *rstd_in;
+    float *bn_mean, *bn_rstd, *bn_a, *bn_c, *running_mean, *running_var; int64_t *nbt;
+    float *g_gamma, *g_beta, *m1, *m2, *bA, *bB, *bC; float inv_keep;
 };
 
-__device__ __forceinline__ float prep_value(const PrepArgs &a, int r, int c) {
+// k0/k1/k2: the per-column constants of column c (from shared memory)
+__device__ __forceinline__ float prep_value(const PrepArgs &a, int r, int c, float k0, float k1, float k2) {
     if (r >= a.rows || c >= a.cols) return 0.0f;
     switch (a.mode) {
         case 0: return __ldg(a.src + (int64_t)r * a.ld_src + c);
-        case 1: return __fmaf_rn(__ldg(a.src + (int64_t)r * a.ld_src + c), __ldg(a.c0 + c), __ldg(a.c1 + c));
+        case 1: return __fmaf_rn(__ldg(a.src + (int64_t)r * a.ld_src + c), k0, k1);
         case 2: {
             const float pv = __ldg(a.p + (int64_t)r * a.ld_src + c);
             if (a.has_dropout && pv == 0.0f) return 0.0f;
-            const float v = __fmaf_rn(__ldg(a.c0 + c), __ldg(a.src + (int64_t)r * a.ld_src + c),
-                                      __fmaf_rn(__ldg(a.c1 + c), pv, __ldg(a.c2 + c)));
+            const float v = __fmaf_rn(k0, __ldg(a.src + (int64_t)r * a.ld_src + c), __fmaf_rn(k1, pv, k2));
             return pv > 0.0f ? v : v * a.slope;
         }
         default: return __ldg(a.data + a.rows_idx[r] * (int64_t)a.data_ld + c);
     }
 }
 
-__device__ __forceinline__ void prep_tile(const PrepArgs &a, int r0, int c0, float (*tile)[33]) {
+// Per-column constants of the block's 32 columns -> s_k[0..2][32]; folds the producer's column sums when asked
+// (row tiles strided over the eight warps, then the eight partial sums in fixed order).
+__device__ __forceinline__ void prep_consts(const PrepArgs &a, int c0, bool first_row_block, float (*s_k)[32],
+                                            double (*s_f)[8][32]) {
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = c0 + tx;
+    if (a.fin) {
+        double u = 0.0, v = 0.0;
+        if (c < a.cols)
+            for (int rt = ty; rt < a.fin_rt; rt += 8) {
+                u += __ldcg(a.fin_part + ((int64_t)rt * 2 + 0) * a.cols + c);
+                v += __ldcg(a.fin_part + ((int64_t)rt * 2 + 1) * a.cols + c);
+            }
+        s_f[0][ty][tx] = u;
+        s_f[1][ty][tx] = v;
+        __syncthreads();
+    }
+    if (ty == 0) {
+        float k0 = 0.0f, k1 = 0.0f, k2 = 0.0f;
+        double u = 0.0, v = 0.0;
+        if (a.fin) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                u += s_f[0][i][tx];
+                v += s_f[1][i][tx];
+            }
+        }
+        if (c < a.cols && a.fin == 1) {
+            // torch.nn.BatchNorm1d in training mode (as bn_forward_finalize)
+            const double mean = u / a.fin_batch;
+            double var = v / a.fin_batch - mean * mean;
+            if (var < 0.0) var = 0.0;
+            const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+            const float fm = (float)mean;
+            k0 = a.gamma[c] * rstd;
+            k1 = a.beta[c] - fm * k0;
+            if (first_row_block) {
+                a.bn_mean[c] = fm;
+                a.bn_rstd[c] = rstd;
+                a.bn_a[c] = k0;
+                a.bn_c[c] = k1;
+                const float unb = a.fin_batch > 1 ? (float)(var * ((double)a.fin_batch / (double)(a.fin_batch - 1))) : (float)var;
+                a.running_mean[c] = 0.9f * a.running_mean[c] + 0.1f * fm;
+                a.running_var[c] = 0.9f * a.running_var[c] + 0.1f * unb;
+                if (c == 0) *a.nbt += 1;
+            }
+        } else if (c < a.cols && a.fin == 2) {
+            // BatchNorm weight / bias gradients and the folded dL/dY constants (as bn_backward_finalize)
+            const float rs = a.rstd_in[c], mu = a.mean_in[c];
+            const float m1 = (float)(u / a.fin_batch), m2 = (float)(v / a.fin_batch);
+            k0 = a.inv_keep * a.gamma[c] * rs;
+            k1 = -k0 * rs * m2;
+            k2 = -k0 * m1 - k1 * mu;
+            if (first_row_block) {
+                a.g_beta[c] = (float)u;
+                a.g_gamma[c] = (float)v;
+                a.m1[c] = m1;
+                a.m2[c] = m2;
+                a.bA[c] = k0;
+                a.bB[c] = k1;
+                a.bC[c] = k2;
+            }
+        } else if (c < a.cols) {
+            if (a.c0) k0 = __ldg(a.c0 + c);
+            if (a.c1) k1 = __ldg(a.c1 + c);
+            if (a.c2) k2 = __ldg(a.c2 + c);
+        }
+        s_k[0][tx] = k0;
+        s_k[1][tx] = k1;
+        s_k[2][tx] = k2;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void prep_tile(const PrepArgs &a, int r0, int c0, float (*tile)[33], float (*s_k)[32]) {
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads
+    const float k0 = s_k[0][tx], k1 = s_k[1][tx], k2 = s_k[2][tx];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int r = r0 + ty * 4 + i, c = c0 + tx;
-        float v = prep_value(a, r, c);
-        if (a.hi && r < a.rows_w && c < a.cols_w) {
+        float v = prep_value(a, r, c, k0, k1, k2);
+        if (a.hi && !a.hi_lane && r < a.rows_w && c < a.cols_w) {
             a.hi[(int64_t)r * a.ld + c] = v;
             if (a.lo) a.lo[(int64_t)r * a.ld + c] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
         }
-        if (a.ones_row && c == a.cols) v = r < a.rows ? 1.0f : 0.0f;
         tile[ty * 4 + i][tx] = v;
     }
     __syncthreads();
-    if (a.hiT) {
+    if (a.hi && a.hi_lane) {
+        // thread = (row tx, float4 group ty): consecutive rows are consecutive float4 of the lane-major block
+        const int r = r0 + tx, c = c0 + 4 * ty;
+        if (r < a.rows_w && c < a.cols_w)
+            *reinterpret_cast<float4 *>(a.hi + tc::lane_major_index(r, c, a.ld)) =
+                make_float4(tile[tx][4 * ty], tile[tx][4 * ty + 1], tile[tx][4 * ty + 2], tile[tx][4 * ty + 3]);
+    }
+    if (a.hiT && a.hiT_lane) {
+        // transposed operand: row = source column, k = source row
+        const int c = c0 + tx, r = r0 + 4 * ty;
+        if (c < a.cols && r < a.rows_w)
+            *reinterpret_cast<float4 *>(a.hiT + tc::lane_major_index(c, r, a.ldT)) =
+                make_float4(tile[4 * ty][tx], tile[4 * ty + 1][tx], tile[4 * ty + 2][tx], tile[4 * ty + 3][tx]);
+    } else if (a.hiT) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int c = c0 + ty * 4 + i, r = r0 + tx;  // transposed element (c, r)
             if (c < a.cols + (a.ones_row ? 1 : 0) && r < a.rows_w) {
-                const float v = tile[tx][ty * 4 + i];
+                float v = tile[tx][ty * 4 + i];
+                if (a.ones_row && c == a.cols) v = r < a.rows ? 1.0f : 0.0f;
                 a.hiT[(int64_t)c * a.ldT + r] = v;
                 if (a.loT) a.loT[(int64_t)c * a.ldT + r] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
             }
@@ -960,9 +1062,14 @@ __device__ __forceinline__ void prep_tile(const PrepArgs &a, int r0, int c0, flo
 }
 
 __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a) {
+    const int tk = tk_begin(10 + a.mode);
     pdl_entry();
     __shared__ float tile[32][33];
-    prep_tile(a, blockIdx.y * 32, blockIdx.x * 32, tile);
+    __shared__ float s_k[3][32];
+    __shared__ double s_f[2][8][32];
+    if (a.mode == 1 || a.mode == 2) prep_consts(a, blockIdx.x * 32, blockIdx.y == 0, s_k, s_f);
+    prep_tile(a, blockIdx.y * 32, blockIdx.x * 32, tile, s_k);
+    tk_end(tk);
 }
 
 struct PrepMulti {
@@ -972,12 +1079,15 @@ struct PrepMulti {
 
 // every layer's weights in one launch (blockIdx.z = layer)
 __global__ void __launch_bounds__(256) prep_weights_kernel(PrepMulti m) {
+    const int tk = tk_begin(14);
     pdl_entry();
     __shared__ float tile[32][33];
     const PrepArgs &a = m.l[blockIdx.z];
     const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    __shared__ float s_k[3][32];
     if (r0 >= a.rows_w || c0 >= a.cols + 1) return;
-    prep_tile(a, r0, c0, tile);
+    prep_tile(a, r0, c0, tile, s_k);  // mode 0: the constants are not used
+    tk_end(tk);
 }
 
 // ------------------------------------------------------------------ D-Adaptation Adam
@@ -989,6 +1099,7 @@ constexpr int OPT_ELEMS = 1024;  // elements per block
 __global__ void __launch_bounds__(256)
 dadapt_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
               float *__restrict__ s, int64_t n, double *part, vk_vae_ctl *ctl, int ticket_id, int nslab, int64_t slab) {
+    const int tk = tk_begin(50);
     pdl_entry();
     __shared__ double s_a[256], s_b[256];
     const double beta1 = 0.9, beta2 = 0.999, eps = 1e-8;
@@ -1023,6 +1134,7 @@ dadapt_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restr
             part[2 * blockIdx.x + 1] = tb;
         }
     }
+    tk_end(tk);
     if (!last_block_done(&ctl->tickets[ticket_id], gridDim.x)) return;
     {   // fixed-order parallel fold of the block partials
         double num = 0.0, l1 = 0.0;
@@ -1119,20 +1231,17 @@ static int tc_tile_n(int B) {
 static inline int r32(int v) { return (v + 31) & ~31; }
 static inline int r128(int v) { return (v + 127) & ~127; }
 
-// ring depth: 4 stages while two operand tiles (hi + lo) of a stage fit, 3 for the 128-column tile
-static inline int tc_stages(int tile_n) { return tile_n > 64 ? 3 : 4; }
+// dynamic shared memory: the B-operand ring, and never less than the 128 x TS epilogue tile
 static int tc_smem_for(int tile_n) {
-    const int need = tc::ws_smem_bytes(tile_n, tc_stages(tile_n)), epi = 128 * TS * 4 + 1024;
+    const int need = tc::ws_smem_bytes(tile_n), epi = 128 * TS * 4 + 1024;
     return need > epi ? need : epi;
 }
 
 static int tc_prepare() {
     static bool done = false;
     if (done) return 0;
-    VK_CUDA(cudaFuncSetAttribute(fwd_layer_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::ws_smem_bytes(128, 3)));
-    VK_CUDA(cudaFuncSetAttribute(fwd_layer_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::ws_smem_bytes(64, 4)));
-    VK_CUDA(cudaFuncSetAttribute(bwd_layer_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::ws_smem_bytes(128, 3)));
-    VK_CUDA(cudaFuncSetAttribute(bwd_layer_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::ws_smem_bytes(64, 4)));
+    VK_CUDA(cudaFuncSetAttribute(fwd_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_for(128)));
+    VK_CUDA(cudaFuncSetAttribute(bwd_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_for(128)));
     done = true;
     return 0;
 }
@@ -1152,13 +1261,19 @@ static int launch_prep_input(const vk_vae *net, int j, int B, int training, cuda
     PrepArgs a;
     memset(&a, 0, sizeof(a));
     a.rows = B; a.cols = L.k_in; a.rows_w = r128(B); a.cols_w = L.k_in;
-    a.hi = L.xop_hi; a.lo = nullptr; a.ld = r32(L.k_in);  // the GEMM derives the tf32 remainders in shared memory
+    a.hi = L.xop_hi; a.lo = nullptr; a.ld = r32(L.k_in); a.hi_lane = 1;  // A of the forward GEMM
     if (training) { a.hiT = L.xt_hi; a.loT = nullptr; a.ldT = net->bmax; a.ones_row = 1; }
     if (L.in_kind == VK_IN_DATA) {
         a.mode = 3; a.data = net->data; a.rows_idx = net->batch_rows; a.data_ld = net->data_ld;
     } else if (L.in_kind == VK_IN_BN) {
         const vk_vae_layer &P = net->layers[j - 1];
         a.mode = 1; a.src = P.act; a.ld_src = P.n_out; a.c0 = P.bn_a; a.c1 = P.bn_c;
+        if (training) {  // fold the batch statistics the forward GEMM of layer j - 1 left behind
+            a.fin = 1; a.fin_rt = (B + 127) / 128; a.fin_batch = B; a.fin_part = P.fwd_part;
+            a.gamma = net->params + P.g_off; a.beta = net->params + P.beta_off;
+            a.bn_mean = P.bn_mean; a.bn_rstd = P.bn_rstd; a.bn_a = P.bn_a; a.bn_c = P.bn_c;
+            a.running_mean = P.running_mean; a.running_var = P.running_var; a.nbt = P.num_batches_tracked;
+        }
     } else {
         a.mode = 0; a.src = net->z; a.ld_src = L.k_in;
     }
@@ -1171,12 +1286,18 @@ static int launch_prep_grad(const vk_vae *net, int j, int B, cudaStream_t s) {
     PrepArgs a;
     memset(&a, 0, sizeof(a));
     a.rows = B; a.cols = L.n_out; a.rows_w = r128(B); a.cols_w = L.n_out;
-    a.hi = L.dy_hi; a.lo = nullptr; a.ld = r32(L.n_out);
-    a.hiT = L.dyt_hi; a.loT = nullptr; a.ldT = net->bmax;
+    a.hi = L.dy_hi; a.lo = nullptr; a.ld = r32(L.n_out); a.hi_lane = 1;
+    a.hiT = L.dyt_hi; a.loT = nullptr; a.ldT = net->bmax; a.hiT_lane = 1;
     a.src = L.dact; a.ld_src = L.n_out;
     if (L.kind == VK_LAYER_HIDDEN) {
         a.mode = 2; a.p = L.act; a.c0 = L.bn_bA; a.c1 = L.bn_bB; a.c2 = L.bn_bC;
         a.slope = net->slope; a.has_dropout = net->dropout > 0.0f ? 1 : 0;
+        // fold the column sums the dgrad of layer j + 1 left behind
+        a.fin = 2; a.fin_rt = (B + 127) / 128; a.fin_batch = B; a.fin_part = L.bwd_part;
+        a.gamma = net->params + L.g_off; a.mean_in = L.bn_mean; a.rstd_in = L.bn_rstd;
+        a.g_gamma = net->grads + L.g_off; a.g_beta = net->grads + L.beta_off;
+        a.m1 = L.bn_m1; a.m2 = L.bn_m2; a.bA = L.bn_bA; a.bB = L.bn_bB; a.bC = L.bn_bC;
+        a.inv_keep = net->dropout > 0.0f ? 1.0f / (1.0f - net->dropout) : 1.0f;
     }
     return launch_prep(a, s);
 }
@@ -1265,8 +1386,7 @@ static int launch_forward(const vk_vae *net, int B, int training, int upto /*exc
             a.a_op = tc::OpRef{L.xop_hi, L.xop_lo, r32(L.k_in)};
             a.b_op = tc::OpRef{L.w_hi, L.w_lo, r32(L.k_in)};
             dim3 grid((L.n_out + a.tile_n - 1) / a.tile_n, (B + 127) / 128);
-            if (a.tile_n > 64) VK_CUDA(vk_launch(fwd_layer_tc_kernel<3>, dim3(grid), dim3(tc::WS_THREADS), (size_t)tc_smem_for(a.tile_n), s, a));
-            else VK_CUDA(vk_launch(fwd_layer_tc_kernel<4>, dim3(grid), dim3(tc::WS_THREADS), (size_t)tc_smem_for(a.tile_n), s, a));
+            VK_CUDA(vk_launch(fwd_layer_tc_kernel, dim3(grid), dim3(tc::WS_THREADS), (size_t)tc_smem_for(a.tile_n), s, a));
         } else {
             dim3 grid((L.n_out + 63) / 64, (B + 63) / 64);
             VK_CUDA(vk_launch(fwd_layer_kernel, dim3(grid), dim3(GT), (size_t)(0), s, a));
@@ -1365,8 +1485,7 @@ static int launch_backward(const vk_vae *net, int B, cudaStream_t s) {
             a.dg_a = tc::OpRef{L.dy_hi, L.dy_lo, r32(L.n_out)};
             a.dg_b = tc::OpRef{L.wt_hi, L.wt_lo, r32(L.n_out)};
             const int blocks = a.wg_tiles_m * a.wg_tiles_n * x.nsplit + a.dg_tiles_m * a.dg_tiles_n;
-            if (a.tile_n > 64) VK_CUDA(vk_launch(bwd_layer_tc_kernel<3>, dim3(blocks), dim3(tc::WS_THREADS), (size_t)tc_smem_for(a.tile_n), s, a, x));
-            else VK_CUDA(vk_launch(bwd_layer_tc_kernel<4>, dim3(blocks), dim3(tc::WS_THREADS), (size_t)tc_smem_for(a.tile_n), s, a, x));
+            VK_CUDA(vk_launch(bwd_layer_tc_kernel, dim3(blocks), dim3(tc::WS_THREADS), (size_t)tc_smem_for(a.tile_n), s, a, x));
         } else {
             const int blocks = a.wg_tiles_m * a.wg_tiles_n + a.dg_tiles_m * a.dg_tiles_n;
             VK_CUDA(vk_launch(bwd_layer_kernel, dim3(blocks), dim3(GT), (size_t)(0), s, a));
@@ -1512,6 +1631,17 @@ extern "C" int vk_vae_profile_step(const vk_vae *net, int batch, const vk_vae_in
 extern "C" int vk_timeline_read(unsigned long long *out_host) {
     VK_CUDA(cudaDeviceSynchronize());
     VK_CUDA(cudaMemcpyFromSymbol(out_host, vk_tl, sizeof(unsigned long long) * 4096));
+    return 0;
+}
+// launch records since the last reset (at most 4096): out_host[4096 * 4], *n_out = launches recorded
+extern "C" int vk_timeline_kernels(unsigned long long *out_host, unsigned int *n_out, int reset) {
+    VK_CUDA(cudaDeviceSynchronize());
+    VK_CUDA(cudaMemcpyFromSymbol(out_host, vk_tk, sizeof(unsigned long long) * 4096 * 4));
+    VK_CUDA(cudaMemcpyFromSymbol(n_out, vk_tk_seq, sizeof(unsigned int)));
+    if (reset) {
+        const unsigned int zero = 0;
+        VK_CUDA(cudaMemcpyToSymbol(vk_tk_seq, &zero, sizeof(zero)));
+    }
     return 0;
 }
 #endif
