@@ -198,7 +198,8 @@ def vae_roofline(vae, n, nepochs):
             j = nl - 1 - i
             k, nn, in_kind = dims[j]
             flops = 2.0 * batch * nn * (k + 1) + (2.0 * batch * nn * k if in_kind != 0 else 0.0)
-            cand = {"kernel": f"bwd_layer_kernel[layer {j}: {k}->{nn}, B={batch}]", "ms": float(ms),
+            kname = "bwd_layer_tc_kernel" if 0 < net.tc_min_batch <= batch else "bwd_layer_kernel"
+            cand = {"kernel": f"{kname}[layer {j}: {k}->{nn}, B={batch}]", "ms": float(ms),
                     "tflops": flops / (ms * 1e-3) / 1e12, "weight_ms": nsteps * float(ms)}
             if best is None or cand["weight_ms"] > best["weight_ms"]:
                 best = cand

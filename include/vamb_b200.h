@@ -184,6 +184,7 @@ typedef struct vk_vae_ctl {
     uint64_t seed;         /* Philox key / Feistel key base                                                   */
     int32_t epoch;         /* current epoch (selects the row permutation)                                     */
     int32_t tickets[2 * VK_VAE_MAX_LAYERS + 4]; /* last-block-done counters (self-resetting)                  */
+    int32_t barrier_gen[2 * VK_VAE_MAX_LAYERS]; /* generation words of the in-kernel grid barriers (fused staging) */
 } vk_vae_ctl;
 
 /* One Linear (+ LeakyReLU + Dropout + BatchNorm1d) block, encode.py:259-295.  All pointers device. */
@@ -231,7 +232,8 @@ typedef struct vk_vae {
     int32_t tc_min_batch;               /* batches >= this run the GEMMs on tcgen05 (3xTF32); 0 = never            */
     int64_t grad_slab;                  /* floats between the split-K gradient slabs of `grads`                    */
     int32_t n_grad_slabs;               /* slabs allocated in `grads` (>= 1)                                       */
-    int32_t reserved_;
+    int32_t staging;                    /* tensor-core operand staging: 0 = fused into the producing kernels' epilogues
+                                           (grid barrier; falls back when a grid exceeds the SM count), 1 = prep kernels */
 } vk_vae;
 
 /* Optional host-injected randomness for parity tests (all device pointers, NULL = on-device RNG). */

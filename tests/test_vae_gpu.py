@@ -25,13 +25,15 @@ def unpack_keep(packed, batch, n):
     return np.unpackbits(packed)[: batch * n].reshape(batch, n)
 
 
-def set_path(vae, tc: bool):
-    """Force the tcgen05 (3xTF32) GEMM path for every batch size, or the fp32 CUDA-core path."""
+def set_path(vae, tc):
+    """Force the tcgen05 (3xTF32) GEMM path for every batch size (True: operands staged by the producing
+    kernels, "prep": by separate prep launches), or the fp32 CUDA-core path (False)."""
     vae._net.tc_min_batch = 1 if tc else 0
+    vae._net.staging = 1 if tc == "prep" else 0
     return vae
 
 
-@pytest.mark.parametrize("tc", [False, True], ids=["ffma", "tcgen05"])
+@pytest.mark.parametrize("tc", [False, True, "prep"], ids=["ffma", "tcgen05", "tcgen05-prep"])
 @pytest.mark.parametrize("case", VAE_CASES, ids=[c[0] for c in VAE_CASES])
 def test_train_steps_and_encode_match_reference_golden(case, tc):
     import vamb_b200.encode as ve
@@ -74,8 +76,10 @@ def test_train_steps_and_encode_match_reference_golden(case, tc):
     assert np.all(np.abs(lat - gl) <= 1e-4 + np.abs(gl) * 2.0 ** -11)
 
 
-@pytest.mark.parametrize("tc,B", [(False, 256), (True, 256), (True, 1024), (True, 4096)],
-                         ids=["ffma-256", "tcgen05-256", "tcgen05-1024-split2", "tcgen05-4096-split8"])
+@pytest.mark.parametrize("tc,B", [(False, 256), (True, 256), (True, 1024), (True, 4096), ("prep", 256), ("prep", 4096),
+                                  (True, 1000)],
+                         ids=["ffma-256", "tcgen05-256", "tcgen05-1024-split2", "tcgen05-4096-split8", "tcgen05-prep-256",
+                              "tcgen05-prep-4096", "tcgen05-1000-ragged"])
 def test_gradients_match_oracle_default_network(tc, B):
     """One fwd+bwd on the bin-default network (S=50, 512-512-32): every gradient tensor."""
     import vamb_b200.encode as ve
@@ -102,7 +106,7 @@ def test_gradients_match_oracle_default_network(tc, B):
         assert rel(got[k].cpu().numpy(), gref.numpy()) < tol, k
 
 
-@pytest.mark.parametrize("tc", [False, True], ids=["ffma", "tcgen05"])
+@pytest.mark.parametrize("tc", [False, True, "prep"], ids=["ffma", "tcgen05", "tcgen05-prep"])
 def test_odd_batch_and_many_steps_match_oracle(tc):
     """B not a multiple of the tile size, 12 steps: parameters track the oracle."""
     import vamb_b200.encode as ve

@@ -350,7 +350,11 @@ struct FwdArgs {
     float *z; const float *eps; int add_eps; int mask_bits; float *latent_out;
     vk_vae_ctl *ctl; int layer_id; float slope;
     int tile_n;           // tensor-core path: output columns per CTA (multiple of 16, <= 128)
-    tc::OpRef a_op, b_op; // v2: staged operands (layer input, W)
+    tc::OpRef a_op, b_op; // staged operands (layer input, W)
+    // fused staging of the NEXT layer's operands from this layer's output tile (tensor-core path):
+    // 0 off; 1 BatchNorm with this batch's statistics (grid barrier, then every CTA folds its own columns);
+    // 2 plain copy (z) or BatchNorm with the precomputed affine bn_a / bn_c (evaluation)
+    int stage; float *stage_a; int stage_a_ld; float *stage_t; int stage_t_ld;
 };
 
 // Fold the per-row-tile column sums of P and P^2 into the BatchNorm affine, the saved batch statistics
@@ -464,15 +468,23 @@ struct LossArgs {
     const float *R; const float *MU; const float *data; const int64_t *batch_rows;
     float *dR; int B, S, ntnf, d_in, nlatent, data_ld; float ce_w, ab_w, sse_w, kld_w;
     double *part; vk_vae_ctl *ctl; int ticket_id; int write_grad;
+    // tensor-core path, fused staging: dL/dR also as the lane-major operands of the output layer's dgrad / wgrad
+    float *stage_a; int stage_a_ld; float *stage_t; int stage_t_ld;
 };
+
+constexpr int LOSS_STAGE_MAX_D = 160;  // widest reconstruction the loss kernel stages itself (else a prep launch does)
 
 __global__ void __launch_bounds__(256) loss_kernel(LossArgs a) {
     const int tk = tk_begin(30);
     pdl_entry();
     __shared__ double s_part[8][4];
+    __shared__ __align__(16) float s_g[8][LOSS_STAGE_MAX_D + 4];  // the block's eight rows of dL/dR (fused staging)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * 8 + warp;
     double l_ce = 0.0, l_sse = 0.0, l_ab = 0.0, l_kld = 0.0;
+    if (a.stage_a)
+        for (int i = threadIdx.x; i < 8 * (LOSS_STAGE_MAX_D + 4); i += 256) (&s_g[0][0])[i] = 0.0f;
+    if (a.stage_a) __syncthreads();
     if (b < a.B) {
         const float *r = a.R + (int64_t)b * a.d_in;
         const float *x = a.data + a.batch_rows[b] * (int64_t)a.data_ld;
@@ -501,17 +513,20 @@ __global__ void __launch_bounds__(256) loss_kernel(LossArgs a) {
                 const float p = expf(r[s] - mx) / sum;
                 const float gs = -gsc * a.ce_w * x[s] / (p + 1e-9f);
                 g[s] = p * (gs - dot);
+                if (a.stage_a) s_g[warp][s] = p * (gs - dot);
             }
         float sse = 0.0f;
         for (int t = lane; t < a.ntnf; t += 32) {
             const float df = r[a.S + t] - x[a.S + t];
             sse = __fmaf_rn(df, df, sse);
             if (a.write_grad) g[a.S + t] = gsc * a.sse_w * 2.0f * df;
+            if (a.stage_a) s_g[warp][a.S + t] = gsc * a.sse_w * 2.0f * df;
         }
         for (int o = 16; o; o >>= 1) sse += __shfl_xor_sync(0xffffffffu, sse, o);
         const int ia = a.S + a.ntnf;
         const float dab = r[ia] - x[ia];
         if (lane == 0 && a.write_grad) g[ia] = gsc * a.ab_w * 2.0f * dab;
+        if (lane == 0 && a.stage_a) s_g[warp][ia] = gsc * a.ab_w * 2.0f * dab;
         float kld = 0.0f;
         for (int k = lane; k < a.nlatent; k += 32) {
             const float m = a.MU[(int64_t)b * a.nlatent + k];
@@ -522,6 +537,20 @@ __global__ void __launch_bounds__(256) loss_kernel(LossArgs a) {
     }
     if (lane == 0) { s_part[warp][0] = l_ab; s_part[warp][1] = l_ce; s_part[warp][2] = l_sse; s_part[warp][3] = l_kld; }
     __syncthreads();
+    if (a.stage_a) {
+        // rows b0 .. b0 + 7 (zeros beyond the batch: the grid covers the batch rounded up to a k-tile)
+        const int b0 = blockIdx.x * 8, ng = (a.d_in + 3) >> 2;
+        for (int q = threadIdx.x; q < ng * 8; q += 256) {
+            const int g4 = q >> 3, r = q & 7;
+            *reinterpret_cast<float4 *>(a.stage_a + tc::lane_major_index(b0 + r, 4 * g4, a.stage_a_ld)) =
+                *reinterpret_cast<const float4 *>(&s_g[r][4 * g4]);
+        }
+        for (int q = threadIdx.x; q < a.d_in * 2; q += 256) {
+            const int h = q / a.d_in, n = q - h * a.d_in;
+            *reinterpret_cast<float4 *>(a.stage_t + tc::lane_major_index(n, b0 + 4 * h, a.stage_t_ld)) =
+                make_float4(s_g[4 * h][n], s_g[4 * h + 1][n], s_g[4 * h + 2][n], s_g[4 * h + 3][n]);
+        }
+    }
     if (threadIdx.x < 4) {
         double t = 0.0;
         for (int w = 0; w < 8; ++w) t += s_part[w][threadIdx.x];
@@ -570,6 +599,10 @@ struct BwdArgs {
     int tile_n;           // tensor-core path: output columns per CTA
     tc::OpRef wg_a, wg_b, dg_a, dg_b;  // v2: dY^T, X^T(+ones) | dY, W^T
     float *bA_prev, *bB_prev, *bC_prev; const float *gamma_prev; float inv_keep;
+    // fused staging of dL/dY of the PREVIOUS layer from the dgrad tile (tensor-core path):
+    // 0 off; 1 hidden layer (grid barrier over the dgrad CTAs, fold, BatchNorm/dropout/LeakyReLU backward);
+    // 2 plain copy (dL/dmu)
+    int stage; float *stage_a; int stage_a_ld; float *stage_t; int stage_t_ld; float slope; int has_dropout;
 };
 
 // Fold the per-row-tile column sums of dH and dH*Phat: BatchNorm weight/bias gradients and the two
@@ -693,6 +726,77 @@ __device__ __forceinline__ void tc_colsum2(int bn, int n0, int N, double (*s_cs)
     __syncthreads();
 }
 
+// ---- fused staging: the producing kernel writes the consumer GEMM's operands from its shared tile ----
+// Grid barrier over `total` CTAs that are all resident (the host guarantees total <= SM count; every CTA of
+// the launch is scheduled before any dependent launch).  Sense-reversing: the last arriver resets the
+// counter and bumps the generation.  A lost CTA traps after ~1 s instead of hanging the device.
+__device__ __forceinline__ void grid_barrier(int32_t *cnt, int32_t *gen, int total) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int g = *reinterpret_cast<volatile int32_t *>(gen);
+        __threadfence();
+        if (atomicAdd(cnt, 1) == total - 1) {
+            atomicExch(cnt, 0);
+            __threadfence();
+            atomicExch(gen, g + 1);
+        } else {
+            unsigned spins = 0;
+            while (*reinterpret_cast<volatile int32_t *>(gen) == g) {
+                __nanosleep(32);
+                if (++spins > (1u << 24)) __trap();
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// The staging passes below read the shared tile [128][TS] and write the consumer GEMM's operands.
+// f(r, c, v) maps the tile value at (row r, column c) to the staged value (affine, mask); rows m0 + r,
+// columns n0 + c.  Lanes are arranged so that both the shared-memory reads and the global writes of a warp
+// are (nearly) conflict-free / fully coalesced.
+//   lane-major A-role operand, k = column:  consecutive rows are consecutive float4
+template <class F>
+__device__ __forceinline__ void stage_tile_lane(const float *tile, int bn, float *dst, int ld, int m0, int n0, const F &f) {
+#pragma unroll 4
+    for (int q = threadIdx.x; q < (bn >> 2) * 128; q += tc::WS_EPI_THREADS) {
+        const int g = q >> 7, r = q & 127;
+        const float4 v = *reinterpret_cast<const float4 *>(tile + r * TS + 4 * g);
+        *reinterpret_cast<float4 *>(dst + tc::lane_major_index(m0 + r, n0 + 4 * g, ld)) =
+            make_float4(f(r, 4 * g, v.x), f(r, 4 * g + 1, v.y), f(r, 4 * g + 2, v.z), f(r, 4 * g + 3, v.w));
+    }
+}
+// A warp takes 16 columns x 2 groups of 4 rows: lane = (column % 16) * 2 + (row group % 2) -- conflict-free
+// shared-memory reads (bank = 16 (group % 2) + column % 16), one full 32-byte sector per column on the way out.
+//   transpose as a plain K-major B-role operand dst[(n0 + c) * ld + m0 + r], columns n0 + c < n_valid
+template <class F>
+__device__ __forceinline__ void stage_tile_transposed_plain(const float *tile, int bn, float *dst, int ld, int m0, int n0,
+                                                            int n_valid, const F &f) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll 4
+    for (int t = warp; t < bn; t += 8) {  // task t: row-group pair t & 15, column block t >> 4
+        const int g = (t & 15) * 2 + (lane & 1), c = (t >> 4) * 16 + (lane >> 1);
+        if (n0 + c < n_valid)
+            *reinterpret_cast<float4 *>(dst + (int64_t)(n0 + c) * ld + m0 + 4 * g) =
+                make_float4(f(4 * g, c, tile[(4 * g) * TS + c]), f(4 * g + 1, c, tile[(4 * g + 1) * TS + c]),
+                            f(4 * g + 2, c, tile[(4 * g + 2) * TS + c]), f(4 * g + 3, c, tile[(4 * g + 3) * TS + c]));
+    }
+}
+//   transpose as a lane-major A-role operand (rows n0 + c < n_valid, k = m0 + r): consecutive columns are
+//   consecutive float4
+template <class F>
+__device__ __forceinline__ void stage_tile_transposed_lane(const float *tile, int bn, float *dst, int ld, int m0, int n0,
+                                                           int n_valid, const F &f) {
+#pragma unroll 4
+    for (int q = threadIdx.x; q < 32 * bn; q += tc::WS_EPI_THREADS) {
+        const int g = q / bn, c = q - g * bn;
+        if (n0 + c < n_valid)
+            *reinterpret_cast<float4 *>(dst + tc::lane_major_index(n0 + c, m0 + 4 * g, ld)) =
+                make_float4(f(4 * g, c, tile[(4 * g) * TS + c]), f(4 * g + 1, c, tile[(4 * g + 1) * TS + c]),
+                            f(4 * g + 2, c, tile[(4 * g + 2) * TS + c]), f(4 * g + 3, c, tile[(4 * g + 3) * TS + c]));
+    }
+}
+
 // grid: [wgrad tiles (tiles_m x tiles_n x nsplit)] + [dgrad tiles (dg_tiles_m x dg_tiles_n)], 128-row tiles
 struct BwdTcExtra {
     int nsplit, k_per_split;   // split-K over the batch for wgrad
@@ -741,7 +845,7 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) fwd_layer_tc_kernel(FwdArgs
         const float4 t = *reinterpret_cast<const float4 *>(tile + r * TS + c);
         const float4 bz = *reinterpret_cast<const float4 *>(s_bias + c);
         const float y[4] = {t.x + bz.x, t.y + bz.y, t.z + bz.z, t.w + bz.w};
-        float o[4];
+        float o[4], zv[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t rnd[4] = {0u, 0u, 0u, 0u};
         if (philox_drop)
             philox4x32((uint32_t)m, (uint32_t)(nb >> 2), step_lo, step_hi ^ ((uint32_t)(a.layer_id + 1) << 24), k0, k1, rnd);
@@ -772,12 +876,17 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) fwd_layer_tc_kernel(FwdArgs
                 }
             } else if (is_mu && inside) {
                 const int64_t oi = (int64_t)m * a.N + nb + j;
-                if (a.add_eps) a.z[oi] = p + (a.eps ? __ldg(a.eps + oi) : nrm[j]);
+                if (a.add_eps) {
+                    zv[j] = p + (a.eps ? __ldg(a.eps + oi) : nrm[j]);
+                    a.z[oi] = zv[j];
+                }
                 if (a.latent_out) a.latent_out[oi] = __uint_as_float(__float_as_uint(p) & ~((1u << a.mask_bits) - 1u));
             }
             o[j] = inside ? p : 0.0f;
         }
-        *reinterpret_cast<float4 *>(tile + r * TS + c) = make_float4(o[0], o[1], o[2], o[3]);
+        // the tile keeps what later phases need: P (column sums, staging) or z (staging of the decoder input)
+        if (is_mu && a.add_eps) *reinterpret_cast<float4 *>(tile + r * TS + c) = make_float4(zv[0], zv[1], zv[2], zv[3]);
+        else *reinterpret_cast<float4 *>(tile + r * TS + c) = make_float4(o[0], o[1], o[2], o[3]);
         if (m < a.B) {
             float *dst = a.out + (int64_t)m * a.N + nb;
             if (vec && nb + 3 < a.N) *reinterpret_cast<float4 *>(dst) = make_float4(o[0], o[1], o[2], o[3]);
@@ -790,16 +899,71 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) fwd_layer_tc_kernel(FwdArgs
     }
     tl_mark(4);
     tk_end(tk);
-    if (!hidden || !a.training) return;
+    __shared__ float s_k[2][128];
+    if (hidden && a.training) {
+        __syncthreads();
+        double *p0 = a.part + ((int64_t)blockIdx.y * 2 + 0) * a.N;
+        double *p1 = a.part + ((int64_t)blockIdx.y * 2 + 1) * a.N;
+        tc_colsum2(bn, n0, a.N, s_cs, p0, p1, [&](int r, int c, float &v0, float &v1) {
+            const float p = tile[r * TS + c];  // rows >= B and columns >= N hold zeros
+            v0 = p;
+            v1 = p * p;
+        });
+        tl_mark(5);
+        if (a.stage != 1) return;  // the consumer (prep_kernel of the next layer) folds the column sums
+        // every CTA's column sums are needed: wait for the whole grid, then fold the own columns
+        grid_barrier(&a.ctl->tickets[a.layer_id], &a.ctl->barrier_gen[a.layer_id], gridDim.x * gridDim.y);
+        if (tid < bn) {
+            const int n = n0 + tid;
+            float k0 = 0.0f, k1 = 0.0f;
+            if (n < a.N) {
+                double sm = 0.0, q = 0.0;
+                for (int rt = 0; rt < (int)gridDim.y; ++rt) {
+                    sm += __ldcg(a.part + ((int64_t)rt * 2 + 0) * a.N + n);
+                    q += __ldcg(a.part + ((int64_t)rt * 2 + 1) * a.N + n);
+                }
+                // torch.nn.BatchNorm1d in training mode (as bn_forward_finalize)
+                const double mean = sm / a.B;
+                double var = q / a.B - mean * mean;
+                if (var < 0.0) var = 0.0;
+                const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+                const float fm = (float)mean;
+                k0 = a.gamma[n] * rstd;
+                k1 = a.beta[n] - fm * k0;
+                if (blockIdx.y == 0) {
+                    a.bn_mean[n] = fm;
+                    a.bn_rstd[n] = rstd;
+                    a.bn_a[n] = k0;
+                    a.bn_c[n] = k1;
+                    const float unb = a.B > 1 ? (float)(var * ((double)a.B / (double)(a.B - 1))) : (float)var;
+                    a.running_mean[n] = 0.9f * a.running_mean[n] + 0.1f * fm;
+                    a.running_var[n] = 0.9f * a.running_var[n] + 0.1f * unb;
+                    if (n == 0) *a.nbt += 1;
+                }
+            }
+            s_k[0][tid] = k0;
+            s_k[1][tid] = k1;
+        }
+    } else if (a.stage == 2) {
+        if (tid < bn) {  // evaluation: the affine of the running statistics; z: identity
+            const int n = n0 + tid;
+            s_k[0][tid] = (hidden && n < a.N) ? __ldg(a.bn_a + n) : 1.0f;
+            s_k[1][tid] = (hidden && n < a.N) ? __ldg(a.bn_c + n) : 0.0f;
+        }
+    } else {
+        return;
+    }
     __syncthreads();
-    double *p0 = a.part + ((int64_t)blockIdx.y * 2 + 0) * a.N;
-    double *p1 = a.part + ((int64_t)blockIdx.y * 2 + 1) * a.N;
-    tc_colsum2(bn, n0, a.N, s_cs, p0, p1, [&](int r, int c, float &v0, float &v1) {
-        const float p = tile[r * TS + c];  // rows >= B and columns >= N hold zeros
-        v0 = p;
-        v1 = p * p;
-    });
-    tl_mark(5);  // the consumer (prep_kernel of the next layer) folds the column sums
+    // the next layer's input X' = BatchNorm(P) (or z): the tile holds P with zeros outside [B, N]
+    auto bn_apply = [&](int r, int c, float v) {
+        return (m0 + r < a.B && n0 + c < a.N) ? __fmaf_rn(v, s_k[0][c], s_k[1][c]) : 0.0f;
+    };
+    stage_tile_lane(tile, bn, a.stage_a, a.stage_a_ld, m0, n0, bn_apply);
+    if (a.stage_t) {
+        stage_tile_transposed_plain(tile, bn, a.stage_t, a.stage_t_ld, m0, n0, a.N, bn_apply);
+        // the row of ones that turns the bias gradient into one more column of the wgrad GEMM
+        if (blockIdx.x == 0 && tid < 128) a.stage_t[(int64_t)a.N * a.stage_t_ld + m0 + tid] = m0 + tid < a.B ? 1.0f : 0.0f;
+    }
     tk_end(tk);
 }
 
@@ -854,11 +1018,32 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(BwdArgs
     const float gsc = (float)(a.ctl->wbar / (double)a.B);
     const int nk = (a.N + tc::KT - 1) / tc::KT;
     if (!tc::ws_mainloop(a.dg_a.hi, a.dg_a.ld, m0, a.dg_b.hi, a.dg_b.ld, n0, bn, 0, nk, smem, &sh)) return;
+    const int q_per_row = bn >> 2;
+    float *ptile = tile + 128 * TS;  // the previous layer's output P for the same rows / columns (zeros outside)
+    if (a.in_kind == VK_IN_BN) {
+        const bool pvec = ((a.K & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.p_prev) & 15) == 0);
+#pragma unroll 4
+        for (int q = tid; q < 128 * q_per_row; q += tc::WS_EPI_THREADS) {
+            const int r = q / q_per_row, c = (q - r * q_per_row) << 2;
+            const int m = m0 + r, nb = n0 + c;
+            float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < a.B) {
+                const float *src = a.p_prev + (int64_t)m * a.K + nb;
+                if (pvec && nb + 3 < a.K) pv = __ldg(reinterpret_cast<const float4 *>(src));
+                else {
+                    if (nb < a.K) pv.x = __ldg(src);
+                    if (nb + 1 < a.K) pv.y = __ldg(src + 1);
+                    if (nb + 2 < a.K) pv.z = __ldg(src + 2);
+                    if (nb + 3 < a.K) pv.w = __ldg(src + 3);
+                }
+            }
+            *reinterpret_cast<float4 *>(ptile + r * TS + c) = pv;
+        }
+    }
     tc::ws_acc_to_tile(&sh, bn, nk, tile, TS);
     tc::ws_tile_end(&sh);
     const bool vec = ((a.K & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.d_in) & 15) == 0);
     const bool add_kld = a.in_kind == VK_IN_Z;
-    const int q_per_row = bn >> 2;
     for (int q = tid; q < 128 * q_per_row; q += tc::WS_EPI_THREADS) {
         const int r = q / q_per_row, c = (q - r * q_per_row) << 2;
         const int m = m0 + r, nb = n0 + c;
@@ -881,20 +1066,78 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(BwdArgs
             }
         }
     }
-    if (a.in_kind != VK_IN_BN) return;
+    __shared__ float s_k[3][128];
+    if (a.in_kind == VK_IN_BN) {
+        __syncthreads();
+        const int row_tile = t / a.dg_tiles_n;
+        double *p0 = a.part_prev + ((int64_t)row_tile * 2 + 0) * a.K;
+        double *p1 = a.part_prev + ((int64_t)row_tile * 2 + 1) * a.K;
+        tc_colsum2(bn, n0, a.K, s_cs, p0, p1, [&](int r, int c, float &v0, float &v1) {
+            const float dv = tile[r * TS + c];
+            float ph = 0.0f;
+            if (m0 + r < a.B && n0 + c < a.K)
+                ph = (ptile[r * TS + c] - __ldg(a.mean_prev + n0 + c)) * __ldg(a.rstd_prev + n0 + c);
+            v0 = dv;
+            v1 = dv * ph;
+        });
+        if (a.stage != 1) return;  // the consumer (prep_kernel staging dL/dY of the previous layer) folds the sums
+        grid_barrier(&a.ctl->tickets[a.ticket_id], &a.ctl->barrier_gen[a.ticket_id - 1], a.dg_tiles_m * a.dg_tiles_n);
+        if (tid < bn) {
+            const int n = n0 + tid;
+            float k0 = 0.0f, k1 = 0.0f, k2 = 0.0f;
+            if (n < a.K) {
+                double u = 0.0, v = 0.0;
+                for (int rt = 0; rt < a.dg_tiles_m; ++rt) {
+                    u += __ldcg(a.part_prev + ((int64_t)rt * 2 + 0) * a.K + n);
+                    v += __ldcg(a.part_prev + ((int64_t)rt * 2 + 1) * a.K + n);
+                }
+                // BatchNorm weight / bias gradients and the folded dL/dY constants (as bn_backward_finalize)
+                const float rs = a.rstd_prev[n], mu = a.mean_prev[n];
+                const float m1 = (float)(u / a.B), m2 = (float)(v / a.B);
+                k0 = a.inv_keep * a.gamma_prev[n] * rs;
+                k1 = -k0 * rs * m2;
+                k2 = -k0 * m1 - k1 * mu;
+                if (row_tile == 0) {
+                    a.g_beta[n] = (float)u;
+                    a.g_gamma[n] = (float)v;
+                    a.m1_prev[n] = m1;
+                    a.m2_prev[n] = m2;
+                    a.bA_prev[n] = k0;
+                    a.bB_prev[n] = k1;
+                    a.bC_prev[n] = k2;
+                }
+            }
+            s_k[0][tid] = k0;
+            s_k[1][tid] = k1;
+            s_k[2][tid] = k2;
+        }
+        __syncthreads();
+        // dL/dY of the previous layer = sgn(P) * (bA dH + bB P + bC), 0 for dropped units, replaces dH in the tile
+#pragma unroll 4
+        for (int q = tid; q < 128 * q_per_row; q += tc::WS_EPI_THREADS) {
+            const int r = q / q_per_row, c = (q - r * q_per_row) << 2;
+            const int m = m0 + r, nb = n0 + c;
+            const float4 p4 = *reinterpret_cast<const float4 *>(ptile + r * TS + c);
+            const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
+            const float4 dh = *reinterpret_cast<const float4 *>(tile + r * TS + c);
+            const float dv[4] = {dh.x, dh.y, dh.z, dh.w};
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float v = __fmaf_rn(s_k[0][c + j], dv[j], __fmaf_rn(s_k[1][c + j], pv[j], s_k[2][c + j]));
+                const float val = pv[j] > 0.0f ? v : v * a.slope;
+                const bool live = m < a.B && nb + j < a.K && !(a.has_dropout && pv[j] == 0.0f);
+                o[j] = live ? val : 0.0f;
+            }
+            *reinterpret_cast<float4 *>(tile + r * TS + c) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    } else if (a.stage != 2) {
+        return;
+    }
     __syncthreads();
-    const int row_tile = t / a.dg_tiles_n;
-    double *p0 = a.part_prev + ((int64_t)row_tile * 2 + 0) * a.K;
-    double *p1 = a.part_prev + ((int64_t)row_tile * 2 + 1) * a.K;
-    tc_colsum2(bn, n0, a.K, s_cs, p0, p1, [&](int r, int c, float &v0, float &v1) {
-        const float dv = tile[r * TS + c];
-        float ph = 0.0f;
-        if (m0 + r < a.B && n0 + c < a.K)
-            ph = (__ldg(a.p_prev + (int64_t)(m0 + r) * a.K + n0 + c) - __ldg(a.mean_prev + n0 + c)) * __ldg(a.rstd_prev + n0 + c);
-        v0 = dv;
-        v1 = dv * ph;
-    });
-    // the consumer (prep_kernel staging dL/dY of the previous layer) folds the column sums
+    auto ident = [](int, int, float v) { return v; };
+    stage_tile_lane(tile, bn, a.stage_a, a.stage_a_ld, m0, n0, ident);
+    stage_tile_transposed_lane(tile, bn, a.stage_t, a.stage_t_ld, m0, n0, a.K, ident);
 }
 
 
@@ -1231,19 +1474,38 @@ static int tc_tile_n(int B) {
 static inline int r32(int v) { return (v + 31) & ~31; }
 static inline int r128(int v) { return (v + 127) & ~127; }
 
-// dynamic shared memory: the B-operand ring, and never less than the 128 x TS epilogue tile
-static int tc_smem_for(int tile_n) {
-    const int need = tc::ws_smem_bytes(tile_n), epi = 128 * TS * 4 + 1024;
+// dynamic shared memory: the B-operand ring, and never less than the 128 x TS epilogue tile(s) (the backward
+// kernel keeps a second tile: the previous layer's output)
+static int tc_smem_for(int tile_n, int epi_tiles) {
+    const int need = tc::ws_smem_bytes(tile_n), epi = epi_tiles * 128 * TS * 4 + 1024;
     return need > epi ? need : epi;
 }
 
 static int tc_prepare() {
     static bool done = false;
     if (done) return 0;
-    VK_CUDA(cudaFuncSetAttribute(fwd_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_for(128)));
-    VK_CUDA(cudaFuncSetAttribute(bwd_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_for(128)));
+    VK_CUDA(cudaFuncSetAttribute(fwd_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_for(128, 1)));
+    VK_CUDA(cudaFuncSetAttribute(bwd_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_for(128, 2)));
     done = true;
     return 0;
+}
+
+// Fused staging needs every CTA of a forward / dgrad grid resident at once (in-kernel grid barrier).
+static bool fused_staging(const vk_vae *net, int B) {
+    if (net->staging != 0) return false;
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            n_sm = -1;
+    }
+    const int tile_n = tc_tile_n(B), rt = (B + 127) / 128;
+    for (int j = 0; j < net->n_layers; ++j) {
+        const vk_vae_layer &L = net->layers[j];
+        const int widest = L.n_out > L.k_in ? L.n_out : L.k_in;
+        if (((widest + tile_n - 1) / tile_n) * rt > n_sm) return false;
+    }
+    return true;
 }
 
 static int launch_prep(const PrepArgs &a, cudaStream_t s) {
@@ -1377,8 +1639,15 @@ static int launch_forward(const vk_vae *net, int B, int training, int upto /*exc
         a.latent_out = (L.kind == VK_LAYER_MU) ? latent_out : nullptr;
         a.ctl = net->ctl; a.layer_id = j; a.slope = net->slope;
         const bool tcp = use_tc(net, B);
-        if (tcp)
+        const bool fused = tcp && fused_staging(net, B);
+        if (tcp && (!fused || j == 0))  // fused: layer j - 1 staged this layer's operands from its output tile
             if (launch_prep_input(net, j, B, training, s)) return 1;
+        if (fused && j + 1 < upto && L.kind != VK_LAYER_OUT) {
+            const vk_vae_layer &Nx = net->layers[j + 1];
+            a.stage = (L.kind == VK_LAYER_HIDDEN && training) ? 1 : 2;
+            a.stage_a = Nx.xop_hi; a.stage_a_ld = r32(Nx.k_in);
+            a.stage_t = training ? Nx.xt_hi : nullptr; a.stage_t_ld = net->bmax;
+        }
         PROF_MARK_K(s, PK_FWD);
         if (tcp) {
             if (tc_prepare()) return 1;
@@ -1386,7 +1655,7 @@ static int launch_forward(const vk_vae *net, int B, int training, int upto /*exc
             a.a_op = tc::OpRef{L.xop_hi, L.xop_lo, r32(L.k_in)};
             a.b_op = tc::OpRef{L.w_hi, L.w_lo, r32(L.k_in)};
             dim3 grid((L.n_out + a.tile_n - 1) / a.tile_n, (B + 127) / 128);
-            VK_CUDA(vk_launch(fwd_layer_tc_kernel, dim3(grid), dim3(tc::WS_THREADS), (size_t)tc_smem_for(a.tile_n), s, a));
+            VK_CUDA(vk_launch(fwd_layer_tc_kernel, dim3(grid), dim3(tc::WS_THREADS), (size_t)tc_smem_for(a.tile_n, 1), s, a));
         } else {
             dim3 grid((L.n_out + 63) / 64, (B + 63) / 64);
             VK_CUDA(vk_launch(fwd_layer_kernel, dim3(grid), dim3(GT), (size_t)(0), s, a));
@@ -1408,7 +1677,14 @@ static int launch_loss(const vk_vae *net, int B, int write_grad, cudaStream_t s)
     a.data_ld = net->data_ld;
     a.ce_w = net->ce_w; a.ab_w = net->ab_w; a.sse_w = net->sse_w; a.kld_w = net->kld_w;
     a.part = net->loss_part; a.ctl = net->ctl; a.ticket_id = VK_VAE_MAX_LAYERS; a.write_grad = write_grad;
-    const int blocks = (B + 7) / 8;
+    a.stage_a = a.stage_t = nullptr; a.stage_a_ld = a.stage_t_ld = 0;
+    int blocks = (B + 7) / 8;
+    if (write_grad && use_tc(net, B) && fused_staging(net, B) && net->d_in <= LOSS_STAGE_MAX_D) {
+        const vk_vae_layer &L = net->layers[nl - 1];
+        a.stage_a = L.dy_hi; a.stage_a_ld = r32(L.n_out);
+        a.stage_t = L.dyt_hi; a.stage_t_ld = net->bmax;
+        blocks = r32(B) / 8;  // whole k-tiles of the wgrad reduction: rows beyond the batch are staged as zeros
+    }
     if (blocks > 1024) {
         vk_set_error("vk_vae: batch too large for the loss partial buffer");
         return 1;
@@ -1464,8 +1740,17 @@ static int launch_backward(const vk_vae *net, int B, cudaStream_t s) {
                 a.kld_w = net->kld_w;
             }
         }
-        if (use_tc(net, B))
+        const bool fused = use_tc(net, B) && fused_staging(net, B);
+        // fused: dL/dY of this layer was staged by the loss kernel (output layer) or by the dgrad of layer j + 1
+        if (use_tc(net, B) && (!fused || (j == nl - 1 && net->d_in > LOSS_STAGE_MAX_D)))
             if (launch_prep_grad(net, j, B, s)) return 1;
+        if (fused && L.in_kind != VK_IN_DATA) {
+            const vk_vae_layer &P = net->layers[L.in_kind == VK_IN_BN ? j - 1 : mu_j];
+            a.stage = L.in_kind == VK_IN_BN ? 1 : 2;
+            a.stage_a = P.dy_hi; a.stage_a_ld = r32(P.n_out);
+            a.stage_t = P.dyt_hi; a.stage_t_ld = net->bmax;
+            a.slope = net->slope; a.has_dropout = net->dropout > 0.0f ? 1 : 0;
+        }
         PROF_MARK_K(s, PK_BWD);
         if (use_tc(net, B)) {
             if (tc_prepare()) return 1;
@@ -1485,7 +1770,7 @@ static int launch_backward(const vk_vae *net, int B, cudaStream_t s) {
             a.dg_a = tc::OpRef{L.dy_hi, L.dy_lo, r32(L.n_out)};
             a.dg_b = tc::OpRef{L.wt_hi, L.wt_lo, r32(L.n_out)};
             const int blocks = a.wg_tiles_m * a.wg_tiles_n * x.nsplit + a.dg_tiles_m * a.dg_tiles_n;
-            VK_CUDA(vk_launch(bwd_layer_tc_kernel, dim3(blocks), dim3(tc::WS_THREADS), (size_t)tc_smem_for(a.tile_n), s, a, x));
+            VK_CUDA(vk_launch(bwd_layer_tc_kernel, dim3(blocks), dim3(tc::WS_THREADS), (size_t)tc_smem_for(a.tile_n, 2), s, a, x));
         } else {
             const int blocks = a.wg_tiles_m * a.wg_tiles_n + a.dg_tiles_m * a.dg_tiles_n;
             VK_CUDA(vk_launch(bwd_layer_kernel, dim3(blocks), dim3(GT), (size_t)(0), s, a));

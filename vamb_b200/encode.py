@@ -21,6 +21,7 @@ Usage is the reference's:
 """
 
 import ctypes as _ct
+import os as _os
 from math import log as _log
 from pathlib import Path
 from typing import IO, Optional, Union
@@ -147,6 +148,7 @@ class _VkCtl(_ct.Structure):
         ("d", _ct.c_double), ("num_w", _ct.c_double), ("loss_sums", _ct.c_double * 5), ("wbar", _ct.c_double),
         ("step", _ct.c_int64), ("epoch_step0", _ct.c_int64), ("n_loss_steps", _ct.c_int64),
         ("seed", _ct.c_uint64), ("epoch", _ct.c_int32), ("tickets", _ct.c_int32 * (2 * _MAXL + 4)),
+        ("barrier_gen", _ct.c_int32 * (2 * _MAXL)),
     ]
 
 
@@ -179,7 +181,7 @@ class _VkVae(_ct.Structure):
         ("ctl", _ct.c_void_p),
         ("layers", _VkLayer * _MAXL),
         ("data_ld", _ct.c_int32), ("tc_min_batch", _ct.c_int32), ("grad_slab", _ct.c_int64),
-        ("n_grad_slabs", _ct.c_int32), ("reserved_", _ct.c_int32),
+        ("n_grad_slabs", _ct.c_int32), ("staging", _ct.c_int32),
     ]
 
 
@@ -346,6 +348,8 @@ class VAE(_nn.Module):
         net.grad_slab, net.n_grad_slabs = total, self._n_slabs
         net.data_ld = (net.d_in + 3) // 4 * 4
         net.tc_min_batch = _TC_MIN_BATCH
+        # 0: the GEMM kernels stage the next GEMM's operands themselves; 1: separate prep launches (same results)
+        net.staging = int(_os.environ.get("VAMB_B200_STAGING", "0"))
         for field, t in (("params", arena), ("grads", self._grads), ("exp_avg", self._exp_avg),
                          ("exp_avg_sq", self._exp_avg_sq), ("s", self._s)):
             setattr(net, field, t.data_ptr())
