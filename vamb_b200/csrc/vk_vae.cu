@@ -596,7 +596,8 @@ struct BwdArgs {
     const float *p_prev, *mean_prev, *rstd_prev; double *part_prev; float *m1_prev, *m2_prev; float *g_gamma, *g_beta;
     const float *MU; float kld_w;
     vk_vae_ctl *ctl; int ticket_id;
-    int tile_n;           // tensor-core path: output columns per CTA
+    int tile_n;           // tensor-core path: output columns per dgrad CTA
+    int wg_tile_n;        // ... per wgrad CTA (plain epilogue, off the critical path: wider)
     tc::OpRef wg_a, wg_b, dg_a, dg_b;  // v2: dY^T, X^T(+ones) | dY, W^T
     float *bA_prev, *bB_prev, *bC_prev; const float *gamma_prev; float inv_keep;
     // fused staging of dL/dY of the PREVIOUS layer from the dgrad tile (tensor-core path):
@@ -985,9 +986,9 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(BwdArgs
         // ---- wgrad slice: gW[n, k] (+ bias column) over batch rows [b0, b0 + nb) ----
         const int split = blockIdx.x / (a.wg_tiles_m * a.wg_tiles_n);
         const int t = blockIdx.x % (a.wg_tiles_m * a.wg_tiles_n);
-        const int m0 = (t / a.wg_tiles_n) * 128, n0 = (t % a.wg_tiles_n) * a.tile_n;
+        const int m0 = (t / a.wg_tiles_n) * 128, n0 = (t % a.wg_tiles_n) * a.wg_tile_n;
         int bn = a.K + 1 - n0;
-        bn = bn > a.tile_n ? a.tile_n : ((bn + 15) & ~15);
+        bn = bn > a.wg_tile_n ? a.wg_tile_n : ((bn + 15) & ~15);
         const int b0 = split * x.k_per_split;
         int nb = a.B - b0;
         nb = nb < 0 ? 0 : (nb > x.k_per_split ? x.k_per_split : nb);
@@ -1467,7 +1468,14 @@ static int tc_nsplit(const vk_vae *net, int B) {
 static int tc_tile_n(int B) {
     static const int forced = env_int("VK_TC_TILE_N");  // tuning / debugging override
     if (forced >= 16 && forced <= 128 && (forced & 15) == 0) return forced;
-    return B <= 512 ? 32 : (B <= 2048 ? 64 : 128);
+    return B <= 256 ? 16 : (B <= 1024 ? 32 : (B <= 2048 ? 64 : 128));
+}
+// ... per wgrad CTA: their epilogue is a plain store, so wider tiles (fewer CTAs next to the dgrad ones)
+static int tc_wg_tile_n(int B) {
+    static const int forced = env_int("VK_TC_WG_TILE_N");
+    if (forced >= 16 && forced <= 128 && (forced & 15) == 0) return forced;
+    const int t = tc_tile_n(B);
+    return t < 32 ? 32 : t;  // measured: 32 for B <= 1024, the dgrad width above (tools/train_speed.py)
 }
 
 // ---- tensor-core path: operand staging + warp-specialised GEMMs ------------------------------------
@@ -1760,7 +1768,8 @@ static int launch_backward(const vk_vae *net, int B, cudaStream_t s) {
             x.slab = net->grad_slab;
             a.tile_n = tc_tile_n(B);
             a.wg_tiles_m = (L.n_out + 127) / 128;
-            a.wg_tiles_n = (L.k_in + 1 + a.tile_n - 1) / a.tile_n;
+            a.wg_tile_n = tc_wg_tile_n(B);
+            a.wg_tiles_n = (L.k_in + 1 + a.wg_tile_n - 1) / a.wg_tile_n;
             if (a.dg_tiles_m) {
                 a.dg_tiles_m = (B + 127) / 128;
                 a.dg_tiles_n = (L.k_in + a.tile_n - 1) / a.tile_n;
@@ -1770,7 +1779,7 @@ static int launch_backward(const vk_vae *net, int B, cudaStream_t s) {
             a.dg_a = tc::OpRef{L.dy_hi, L.dy_lo, r32(L.n_out)};
             a.dg_b = tc::OpRef{L.wt_hi, L.wt_lo, r32(L.n_out)};
             const int blocks = a.wg_tiles_m * a.wg_tiles_n * x.nsplit + a.dg_tiles_m * a.dg_tiles_n;
-            VK_CUDA(vk_launch(bwd_layer_tc_kernel, dim3(blocks), dim3(tc::WS_THREADS), (size_t)tc_smem_for(a.tile_n, 2), s, a, x));
+            VK_CUDA(vk_launch(bwd_layer_tc_kernel, dim3(blocks), dim3(tc::WS_THREADS), (size_t)tc_smem_for(a.tile_n > a.wg_tile_n ? a.tile_n : a.wg_tile_n, 2), s, a, x));
         } else {
             const int blocks = a.wg_tiles_m * a.wg_tiles_n + a.dg_tiles_m * a.dg_tiles_n;
             VK_CUDA(vk_launch(bwd_layer_kernel, dim3(blocks), dim3(GT), (size_t)(0), s, a));
