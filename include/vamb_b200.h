@@ -77,6 +77,16 @@ int vk_probe_sync(const float *matrix, const float *lengths, const uint8_t *kept
                   vk_probe_header *hdr, int32_t *within_overflow,
                   int32_t *nl_rows, float *nl_dists, vk_probe_header *hdr_host, void *stream);
 
+/* Same pass with a "mapped" completion: the last block copies the header into PINNED host memory
+ * (`hdr_pinned`, device-visible), leaves the device accumulators of `hdr` zeroed for the next call and sets
+ * `*done_flag_pinned = seq`; the call returns once the host has seen the flag.  `hdr` must be all zero before
+ * the first call, `*done_ticket` (device) zero.  One launch per probe instead of memset + kernel + copy +
+ * stream synchronisation.  Used by the native cluster driver (vk_cluster_next). */
+int vk_probe_mapped(const float *matrix, const float *lengths, const uint8_t *kept, int64_t n, int d,
+                    int64_t medoid_row, float nl_radius, const float *edges, vk_probe_header *hdr,
+                    int32_t *within_overflow, int32_t *nl_rows, float *nl_dists, vk_probe_header *hdr_pinned,
+                    int32_t *done_ticket, int32_t *done_flag_pinned, int32_t seq, void *stream);
+
 /* Local densities of up to VK_MAX_CAND candidate medoids in one pass over the neighbour
  * list (the <= maxsteps sample_medoid calls of one wander_medoid round,
  * vamb/cluster.py:427-448, whose densities are independent of each other).  Only list
@@ -87,6 +97,12 @@ int vk_eval_candidates_sync(const float *matrix, const float *lengths, int d,
                             const int32_t *nl_rows, const float *nl_dists, int32_t n_nl,
                             float prune_radius, const int32_t *cand_rows_host, int n_cand,
                             uint64_t *out_dev, uint64_t *out_host, void *stream);
+
+/* vk_eval_candidates_sync through the mapped completion (out_dev all zero on entry, left zeroed). */
+int vk_eval_candidates_mapped(const float *matrix, const float *lengths, int d, const int32_t *nl_rows,
+                              const float *nl_dists, int32_t n_nl, float prune_radius, const int32_t *cand_rows_host,
+                              int n_cand, uint64_t *out_dev, uint64_t *out_pinned, int32_t *done_ticket,
+                              int32_t *done_flag_pinned, int32_t seq, void *stream);
 
 /* vamb/cluster.py:640-650 (_smaller_indices) + :308-309 (kept_mask[point] = 0):
  * appends orig_ids[row] of every neighbour-list entry with d <= threshold to `members`

@@ -147,7 +147,8 @@ __global__ void __launch_bounds__(PB_THREADS, 4)
 probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths,
              const uint8_t *__restrict__ kept, int64_t n, int d_rt, int64_t mrow, float nl_radius,
              const float *__restrict__ edges_g, vk_probe_header *hdr, int32_t *within_overflow,
-             int32_t *nl_rows, float *nl_dists, int n_tiles) {
+             int32_t *nl_rows, float *nl_dists, int n_tiles, vk_probe_header *hdr_mapped, int32_t *done_ticket,
+             volatile int32_t *done_flag, int32_t seq) {
     const int d = DFIX ? DFIX : d_rt;
     __shared__ float s_edges[VK_NBINS + 1];
     __shared__ u64 s_hist[VK_NBINS];
@@ -283,6 +284,31 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
         if (s_acc.dens_hi) atomicAdd(reinterpret_cast<u64 *>(&hdr->density_hi), s_acc.dens_hi);
         if (s_acc.nlt) atomicAdd(&hdr->n_lt, (int)s_acc.nlt);
     }
+    if (hdr_mapped == nullptr) return;
+    // Mapped completion (vk_probe_mapped): the last block to finish copies the header into pinned host memory,
+    // leaves the device accumulators zeroed for the next probe and raises the flag the host is spinning on --
+    // one launch per probe instead of memset + kernel + copy + stream synchronisation.
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const int t = atomicAdd(done_ticket, 1);
+        s_last = (t == (int)gridDim.x - 1);
+        if (s_last) *done_ticket = 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    constexpr int HEAD_WORDS = (int)(offsetof(vk_probe_header, within) / sizeof(u64));  // accumulators + counters
+    if (tid < HEAD_WORDS) reinterpret_cast<u64 *>(hdr_mapped)[tid] = __ldcg(reinterpret_cast<const u64 *>(hdr) + tid);
+    int nw = __ldcg(&hdr->n_within);
+    nw = nw < VK_PROBE_INLINE ? nw : VK_PROBE_INLINE;
+    for (int i = tid; i < nw; i += PB_THREADS) hdr_mapped->within[i] = __ldcg(&hdr->within[i]);
+    __syncthreads();
+    if (tid < HEAD_WORDS) reinterpret_cast<u64 *>(hdr)[tid] = 0ull;
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) *done_flag = seq;
 }
 
 // rank = number of kept rows before the medoid row (the reference's packed index of the seed,
@@ -299,9 +325,10 @@ static int probe_grid(int n_tiles) {
     return n_tiles < cap ? n_tiles : cap;
 }
 
-extern "C" int vk_probe(const float *matrix, const float *lengths, const uint8_t *kept, int64_t n, int d,
+static int probe_launch(const float *matrix, const float *lengths, const uint8_t *kept, int64_t n, int d,
                         int64_t medoid_row, float nl_radius, const float *edges, vk_probe_header *hdr,
-                        int32_t *within_overflow, int32_t *nl_rows, float *nl_dists, void *stream) {
+                        int32_t *within_overflow, int32_t *nl_rows, float *nl_dists, vk_probe_header *hdr_mapped,
+                        int32_t *done_ticket, int32_t *done_flag, int32_t seq, cudaStream_t s) {
     if (n <= 0 || medoid_row < 0 || medoid_row >= n) {
         vk_set_error("vk_probe: bad arguments (n=%lld, medoid_row=%lld)", (long long)n, (long long)medoid_row);
         return 1;
@@ -314,25 +341,65 @@ extern "C" int vk_probe(const float *matrix, const float *lengths, const uint8_t
         vk_set_error("vk_probe: n=%lld exceeds int32 row ids", (long long)n);
         return 1;
     }
-    cudaStream_t s = (cudaStream_t)stream;
-    // only the accumulators need zeroing, not the inline id list
-    VK_CUDA(cudaMemsetAsync(hdr, 0, offsetof(vk_probe_header, within), s));
-    const int n_tiles = (int)((n + PB_TILE - 1) / PB_TILE);
-    const int grid = probe_grid(n_tiles);
-    if (d == 32)
-        probe_kernel<32><<<grid, PB_THREADS, 0, s>>>(matrix, lengths, kept, n, d, medoid_row, nl_radius, edges,
-                                                     hdr, within_overflow, nl_rows, nl_dists, n_tiles);
-    else
-        probe_kernel<0><<<grid, PB_THREADS, 0, s>>>(matrix, lengths, kept, n, d, medoid_row, nl_radius, edges,
-                                                    hdr, within_overflow, nl_rows, nl_dists, n_tiles);
-    VK_LAUNCH_CHECK();
-    if (medoid_row > 0) {
+    // only the accumulators need zeroing, not the inline id list (the mapped variant leaves them zeroed itself)
+    if (!hdr_mapped) VK_CUDA(cudaMemsetAsync(hdr, 0, offsetof(vk_probe_header, within), s));
+    if (medoid_row > 0) {  // before the probe: its last block publishes the whole header
         int rb = (int)((medoid_row + 256 * 64 - 1) / (256 * 64));
         if (rb > 2 * vk_num_sms()) rb = 2 * vk_num_sms();
         rank_kernel<<<rb, 256, 0, s>>>(kept, medoid_row, hdr);
         VK_LAUNCH_CHECK();
     }
+    const int n_tiles = (int)((n + PB_TILE - 1) / PB_TILE);
+    const int grid = probe_grid(n_tiles);
+    if (d == 32)
+        probe_kernel<32><<<grid, PB_THREADS, 0, s>>>(matrix, lengths, kept, n, d, medoid_row, nl_radius, edges,
+                                                     hdr, within_overflow, nl_rows, nl_dists, n_tiles, hdr_mapped,
+                                                     done_ticket, done_flag, seq);
+    else
+        probe_kernel<0><<<grid, PB_THREADS, 0, s>>>(matrix, lengths, kept, n, d, medoid_row, nl_radius, edges,
+                                                    hdr, within_overflow, nl_rows, nl_dists, n_tiles, hdr_mapped,
+                                                    done_ticket, done_flag, seq);
+    VK_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int vk_probe(const float *matrix, const float *lengths, const uint8_t *kept, int64_t n, int d,
+                        int64_t medoid_row, float nl_radius, const float *edges, vk_probe_header *hdr,
+                        int32_t *within_overflow, int32_t *nl_rows, float *nl_dists, void *stream) {
+    return probe_launch(matrix, lengths, kept, n, d, medoid_row, nl_radius, edges, hdr, within_overflow, nl_rows,
+                        nl_dists, nullptr, nullptr, nullptr, 0, (cudaStream_t)stream);
+}
+
+// Spin on a flag in pinned host memory that the last block of a kernel sets to `seq`; the stream is only
+// queried now and then, to turn a failed launch into an error instead of a hang.
+static int wait_flag(const volatile int32_t *flag, int32_t seq, cudaStream_t s, const char *what) {
+    for (uint64_t it = 1;; ++it) {
+        if (*flag == seq) return 0;
+        if ((it & 0x3FFFFull) == 0) {
+            const cudaError_t e = cudaStreamQuery(s);
+            if (e == cudaSuccess) {
+                if (*flag == seq) return 0;
+                vk_set_error("%s: the stream drained without raising the completion flag", what);
+                return 1;
+            }
+            if (e != cudaErrorNotReady) {
+                vk_set_error("%s: %s", what, cudaGetErrorString(e));
+                return 1;
+            }
+        }
+    }
+}
+
+extern "C" int vk_probe_mapped(const float *matrix, const float *lengths, const uint8_t *kept, int64_t n, int d,
+                               int64_t medoid_row, float nl_radius, const float *edges, vk_probe_header *hdr,
+                               int32_t *within_overflow, int32_t *nl_rows, float *nl_dists,
+                               vk_probe_header *hdr_pinned, int32_t *done_ticket, int32_t *done_flag_pinned, int32_t seq,
+                               void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (probe_launch(matrix, lengths, kept, n, d, medoid_row, nl_radius, edges, hdr, within_overflow, nl_rows, nl_dists,
+                     hdr_pinned, done_ticket, done_flag_pinned, seq, s))
+        return 1;
+    return wait_flag(done_flag_pinned, seq, s, "vk_probe_mapped");
 }
 
 extern "C" int vk_probe_sync(const float *matrix, const float *lengths, const uint8_t *kept, int64_t n, int d,
@@ -419,7 +486,8 @@ constexpr int EC_THREADS = 256;
 __global__ void __launch_bounds__(EC_THREADS)
 eval_candidates_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths, int d,
                        const int32_t *__restrict__ nl_rows, const float *__restrict__ nl_dists, int n_nl,
-                       float prune_radius, CandRows cand, int n_cand, u64 *out) {
+                       float prune_radius, CandRows cand, int n_cand, u64 *out, u64 *out_mapped, int32_t *done_ticket,
+                       volatile int32_t *done_flag, int32_t seq) {
     extern __shared__ __align__(16) float s_qs[];  // [n_cand][dpad]
     __shared__ u64 s_dens[VK_MAX_CAND];
     __shared__ u64 s_dens_hi[VK_MAX_CAND];
@@ -471,6 +539,26 @@ eval_candidates_kernel(const float *__restrict__ matrix, const float *__restrict
         if (s_dens_hi[tid]) atomicAdd(&out[VK_MAX_CAND + tid], s_dens_hi[tid]);
         if (s_cnt[tid]) atomicAdd(&out[2 * VK_MAX_CAND + tid], (u64)s_cnt[tid]);
     }
+    if (out_mapped == nullptr) return;
+    // mapped completion, as in probe_kernel: results to pinned host memory, accumulators left zeroed, flag raised
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const int t = atomicAdd(done_ticket, 1);
+        s_last = (t == (int)gridDim.x - 1);
+        if (s_last) *done_ticket = 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (tid < 3 * VK_MAX_CAND) {
+        out_mapped[tid] = __ldcg(out + tid);
+        out[tid] = 0ull;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) *done_flag = seq;
 }
 
 extern "C" int vk_eval_candidates_sync(const float *matrix, const float *lengths, int d, const int32_t *nl_rows,
@@ -501,12 +589,51 @@ extern "C" int vk_eval_candidates_sync(const float *matrix, const float *lengths
         const int cap = vk_num_sms() * 4;
         if (grid > cap) grid = cap;
         eval_candidates_kernel<<<grid, EC_THREADS, smem, s>>>(matrix, lengths, d, nl_rows, nl_dists, n_nl,
-                                                              prune_radius, cand, n_cand, (u64 *)out_dev);
+                                                              prune_radius, cand, n_cand, (u64 *)out_dev, nullptr,
+                                                              nullptr, nullptr, 0);
         VK_LAUNCH_CHECK();
     }
     VK_CUDA(cudaMemcpyAsync(out_host, out_dev, sizeof(uint64_t) * 3 * VK_MAX_CAND, cudaMemcpyDeviceToHost, s));
     VK_CUDA(cudaStreamSynchronize(s));
     return 0;
+}
+
+// Same results through the mapped completion: out_dev must be all zero on entry (it is left zeroed again).
+extern "C" int vk_eval_candidates_mapped(const float *matrix, const float *lengths, int d, const int32_t *nl_rows,
+                                         const float *nl_dists, int32_t n_nl, float prune_radius,
+                                         const int32_t *cand_rows_host, int n_cand, uint64_t *out_dev,
+                                         uint64_t *out_pinned, int32_t *done_ticket, int32_t *done_flag_pinned,
+                                         int32_t seq, void *stream) {
+    if (n_cand < 1 || n_cand > VK_MAX_CAND) {
+        vk_set_error("vk_eval_candidates_mapped: n_cand=%d outside [1, %d]", n_cand, VK_MAX_CAND);
+        return 1;
+    }
+    if (d < 1 || d > PB_MAX_D) {
+        vk_set_error("vk_eval_candidates_mapped: d=%d outside [1, %d]", d, PB_MAX_D);
+        return 1;
+    }
+    if (n_nl <= 0) {
+        memset(out_pinned, 0, sizeof(uint64_t) * 3 * VK_MAX_CAND);
+        return 0;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    CandRows cand;
+    memset(&cand, 0, sizeof(cand));
+    for (int k = 0; k < n_cand; ++k) cand.rows[k] = cand_rows_host[k];
+    const int dpad = (d + 3) & ~3;
+    const size_t smem = sizeof(float) * (size_t)n_cand * dpad;
+    if (smem > 48 * 1024) {
+        VK_CUDA(cudaFuncSetAttribute(eval_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    const int per_block = EC_THREADS / 8;
+    int grid = (n_nl + per_block - 1) / per_block;
+    const int cap = vk_num_sms() * 4;
+    if (grid > cap) grid = cap;
+    eval_candidates_kernel<<<grid, EC_THREADS, smem, s>>>(matrix, lengths, d, nl_rows, nl_dists, n_nl, prune_radius, cand,
+                                                          n_cand, (u64 *)out_dev, (u64 *)out_pinned, done_ticket,
+                                                          done_flag_pinned, seq);
+    VK_LAUNCH_CHECK();
+    return wait_flag(done_flag_pinned, seq, s, "vk_eval_candidates_mapped");
 }
 
 // ------------------------------------------------------------------ member selection

@@ -118,6 +118,12 @@ struct State {
     MT19937 rng;
     float pdf[31];
     float edges[VK_NBINS + 1];
+    // mapped completion (vk_probe_mapped / vk_eval_candidates_mapped): pinned results + flags, device tickets
+    vk_probe_header *hdr_pin = nullptr;
+    uint64_t *cand_pin = nullptr;
+    int32_t *flags_pin = nullptr;   // [0] probe, [1] candidate evaluation
+    int32_t *tickets_dev = nullptr; // [0] probe, [1] candidate evaluation
+    int32_t seq = 0;
     std::vector<int64_t> members;
     int64_t n_probes, n_evals, n_packs;
 
@@ -130,10 +136,10 @@ struct State {
 int do_probe(State &st, int32_t row, Probe &p) {
     ++st.n_probes;
     const vk_cluster_config &c = st.c;
-    if (vk_probe_sync(st.M(), st.LEN(), st.KEPT(), st.n_act, c.d, row, c.nl_radius, c.edges, c.hdr, c.within_overflow,
-                      c.nl_rows, c.nl_dists, c.hdr_host, c.stream))
+    if (vk_probe_mapped(st.M(), st.LEN(), st.KEPT(), st.n_act, c.d, row, c.nl_radius, c.edges, c.hdr, c.within_overflow,
+                        c.nl_rows, c.nl_dists, st.hdr_pin, st.tickets_dev, st.flags_pin, ++st.seq, c.stream))
         return 1;
-    const vk_probe_header *h = c.hdr_host;
+    const vk_probe_header *h = st.hdr_pin;
     p.medoid = row;
     p.density = ((unsigned __int128)h->density_hi << 12) + h->density_lo;
     memcpy(p.hist, h->hist, sizeof(p.hist));
@@ -157,11 +163,12 @@ int do_eval(State &st, const Probe &p, const std::vector<int32_t> &rows, std::ve
     for (size_t i = 0; i < rows.size(); i += VK_MAX_CAND) {
         const int n = (int)std::min<size_t>(VK_MAX_CAND, rows.size() - i);
         ++st.n_evals;
-        if (vk_eval_candidates_sync(st.M(), st.LEN(), c.d, c.nl_rows, c.nl_dists, p.n_nl, c.prune_radius,
-                                    rows.data() + i, n, c.cand_out, c.cand_out_host, c.stream))
+        if (vk_eval_candidates_mapped(st.M(), st.LEN(), c.d, c.nl_rows, c.nl_dists, p.n_nl, c.prune_radius,
+                                      rows.data() + i, n, c.cand_out, st.cand_pin, st.tickets_dev + 1, st.flags_pin + 1,
+                                      ++st.seq, c.stream))
             return 1;
         for (int k = 0; k < n; ++k)
-            dens.push_back(((unsigned __int128)c.cand_out_host[VK_MAX_CAND + k] << 12) + c.cand_out_host[k]);
+            dens.push_back(((unsigned __int128)st.cand_pin[VK_MAX_CAND + k] << 12) + st.cand_pin[k]);
     }
     return 0;
 }
@@ -329,6 +336,8 @@ int find_threshold(State &st, const Probe &p, double &threshold, double &observe
 
 }  // namespace
 
+extern "C" void vk_cluster_destroy(void *handle);
+
 extern "C" int vk_cluster_create(void **handle, const vk_cluster_config *cfg) {
     State *st = new (std::nothrow) State();
     if (!st) {
@@ -350,11 +359,35 @@ extern "C" int vk_cluster_create(void **handle, const vk_cluster_config *cfg) {
     st->n_probes = st->n_evals = st->n_packs = 0;
     st->rng.init_by_array(cfg->seed_key, cfg->seed_key_len);
     memcpy(st->pdf, cfg->normalpdf_host, sizeof(st->pdf));
+    // mapped completion: pinned (device-visible) result buffers, and accumulators that start out zeroed
+    cudaStream_t s = (cudaStream_t)cfg->stream;
+    if (cudaHostAlloc((void **)&st->hdr_pin, sizeof(vk_probe_header), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostAlloc((void **)&st->cand_pin, sizeof(uint64_t) * 3 * VK_MAX_CAND, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostAlloc((void **)&st->flags_pin, sizeof(int32_t) * 2, cudaHostAllocMapped) != cudaSuccess ||
+        cudaMalloc((void **)&st->tickets_dev, sizeof(int32_t) * 2) != cudaSuccess ||
+        cudaMemsetAsync(st->tickets_dev, 0, sizeof(int32_t) * 2, s) != cudaSuccess ||
+        cudaMemsetAsync(cfg->hdr, 0, sizeof(vk_probe_header), s) != cudaSuccess ||
+        cudaMemsetAsync(cfg->cand_out, 0, sizeof(uint64_t) * 3 * VK_MAX_CAND, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess) {
+        vk_set_error("vk_cluster_create: %s", cudaGetErrorString(cudaGetLastError()));
+        vk_cluster_destroy(st);
+        return 1;
+    }
+    memset(st->hdr_pin, 0, sizeof(vk_probe_header));
+    st->flags_pin[0] = st->flags_pin[1] = 0;
     *handle = st;
     return 0;
 }
 
-extern "C" void vk_cluster_destroy(void *handle) { delete static_cast<State *>(handle); }
+extern "C" void vk_cluster_destroy(void *handle) {
+    State *st = static_cast<State *>(handle);
+    if (!st) return;
+    if (st->hdr_pin) cudaFreeHost(st->hdr_pin);
+    if (st->cand_pin) cudaFreeHost(st->cand_pin);
+    if (st->flags_pin) cudaFreeHost(st->flags_pin);
+    if (st->tickets_dev) cudaFree(st->tickets_dev);
+    delete st;
+}
 
 extern "C" int vk_cluster_stats(void *handle, int64_t *out4) {
     State *st = static_cast<State *>(handle);
