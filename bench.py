@@ -162,9 +162,16 @@ def run_hot_path(tensors_dl, lengths, nsamples, nepochs, seed, resident: bool, m
     train_steps = sum(s * e for _, s, e in sched)
     nl = vae._net.n_layers
     tcm = vae._net.tc_min_batch
-    # per step: batch rows + nl forward + loss + nl backward + optimiser (+ operand staging on the tensor-core path)
-    launches = sum(s * e * ((2 * nl + 3) + ((2 * nl + 1) if (tcm and b >= tcm) else 0)) for b, s, e in sched) \
-        + ((n + vae._net.bmax - 1) // vae._net.bmax) * (nl + 2) + 2 * gen._n_probes + gen._n_evals + n_clusters + 1
+    # per step: batch rows + nl forward + loss + nl backward + optimiser; on the tensor-core path + weight staging,
+    # row gather and the loss fold (fused staging), or + one staging launch per GEMM (staging = 1)
+    def per_step(b):
+        base = 2 * nl + 3
+        if not (tcm and b >= tcm):
+            return base
+        return base + (3 if vae._net.staging == 0 else 2 * nl + 1)
+    launches = sum(s * e * per_step(b) for b, s, e in sched) \
+        + ((n + vae._net.bmax - 1) // vae._net.bmax) * (nl + 2) \
+        + gen._n_probes + gen._n_evals + 2 * n_clusters + 1  # probe, evaluation, (rank + selection) per cluster
     return {
         "t_train": t1 - t0, "t_encode": t2 - t1, "t_cluster": t3 - t2, "t_total": t3 - t0,
         "event_ms": ev0.elapsed_time(ev1), "n_clusters": n_clusters, "n_clustered": n_members,

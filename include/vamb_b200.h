@@ -276,6 +276,11 @@ int vk_vae_forward(const vk_vae *net, int64_t row0, int batch, int training, int
  * cleared (vambtools.py:324-330), written to latent_out[n, nlatent] (device). */
 int vk_vae_encode(const vk_vae *net, int64_t row0, int64_t n, int mask_bits, float *latent_out, void *stream);
 
+/* Once per process and device, outside any stream capture: creates the side stream / events on which a
+ * training step runs its off-critical-path work (weight staging, loss bookkeeping).  Optional: without it
+ * everything runs on the caller's stream. */
+int vk_vae_init_device(void);
+
 /* Eval-mode BatchNorm affine from the running statistics into bn_a / bn_c. */
 int vk_vae_prepare_eval(const vk_vae *net, void *stream);
 

@@ -470,7 +470,36 @@ struct LossArgs {
     double *part; vk_vae_ctl *ctl; int ticket_id; int write_grad;
     // tensor-core path, fused staging: dL/dR also as the lane-major operands of the output layer's dgrad / wgrad
     float *stage_a; int stage_a_ld; float *stage_t; int stage_t_ld;
+    int fold_later;  // 1: the caller launches loss_fold_kernel on a side stream
 };
+
+// Fold the per-block partial sums of one step into the running loss sums (256 threads, fixed order).
+__device__ __forceinline__ void loss_fold(const LossArgs &a, unsigned n_blocks) {
+    // fixed-order parallel fold of the block partials: thread t sums blocks t, t+256, ...; then a serial
+    // fold of the 256 thread sums (same order every run)
+    __shared__ double s_fold[4][16];
+    {
+        double t[4] = {0.0, 0.0, 0.0, 0.0};
+        for (unsigned i = threadIdx.x; i < n_blocks; i += 256)
+            for (int c = 0; c < 4; ++c) t[c] += __ldcg(a.part + (int64_t)i * 4 + c);
+        for (int c = 0; c < 4; ++c) {
+            const double r = block_sum256(t[c], &s_fold[c][0]);
+            if (threadIdx.x == 0) s_fold[c][8] = r;
+        }
+    }
+    if (threadIdx.x == 0) {
+        const double ab = s_fold[0][8] / a.B * a.ab_w, ce = s_fold[1][8] / a.B * a.ce_w,
+                     sse = s_fold[2][8] / a.B * a.sse_w, kld = s_fold[3][8] / a.B * a.kld_w;
+        // loss.mean() over the [B, B] broadcast = mean_j(l_j) * mean_i(w_i)   (encode.py:349-352)
+        a.ctl->loss_sums[0] += ((ce + ab + sse) + kld) * a.ctl->wbar;
+        a.ctl->loss_sums[1] += ab;
+        a.ctl->loss_sums[2] += ce;
+        a.ctl->loss_sums[3] += sse;
+        a.ctl->loss_sums[4] += kld;
+        a.ctl->n_loss_steps += 1;
+    }
+}
+
 
 constexpr int LOSS_STAGE_MAX_D = 160;  // widest reconstruction the loss kernel stages itself (else a prep launch does)
 
@@ -557,30 +586,15 @@ __global__ void __launch_bounds__(256) loss_kernel(LossArgs a) {
         a.part[(int64_t)blockIdx.x * 4 + threadIdx.x] = t;
     }
     tk_end(tk);
+    if (a.fold_later) return;  // loss_fold_kernel does it off the critical path
     if (!last_block_done(&a.ctl->tickets[a.ticket_id], gridDim.x)) return;
-    // fixed-order parallel fold of the block partials: thread t sums blocks t, t+256, ...; then a serial
-    // fold of the 256 thread sums (same order every run)
-    __shared__ double s_fold[4][16];
-    {
-        double t[4] = {0.0, 0.0, 0.0, 0.0};
-        for (unsigned i = threadIdx.x; i < gridDim.x; i += 256)
-            for (int c = 0; c < 4; ++c) t[c] += __ldcg(a.part + (int64_t)i * 4 + c);
-        for (int c = 0; c < 4; ++c) {
-            const double r = block_sum256(t[c], &s_fold[c][0]);
-            if (threadIdx.x == 0) s_fold[c][8] = r;
-        }
-    }
-    if (threadIdx.x == 0) {
-        const double ab = s_fold[0][8] / a.B * a.ab_w, ce = s_fold[1][8] / a.B * a.ce_w,
-                     sse = s_fold[2][8] / a.B * a.sse_w, kld = s_fold[3][8] / a.B * a.kld_w;
-        // loss.mean() over the [B, B] broadcast = mean_j(l_j) * mean_i(w_i)   (encode.py:349-352)
-        a.ctl->loss_sums[0] += ((ce + ab + sse) + kld) * a.ctl->wbar;
-        a.ctl->loss_sums[1] += ab;
-        a.ctl->loss_sums[2] += ce;
-        a.ctl->loss_sums[3] += sse;
-        a.ctl->loss_sums[4] += kld;
-        a.ctl->n_loss_steps += 1;
-    }
+    loss_fold(a, gridDim.x);
+}
+
+// one block: the running loss sums of the control block (read by the host once per epoch)
+__global__ void __launch_bounds__(256) loss_fold_kernel(LossArgs a, int n_blocks) {
+    pdl_entry();
+    loss_fold(a, (unsigned)n_blocks);
 }
 
 // ------------------------------------------------------------------ backward layer (wgrad + dgrad)
@@ -1436,6 +1450,42 @@ extern "C" int64_t vk_vae_sizeof(int which) {
     return -1;
 }
 
+static int env_int_early(const char *name) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : 0;
+}
+
+// ---- side stream: work that is off the critical path of a step (weight staging, loss bookkeeping) runs on a
+// second stream, forked from / joined to the caller's stream with events (also inside a stream capture).
+struct SideCtx {
+    cudaStream_t side;
+    cudaEvent_t fork, weights_done, loss_done, fold_done;
+};
+static SideCtx *g_side[64];
+
+static SideCtx *side_ctx() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    return g_side[dev];
+}
+
+// Create the per-device helper objects outside any stream capture (called once by the host wrapper).
+extern "C" int vk_vae_init_device(void) {
+    int dev = 0;
+    VK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || g_side[dev]) return 0;
+    static const int off = env_int_early("VK_SIDE_STREAM_OFF");
+    if (off > 0) return 0;
+    SideCtx *c = new SideCtx();
+    VK_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    VK_CUDA(cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming));
+    VK_CUDA(cudaEventCreateWithFlags(&c->weights_done, cudaEventDisableTiming));
+    VK_CUDA(cudaEventCreateWithFlags(&c->loss_done, cudaEventDisableTiming));
+    VK_CUDA(cudaEventCreateWithFlags(&c->fold_done, cudaEventDisableTiming));
+    g_side[dev] = c;
+    return 0;
+}
+
 static int check_net(const vk_vae *net, int batch) {
     if (!net || net->n_layers < 2 || net->n_layers > VK_VAE_MAX_LAYERS) {
         vk_set_error("vk_vae: bad layer count");
@@ -1621,7 +1671,8 @@ static int launch_batch_rows(const vk_vae *net, int B, int mode, int64_t row0, c
 }
 
 static int launch_forward(const vk_vae *net, int B, int training, int upto /*exclusive layer index*/,
-                          const vk_vae_inject *inj, int mask_bits, float *latent_out, cudaStream_t s) {
+                          const vk_vae_inject *inj, int mask_bits, float *latent_out, cudaStream_t s,
+                          cudaEvent_t weights_ready = nullptr) {
     for (int j = 0; j < upto; ++j) {
         const vk_vae_layer &L = net->layers[j];
         FwdArgs a;
@@ -1656,6 +1707,7 @@ static int launch_forward(const vk_vae *net, int B, int training, int upto /*exc
             a.stage_a = Nx.xop_hi; a.stage_a_ld = r32(Nx.k_in);
             a.stage_t = training ? Nx.xt_hi : nullptr; a.stage_t_ld = net->bmax;
         }
+        if (j == 0 && weights_ready) VK_CUDA(cudaStreamWaitEvent(s, weights_ready, 0));  // staged on the side stream
         PROF_MARK_K(s, PK_FWD);
         if (tcp) {
             if (tc_prepare()) return 1;
@@ -1673,7 +1725,7 @@ static int launch_forward(const vk_vae *net, int B, int training, int upto /*exc
     return 0;
 }
 
-static int launch_loss(const vk_vae *net, int B, int write_grad, cudaStream_t s) {
+static int launch_loss(const vk_vae *net, int B, int write_grad, cudaStream_t s, SideCtx *sc = nullptr) {
     const int nl = net->n_layers;
     int mu_j = -1;
     for (int j = 0; j < nl; ++j)
@@ -1686,6 +1738,7 @@ static int launch_loss(const vk_vae *net, int B, int write_grad, cudaStream_t s)
     a.ce_w = net->ce_w; a.ab_w = net->ab_w; a.sse_w = net->sse_w; a.kld_w = net->kld_w;
     a.part = net->loss_part; a.ctl = net->ctl; a.ticket_id = VK_VAE_MAX_LAYERS; a.write_grad = write_grad;
     a.stage_a = a.stage_t = nullptr; a.stage_a_ld = a.stage_t_ld = 0;
+    a.fold_later = sc ? 1 : 0;
     int blocks = (B + 7) / 8;
     if (write_grad && use_tc(net, B) && fused_staging(net, B) && net->d_in <= LOSS_STAGE_MAX_D) {
         const vk_vae_layer &L = net->layers[nl - 1];
@@ -1700,6 +1753,13 @@ static int launch_loss(const vk_vae *net, int B, int write_grad, cudaStream_t s)
     PROF_MARK_K(s, PK_LOSS);
     VK_CUDA(vk_launch(loss_kernel, dim3(blocks), dim3(256), (size_t)(0), s, a));
     VK_LAUNCH_CHECK();
+    if (sc) {  // the running loss sums are bookkeeping: fold them next to the backward pass
+        VK_CUDA(cudaEventRecord(sc->loss_done, s));
+        VK_CUDA(cudaStreamWaitEvent(sc->side, sc->loss_done, 0));
+        VK_CUDA(vk_launch(loss_fold_kernel, dim3(1), dim3(256), (size_t)(0), sc->side, a, blocks));
+        VK_LAUNCH_CHECK();
+        VK_CUDA(cudaEventRecord(sc->fold_done, sc->side));
+    }
     return 0;
 }
 
@@ -1816,11 +1876,19 @@ static int grad_step_impl(const vk_vae *net, int batch, const vk_vae_inject *inj
     if (check_net(net, batch)) return 1;
     cudaStream_t s = (cudaStream_t)stream;
     const int mode = (inject && inject->batch_idx) ? 0 : 1;
+    SideCtx *sc = (use_tc(net, batch) && g_prof_events == nullptr) ? side_ctx() : nullptr;
+    if (sc) {  // weight staging only depends on the previous optimiser step: next to batch rows + gather
+        VK_CUDA(cudaEventRecord(sc->fork, s));
+        VK_CUDA(cudaStreamWaitEvent(sc->side, sc->fork, 0));
+        if (launch_prep_weights(net, sc->side)) return 1;
+        VK_CUDA(cudaEventRecord(sc->weights_done, sc->side));
+    }
     if (launch_batch_rows(net, batch, mode, 0, inject, s)) return 1;
-    if (use_tc(net, batch) && launch_prep_weights(net, s)) return 1;
-    if (launch_forward(net, batch, 1, net->n_layers, inject, 0, nullptr, s)) return 1;
-    if (launch_loss(net, batch, 1, s)) return 1;
+    if (!sc && use_tc(net, batch) && launch_prep_weights(net, s)) return 1;
+    if (launch_forward(net, batch, 1, net->n_layers, inject, 0, nullptr, s, sc ? sc->weights_done : nullptr)) return 1;
+    if (launch_loss(net, batch, 1, s, sc)) return 1;
     if (launch_backward(net, batch, s)) return 1;
+    if (sc) VK_CUDA(cudaStreamWaitEvent(s, sc->fold_done, 0));  // join before the optimiser / the end of a capture
     return 0;
 }
 

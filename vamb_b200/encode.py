@@ -202,6 +202,8 @@ for _name, _args in {
 }.items():
     getattr(_L, _name).argtypes = _args
     getattr(_L, _name).restype = _ct.c_int
+_L.vk_vae_init_device.argtypes = []
+_L.vk_vae_init_device.restype = _ct.c_int
 _L.vk_vae_sizeof.argtypes = [_ct.c_int]
 _L.vk_vae_sizeof.restype = _ct.c_int64
 for _i, _cls in enumerate((_VkVae, _VkLayer, _VkCtl, _VkInject)):
@@ -350,6 +352,8 @@ class VAE(_nn.Module):
         net.tc_min_batch = _TC_MIN_BATCH
         # 0: the GEMM kernels stage the next GEMM's operands themselves; 1: separate prep launches (same results)
         net.staging = int(_os.environ.get("VAMB_B200_STAGING", "0"))
+        with _torch.cuda.device(dev):
+            _lib.check(_L.vk_vae_init_device())  # side stream / events of the training step (once per device)
         for field, t in (("params", arena), ("grads", self._grads), ("exp_avg", self._exp_avg),
                          ("exp_avg_sq", self._exp_avg_sq), ("s", self._s)):
             setattr(net, field, t.data_ptr())
