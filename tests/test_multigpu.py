@@ -49,7 +49,9 @@ def _worker(rank, world, port, q):
     q.put((rank, {"loss": first, "digest": digest, "same": bool(same), "finite": bool(np.isfinite(lat).all()),
                   "clusters": clusters, "graphs": bool(vae._use_graphs)}))
     dist.barrier()
-    dist.destroy_process_group()
+    # CUDA graphs that captured NCCL collectives can hang NCCL's communicator teardown; the result is already
+    # reported, so leave without running destructors (bench.py does the same)
+    os._exit(0)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
@@ -64,7 +66,7 @@ def test_data_parallel_replicas_stay_identical():
         p.start()
     res = dict(q.get(timeout=600) for _ in range(2))
     for p in procs:
-        p.join(timeout=120)
+        p.join(timeout=60)
         assert p.exitcode == 0
     assert res[0]["same"] and res[1]["same"], "replicas diverged"
     assert res[0]["digest"] == res[1]["digest"]
