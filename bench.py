@@ -206,7 +206,11 @@ def vae_roofline(vae, n, nepochs):
             k, nn, in_kind = dims[j]
             flops = 2.0 * batch * nn * (k + 1) + (2.0 * batch * nn * k if in_kind != 0 else 0.0)
             kname = "bwd_layer_tc_kernel" if 0 < net.tc_min_batch <= batch else "bwd_layer_kernel"
-            cand = {"kernel": f"{kname}[layer {j}: {k}->{nn}, B={batch}]", "ms": float(ms),
+            # MMA-issue floor of the longest CTA of the launch (dgrad: n_out / 32 k-tiles, wgrad: batch / splits / 32), 12
+            # tcgen05.mma per k-tile, one every 47 cycles (64 for 128-column tiles) -- tools/tc_fixed_cost.py
+            ktiles = max((nn + 31) // 32 if in_kind != 0 else 0, (min(batch, 512) + 31) // 32)
+            floor_us = ktiles * 12 * (64 if batch > 2048 else 47) / 1965.0
+            cand = {"kernel": f"{kname}[layer {j}: {k}->{nn}, B={batch}]", "ms": float(ms), "floor_us": floor_us,
                     "tflops": flops / (ms * 1e-3) / 1e12, "weight_ms": nsteps * float(ms)}
             if best is None or cand["weight_ms"] > best["weight_ms"]:
                 best = cand
@@ -419,9 +423,15 @@ def main():
         roof = {"bound": "tensor", "kernel": best["kernel"], "achieved": best["tflops"], "peak": tf_peak,
                 "unit": "TFLOP/s", "frac": best["tflops"] / tf_peak, "traffic": None,
                 "peak_source": f"{which} bf16 dense sustained (MEASURED_PEAKS.json)",
-                "time_share": share, "ms_per_launch": best["ms"]}
+                "time_share": share, "ms_per_launch": best["ms"],
+                # these GEMMs are 0.1-4 GFLOP each: the bound that matters is the serial MMA issue of one CTA
+                "mma_issue_floor_us": best["floor_us"], "frac_of_issue_floor": best["floor_us"] / (best["ms"] * 1e3),
+                "note": "traffic: ncu dram bytes of this kernel are ~3 MB per launch (operands L2-resident), "
+                        "profiles/r01_ncu_summary.md"}
+        # ncu --set full at N = 1,000,000 x 32: dram read 130.0 MB + write 3.3 MB per launch (profiles/r01_ncu_summary.md)
+        probe_traffic = 133.3e6 if (pr["bytes"] == 133000000) else None
         roof_cluster = {"bound": "hbm", "kernel": pr["kernel"], "achieved": pr["gbs"], "peak": hbm_peak,
-                        "unit": "GB/s", "frac": pr["gbs"] / hbm_peak, "traffic": None,
+                        "unit": "GB/s", "frac": pr["gbs"] / hbm_peak, "traffic": probe_traffic,
                         "algorithmic_bytes": pr["bytes"], "ms_per_launch": pr["ms"],
                         "peak_source": f"{which} copy bandwidth (MEASURED_PEAKS.json)"}
         base = None
