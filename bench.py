@@ -408,7 +408,7 @@ def main():
             t2 = float(tt.item())
         d_in = args.nsamples + 104
         h2d = args.n * (d_in + 1) * 4 + args.n * 32 * 4 + args.n * 4
-        d2h = args.n * 32 * 4 + args.n * 4 + r2["probes"] * 8700
+        d2h = args.n * 32 * 4 + args.n * 4 + r2["probes"] * 512 + r2["evals"] * 768  # latent, ids, probe heads, densities
         e2e = {"value": world * args.n / t2, "unit": "contigs/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "t_train": r2["t_train"], "t_encode": r2["t_encode"],
                "t_cluster": r2["t_cluster"]}

@@ -76,16 +76,20 @@ def test_train_steps_and_encode_match_reference_golden(case, tc):
     assert np.all(np.abs(lat - gl) <= 1e-4 + np.abs(gl) * 2.0 ** -11)
 
 
-@pytest.mark.parametrize("tc,B", [(False, 256), (True, 256), (True, 1024), (True, 4096), ("prep", 256), ("prep", 4096),
-                                  (True, 1000)],
+@pytest.mark.parametrize("tc,B,S", [(False, 256, 50), (True, 256, 50), (True, 1024, 50), (True, 4096, 50),
+                                    ("prep", 256, 50), ("prep", 4096, 50), (True, 1000, 50), (True, 256, 80),
+                                    (True, 8192, 50)],
                          ids=["ffma-256", "tcgen05-256", "tcgen05-1024-split2", "tcgen05-4096-split8", "tcgen05-prep-256",
-                              "tcgen05-prep-4096", "tcgen05-1000-ragged"])
-def test_gradients_match_oracle_default_network(tc, B):
-    """One fwd+bwd on the bin-default network (S=50, 512-512-32): every gradient tensor."""
+                              "tcgen05-prep-4096", "tcgen05-1000-ragged", "tcgen05-256-wide-input",
+                              "tcgen05-8192-grid-fallback"])
+def test_gradients_match_oracle_default_network(tc, B, S):
+    """One fwd+bwd on the bin-default network (512-512-32): every gradient tensor.  S = 80 makes the
+    reconstruction wider than the loss kernel stages itself (a prep launch takes over for that layer);
+    B = 8192 exceeds the SM count with its forward grid, so operand staging falls back to prep launches."""
     import vamb_b200.encode as ve
     from oracle import vae_oracle as vo
 
-    S, n = 50, 5000
+    n = max(5000, B + 1000)
     rpkm, tnfs, lens = vae_inputs(S, n, 7)
     dl = ve.make_dataloader(rpkm.copy(), tnfs.copy(), lens, batchsize=B)
     d, t, a, w = dl.dataset.tensors
@@ -101,7 +105,7 @@ def test_gradients_match_oracle_default_network(tc, B):
     # (tools/vae_bwd_diag.py); the weight gradients are B-term sums of products of random sign, so their
     # relative error grows with the length of the fp32 accumulation chain: 3e-5 up to B = 256, and up to
     # ~1e-3 on the most cancelling tensors at B = 4096 (tensor-core accumulators truncate).
-    tol = 3e-5 if B <= 256 else (2e-4 if B <= 1024 else 3e-3)
+    tol = 3e-5 if B <= 256 else (2e-4 if B <= 1024 else (3e-3 if B <= 4096 else 6e-3))
     for k, gref in grads.items():
         assert rel(got[k].cpu().numpy(), gref.numpy()) < tol, k
 
