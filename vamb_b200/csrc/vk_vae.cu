@@ -94,21 +94,6 @@ __device__ __forceinline__ bool last_block_done(int32_t *ticket, int total) {
     return s_last != 0;
 }
 
-// Dataset row of batch position b.  mode 0: rows from inject->batch_idx; 1: epoch permutation; 2: contiguous
-__device__ __forceinline__ int64_t batch_row_index(int mode, int b, int B, const int64_t *batch_idx, const vk_vae_ctl *ctl,
-                                                   int64_t n_rows, int64_t row0, int steps_per_epoch) {
-    if (mode == 0) return batch_idx[b];
-    if (mode == 1) {
-        int half_bits = 1;
-        while ((1ull << (2 * half_bits)) < (uint64_t)n_rows) ++half_bits;
-        const uint64_t key = mix64(ctl->seed ^ (0x5851F42D4C957F2Dull * (uint64_t)(ctl->epoch + 1)));
-        int64_t t = ctl->step - ctl->epoch_step0;
-        if (steps_per_epoch > 0) t %= steps_per_epoch;
-        return (int64_t)feistel_perm((uint64_t)(t * (int64_t)B + b), (uint64_t)n_rows, half_bits, key);
-    }
-    return row0 + b;
-}
-
 // One thread per batch row (grid = ceil(B / 256) blocks); the batch-mean weight is folded by the last
 // block from per-block partial sums in block order (fixed order -> reproducible).
 __global__ void __launch_bounds__(256)
@@ -121,7 +106,16 @@ batch_rows_kernel(int64_t *batch_rows, const int64_t *batch_idx, const float *we
     const int b = blockIdx.x * 256 + tid;
     double acc = 0.0;
     if (b < B) {
-        const int64_t r = batch_row_index(mode, b, B, batch_idx, ctl, n_rows, row0, steps_per_epoch);
+        int64_t r;
+        if (mode == 0) r = batch_idx[b];
+        else if (mode == 1) {
+            int half_bits = 1;
+            while ((1ull << (2 * half_bits)) < (uint64_t)n_rows) ++half_bits;
+            const uint64_t key = mix64(ctl->seed ^ (0x5851F42D4C957F2Dull * (uint64_t)(ctl->epoch + 1)));
+            int64_t t = ctl->step - ctl->epoch_step0;
+            if (steps_per_epoch > 0) t %= steps_per_epoch;
+            r = (int64_t)feistel_perm((uint64_t)(t * (int64_t)B + b), (uint64_t)n_rows, half_bits, key);
+        } else r = row0 + b;
         batch_rows[b] = r;
         acc = (double)weights[r];
     }
@@ -1176,9 +1170,6 @@ struct PrepArgs {
     const float *p;
     const float *c0, *c1, *c2;
     const float *data; const int64_t *rows_idx; int data_ld;
-    // rows_mode >= 0: the gather computes the dataset row itself (batch_row_index) instead of reading rows_idx,
-    // so it does not depend on the batch_rows launch
-    int rows_mode; const int64_t *batch_idx; const vk_vae_ctl *rows_ctl; int64_t n_rows; int steps_per_epoch;
     float slope; int has_dropout;
     int rows, cols;            // logical extent
     int rows_w, cols_w;        // extent written (zeros outside the logical extent): rows_w >= rows, multiple of 32
@@ -1209,12 +1200,7 @@ __device__ __forceinline__ float prep_value(const PrepArgs &a, int r, int c, flo
             const float v = __fmaf_rn(k0, __ldg(a.src + (int64_t)r * a.ld_src + c), __fmaf_rn(k1, pv, k2));
             return pv > 0.0f ? v : v * a.slope;
         }
-        default: {
-            const int64_t row = a.rows_mode >= 0
-                                    ? batch_row_index(a.rows_mode, r, a.rows, a.batch_idx, a.rows_ctl, a.n_rows, 0, a.steps_per_epoch)
-                                    : a.rows_idx[r];
-            return __ldg(a.data + row * (int64_t)a.data_ld + c);
-        }
+        default: return __ldg(a.data + a.rows_idx[r] * (int64_t)a.data_ld + c);
     }
 }
 
@@ -1473,7 +1459,7 @@ static int env_int_early(const char *name) {
 // second stream, forked from / joined to the caller's stream with events (also inside a stream capture).
 struct SideCtx {
     cudaStream_t side;
-    cudaEvent_t fork, weights_done, rows_done, loss_done, fold_done;
+    cudaEvent_t fork, weights_done, loss_done, fold_done;
 };
 static SideCtx *g_side[64];
 
@@ -1494,7 +1480,6 @@ extern "C" int vk_vae_init_device(void) {
     VK_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
     VK_CUDA(cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming));
     VK_CUDA(cudaEventCreateWithFlags(&c->weights_done, cudaEventDisableTiming));
-    VK_CUDA(cudaEventCreateWithFlags(&c->rows_done, cudaEventDisableTiming));
     VK_CUDA(cudaEventCreateWithFlags(&c->loss_done, cudaEventDisableTiming));
     VK_CUDA(cudaEventCreateWithFlags(&c->fold_done, cudaEventDisableTiming));
     g_side[dev] = c;
@@ -1591,11 +1576,7 @@ static int launch_prep(const PrepArgs &a, cudaStream_t s) {
 }
 
 // stage the input of layer j (A of its forward GEMM; its transpose is B of its wgrad)
-struct RowsSpec {
-    int mode; const int64_t *batch_idx;
-};
-
-static int launch_prep_input(const vk_vae *net, int j, int B, int training, cudaStream_t s, const RowsSpec *rows = nullptr) {
+static int launch_prep_input(const vk_vae *net, int j, int B, int training, cudaStream_t s) {
     const vk_vae_layer &L = net->layers[j];
     PrepArgs a;
     memset(&a, 0, sizeof(a));
@@ -1604,11 +1585,6 @@ static int launch_prep_input(const vk_vae *net, int j, int B, int training, cuda
     if (training) { a.hiT = L.xt_hi; a.loT = nullptr; a.ldT = net->bmax; a.ones_row = 1; }
     if (L.in_kind == VK_IN_DATA) {
         a.mode = 3; a.data = net->data; a.rows_idx = net->batch_rows; a.data_ld = net->data_ld;
-        a.rows_mode = -1;
-        if (rows) {
-            a.rows_mode = rows->mode; a.batch_idx = rows->batch_idx; a.rows_ctl = net->ctl; a.n_rows = net->n_rows;
-            a.steps_per_epoch = net->n_rows > B ? (int)(net->n_rows / B) : 1;
-        }
     } else if (L.in_kind == VK_IN_BN) {
         const vk_vae_layer &P = net->layers[j - 1];
         a.mode = 1; a.src = P.act; a.ld_src = P.n_out; a.c0 = P.bn_a; a.c1 = P.bn_c;
@@ -1696,7 +1672,7 @@ static int launch_batch_rows(const vk_vae *net, int B, int mode, int64_t row0, c
 
 static int launch_forward(const vk_vae *net, int B, int training, int upto /*exclusive layer index*/,
                           const vk_vae_inject *inj, int mask_bits, float *latent_out, cudaStream_t s,
-                          cudaEvent_t weights_ready = nullptr, const RowsSpec *rows = nullptr) {
+                          cudaEvent_t weights_ready = nullptr) {
     for (int j = 0; j < upto; ++j) {
         const vk_vae_layer &L = net->layers[j];
         FwdArgs a;
@@ -1724,7 +1700,7 @@ static int launch_forward(const vk_vae *net, int B, int training, int upto /*exc
         const bool tcp = use_tc(net, B);
         const bool fused = tcp && fused_staging(net, B);
         if (tcp && (!fused || j == 0))  // fused: layer j - 1 staged this layer's operands from its output tile
-            if (launch_prep_input(net, j, B, training, s, rows)) return 1;
+            if (launch_prep_input(net, j, B, training, s)) return 1;
         if (fused && j + 1 < upto && L.kind != VK_LAYER_OUT) {
             const vk_vae_layer &Nx = net->layers[j + 1];
             a.stage = (L.kind == VK_LAYER_HIDDEN && training) ? 1 : 2;
@@ -1907,17 +1883,9 @@ static int grad_step_impl(const vk_vae *net, int batch, const vk_vae_inject *inj
         if (launch_prep_weights(net, sc->side)) return 1;
         VK_CUDA(cudaEventRecord(sc->weights_done, sc->side));
     }
-    RowsSpec rs{mode, inject ? inject->batch_idx : nullptr};
-    if (sc) {  // batch rows + batch-mean weight feed the loss kernel; the gather computes its rows itself
-        if (launch_batch_rows(net, batch, mode, 0, inject, sc->side)) return 1;
-        VK_CUDA(cudaEventRecord(sc->rows_done, sc->side));
-    } else {
-        if (launch_batch_rows(net, batch, mode, 0, inject, s)) return 1;
-        if (use_tc(net, batch) && launch_prep_weights(net, s)) return 1;
-    }
-    if (launch_forward(net, batch, 1, net->n_layers, inject, 0, nullptr, s, sc ? sc->weights_done : nullptr, sc ? &rs : nullptr))
-        return 1;
-    if (sc) VK_CUDA(cudaStreamWaitEvent(s, sc->rows_done, 0));
+    if (launch_batch_rows(net, batch, mode, 0, inject, s)) return 1;
+    if (!sc && use_tc(net, batch) && launch_prep_weights(net, s)) return 1;
+    if (launch_forward(net, batch, 1, net->n_layers, inject, 0, nullptr, s, sc ? sc->weights_done : nullptr)) return 1;
     if (launch_loss(net, batch, 1, s, sc)) return 1;
     if (launch_backward(net, batch, s)) return 1;
     if (sc) VK_CUDA(cudaStreamWaitEvent(s, sc->fold_done, 0));  // join before the optimiser / the end of a capture
