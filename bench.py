@@ -322,6 +322,12 @@ def cpu_baseline(abundance, tnf, lengths, nsamples, nepochs, seed, budget_s, lat
             "t_train_est": t_train, "t_encode_est": t_encode, "t_cluster_est": t_cluster}
 
 
+def workload_name(args) -> str:
+    """The same string on both arms (the driver compares the `config` of the two JSON lines)."""
+    return (f"{args.n} contigs/GPU x (103 TNF + {args.nsamples} abundance), bin default VAE 512-512-32, {args.nepochs} "
+            "epochs (batch 256 doubling at 25/75/150/225) + encode + medoid clustering to exhaustion")
+
+
 def main():
     args = parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -343,9 +349,9 @@ def main():
             "impl": "reference", "metric": METRIC, "value": v, "unit": "contigs/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.n / v,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.n} contigs x (103 TNF + {args.nsamples} abundance), bin default VAE "
-                                   f"nlatent=32, {args.nepochs} epochs + medoid clustering",
-                       "note": "CPU port of the reference path (oracle/), bounded sample extrapolated"},
+            "config": {"workload": workload_name(args),
+                       "parallelism": "cpu: the reference's own thread cap min(ncpu, 8)",
+                       "note": "CPU port of the reference path (oracle/), bounded sample of this workload extrapolated"},
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": "contigs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
@@ -443,9 +449,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "contigs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.n} contigs/GPU x (103 TNF + {args.nsamples} abundance), bin default VAE "
-                                   f"512-512-32, {args.nepochs} epochs (batch 256 doubling at 25/75/150/225) + "
-                                   "encode + medoid clustering to exhaustion",
+            "config": {"workload": workload_name(args),
                        "parallelism": f"dp{world}: row-sharded VAE training (1 gradient all-reduce / minibatch), per-shard encode + clustering", "l2": "inputs larger than L2 (620 MB dataset, "
                        "128 MB latent); probe roofline flushes L2 between launches",
                        "warmup_workload": "same path, 6 epochs covering all 5 batch sizes, clustering capped at 300"},
