@@ -300,6 +300,12 @@ int vk_vae_grad_step(const vk_vae *net, int batch, const vk_vae_inject *inject, 
  * a_mn != 0: A is stored [K][M] (else [M][K]); b_mn != 0: B is stored [K][N] (else [N][K]). */
 int vk_tc_gemm_test(const float *A, const float *B, float *C, int M, int N, int K, int a_mn, int b_mn, void *stream);
 
+/* Host-side: float offset of element (r, k) of an A-role operand in the "lane-major" staging layout
+ * (128-row panels; each 32-wide k-tile of a panel is one 16 KB block [k/4][row][k%4]); ld = floats per row,
+ * a multiple of 32.  Same footprint as the row-major [rows][ld] array.  (Layout contract of the tensor-core
+ * path, checked by the CPU tests.) */
+int64_t vk_lane_major_index(int r, int k, int ld);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,3 +89,20 @@ def test_native_rng_matches_cpython_sample():
             got = cn.rng_selftest(seed, ns, k)
             r = random.Random(seed)
             assert got == [r.sample(list(range(n)), min(n, k)) for n in ns], (seed, k)
+
+
+def test_lane_major_layout_is_a_bijection_with_the_documented_block_structure():
+    """include/vamb_b200.h: A-role operands of the tensor-core GEMMs are stored in 128-row panels whose
+    32-wide k-tiles are 16 KB blocks [k/4][row][k%4] -- same footprint as the row-major array."""
+    import numpy as np
+    from vamb_b200 import _lib
+
+    f = _lib.lib.vk_lane_major_index
+    rows, ld = 256, 96
+    idx = np.array([[f(r, k, ld) for k in range(ld)] for r in range(rows)], dtype=np.int64)
+    assert sorted(idx.reshape(-1).tolist()) == list(range(rows * ld))          # bijection onto the same footprint
+    r, k = np.meshgrid(np.arange(rows), np.arange(ld), indexing="ij")
+    expect = (r // 128) * 128 * ld + (k // 32) * 4096 + ((k % 32) // 4) * 512 + (r % 128) * 4 + (k % 4)
+    assert np.array_equal(idx, expect)
+    # what the producer warps rely on: for a fixed group of four k, consecutive rows are consecutive float4
+    assert f(5, 8, ld) - f(4, 8, ld) == 4 and f(4, 9, ld) - f(4, 8, ld) == 1

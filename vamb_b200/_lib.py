@@ -68,6 +68,7 @@ _SIGNATURES = {
     "vk_compact_rows_sync": [_p, _p, _p, _p, c_int64, c_int, _p, _p, _p, _p, _p, POINTER(c_int64), _p],
     "vk_distances": [_p, c_int64, c_int, c_int64, _p, _p],
     "vk_tc_gemm_test": [_p, _p, _p, c_int, c_int, c_int, c_int, c_int, _p],
+    "vk_lane_major_index": [c_int, c_int, c_int],
 }
 
 
@@ -79,6 +80,7 @@ def _bind():
 
 
 _bind()
+lib.vk_lane_major_index.restype = c_int64
 
 
 # bound (with argtypes) in vamb_b200/encode.py next to the ctypes mirrors of their structs

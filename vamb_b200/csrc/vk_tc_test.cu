@@ -194,3 +194,5 @@ extern "C" int vk_tc_mma_rate_test(int n_mma, int n, int swizzle, long long *out
     VK_LAUNCH_CHECK();
     return 0;
 }
+
+extern "C" int64_t vk_lane_major_index(int r, int k, int ld) { return (int64_t)tc::lane_major_index(r, k, ld); }
