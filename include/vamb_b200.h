@@ -173,7 +173,9 @@ typedef struct vk_cluster_result {
 
 int vk_cluster_create(void **handle, const vk_cluster_config *cfg);
 int vk_cluster_next(void *handle, vk_cluster_result *out); /* 0 = cluster, 2 = exhausted, 1 = error */
-int vk_cluster_stats(void *handle, int64_t *out4);         /* probes, evals, packs, physical rows   */
+int vk_cluster_stats(void *handle, int64_t *out8);         /* probes, evals, packs, physical rows, live buffer set (0/1),
+                                                              successes, attempts in the window, order_index */
+int vk_cluster_timing(void *handle, double *out5);         /* host seconds in probes, evaluations, selections, packs, total */
 void vk_cluster_destroy(void *handle);
 int64_t vk_cluster_sizeof(int which);                      /* 0: vk_cluster_config, 1: vk_cluster_result */
 /* CPython-compatible random.Random(seed).sample(range(n_i), min(n_i, k)) for each i: writes k slots per
@@ -240,8 +242,8 @@ typedef struct vk_vae {
     float *params, *grads, *exp_avg, *exp_avg_sq, *s; /* flat arenas, module.parameters() order */
     float *z;                           /* [bmax, nlatent] mu + eps                            */
     int64_t *batch_rows;                /* [bmax] dataset row of every batch row               */
-    double *opt_part;                   /* [2 * 1024] optimiser block partials                 */
-    double *loss_part;                  /* [5 * 1024] loss block partials                      */
+    double *opt_part;                   /* [2 * ceil(n_params / 1024) + bmax / 256 + 8] optimiser block partials, then the batch-weight partials */
+    double *loss_part;                  /* [4 * ceil(bmax / 32) * 4 + 64] loss block partials (4 per 8 rows) */
     vk_vae_ctl *ctl;
     vk_vae_layer layers[VK_VAE_MAX_LAYERS];
     int32_t data_ld;                    /* floats per dataset row (>= d_in; a multiple of 4 keeps rows 16-byte aligned) */

@@ -2,7 +2,7 @@
 
 Run in the build container (needs /root/reference):  python -m oracle.make_golden
 The fixtures are small and committed; tests compare the oracle (and, on the GPU box,
-the CUDA path) against them.  Inputs are regenerated from vamb_b200.synth with the
+the CUDA path) against them.  Inputs are regenerated from oracle.synth with the
 seeds stored in the fixture, so only outputs are stored.
 
 Lengths are tie-free (``unique_lengths=True``): the reference orders seeds by
@@ -34,7 +34,7 @@ CLUSTER_CASES = [
 
 
 def cluster_inputs(n, nlatent, data_seed, spread):
-    from vamb_b200 import synth
+    from oracle import synth
 
     return synth.make_latent(n, nlatent, data_seed, spread, unique_lengths=True)
 

@@ -22,7 +22,7 @@ def load_cluster_golden(name):
     g = np.load(os.path.join(GOLDEN, f"cluster_{name}.npz"))
     n, nlatent, data_seed, rng_seed = (int(x) for x in g["params"])
     spread = float(g["spread"][0])
-    from vamb_b200 import synth
+    from oracle import synth
 
     lat, lens = synth.make_latent(n, nlatent, data_seed, spread, unique_lengths=True)
     return g, lat, lens, rng_seed

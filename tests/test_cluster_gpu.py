@@ -49,7 +49,7 @@ def test_normalize_and_distances_bit_exact(vk, d):
 @pytest.mark.parametrize("d,n", [(32, 30000), (40, 5000), (283, 3000)])
 def test_probe_header_matches_oracle(vk, d, n):
     from oracle import cluster_oracle as co
-    from vamb_b200 import synth
+    from oracle import synth
 
     lat, lens = synth.make_latent(n, d, seed=d, spread=0.2)
     host = lat.copy()
@@ -111,7 +111,7 @@ def test_cuda_clusterer_matches_reference_golden(name, driver):
 def test_cuda_clusterer_matches_oracle_larger(n, d, spread, seed):
     import vamb_b200.cluster as vc
     from oracle import cluster_oracle as co
-    from vamb_b200 import synth
+    from oracle import synth
 
     lat, lens = synth.make_latent(n, d, seed, spread)
     oc = list(co.OracleClusterGenerator(lat, lens, rng_seed=seed))
@@ -124,7 +124,7 @@ def test_cuda_clusterer_matches_oracle_larger(n, d, spread, seed):
 def test_forced_packing_and_unpruned_paths_agree():
     """pack() at every cluster and the no-pruning path give the same clusters."""
     import vamb_b200.cluster as vc
-    from vamb_b200 import synth
+    from oracle import synth
 
     lat, lens = synth.make_latent(6000, 32, 31, 0.3)
     base = list(vc.ClusterGenerator(lat, lens, rng_seed=1))

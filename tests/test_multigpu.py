@@ -26,7 +26,7 @@ def _worker(rank, world, port, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     import vamb_b200.cluster as vc
     import vamb_b200.encode as ve
-    from vamb_b200 import synth
+    from oracle import synth
 
     ab, tnf, lens = synth.make_contigs(40000, 6, seed=10 + rank)  # every rank owns its own shard
     dl = ve.make_dataloader(ab, tnf, lens, batchsize=128)

@@ -220,7 +220,7 @@ class TestReferenceVAESuite:
 def test_graph_replay_training_is_deterministic_and_learns():
     """Enough steps per epoch to go through the CUDA-graph path; same seed -> same bits."""
     import vamb_b200.encode as ve
-    from vamb_b200 import synth
+    from oracle import synth
 
     ab, tnf, lens = synth.make_contigs(80000, 8, seed=0)
     lats = []

@@ -7,7 +7,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 
-from vamb_b200 import _lib, synth
+from vamb_b200 import _lib
+from oracle import synth
 import vamb_b200.cluster as vc
 
 

@@ -10,7 +10,8 @@ import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import vamb_b200.encode as ve
-from vamb_b200 import synth, _lib
+from vamb_b200 import _lib
+from oracle import synth
 
 n = int(os.environ.get("N", 200_000))
 ab, tnf, lens = synth.make_contigs(n, 50, seed=0)

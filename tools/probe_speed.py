@@ -3,7 +3,8 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import vamb_b200.cluster as vc
-from vamb_b200 import synth, _lib
+from vamb_b200 import _lib
+from oracle import synth
 
 for n in (1_000_000, 5_000_000):
     lat, ln = synth.make_latent(n, 32, seed=0, spread=0.1)

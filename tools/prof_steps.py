@@ -3,7 +3,8 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import vamb_b200.encode as ve, vamb_b200.cluster as vc
-from vamb_b200 import synth, _lib
+from vamb_b200 import _lib
+from oracle import synth
 
 n = int(os.environ.get("N", 200_000))
 ab, tnf, lens = synth.make_contigs(n, 50, seed=0)

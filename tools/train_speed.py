@@ -3,7 +3,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import vamb_b200.encode as ve
-from vamb_b200 import synth
+from oracle import synth
 
 n = int(os.environ.get("N", 1_000_000))
 tcmin = int(os.environ.get("TC_MIN", 512))

@@ -46,6 +46,8 @@ _L.vk_cluster_next.argtypes = [_ct.c_void_p, _ct.POINTER(VkClusterResult)]
 _L.vk_cluster_next.restype = _ct.c_int
 _L.vk_cluster_stats.argtypes = [_ct.c_void_p, _ct.POINTER(_ct.c_int64)]
 _L.vk_cluster_stats.restype = _ct.c_int
+_L.vk_cluster_timing.argtypes = [_ct.c_void_p, _ct.POINTER(_ct.c_double)]
+_L.vk_cluster_timing.restype = _ct.c_int
 _L.vk_cluster_destroy.argtypes = [_ct.c_void_p]
 _L.vk_cluster_destroy.restype = None
 _L.vk_cluster_rng_selftest.argtypes = [_ct.POINTER(_ct.c_uint32), _ct.c_int, _ct.POINTER(_ct.c_int32), _ct.c_int,

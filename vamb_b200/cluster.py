@@ -140,7 +140,7 @@ class ClusterGenerator:
         "_orig2", "_nl_rows", "_nl_d", "_hdr", "_hdr_host", "_hdr_np", "_within_over", "_edges",
         "_cand_out", "_cand_out_host", "_members", "_members_host", "_tile_scratch", "_row_of_orig",
         "_user_matrix", "_prune_radius", "_nl_radius", "_n_probes", "_n_evals", "_pack_fraction",
-        "_native", "_native_cfg", "_native_keep", "_result",
+        "_native", "_native_cfg", "_native_keep", "_result", "_native_cur",
     ]
 
     def __repr__(self) -> str:
@@ -314,6 +314,7 @@ class ClusterGenerator:
         handle = _lib.ctypes.c_void_p()
         _lib.check(_cn._L.vk_cluster_create(_lib.ctypes.byref(handle), _lib.ctypes.byref(cfg)))
         self._native = handle
+        self._native_cur = 0
         self._native_cfg = cfg
         self._native_keep = (key, order, pdf)
         self._result = _cn.VkClusterResult()
@@ -347,10 +348,32 @@ class ClusterGenerator:
         self.n_emitted_clusters += 1
         self.n_remaining_points = int(res.n_remaining)
         self.peak_valley_ratio = res.peak_valley_ratio
-        stats = (_lib.ctypes.c_int64 * 4)()
+        stats = (_lib.ctypes.c_int64 * 8)()
         _cn._L.vk_cluster_stats(self._native, stats)
         self._n_probes, self._n_evals, self._n_act = int(stats[0]), int(stats[1]), int(stats[3])
+        if int(stats[4]) != self._native_cur:
+            # the driver packed into the other buffer set: keep the Python-side views on the live one
+            self._native_cur = int(stats[4])
+            self._m, self._m2 = self._m2, self._m
+            self._len, self._len2 = self._len2, self._len
+            self._kept, self._kept2 = self._kept2, self._kept
+            self._orig, self._orig2 = self._orig2, self._orig
+        # mirror the window counters (``__str__``, callers that inspect them); ``indices`` / ``kept_mask`` / ``order``
+        # are O(N) host arrays owned by the C++ driver in this mode and are not mirrored per cluster
+        self.successes, self.order_index = int(stats[5]), int(stats[7])
+        if len(self.attempts) != int(stats[6]):
+            self.attempts = _deque([False] * int(stats[6]), maxlen=self.attempts.maxlen)
         return cluster
+
+    def _timing(self) -> dict:
+        "Host seconds the native driver spent per call kind so far (diagnostics / bench)."
+        from . import _cluster_native as _cn
+
+        out = (_lib.ctypes.c_double * 5)()
+        if self._native is None:
+            return {}
+        _cn._L.vk_cluster_timing(self._native, out)
+        return dict(zip(("probe", "eval", "select", "pack", "total"), (float(x) for x in out)))
 
     # ------------------------------------------------------------------ API extras
     @property

@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <deque>
 #include <new>
 #include <unordered_set>
@@ -126,6 +127,7 @@ struct State {
     int32_t seq = 0;
     std::vector<int64_t> members;
     int64_t n_probes, n_evals, n_packs;
+    double t_probe = 0.0, t_eval = 0.0, t_select = 0.0, t_pack = 0.0, t_total = 0.0;  // host wall seconds per call kind
 
     float *M() const { return cur ? c.matrix2 : c.matrix; }
     float *LEN() const { return cur ? c.lengths2 : c.lengths; }
@@ -133,7 +135,15 @@ struct State {
     int32_t *ORIG() const { return cur ? c.orig2 : c.orig; }
 };
 
+struct Stopwatch {  // adds the enclosing scope's wall time to `acc`
+    double &acc;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    explicit Stopwatch(double &a) : acc(a) {}
+    ~Stopwatch() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
 int do_probe(State &st, int32_t row, Probe &p) {
+    Stopwatch sw(st.t_probe);
     ++st.n_probes;
     const vk_cluster_config &c = st.c;
     if (vk_probe_mapped(st.M(), st.LEN(), st.KEPT(), st.n_act, c.d, row, c.nl_radius, c.edges, c.hdr, c.within_overflow,
@@ -158,6 +168,7 @@ int do_probe(State &st, int32_t row, Probe &p) {
 }
 
 int do_eval(State &st, const Probe &p, const std::vector<int32_t> &rows, std::vector<unsigned __int128> &dens) {
+    Stopwatch sw(st.t_eval);
     const vk_cluster_config &c = st.c;
     dens.clear();
     for (size_t i = 0; i < rows.size(); i += VK_MAX_CAND) {
@@ -174,6 +185,7 @@ int do_eval(State &st, const Probe &p, const std::vector<int32_t> &rows, std::ve
 }
 
 int do_select(State &st, const Probe &p, float threshold) {
+    Stopwatch sw(st.t_select);
     const vk_cluster_config &c = st.c;
     if (vk_select_members_sync(c.nl_rows, c.nl_dists, p.n_nl, threshold, st.ORIG(), st.KEPT(), c.members,
                                c.members_host, c.members_host_cap, c.stream))
@@ -194,6 +206,7 @@ int do_select(State &st, const Probe &p, float threshold) {
 }
 
 int do_pack(State &st) {
+    Stopwatch sw(st.t_pack);
     const vk_cluster_config &c = st.c;
     ++st.n_packs;
     int64_t n_out = 0;
@@ -389,9 +402,17 @@ extern "C" void vk_cluster_destroy(void *handle) {
     delete st;
 }
 
-extern "C" int vk_cluster_stats(void *handle, int64_t *out4) {
+extern "C" int vk_cluster_stats(void *handle, int64_t *out8) {
     State *st = static_cast<State *>(handle);
-    out4[0] = st->n_probes; out4[1] = st->n_evals; out4[2] = st->n_packs; out4[3] = st->n_act;
+    out8[0] = st->n_probes; out8[1] = st->n_evals; out8[2] = st->n_packs; out8[3] = st->n_act;
+    out8[4] = st->cur; out8[5] = st->successes; out8[6] = (int64_t)st->attempts.size(); out8[7] = st->order_index;
+    return 0;
+}
+
+// host wall-clock seconds spent so far in: probes, candidate evaluations, member selections, packs, all of vk_cluster_next
+extern "C" int vk_cluster_timing(void *handle, double *out5) {
+    State *st = static_cast<State *>(handle);
+    out5[0] = st->t_probe; out5[1] = st->t_eval; out5[2] = st->t_select; out5[3] = st->t_pack; out5[4] = st->t_total;
     return 0;
 }
 
@@ -399,6 +420,7 @@ extern "C" int vk_cluster_stats(void *handle, int64_t *out4) {
 extern "C" int vk_cluster_next(void *handle, vk_cluster_result *out) {
     State &st = *static_cast<State *>(handle);
     if (st.n_remaining == 0) return 2;
+    Stopwatch sw_total(st.t_total);
     Probe probe;
     for (;;) {  // find_cluster, vamb/cluster.py:545-604
         const int32_t seed = next_seed(st);

@@ -1664,7 +1664,8 @@ static int launch_batch_rows(const vk_vae *net, int B, int mode, int64_t row0, c
     const int spe = n > B ? (int)(n / B) : 1;
     PROF_MARK_K(s, PK_ROWS);
     VK_CUDA(vk_launch(batch_rows_kernel, dim3((B + 255) / 256), dim3(256), (size_t)(0), s, net->batch_rows, inj ? inj->batch_idx : nullptr, net->weights,
-                                                       net->ctl, B, n, mode, row0, spe, net->opt_part + 1024,
+                                                       net->ctl, B, n, mode, row0, spe,
+                                                       net->opt_part + 2 * ((net->n_params + OPT_ELEMS - 1) / OPT_ELEMS),
                                                        2 * VK_VAE_MAX_LAYERS + 3));
     VK_LAUNCH_CHECK();
     return 0;
@@ -1746,10 +1747,7 @@ static int launch_loss(const vk_vae *net, int B, int write_grad, cudaStream_t s,
         a.stage_t = L.dyt_hi; a.stage_t_ld = net->bmax;
         blocks = r32(B) / 8;  // whole k-tiles of the wgrad reduction: rows beyond the batch are staged as zeros
     }
-    if (blocks > 1024) {
-        vk_set_error("vk_vae: batch too large for the loss partial buffer");
-        return 1;
-    }
+    // loss_part holds 4 doubles per 8-row block of the largest batch (r32(bmax) / 8 blocks): vk_vae.loss_part
     PROF_MARK_K(s, PK_LOSS);
     VK_CUDA(vk_launch(loss_kernel, dim3(blocks), dim3(256), (size_t)(0), s, a));
     VK_LAUNCH_CHECK();
@@ -1860,11 +1858,8 @@ __global__ void reduce_slabs_kernel(float *g, int64_t n, int nslab, int64_t slab
 
 static int launch_dadapt(const vk_vae *net, int nslab, cudaStream_t s) {
     PROF_MARK_K(s, PK_OPT);
+    // opt_part holds two doubles per block (sized from n_params by the host: vk_vae.opt_part), no fixed cap
     const int opt_blocks = (int)((net->n_params + OPT_ELEMS - 1) / OPT_ELEMS);
-    if (opt_blocks > 1024) {
-        vk_set_error("vk_vae: parameter arena too large for the optimiser partial buffer");
-        return 1;
-    }
     VK_CUDA(vk_launch(dadapt_kernel, dim3(opt_blocks), dim3(256), (size_t)(0), s, net->params, net->grads, net->exp_avg, net->exp_avg_sq, net->s,
                                              net->n_params, net->opt_part, net->ctl, 2 * VK_VAE_MAX_LAYERS + 2,
                                              nslab, net->grad_slab));

@@ -46,8 +46,17 @@ except ImportError:  # pragma: no cover
 
     logger = logging.getLogger("vamb_b200")
 
+_warned = set()
+
+
+def _warn_once(msg: str) -> None:
+    if msg not in _warned:
+        _warned.add(msg)
+        logger.warning(msg)
+
+
 _MAX_BATCH = 8192  # rows of the activation workspaces (training batches double up to 4096)
-_GRAPH_CHUNK = 128  # optimiser steps per captured CUDA graph
+_GRAPH_CHUNKS = (128, 16, 4)  # optimiser steps per captured CUDA graph, largest first
 _TC_MIN_BATCH = 128  # batches >= this run their GEMMs on the tcgen05 tensor-core path (0 = never)
 
 
@@ -271,6 +280,11 @@ class VAE(_nn.Module):
         if 2 * len(nhiddens) + 2 > _MAXL:
             raise ValueError(f"at most {(_MAXL - 2) // 2} hidden layers are supported")
 
+        if not cuda:
+            # The reference's default (cuda=False) selects its CPU path.  This implementation has none -- it IS the
+            # GPU path -- so the flag cannot be honoured; say so once instead of silently ignoring it.
+            _warn_once("vamb_b200.encode.VAE always runs on the GPU (sm_100a); cuda=False is not honoured")
+
         # Parameters are drawn by CPU torch in the reference's construction order
         # (vamb/encode.py:210-249) so that the same seed gives the same initial weights.
         _torch.manual_seed(seed)
@@ -287,6 +301,7 @@ class VAE(_nn.Module):
         self.nlatent = nlatent
         self.dropout = dropout
         self._seed = int(seed)
+        self._bmax = _MAX_BATCH  # rows of the activation workspaces; grown on demand by _ensure_capacity
 
         self.encoderlayers = _nn.ModuleList()
         self.encodernorms = _nn.ModuleList()
@@ -334,7 +349,7 @@ class VAE(_nn.Module):
         self._exp_avg_sq = _torch.zeros(total, **f32)
         self._s = _torch.zeros(total, **f32)
 
-        bmax = _MAX_BATCH
+        bmax = self._bmax
         n_rt = (bmax + 31) // 32
         net = _VkVae()
         L = len(self.nhiddens)
@@ -365,8 +380,10 @@ class VAE(_nn.Module):
 
         net.z = buf("z", bmax, self.nlatent)
         net.batch_rows = buf("batch_rows", bmax, dtype=_torch.int64)
-        net.opt_part = buf("opt_part", 2 * 1024, dtype=_torch.float64)
-        net.loss_part = buf("loss_part", 5 * 1024, dtype=_torch.float64)
+        # partial sums: two doubles per 1024-parameter block of the optimiser + one per 256 batch rows (weight fold); four
+        # doubles per 8-row block of the loss kernel (include/vamb_b200.h: vk_vae.opt_part / loss_part)
+        net.opt_part = buf("opt_part", 2 * ((total + 1023) // 1024) + bmax // 256 + 8, dtype=_torch.float64)
+        net.loss_part = buf("loss_part", 4 * ((bmax + 31) // 32 * 32 // 8) + 64, dtype=_torch.float64)
         self._ctl = _torch.zeros(_ct.sizeof(_VkCtl), dtype=_torch.uint8, device=dev)
         net.ctl = self._ctl.data_ptr()
 
@@ -419,6 +436,22 @@ class VAE(_nn.Module):
     def _stream(self) -> int:
         return _torch.cuda.current_stream().cuda_stream
 
+    def _ensure_capacity(self, rows: int) -> None:
+        """Grow the activation workspaces to hold ``rows`` batch rows (the reference has no batch cap:
+        ``-t 1024`` with four batchsteps reaches 16384).  Parameters and BatchNorm buffers are carried over;
+        the optimiser state is reset, so this is only called before training starts."""
+        if rows <= self._net.bmax:
+            return
+        self._bmax = (int(rows) + 127) // 128 * 128
+        dataset, group, use_graphs = self._dataset, self._dp_group, self._use_graphs
+        seed = int(self._ctl_i64[_VkCtl.seed.offset // 8].item())  # carries the per-rank perturbation
+        self._build_device_state()  # copies the current parameter values into the new arena
+        self._dp_group, self._use_graphs = group, use_graphs
+        self._ctl_i64[_VkCtl.seed.offset // 8] = seed
+        if dataset is not None:
+            self._dataset = dataset
+            self._net.data, self._net.weights, self._net.n_rows = dataset[1].data_ptr(), dataset[2].data_ptr(), len(dataset[2])
+
     def _reset_optimizer(self) -> None:
         "A fresh DAdaptAdam(params, decouple=True) (vamb/encode.py:578): zero state, d = 1e-6."
         for t in (self._exp_avg, self._exp_avg_sq, self._s):
@@ -446,8 +479,12 @@ class VAE(_nn.Module):
     def _bind_dataset(self, tensors) -> int:
         """Upload (depths, tnf, abundance, weights) once: [N, S | 103 | 1] rows + weights."""
         depths, tnf, ab, w = tensors
-        key = (depths.data_ptr(), tnf.data_ptr(), len(depths))
-        if self._dataset is not None and self._dataset[0] == key:
+        # the cache is keyed on the source tensors themselves (kept alive here, so their addresses cannot be
+        # recycled) and their in-place version counters, not on raw addresses
+        src = (depths, tnf, ab, w)
+        key = tuple(t._version for t in src)
+        if (self._dataset is not None and all(a is b for a, b in zip(self._dataset[3], src))
+                and self._dataset[0] == key):
             return len(depths)
         dev = self._arena.device
         n = len(depths)
@@ -457,7 +494,7 @@ class VAE(_nn.Module):
         data[:, s:s + self.ntnf] = tnf.to(dev, non_blocking=True)
         data[:, s + self.ntnf:s + self.ntnf + 1] = ab.reshape(n, 1).to(dev, non_blocking=True)
         weights = w.reshape(n).to(dev).contiguous()
-        self._dataset = (key, data, weights)
+        self._dataset = (key, data, weights, src)
         self._net.data, self._net.weights, self._net.n_rows = data.data_ptr(), weights.data_ptr(), n
         self._graphs = {}
         return n
@@ -581,48 +618,56 @@ class VAE(_nn.Module):
         return out.cpu().numpy()
 
     # ------------------------------------------------------------------ training
-    def _run_steps(self, batch: int, nsteps: int) -> None:
-        """``nsteps`` optimiser steps at batch size ``batch`` through replayed CUDA graphs."""
-        stream = _torch.cuda.current_stream()
-        done = 0
+    def _one_step(self, batch: int) -> None:
+        if self._dp_group is None:
+            _lib.check(_L.vk_vae_train_step(_ct.byref(self._net), batch, None, self._stream()))
+        else:
+            # row-sharded data parallelism: local gradients, ONE all-reduce (average) of the
+            # packed gradient arena over NCCL / NVLink, then the identical optimiser step on every rank
+            _lib.check(_L.vk_vae_grad_step(_ct.byref(self._net), batch, None, self._stream()))
+            _par.allreduce_mean_(self._grads, self._dp_group)
+            _lib.check(_L.vk_vae_dadapt_step(_ct.byref(self._net), self._stream()))
 
-        def one_step():
+    def _graph_for(self, batch: int, chunk: int):
+        """The captured graph of ``chunk`` optimiser steps at ``batch`` (None when capture is unavailable).
+        Capture executes nothing; the steps run at replay."""
+        key = (batch, chunk)
+        g = self._graphs.get(key)
+        if g is not None or not self._use_graphs:
+            return g
+        g = _torch.cuda.CUDAGraph()
+        try:
+            with _torch.cuda.graph(g):
+                for _ in range(chunk):
+                    self._one_step(batch)
+            self._graphs[key] = g
+            return g
+        except Exception:
             if self._dp_group is None:
-                _lib.check(_L.vk_vae_train_step(_ct.byref(self._net), batch, None, self._stream()))
-            else:
-                # row-sharded data parallelism (SURVEY 8e): local gradients, ONE all-reduce (average) of the
-                # packed gradient arena over NCCL / NVLink, then the identical optimiser step on every rank
-                _lib.check(_L.vk_vae_grad_step(_ct.byref(self._net), batch, None, self._stream()))
-                _par.allreduce_mean_(self._grads, self._dp_group)
-                _lib.check(_L.vk_vae_dadapt_step(_ct.byref(self._net), self._stream()))
+                raise
+            self._use_graphs = False  # this NCCL build cannot be captured: run the steps eagerly
+            _torch.cuda.synchronize()
+            return None
 
-        def eager(k):
-            for _ in range(k):
-                one_step()
-
-        if nsteps >= 2 * _GRAPH_CHUNK and self._use_graphs:
-            key = (batch, _GRAPH_CHUNK)
-            if key not in self._graphs:
-                eager(1)  # warm-up outside capture (also advances training by one step)
+    def _run_steps(self, batch: int, nsteps: int) -> None:
+        """``nsteps`` optimiser steps at batch size ``batch`` through replayed CUDA graphs: chunks of 128, then
+        16, then 4 steps (short epochs -- row shards, large batches -- still run from graphs), the rest eagerly."""
+        done = 0
+        if self._use_graphs and nsteps > _GRAPH_CHUNKS[-1]:
+            if ("warm", batch) not in self._graphs:
+                self._one_step(batch)  # first use of this batch size: one step outside capture
                 done += 1
-                stream.synchronize()
-                g = _torch.cuda.CUDAGraph()
-                try:
-                    with _torch.cuda.graph(g):
-                        # NB: capture executes nothing; the graph's steps run at replay
-                        for _ in range(_GRAPH_CHUNK):
-                            one_step()
-                    self._graphs[key] = g
-                except Exception:
-                    if self._dp_group is None:
-                        raise
-                    self._use_graphs = False  # this NCCL build cannot be captured: run the steps eagerly
-                    _torch.cuda.synchronize()
-            g = self._graphs.get(key)
-            while g is not None and nsteps - done >= _GRAPH_CHUNK:
-                g.replay()
-                done += _GRAPH_CHUNK
-        eager(nsteps - done)
+                _torch.cuda.current_stream().synchronize()
+                self._graphs[("warm", batch)] = True
+            for chunk in _GRAPH_CHUNKS:
+                if nsteps - done < chunk:
+                    continue
+                g = self._graph_for(batch, chunk)
+                while g is not None and nsteps - done >= chunk:
+                    g.replay()
+                    done += chunk
+        for _ in range(nsteps - done):
+            self._one_step(batch)
 
     # ------------------------------------------------------------------ multi-GPU (row-sharded data parallel)
     def enable_data_parallel(self, group=None) -> None:
@@ -662,7 +707,10 @@ class VAE(_nn.Module):
         self._bind_dataset(data_loader.dataset.tensors)
         batch = data_loader.batch_size if n_seq > data_loader.batch_size else n_seq
         if batch > self._net.bmax:
-            raise ValueError(f"batch size {batch} exceeds the workspace limit {self._net.bmax}")
+            raise ValueError(
+                f"batch size {batch} exceeds the workspace capacity {self._net.bmax}: call trainmodel(), which sizes the "
+                "workspaces for the whole schedule before the first epoch"
+            )
         nsteps = len(data_loader)  # N // batch with drop_last, else 1
         if self._dp_group is not None:
             nsteps = _par.agree_min(nsteps, self._dp_group, self._arena.device)  # every rank takes the same steps
@@ -707,6 +755,7 @@ class VAE(_nn.Module):
         Input: Path or binary opened filehandle
         Output: None
         """
+        self.sync_running_stats()  # data-parallel: BatchNorm running statistics are per GPU until averaged
         state = {
             "nsamples": self.nsamples,
             "alpha": self.alpha,
@@ -770,6 +819,9 @@ class VAE(_nn.Module):
             batchsteps_set = set(batchsteps)
 
         ncontigs, nsamples = dataloader.dataset.tensors[0].shape
+        # the largest batch the schedule will reach must fit the workspaces BEFORE any epoch runs (the batch
+        # doubles at every batchstep, vamb/encode.py:383-388); grow them now instead of failing at epoch 300
+        self._ensure_capacity(min(ncontigs, dataloader.batch_size * 2 ** len(batchsteps_set)))
         self._reset_optimizer()  # the reference builds a new DAdaptAdam per trainmodel call
 
         logger.info("\tNetwork properties:")
