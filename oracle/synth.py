@@ -9,7 +9,7 @@ from __future__ import annotations
 import numpy as np
 
 
-def make_contigs(n: int, nsamples: int, seed: int = 0, unique_lengths: bool = False):
+def make_contigs(n: int, nsamples: int, seed: int = 0, unique_lengths: bool = False, return_genome: bool = False):
     """Return ``(abundance[n, S], tnf[n, 103], lengths[n])`` float32/float32/int64.
 
     G = max(10, n // 50) genomes; TNF centroid c_g ~ N(0, I_103); abundance profile
@@ -31,11 +31,12 @@ def make_contigs(n: int, nsamples: int, seed: int = 0, unique_lengths: bool = Fa
     scale = (0.3 * np.sqrt(2000.0 / lengths)).astype(np.float32)
     tnf = centroids[genome] + noise * scale[:, None]
     abundance = profiles[genome] * rng.gamma(20.0, 1.0 / 20.0, size=(n, nsamples)).astype(np.float32)
-    return (
+    out = (
         np.ascontiguousarray(abundance, dtype=np.float32),
         np.ascontiguousarray(tnf, dtype=np.float32),
         lengths,
     )
+    return out + (genome,) if return_genome else out  # the planted genome of every contig (for ARI checks)
 
 
 def make_latent(n: int, nlatent: int = 32, seed: int = 0, spread: float = 0.05,
