@@ -298,9 +298,12 @@ int vk_vae_profile_step(const vk_vae *net, int batch, const vk_vae_inject *injec
 /* Backward + gradients only (no optimiser): used by the multi-GPU path and by the tests. */
 int vk_vae_grad_step(const vk_vae *net, int batch, const vk_vae_inject *inject, void *stream);
 
-/* Stand-alone check of the tcgen05 3xTF32 tile GEMM: C[M,N] = A * B^T, fp32 in/out.
- * a_mn != 0: A is stored [K][M] (else [M][K]); b_mn != 0: B is stored [K][N] (else [N][K]). */
-int vk_tc_gemm_test(const float *A, const float *B, float *C, int M, int N, int K, int a_mn, int b_mn, void *stream);
+/* Stand-alone check of the PRODUCTION tcgen05 3xTF32 main loop (tc::ws_mainloop -- the loop of the layer kernels):
+ * C[M,N] = A * B^T over k-tiles [kt0, kt0 + nk) of 32.  A_lane: the 128-row operand in the lane-major staging layout
+ * (vk_lane_major_index), zero padded to whole 128-row panels; B: plain row-major [rows][ldb], zero padded to whole
+ * tile_n-row tiles; lda, ldb multiples of 32; tile_n (output columns per CTA) a multiple of 16 in [16, 128]. */
+int vk_tc_gemm_test(const float *A_lane, int lda, const float *B, int ldb, float *C, int M, int N, int tile_n,
+                    int kt0, int nk, void *stream);
 
 /* Host-side: float offset of element (r, k) of an A-role operand in the "lane-major" staging layout
  * (128-row panels; each 32-wide k-tile of a panel is one 16 KB block [k/4][row][k%4]); ld = floats per row,

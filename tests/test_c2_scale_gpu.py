@@ -1,0 +1,94 @@
+"""GPU suite at BASELINE's C2 shapes (1,000,000 contigs): the sizes the bench actually runs.
+
+  * clustering: the CUDA clusterer against the CPU oracle on the first clusters of a 1M x 32 latent
+    (``itertools.islice``, the reference's own ``max_clusters`` mechanism, vamb/__main__.py:1289) -- bit-exact, which
+    covers the full-size probe (int32 row ids, > 2040 within-ids, neighbour lists of 10^4-10^5 rows);
+  * compaction at scale: forcing a pack after every cluster must not change any cluster (1M-row compaction kernels);
+  * encode: ``vk_vae_encode`` over 1M x (50 + 103 + 1) rows against the torch-fp32 oracle on a 50k-row sample, within the
+    north-star tolerance 1e-4.
+The oracle needs ~0.6 s per cluster at 1M rows (35 full scans + a pack), which bounds the prefix length.
+"""
+from itertools import islice
+
+import numpy as np
+import pytest
+import torch
+
+from tests import _util
+
+pytestmark = pytest.mark.gpu
+
+N = 1_000_000
+
+
+@pytest.fixture(scope="module")
+def latent_1m():
+    from oracle import synth
+
+    return synth.make_latent(N, 32, seed=21, spread=0.2, unique_lengths=True)
+
+
+def test_cluster_prefix_at_1m_rows_matches_oracle_bit_exact(latent_1m):
+    import vamb_b200.cluster as vc
+    from oracle import cluster_oracle as co
+
+    lat, lens = latent_1m
+    k = 40
+    got = list(islice(vc.ClusterGenerator(lat, lens, windowsize=300, minsuccesses=15, rng_seed=3), k))
+    ref = list(islice(co.OracleClusterGenerator(lat, lens, windowsize=300, minsuccesses=15, rng_seed=3), k))
+    _util.assert_clusters_equal(got, ref)
+    assert sum(len(c.members) for c in got) > k  # planted data: real clusters, not 40 loners
+
+
+def test_cluster_prefix_at_1m_rows_is_pack_invariant(latent_1m):
+    """Native driver with a physical compaction after EVERY cluster (1M-row compact_count/scatter, buffer ping-pong)
+    == default packing policy == Python driver, on the first 150 clusters."""
+    import vamb_b200.cluster as vc
+
+    lat, lens = latent_1m
+    k = 150
+    a = list(islice(vc.ClusterGenerator(lat, lens, rng_seed=5), k))
+    b = list(islice(vc.ClusterGenerator(lat, lens, rng_seed=5, _pack_fraction=1.0), k))
+    c = list(islice(vc.ClusterGenerator(lat, lens, rng_seed=5, _driver="python"), k))
+    _util.assert_clusters_equal(a, b)
+    _util.assert_clusters_equal(a, c)
+
+
+def test_matrix_property_follows_native_packs(latent_1m):
+    """After an odd number of packs the live rows are in the second buffer set: ``matrix`` must
+    still return exactly the unclustered rows."""
+    import vamb_b200.cluster as vc
+
+    lat, lens = latent_1m
+    lat, lens = lat[:50_000], lens[:50_000]
+    gen = vc.ClusterGenerator(lat, lens, rng_seed=1, _pack_fraction=1.0)
+    seen = []
+    for c in islice(gen, 7):
+        seen.append(np.asarray(c.members))
+    gone = np.zeros(len(lat), dtype=bool)
+    gone[np.concatenate(seen)] = True
+    ref = vc.ClusterGenerator(lat, lens, rng_seed=1)  # normalised copy of all rows
+    want = ref.matrix.numpy()[~gone]
+    assert np.array_equal(gen.matrix.numpy(), want)
+
+
+def test_encode_1m_rows_within_1e4_of_oracle_sample():
+    import vamb_b200.encode as ve
+    from oracle import synth
+    from oracle import vae_oracle as vo
+
+    S = 50
+    ab, tnf, lens = synth.make_contigs(N, S, seed=0)
+    dl = ve.make_dataloader(ab, tnf, lens, batchsize=256, destroy=True)
+    vae = ve.VAE(S, seed=0)
+    vae.trainmodel(dl, nepochs=2, batchsteps=[1])  # a trained-ish model: BatchNorm running statistics are live
+    latent = vae.encode(dl)
+    assert latent.shape == (N, 32) and np.all(latent.view(np.uint32) & 0xFFF == 0)
+    raw = vae._encode_device(dl.dataset.tensors, mask_bits=0)
+    o = vo.OracleVAE(S, seed=0)
+    o.load_reference_state({k: v.detach().cpu() for k, v in vae.state_dict().items()})
+    rows = np.arange(0, N, 20)  # 50,000 rows spread over every 8192-row encode chunk
+    d, t, a, _ = dl.dataset.tensors
+    _, oraw = o.encode(d[rows], t[rows], a[rows], batch=4096)
+    err = np.abs(raw[rows] - oraw).max()
+    assert err < 1e-4, err

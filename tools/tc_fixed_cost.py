@@ -1,4 +1,4 @@
-"""Fixed cost vs per-k-tile cost of the tcgen05 tile kernel (v1 main loop, plain epilogue)."""
+"""Launch / prologue overhead probes and the issue rate of back-to-back tcgen05.mma (vk_tc_test.cu)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -15,11 +15,6 @@ def timeit(fn, iters=50):
     return a.elapsed_time(b) / iters * 1e3
 x = torch.zeros(1, device="cuda")
 print(f"empty torch kernel (x.add_): {timeit(lambda: x.add_(1)):.1f} us per launch")
-for M, N in ((256, 512), (4096, 512)):
-    for K in (32, 64, 128, 256, 512, 1024):
-        A = torch.randn(M, K, device="cuda"); B = torch.randn(N, K, device="cuda"); C = torch.empty(M, N, device="cuda")
-        t = timeit(lambda: _lib.check(_lib.lib.vk_tc_gemm_test(A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, 0, 0, s)))
-        print(f"tc_gemm_test M={M} N={N} K={K}: {t:.1f} us per launch (back-to-back)")
 lib = _lib.lib
 import ctypes
 lib.vk_tc_mma_rate_test.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]

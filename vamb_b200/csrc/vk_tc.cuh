@@ -1,11 +1,9 @@
 // tcgen05 (5th-gen tensor core) building blocks for sm_100a: raw PTX wrappers, UMMA shared-memory /
 // instruction descriptors, and a 128 x BN x K tile GEMM in error-compensated 3xTF32.
 //
-// Why operands go through registers instead of TMA: every GEMM of the VAE consumes a *transformed*
-// operand (BatchNorm affine on load, or the BatchNorm/dropout/LeakyReLU backward on load) and needs
-// the tf32 hi/lo split of both operands, so the producer threads load fp32 from global (coalesced
-// float4), transform, split and write the UMMA canonical no-swizzle layouts themselves.  The matrices
-// are small and L2-resident; what matters is that the tensor pipe never waits for more than one stage.
+// Operands are materialised ONCE per layer by the producing kernel (vk_vae.cu: fused staging / prep kernels) as
+// plain zero-padded fp32 arrays; the warp-specialised main loop below (ws_mainloop) keeps the 128-row operand in
+// tensor memory and streams the narrow operand through a shared-memory ring.
 //
 // 3xTF32: kind::tf32 reads the top 19 bits of each fp32 operand word (low 13 mantissa bits ignored),
 // so hi = x as stored, lo = x - (x & 0xFFFFE000) (exact).  D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo leaves
@@ -114,6 +112,7 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
 //  MN-major : core matrix = 8 k x 16 B (4 consecutive m); offset(m, k) = (k/8)*(ROWS*32) + (m/4)*128 + (k%8)*16 + (m%4)*4
 //             -> SBO = 128 (next 4 m), LBO = ROWS*32 (next 8 k, unused by a K=8 instruction); k8-step j starts at +ROWS*32*j.
 constexpr int KT = 32;
+__host__ __device__ constexpr int b_tile_bytes(int bn) { return bn * KT * 4; }
 
 __device__ __forceinline__ uint32_t off_kmajor(int r, int k4) {  // k4 = k / 4 (one float4 per call)
     return (uint32_t)((r >> 3) * 1024 + k4 * 128 + (r & 7) * 16);
@@ -131,171 +130,21 @@ __device__ __forceinline__ float4 tf32_lo(const float4 v) {
     return r;
 }
 
-// Shared-memory plan of one CTA (dynamic smem, 1024-byte aligned by the caller):
-//   stage s in {0,1}: A_hi | A_lo (128 x KT x 4 B = 16 KB each) | B_hi | B_lo (BN x KT x 4 B each)
 constexpr int TC_BM = 128;
-#ifndef TC_MN_SWAP
-#define TC_MN_SWAP 0  // which descriptor field carries the M/N-group stride of an MN-major no-swizzle operand
-#endif
 constexpr int TC_THREADS = 256;
-constexpr int A_TILE_BYTES = TC_BM * KT * 4;  // 16 KB
-__host__ __device__ constexpr int b_tile_bytes(int bn) { return bn * KT * 4; }
-__host__ __device__ constexpr int stage_bytes(int bn) { return 2 * A_TILE_BYTES + 2 * b_tile_bytes(bn); }
-__host__ __device__ constexpr int tc_smem_bytes(int bn) { return 2 * stage_bytes(bn) + 1024; }
 
-struct TcShared {
+struct TcShared {  // micro-benchmark kernels of vk_tc_test.cu (tools/tc_fixed_cost.py)
     uint64_t bar_stage[2];
     uint64_t bar_done;
     uint32_t tmem_base;
 };
 
-__device__ __forceinline__ float f4_get(const float4 &v, int e) {
-    return e == 0 ? v.x : (e == 1 ? v.y : (e == 2 ? v.z : v.w));
-}
-
-// Per-thread slice of one operand tile (rows x KT): up to TC_ITEMS float4, fetched in ONE batch of
-// independent global loads (so a k-tile costs one memory round trip, not one per item) and written to
-// shared memory later, which lets the loads of tile kt+1 fly while the tensor core works on tile kt.
-//  MN == false: source [row][k], k contiguous.  Lane l of a quarter-warp fills one 128-byte core matrix
-//               -> conflict-free 16-byte stores.
-//  MN == true : source [k][row], row contiguous (MN-major UMMA operands measured to produce zeros with
-//               the no-swizzle descriptor, so they are transposed on the fly instead).  A warp loads
-//               4 k x 32 rows as float4 and scatters the 4 row-elements with a lane-dependent rotation so
-//               that the 32 scalar stores of each instruction hit 32 different banks
-//               (bank = (row%8)*4 + k%4).
-constexpr int TC_ITEMS = 4;  // 128 rows x 32 k / 4 / 256 threads
-
-template <bool MN>
-__device__ __forceinline__ bool item_coords(int i, int rows, int &r, int &c) {
-    const int tid = threadIdx.x;
-    if (!MN) {
-        const int q = tid + i * TC_THREADS;
-        r = ((q >> 6) << 3) | (q & 7);  // row
-        c = (q >> 3) & 7;               // k / 4
-        return q < rows * (KT / 4);
-    } else {
-        const int lane = tid & 31, u = (tid >> 5) + i * (TC_THREADS / 32);
-        const int row_blocks = (rows + 31) >> 5;
-        const int rb = u % row_blocks, kb = u / row_blocks;
-        r = kb * 4 + (lane & 3);        // k
-        c = rb * 8 + (lane >> 2);       // row / 4
-        return kb < KT / 4 && c * 4 < rows;
-    }
-}
-
-template <bool MN, class L>
-__device__ __forceinline__ void load_items(const L &ld, int r0, int k0, int rows, float4 (&v)[TC_ITEMS]) {
-#pragma unroll
-    for (int i = 0; i < TC_ITEMS; ++i) {
-        int r, c;
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (item_coords<MN>(i, rows, r, c)) v[i] = MN ? ld.ld4(k0 + r, (r0 >> 2) + c) : ld.ld4(r0 + r, (k0 >> 2) + c);
-    }
-}
-
-template <bool MN>
-__device__ __forceinline__ void store_items(const float4 (&v)[TC_ITEMS], int rows, uint8_t *hi, uint8_t *lo) {
-#pragma unroll
-    for (int i = 0; i < TC_ITEMS; ++i) {
-        int r, c;
-        if (!item_coords<MN>(i, rows, r, c)) continue;
-        const float4 w = tf32_lo(v[i]);
-        if (!MN) {
-            const uint32_t off = off_kmajor(r, c);
-            *reinterpret_cast<float4 *>(hi + off) = v[i];
-            *reinterpret_cast<float4 *>(lo + off) = w;
-        } else {
-            const int k = r, rot = ((threadIdx.x & 31) >> 3) & 3;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int ee = (e + rot) & 3;
-                const int row = c * 4 + ee;
-                const uint32_t off = (uint32_t)((row >> 3) * 1024 + (k >> 2) * 128 + (row & 7) * 16 + (k & 3) * 4);
-                *reinterpret_cast<float *>(hi + off) = f4_get(v[i], ee);
-                *reinterpret_cast<float *>(lo + off) = f4_get(w, ee);
-            }
-        }
-    }
-}
-
-// One 128 x bn output tile: D[m, n] = sum_k A(m, k) * B(n, k), k in [0, K).
-//   LA / LB: loaders with  float4 ld4(int r, int c4)  returning 4 consecutive elements along the
-//   CONTIGUOUS dimension of the operand's storage:
-//     A_MN == false: storage [m][k] -> ld4(m, k/4);   A_MN == true: storage [k][m] -> ld4(k, m/4)
-//   and zeros outside the logical bounds.  bn: multiple of 16, 16 <= bn <= 128.  The accumulator is left
-//   in TMEM (128 lanes x bn columns at sh->tmem_base); the caller runs the epilogue with tc_read_acc and
-//   then calls tc_tile_end().
-template <bool A_MN, bool B_MN, class LA, class LB>
-__device__ __forceinline__ void tc_tile_mainloop(int K, int m0, int n0, int bn, const LA &la, const LB &lb,
-                                                 uint8_t *smem, TcShared *sh) {
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int nk = (K + KT - 1) / KT;
-    // the first tile's loads are in flight while the barriers / tensor memory are set up
-    float4 ra[TC_ITEMS], rb[TC_ITEMS];
-    load_items<A_MN>(la, m0, 0, TC_BM, ra);
-    load_items<B_MN>(lb, n0, 0, bn, rb);
-    if (tid == 0) {
-        mbar_init(&sh->bar_stage[0], 1);
-        mbar_init(&sh->bar_stage[1], 1);
-        mbar_init(&sh->bar_done, 1);
-        mbar_fence_init();
-    }
-    if (warp == 0) tmem_alloc(&sh->tmem_base, 128);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_d = sh->tmem_base;
-    const uint32_t idesc = make_idesc_tf32(TC_BM, bn, 0, 0);  // both operand tiles are K-major in shared memory
-    const int bbytes = b_tile_bytes(bn);
-
-    for (int kt = 0; kt < nk; ++kt) {
-        const int s = kt & 1;
-        uint8_t *st = smem + s * stage_bytes(bn);
-        uint8_t *a_hi = st, *a_lo = st + A_TILE_BYTES, *b_hi = st + 2 * A_TILE_BYTES, *b_lo = b_hi + bbytes;
-        // the MMAs that read this stage two iterations ago must have finished
-        if (kt >= 2) mbar_wait(&sh->bar_stage[s], (uint32_t)(((kt >> 1) - 1) & 1));
-        tc_fence_after();
-        store_items<A_MN>(ra, TC_BM, a_hi, a_lo);
-        store_items<B_MN>(rb, bn, b_hi, b_lo);
-        fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
-        __syncthreads();
-        if (kt + 1 < nk) {  // next tile's global loads overlap the MMAs issued below
-            load_items<A_MN>(la, m0, (kt + 1) * KT, TC_BM, ra);
-            load_items<B_MN>(lb, n0, (kt + 1) * KT, bn, rb);
-        }
-        if (tid == 0) {
-            tc_fence_after();
-            const uint32_t lbo = 128, sbo = 1024, step = 256;
-#pragma unroll
-            for (int j = 0; j < KT / 8; ++j) {
-                const uint64_t dah = make_smem_desc(smem_u32(a_hi) + j * step, lbo, sbo);
-                const uint64_t dal = make_smem_desc(smem_u32(a_lo) + j * step, lbo, sbo);
-                const uint64_t dbh = make_smem_desc(smem_u32(b_hi) + j * step, lbo, sbo);
-                const uint64_t dbl = make_smem_desc(smem_u32(b_lo) + j * step, lbo, sbo);
-                umma_tf32(tmem_d, dal, dbh, idesc, (kt | j) ? 1u : 0u);  // small terms first
-                umma_tf32(tmem_d, dah, dbl, idesc, 1u);
-                umma_tf32(tmem_d, dah, dbh, idesc, 1u);
-            }
-            umma_commit(&sh->bar_stage[s]);
-            if (kt == nk - 1) umma_commit(&sh->bar_done);
-        }
-    }
-    mbar_wait(&sh->bar_done, 0);
-    tc_fence_after();
-}
-
-// Read the accumulator rows of this thread's TMEM quadrant: warp w owns lanes 32*(w%4)..+31 and
-// column half (w/4); v receives 32 consecutive columns starting at `col`.
+// Read the accumulator rows of this thread's TMEM quadrant: warp w owns lanes 32*(w%4)..+31; v receives 32
+// consecutive columns starting at `col`.
 __device__ __forceinline__ void tc_read_acc(const TcShared *sh, int col, float (&v)[32]) {
     const int warp = threadIdx.x >> 5;
     const uint32_t taddr = sh->tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col;
     tmem_ld32(taddr, v);
-}
-
-__device__ __forceinline__ void tc_tile_end(TcShared *sh) {
-    tc_fence_before();
-    __syncthreads();
-    if ((threadIdx.x >> 5) == 0) tmem_dealloc(sh->tmem_base, 128);
 }
 
 }  // namespace tc

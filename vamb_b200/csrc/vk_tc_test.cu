@@ -1,77 +1,47 @@
-// Stand-alone check of the tcgen05 3xTF32 tile GEMM (vk_tc.cuh): C[M, N] = A * B^T for every
-// combination of operand storage orders.  Used by tests/test_tc_gpu.py before the core is trusted
-// inside the VAE kernels.
+// Stand-alone check of the production tcgen05 3xTF32 main loop (tc::ws_mainloop, vk_tc.cuh): C[M, N] = A * B^T on
+// staged operands, every tile width and split-K offsets.  Used by tests/test_tc_gpu.py.
 #include "vk_tc.cuh"
 
 namespace {
 
-struct Ld4Plain {
-    const float *p;
-    int ld, rows, cols, aligned;
-    __device__ __forceinline__ float4 ld4(int r, int c4) const {
-        const int c = c4 * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r >= rows || c >= cols) return v;
-        const float *q = p + (int64_t)r * ld + c;
-        if (aligned && c + 3 < cols) return __ldg(reinterpret_cast<const float4 *>(q));
-        v.x = __ldg(q);
-        if (c + 1 < cols) v.y = __ldg(q + 1);
-        if (c + 2 < cols) v.z = __ldg(q + 2);
-        if (c + 3 < cols) v.w = __ldg(q + 3);
-        return v;
-    }
-};
-
-// a_mn: A stored [K][M] (else [M][K]); b_mn: B stored [K][N] (else [N][K])
-template <bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(tc::TC_THREADS, 1)
-tc_gemm_test_kernel(const float *A, const float *B, float *C, int M, int N, int K, int lda, int ldb, int variant) {
+// C[M, N] = A * B^T through the PRODUCTION main loop (tc::ws_mainloop, the one fwd_layer_tc_kernel /
+// bwd_layer_tc_kernel run): A in the lane-major layout (zero padded to 128-row panels and whole k-tiles),
+// B plain K-major (zero padded to whole tiles), k-tiles [kt0, kt0 + nk) only (split-K slices as in wgrad).
+__global__ void __launch_bounds__(tc::WS_THREADS, 1)
+ws_gemm_test_kernel(const float *A, int lda, const float *B, int ldb, float *C, int M, int N, int tile_n, int kt0, int nk) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ tc::TcShared sh;
+    __shared__ tc::WsShared sh;
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 128;
+    const int m0 = blockIdx.y * 128, n0 = blockIdx.x * tile_n;
     int bn = N - n0;
-    bn = bn > 128 ? 128 : ((bn + 15) & ~15);
-    const int al_a = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
-    const int al_b = ((ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
-    Ld4Plain la{A, lda, A_MN ? K : M, A_MN ? M : K, al_a};
-    Ld4Plain lb{B, ldb, B_MN ? K : N, B_MN ? N : K, al_b};
-    tc::tc_tile_mainloop<A_MN, B_MN>(K, m0, n0, bn, la, lb, smem, &sh);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m = m0 + (warp & 3) * 32 + lane;
-    for (int c = (warp >> 2) * 64; c < (warp >> 2) * 64 + 64 && c < bn; c += 32) {
-        float v[32];
-        tc::tc_read_acc(&sh, c, v);
-        if (m < M) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (n0 + c + j < N) C[(int64_t)m * N + n0 + c + j] = v[j];
-        }
+    bn = bn > tile_n ? tile_n : ((bn + 15) & ~15);
+    if (!tc::ws_mainloop(A, lda, m0, B, ldb, n0, bn, kt0, nk, smem, &sh)) return;
+    constexpr int TS = 132;
+    float *tile = reinterpret_cast<float *>(smem);
+    tc::ws_acc_to_tile(&sh, bn, nk, tile, TS);
+    tc::ws_tile_end(&sh);
+    for (int q = threadIdx.x; q < 128 * bn; q += tc::WS_EPI_THREADS) {
+        const int r = q / bn, c = q - r * bn;
+        if (m0 + r < M && n0 + c < N) C[(int64_t)(m0 + r) * N + n0 + c] = tile[r * TS + c];
     }
-    tc::tc_tile_end(&sh);
 }
 
 }  // namespace
 
-static int g_variant = -1;
-extern "C" void vk_tc_set_variant(int v) { g_variant = v; }
-
-extern "C" int vk_tc_gemm_test(const float *A, const float *B, float *C, int M, int N, int K, int a_mn, int b_mn,
-                               void *stream) {
+// A_lane: [ceil(M / 128) * 128 rows, lda] in tc::lane_major_index order; B: [ceil(N / tile_n) * tile_n rows, ldb]
+// row-major; lda, ldb multiples of 32 covering k-tiles [0, kt0 + nk).  tile_n: multiple of 16 in [16, 128].
+extern "C" int vk_tc_gemm_test(const float *A_lane, int lda, const float *B, int ldb, float *C, int M, int N, int tile_n,
+                               int kt0, int nk, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
-    const int lda = a_mn ? M : K, ldb = b_mn ? N : K;
-    dim3 grid((N + 127) / 128, (M + 127) / 128);
-    const int smem = tc::tc_smem_bytes(128);
-#define LAUNCH(AM, BM_)                                                                                     \
-    do {                                                                                                    \
-        VK_CUDA(cudaFuncSetAttribute(tc_gemm_test_kernel<AM, BM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        tc_gemm_test_kernel<AM, BM_><<<grid, tc::TC_THREADS, smem, s>>>(A, B, C, M, N, K, lda, ldb, g_variant);        \
-    } while (0)
-    if (!a_mn && !b_mn) LAUNCH(false, false);
-    else if (!a_mn && b_mn) LAUNCH(false, true);
-    else if (a_mn && !b_mn) LAUNCH(true, false);
-    else LAUNCH(true, true);
-#undef LAUNCH
+    if (tile_n < 16 || tile_n > 128 || (tile_n & 15) || (lda & 31) || (ldb & 31)) {
+        vk_set_error("vk_tc_gemm_test: bad tile / leading dimensions");
+        return 1;
+    }
+    dim3 grid((N + tile_n - 1) / tile_n, (M + 127) / 128);
+    int smem = tc::ws_smem_bytes(tile_n);
+    if (smem < 128 * 132 * 4 + 1024) smem = 128 * 132 * 4 + 1024;  // the epilogue tile reuses the operand ring
+    VK_CUDA(cudaFuncSetAttribute(ws_gemm_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ws_gemm_test_kernel<<<grid, tc::WS_THREADS, smem, s>>>(A_lane, lda, B, ldb, C, M, N, tile_n, kt0, nk);
     VK_LAUNCH_CHECK();
     return 0;
 }
