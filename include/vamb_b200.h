@@ -252,6 +252,9 @@ typedef struct vk_vae {
     int32_t n_grad_slabs;               /* slabs allocated in `grads` (>= 1)                                       */
     int32_t staging;                    /* tensor-core operand staging: 0 = fused into the producing kernels' epilogues
                                            (grid barrier; falls back when a grid exceeds the SM count), 1 = prep kernels */
+    int32_t use_tma;                    /* 1 = the weight operand (B) of the forward / dgrad GEMMs is fetched by TMA
+                                           (cp.async.bulk.tensor, 128B swizzle; needs w_lo / wt_lo), 0 = cp.async ring  */
+    int32_t reserved0;
 } vk_vae;
 
 /* Optional host-injected randomness for parity tests (all device pointers, NULL = on-device RNG). */
@@ -301,9 +304,11 @@ int vk_vae_grad_step(const vk_vae *net, int batch, const vk_vae_inject *inject, 
 /* Stand-alone check of the PRODUCTION tcgen05 3xTF32 main loop (tc::ws_mainloop -- the loop of the layer kernels):
  * C[M,N] = A * B^T over k-tiles [kt0, kt0 + nk) of 32.  A_lane: the 128-row operand in the lane-major staging layout
  * (vk_lane_major_index), zero padded to whole 128-row panels; B: plain row-major [rows][ldb], zero padded to whole
- * tile_n-row tiles; lda, ldb multiples of 32; tile_n (output columns per CTA) a multiple of 16 in [16, 128]. */
-int vk_tc_gemm_test(const float *A_lane, int lda, const float *B, int ldb, float *C, int M, int N, int tile_n,
-                    int kt0, int nk, void *stream);
+ * tile_n-row tiles; lda, ldb multiples of 32; tile_n (output columns per CTA) a multiple of 16 in [16, 128].
+ * B_lo != NULL selects the TMA-fed B operand (cp.async.bulk.tensor through 128B-swizzled tensor maps), B_lo holding the
+ * tf32 remainders x - trunc13(x) of B -- the way the forward / dgrad GEMMs fetch the weights staged by prep_weights. */
+int vk_tc_gemm_test(const float *A_lane, int lda, const float *B, const float *B_lo, int ldb, float *C, int M, int N,
+                    int tile_n, int kt0, int nk, void *stream);
 
 /* Host-side: float offset of element (r, k) of an A-role operand in the "lane-major" staging layout
  * (128-row panels; each 32-wide k-tile of a panel is one 16 KB block [k/4][row][k%4]); ld = floats per row,

@@ -27,7 +27,7 @@ def lane_major(a: torch.Tensor, ld: int) -> torch.Tensor:
     return out
 
 
-def run(A, B, tile_n, kt0=0, nk=None):
+def run(A, B, tile_n, kt0=0, nk=None, tma=False):
     from vamb_b200 import _lib
 
     _lib.require_device()
@@ -43,17 +43,22 @@ def run(A, B, tile_n, kt0=0, nk=None):
     C = torch.full((M, N), float("nan"), device="cuda")
     s = torch.cuda.current_stream().cuda_stream
     nk = ld // 32 - kt0 if nk is None else nk
-    _lib.check(_lib.lib.vk_tc_gemm_test(Al.data_ptr(), ld, Bp.data_ptr(), ld, C.data_ptr(), M, N, tile_n, kt0, nk, s))
+    b_lo = None
+    if tma:  # the tf32 remainder the tensor core does not see: x - (x with the low 13 mantissa bits cleared)
+        b_lo = Bp - (Bp.view(torch.int32) & -8192).view(torch.float32)
+    _lib.check(_lib.lib.vk_tc_gemm_test(Al.data_ptr(), ld, Bp.data_ptr(), b_lo.data_ptr() if tma else None, ld, C.data_ptr(),
+                                        M, N, tile_n, kt0, nk, s))
     torch.cuda.synchronize()
     return C
 
 
+@pytest.mark.parametrize("tma", [False, True], ids=["cp.async-B", "tma-B"])
 @pytest.mark.parametrize("M,N,K,tile_n", SHAPES)
-def test_ws_mainloop_matches_fp64(M, N, K, tile_n):
+def test_ws_mainloop_matches_fp64(M, N, K, tile_n, tma):
     g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
     A = torch.randn(M, K, device="cuda", generator=g)
     B = torch.randn(N, K, device="cuda", generator=g)
-    C = run(A, B, tile_n)
+    C = run(A, B, tile_n, tma=tma)
     ref = A.double() @ B.double().t()
     assert torch.isfinite(C).all()
     err = float((C.double() - ref).norm() / ref.norm())

@@ -30,10 +30,11 @@ def set_path(vae, tc):
     kernels, "prep": by separate prep launches), or the fp32 CUDA-core path (False)."""
     vae._net.tc_min_batch = 1 if tc else 0
     vae._net.staging = 1 if tc == "prep" else 0
+    vae._net.use_tma = 1 if tc == "tma" else 0  # weight operand through TMA (cp.async.bulk.tensor) vs the cp.async ring
     return vae
 
 
-@pytest.mark.parametrize("tc", [False, True, "prep"], ids=["ffma", "tcgen05", "tcgen05-prep"])
+@pytest.mark.parametrize("tc", [False, True, "prep", "tma"], ids=["ffma", "tcgen05", "tcgen05-prep", "tcgen05-tma"])
 @pytest.mark.parametrize("case", VAE_CASES, ids=[c[0] for c in VAE_CASES])
 def test_train_steps_and_encode_match_reference_golden(case, tc):
     import vamb_b200.encode as ve
@@ -78,10 +79,10 @@ def test_train_steps_and_encode_match_reference_golden(case, tc):
 
 @pytest.mark.parametrize("tc,B,S", [(False, 256, 50), (True, 256, 50), (True, 1024, 50), (True, 4096, 50),
                                     ("prep", 256, 50), ("prep", 4096, 50), (True, 1000, 50), (True, 256, 80),
-                                    (True, 8192, 50)],
+                                    (True, 8192, 50), ("tma", 256, 50), ("tma", 1000, 50), ("tma", 4096, 50)],
                          ids=["ffma-256", "tcgen05-256", "tcgen05-1024-split2", "tcgen05-4096-split8", "tcgen05-prep-256",
                               "tcgen05-prep-4096", "tcgen05-1000-ragged", "tcgen05-256-wide-input",
-                              "tcgen05-8192-grid-fallback"])
+                              "tcgen05-8192-grid-fallback", "tcgen05-tma-256", "tcgen05-tma-1000-ragged", "tcgen05-tma-4096"])
 def test_gradients_match_oracle_default_network(tc, B, S):
     """One fwd+bwd on the bin-default network (512-512-32): every gradient tensor.  S = 80 makes the
     reconstruction wider than the loss kernel stages itself (a prep launch takes over for that layer);
@@ -110,7 +111,7 @@ def test_gradients_match_oracle_default_network(tc, B, S):
         assert rel(got[k].cpu().numpy(), gref.numpy()) < tol, k
 
 
-@pytest.mark.parametrize("tc", [False, True, "prep"], ids=["ffma", "tcgen05", "tcgen05-prep"])
+@pytest.mark.parametrize("tc", [False, True, "prep", "tma"], ids=["ffma", "tcgen05", "tcgen05-prep", "tcgen05-tma"])
 def test_odd_batch_and_many_steps_match_oracle(tc):
     """B not a multiple of the tile size, 12 steps: parameters track the oracle."""
     import vamb_b200.encode as ve

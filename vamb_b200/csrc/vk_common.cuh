@@ -31,6 +31,12 @@ void vk_set_error(const char *fmt, ...);
 
 int vk_num_sms();
 
+// 128-byte CUtensorMap (vk_tma.cu) of an fp32 [rows][ld] array, box 32 x box_rows, 128B swizzle; 0 = ok
+int vk_make_tmap_2d(void *out128, const float *base, int ld, int rows, int box_rows);
+struct alignas(64) VkTmap {
+    unsigned char opaque[128];
+};
+
 // ---- streaming (read-once) global loads: bypass L1 allocation ----
 __device__ __forceinline__ float4 ldg_stream4(const float *p) {
     float4 v;

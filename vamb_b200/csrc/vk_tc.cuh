@@ -22,16 +22,23 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void mbar_fence_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+// A wait that never completes (a lost arrival, a bulk copy that never lands) traps after ~2 s instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "LAB_WAIT%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra LAB_DONE%=;\n\t"
-        "bra LAB_WAIT%=;\n\t"
-        "LAB_DONE%=:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+    const uint32_t addr = smem_u32(bar);
+    long long t0 = 0;
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) return;
+        const long long now = clock64();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 4000000000LL) __trap();
+    }
 }
 
 // ---- fences ----
@@ -172,6 +179,30 @@ __device__ __forceinline__ void cp_async_wait() {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// ---- TMA: bulk tensor copies global -> shared, completion counted in bytes on an mbarrier ----
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// box of the 2-D tensor map `tmap` at (c0 = innermost element, c1 = row) -> shared memory at smem_dst
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void *tmap, uint64_t *bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
+        "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+// shared-memory matrix descriptor of a K-major tile written by TMA with CU_TENSOR_MAP_SWIZZLE_128B: rows of 128 bytes
+// (one 32-float k-tile), 8-row swizzle atoms of 1024 bytes (SBO), layout_type = SWIZZLE_128B (2); the tile base must be
+// 1024-byte aligned; a K = 8 (32-byte) step advances the start address by 32 bytes inside the atom.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)1 << 16;                  // LBO: unused for swizzled K-major operands
+    d |= (uint64_t)(1024u >> 4) << 32;       // SBO: next group of 8 rows
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
 // 32 lanes x 16 consecutive columns
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
@@ -235,7 +266,7 @@ constexpr int WS_THREADS = 288;
 constexpr int WS_EPI_THREADS = 256;
 constexpr int WS_STAGES = 4;
 constexpr uint32_t WS_TMEM_COLS = 512;  // 128 + 4 * 64 rounded up to a power of two
-__host__ __device__ constexpr int ws_smem_bytes(int bn) { return WS_STAGES * 2 * b_tile_bytes(bn) + 1024; }
+__host__ __device__ constexpr int ws_smem_bytes(int bn) { return WS_STAGES * 2 * b_tile_bytes(bn) + 1024; }  // bn = slot rows
 
 struct WsShared {
     uint64_t full[WS_STAGES], empty[WS_STAGES], done;
@@ -245,11 +276,19 @@ struct WsShared {
 // D[128 x bn] = sum over k-tiles [kt0, kt0 + nk) of A[m0.., k] * B[n0.., k]^T.  A: lane-major (m0 a multiple
 // of 128), B: plain K-major; both fp32, zero padded to whole tiles (ld = floats per row, multiple of 32).
 // Returns true for the 256 epilogue threads (accumulator complete), false for the MMA warp (which is done).
+//
+// TMA_B: the B operand (weights) is fetched by the TMA engine instead: one elected thread arms full[stage] with the
+// byte count and issues two bulk tensor copies (the fp32 tile and its pre-split tf32 remainder, written once per step by
+// prep_weights) through 128B-swizzled tensor maps whose box is 32 floats x `slot_rows` rows; the producer warps then
+// only feed A.  `slot_rows` (= the launch's tile width, >= bn) sizes the ring slots; tm_hi / tm_lo point to CUtensorMap
+// objects in kernel-parameter space (__grid_constant__).
+template <bool TMA_B = false>
 __device__ __forceinline__ bool ws_mainloop(const float *A, int lda, int m0, const float *B, int ldb, int n0, int bn,
-                                            int kt0, int nk, uint8_t *smem, WsShared *sh) {
+                                            int kt0, int nk, uint8_t *smem, WsShared *sh, int slot_rows = 0,
+                                            const void *tm_hi = nullptr, const void *tm_lo = nullptr) {
     constexpr int S = WS_STAGES, P = 2;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int bbytes = b_tile_bytes(bn), sbytes = 2 * bbytes;
+    const int bbytes = b_tile_bytes(TMA_B ? slot_rows : bn), sbytes = 2 * bbytes;
     const uint32_t smem_base = smem_u32(smem);
     // B chunk q = tid + 256 i of a tile: row ((q >> 6) << 3) | (q & 7) = r0 + 32 i, 16-byte column k4, at byte q * 16
     const int r0 = ((tid >> 6) << 3) | (tid & 7), k4 = (tid >> 3) & 7;
@@ -262,6 +301,14 @@ __device__ __forceinline__ bool ws_mainloop(const float *A, int lda, int m0, con
     const float4 *pa = reinterpret_cast<const float4 *>(A + (size_t)(m0 >> 7) * 128 * lda + (size_t)kt0 * 4096) +
                        (warp >> 2) * 4 * 128 + (warp & 3) * 32 + lane;
     auto issue_b = [&](int kt, int slot) {
+        if (TMA_B) {
+            if (tid == 0) {
+                mbar_expect_tx(&sh->full[slot], (uint32_t)sbytes);
+                tma_load_2d(smem_base + slot * sbytes, tm_hi, &sh->full[slot], (kt0 + kt) * KT, n0);
+                tma_load_2d(smem_base + slot * sbytes + bbytes, tm_lo, &sh->full[slot], (kt0 + kt) * KT, n0);
+            }
+            return;
+        }
         const uint32_t st = smem_base + slot * sbytes + soff;
         const float *gb = pb + (size_t)kt * KT;
         for (int i = 0; i < nbi; ++i) cp_async16(st + i * 4096, gb + i * b_step);
@@ -285,10 +332,10 @@ __device__ __forceinline__ bool ws_mainloop(const float *A, int lda, int m0, con
 #pragma unroll
         for (int t = 0; t < P; ++t) {
             if (t < nk) {
-                issue_b(t, t);
+                if (!TMA_B) issue_b(t, t);  // (the bulk copies need the barriers: issued after the set-up below)
                 load_a(t, ra[t]);
             }
-            cp_async_commit();
+            if (!TMA_B) cp_async_commit();
         }
     }
     if (tid == 0) {
@@ -305,11 +352,17 @@ __device__ __forceinline__ bool ws_mainloop(const float *A, int lda, int m0, con
     __syncthreads();
     tc_fence_after();
     tl_mark(8);
+    if (TMA_B && warp < 8) {
+#pragma unroll
+        for (int t = 0; t < P; ++t)
+            if (t < nk) issue_b(t, t);
+    }
     const uint32_t tmem_d = sh->tmem_base;
     if (warp == 8) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(TC_BM, bn, 0, 0);
-            const uint64_t desc0 = make_smem_desc(smem_base, 128, 1024);
+            const uint64_t desc0 = TMA_B ? make_smem_desc_sw128(smem_base) : make_smem_desc(smem_base, 128, 1024);
+            const uint32_t kstep = TMA_B ? 2u : 16u;  // start-address units (16 bytes) per K = 8 step
             int slot = 0;
             uint32_t phase = 0;
             for (int kt = 0; kt < nk; ++kt) {
@@ -321,9 +374,9 @@ __device__ __forceinline__ bool ws_mainloop(const float *A, int lda, int m0, con
                 const uint64_t bl = bh + (uint64_t)((uint32_t)bbytes >> 4);
 #pragma unroll
                 for (int j = 0; j < KT / 8; ++j) {
-                    umma_tf32_ts(tmem_d, al + 8u * j, bh + 16u * j, idesc, (kt | j) ? 1u : 0u);  // small terms first
-                    umma_tf32_ts(tmem_d, ah + 8u * j, bl + 16u * j, idesc, 1u);
-                    umma_tf32_ts(tmem_d, ah + 8u * j, bh + 16u * j, idesc, 1u);
+                    umma_tf32_ts(tmem_d, al + 8u * j, bh + kstep * j, idesc, (kt | j) ? 1u : 0u);  // small terms first
+                    umma_tf32_ts(tmem_d, ah + 8u * j, bl + kstep * j, idesc, 1u);
+                    umma_tf32_ts(tmem_d, ah + 8u * j, bh + kstep * j, idesc, 1u);
                 }
                 umma_commit(&sh->empty[slot]);
                 if (kt == nk - 1) umma_commit(&sh->done);
@@ -343,7 +396,7 @@ __device__ __forceinline__ bool ws_mainloop(const float *A, int lda, int m0, con
             if (nt >= S) mbar_wait(&sh->empty[nt % S], (uint32_t)(((nt / S) - 1) & 1));
             issue_b(nt, nt % S);
         }
-        cp_async_commit();
+        if (!TMA_B) cp_async_commit();
         // A tile kt: registers -> tensor memory (its stage was released before B of this tile was issued)
         float hi[16], lo[16];
 #pragma unroll
@@ -356,10 +409,12 @@ __device__ __forceinline__ bool ws_mainloop(const float *A, int lda, int m0, con
         tmem_st16(a_lane + 64u * slot, hi);
         tmem_st16(a_lane + 64u * slot + 32u, lo);
         if (nt < nk) load_a(nt, v);  // v's registers are free again: next-but-one tile
-        cp_async_wait<P>();          // this thread's B copies of tile kt have landed
-        split_b(slot);
+        if (!TMA_B) {
+            cp_async_wait<P>();      // this thread's B copies of tile kt have landed
+            split_b(slot);
+        }
         tmem_wait_st();
-        fence_async_smem();          // shared-memory writes visible to the tensor core (async proxy)
+        if (!TMA_B) fence_async_smem();  // shared-memory writes visible to the tensor core (async proxy)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sh->full[slot]);

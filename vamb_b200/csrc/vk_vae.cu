@@ -355,6 +355,8 @@ struct FwdArgs {
     // 0 off; 1 BatchNorm with this batch's statistics (grid barrier, then every CTA folds its own columns);
     // 2 plain copy (z) or BatchNorm with the precomputed affine bn_a / bn_c (evaluation)
     int stage; float *stage_a; int stage_a_ld; float *stage_t; int stage_t_ld;
+    // B operand (W and its tf32 remainder) through TMA: 128B-swizzled tensor maps, box = 32 floats x tile_n rows
+    int use_tma; VkTmap tm_b_hi, tm_b_lo;
 };
 
 // Fold the per-row-tile column sums of P and P^2 into the BatchNorm affine, the saved batch statistics
@@ -618,6 +620,7 @@ struct BwdArgs {
     // 0 off; 1 hidden layer (grid barrier over the dgrad CTAs, fold, BatchNorm/dropout/LeakyReLU backward);
     // 2 plain copy (dL/dmu)
     int stage; float *stage_a; int stage_a_ld; float *stage_t; int stage_t_ld; float slope; int has_dropout;
+    int use_tma; VkTmap tm_dg_hi, tm_dg_lo;  // dgrad B operand (W^T and its tf32 remainder) through TMA
 };
 
 // Fold the per-row-tile column sums of dH and dH*Phat: BatchNorm weight/bias gradients and the two
@@ -821,7 +824,7 @@ struct BwdTcExtra {
 // Forward layer: D = X' W^T on the tensor core, then one coalesced pass over the shared tile does bias,
 // LeakyReLU, dropout (one Philox call per four outputs) / the reparameterisation, and the global stores;
 // hidden layers in training add the BatchNorm column sums and the last CTA folds them.
-__global__ void __launch_bounds__(tc::WS_THREADS, 1) fwd_layer_tc_kernel(FwdArgs a) {
+__global__ void __launch_bounds__(tc::WS_THREADS, 1) fwd_layer_tc_kernel(const __grid_constant__ FwdArgs a) {
     tl_begin(a.layer_id);
     const int tk = tk_begin(20 + a.layer_id);
     pdl_entry();
@@ -839,7 +842,10 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) fwd_layer_tc_kernel(FwdArgs
     const uint32_t k0 = (uint32_t)a.ctl->seed, k1 = (uint32_t)(a.ctl->seed >> 32);
     const uint32_t step_lo = (uint32_t)a.ctl->step, step_hi = (uint32_t)(a.ctl->step >> 32);
     const int nk = (a.K + tc::KT - 1) / tc::KT;
-    if (!tc::ws_mainloop(a.a_op.hi, a.a_op.ld, m0, a.b_op.hi, a.b_op.ld, n0, bn, 0, nk, smem, &sh)) return;
+    const bool alive = a.use_tma
+        ? tc::ws_mainloop<true>(a.a_op.hi, a.a_op.ld, m0, a.b_op.hi, a.b_op.ld, n0, bn, 0, nk, smem, &sh, a.tile_n, &a.tm_b_hi, &a.tm_b_lo)
+        : tc::ws_mainloop<false>(a.a_op.hi, a.a_op.ld, m0, a.b_op.hi, a.b_op.ld, n0, bn, 0, nk, smem, &sh);
+    if (!alive) return;
     tl_mark(2);
     float *tile = reinterpret_cast<float *>(smem);  // [128][TS]; the operand stages are dead now
     tc::ws_acc_to_tile(&sh, bn, nk, tile, TS);
@@ -984,7 +990,7 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) fwd_layer_tc_kernel(FwdArgs
 
 // Backward layer: wgrad slices (split-K over the batch, one gradient slab per split) and dgrad tiles in
 // one launch.
-__global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(BwdArgs a, BwdTcExtra x) {
+__global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(const __grid_constant__ BwdArgs a, BwdTcExtra x) {
     tl_begin(8 + a.ticket_id);
     const int tk = tk_begin(40 + a.ticket_id);
     pdl_entry();
@@ -1032,7 +1038,10 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(BwdArgs
     bn = bn > a.tile_n ? a.tile_n : ((bn + 15) & ~15);
     const float gsc = (float)(a.ctl->wbar / (double)a.B);
     const int nk = (a.N + tc::KT - 1) / tc::KT;
-    if (!tc::ws_mainloop(a.dg_a.hi, a.dg_a.ld, m0, a.dg_b.hi, a.dg_b.ld, n0, bn, 0, nk, smem, &sh)) return;
+    const bool alive = a.use_tma
+        ? tc::ws_mainloop<true>(a.dg_a.hi, a.dg_a.ld, m0, a.dg_b.hi, a.dg_b.ld, n0, bn, 0, nk, smem, &sh, a.tile_n, &a.tm_dg_hi, &a.tm_dg_lo)
+        : tc::ws_mainloop<false>(a.dg_a.hi, a.dg_a.ld, m0, a.dg_b.hi, a.dg_b.ld, n0, bn, 0, nk, smem, &sh);
+    if (!alive) return;
     const int q_per_row = bn >> 2;
     float *ptile = tile + 128 * TS;  // the previous layer's output P for the same rows / columns (zeros outside)
     if (a.in_kind == VK_IN_BN) {
@@ -1539,6 +1548,12 @@ static int tc_smem_for(int tile_n, int epi_tiles) {
     return need > epi ? need : epi;
 }
 
+// B operand of the forward / dgrad GEMMs through TMA (needs the pre-split remainders w_lo / wt_lo); vk_vae.use_tma = 0
+// keeps the cp.async ring (same results) for A/B timing.
+static bool use_tma(const vk_vae *net, const vk_vae_layer &L) {
+    return net->use_tma && L.w_lo != nullptr && L.wt_lo != nullptr;
+}
+
 static int tc_prepare() {
     static bool done = false;
     if (done) return 0;
@@ -1632,8 +1647,8 @@ static int launch_prep_weights(const vk_vae *net, cudaStream_t s) {
         PrepArgs &a = m.l[j];
         a.mode = 0; a.src = net->params + L.w_off; a.ld_src = L.k_in;
         a.rows = L.n_out; a.cols = L.k_in; a.rows_w = r32(L.n_out); a.cols_w = L.k_in;
-        a.hi = L.w_hi; a.lo = nullptr; a.ld = r32(L.k_in);
-        a.hiT = L.wt_hi; a.loT = nullptr; a.ldT = r32(L.n_out);
+        a.hi = L.w_hi; a.lo = L.w_lo; a.ld = r32(L.k_in);        // the remainders feed the TMA path (nullable)
+        a.hiT = L.wt_hi; a.loT = L.wt_lo; a.ldT = r32(L.n_out);
         gx = gx > (L.k_in + 32) / 32 ? gx : (L.k_in + 32) / 32;
         gy = gy > a.rows_w / 32 ? gy : a.rows_w / 32;
     }
@@ -1715,6 +1730,10 @@ static int launch_forward(const vk_vae *net, int B, int training, int upto /*exc
             a.tile_n = tc_tile_n(B);
             a.a_op = tc::OpRef{L.xop_hi, L.xop_lo, r32(L.k_in)};
             a.b_op = tc::OpRef{L.w_hi, L.w_lo, r32(L.k_in)};
+            a.use_tma = use_tma(net, L) ? 1 : 0;
+            if (a.use_tma && (vk_make_tmap_2d(&a.tm_b_hi, L.w_hi, r32(L.k_in), r128(L.n_out), a.tile_n) ||
+                              vk_make_tmap_2d(&a.tm_b_lo, L.w_lo, r32(L.k_in), r128(L.n_out), a.tile_n)))
+                return 1;
             dim3 grid((L.n_out + a.tile_n - 1) / a.tile_n, (B + 127) / 128);
             VK_CUDA(vk_launch(fwd_layer_tc_kernel, dim3(grid), dim3(tc::WS_THREADS), (size_t)tc_smem_for(a.tile_n, 1), s, a));
         } else {
@@ -1836,6 +1855,10 @@ static int launch_backward(const vk_vae *net, int B, cudaStream_t s) {
             a.wg_b = tc::OpRef{L.xt_hi, L.xt_lo, net->bmax};
             a.dg_a = tc::OpRef{L.dy_hi, L.dy_lo, r32(L.n_out)};
             a.dg_b = tc::OpRef{L.wt_hi, L.wt_lo, r32(L.n_out)};
+            a.use_tma = (a.dg_tiles_m && use_tma(net, L)) ? 1 : 0;
+            if (a.use_tma && (vk_make_tmap_2d(&a.tm_dg_hi, L.wt_hi, r32(L.n_out), r128(L.k_in), a.tile_n) ||
+                              vk_make_tmap_2d(&a.tm_dg_lo, L.wt_lo, r32(L.n_out), r128(L.k_in), a.tile_n)))
+                return 1;
             const int blocks = a.wg_tiles_m * a.wg_tiles_n * x.nsplit + a.dg_tiles_m * a.dg_tiles_n;
             VK_CUDA(vk_launch(bwd_layer_tc_kernel, dim3(blocks), dim3(tc::WS_THREADS), (size_t)tc_smem_for(a.tile_n > a.wg_tile_n ? a.tile_n : a.wg_tile_n, 2), s, a, x));
         } else {

@@ -57,6 +57,7 @@ def _warn_once(msg: str) -> None:
 
 _MAX_BATCH = 8192  # rows of the activation workspaces (training batches double up to 4096)
 _GRAPH_CHUNKS = (128, 16, 4)  # optimiser steps per captured CUDA graph, largest first
+_USE_TMA = 0  # default of vk_vae.use_tma (opt-in until validated on the GPU box)
 _TC_MIN_BATCH = 128  # batches >= this run their GEMMs on the tcgen05 tensor-core path (0 = never)
 
 
@@ -191,6 +192,7 @@ class _VkVae(_ct.Structure):
         ("layers", _VkLayer * _MAXL),
         ("data_ld", _ct.c_int32), ("tc_min_batch", _ct.c_int32), ("grad_slab", _ct.c_int64),
         ("n_grad_slabs", _ct.c_int32), ("staging", _ct.c_int32),
+        ("use_tma", _ct.c_int32), ("reserved0", _ct.c_int32),
     ]
 
 
@@ -367,6 +369,8 @@ class VAE(_nn.Module):
         net.tc_min_batch = _TC_MIN_BATCH
         # 0: the GEMM kernels stage the next GEMM's operands themselves; 1: separate prep launches (same results)
         net.staging = int(_os.environ.get("VAMB_B200_STAGING", "0"))
+        # weight operand of the forward / dgrad GEMMs through TMA (cp.async.bulk.tensor) or the cp.async ring
+        net.use_tma = int(_os.environ.get("VAMB_B200_TMA", str(_USE_TMA)))
         with _torch.cuda.device(dev):
             _lib.check(_L.vk_vae_init_device())  # side stream / events of the training step (once per device)
         for field, t in (("params", arena), ("grads", self._grads), ("exp_avg", self._exp_avg),
@@ -420,7 +424,9 @@ class VAE(_nn.Module):
             for name, rows, cols in (("xop", bmax, r32(k)), ("xt", r128(k + 1), bmax), ("dy", bmax, r32(n)),
                                      ("dyt", r128(n), bmax), ("w", r128(n), r32(k)), ("wt", r128(k), r32(n))):
                 setattr(ly, f"{name}_hi", buf(f"{name}_hi{j}", rows, cols))
-                setattr(ly, f"{name}_lo", None)  # the GEMM derives the tf32 remainders in shared memory
+                # weights: the tf32 remainders are written once per step by prep_weights and fetched by TMA;
+                # activations: the GEMM derives them in shared memory
+                setattr(ly, f"{name}_lo", buf(f"{name}_lo{j}", rows, cols) if name in ("w", "wt") else None)
         self._net = net
         self._dataset = None  # (data [N, d_in], weights [N]) resident on the device
         self._ctl_f64 = self._ctl[: (_ct.sizeof(_VkCtl) // 8) * 8].view(_torch.float64)
