@@ -235,3 +235,43 @@ def test_graph_replay_training_is_deterministic_and_learns():
     assert np.array_equal(lats[0], lats[1])
     # planted genomes: the loss after 3 epochs is well below the untrained level
     assert first[0] < 0.9
+
+
+def test_subclass_contract_autograd_route_matches_the_kernels():
+    """``_encode`` / ``reparameterize`` / ``_decode`` (the methods VAELabels / VAEConcat build on,
+    vamb/semisupervised_encode.py:189,438) are differentiable module code over the SAME arena the kernels train: with
+    dropout off and the same noise, ``calc_loss(...)[0].backward()`` through ``forward`` gives the kernels' gradients."""
+    import vamb_b200.encode as ve
+
+    S, n, B = 6, 700, 256
+    rpkm, tnfs, lens = vae_inputs(S, n, 13)
+    dl = ve.make_dataloader(rpkm.copy(), tnfs.copy(), lens, batchsize=B)
+    d, t, a, w = dl.dataset.tensors
+    vae = ve.VAE(S, nhiddens=[96, 64], nlatent=12, dropout=0.0, seed=5)
+    idx = np.random.default_rng(2).choice(n, B, replace=False)
+    ti = torch.from_numpy(idx)
+    vae.train()
+    torch.manual_seed(77)
+    do, to, ao, mu = vae(d[ti], t[ti], a[ti])
+    assert mu.requires_grad and do.shape == (B, S)
+    loss = vae.calc_loss(d[ti], do, t[ti], to, a[ti], ao, mu, w[ti])
+    vae.zero_grad()
+    loss[0].backward()
+    auto = {k: p.grad.detach().clone() for k, p in vae.named_parameters()}
+    torch.manual_seed(77)
+    eps = torch.randn(B, 12)  # what reparameterize drew
+    for bn in list(vae.encodernorms) + list(vae.decodernorms):  # undo the running-stat update of the first pass
+        bn.reset_running_stats()
+    losses = vae._step_injected(dl.dataset.tensors, idx, eps.numpy(), None, optimize=False)
+    assert np.allclose(losses[0], float(loss[0]), rtol=2e-5)
+    got = vae._grad_dict()
+    for k, g in auto.items():
+        assert rel(got[k].cpu().numpy(), g.cpu().numpy()) < 1e-4, k
+    # eval mode / no_grad: the fused kernels, graph-less outputs
+    vae.eval()
+    out = vae(d[:64], t[:64], a[:64])
+    assert not out[3].requires_grad
+    with torch.no_grad():
+        vae.train()
+        out = vae(d[:64], t[:64], a[:64])
+        assert not out[3].requires_grad

@@ -506,15 +506,49 @@ class VAE(_nn.Module):
         return n
 
     # ------------------------------------------------------------------ reference API
+    # Subclass contract: the TaxVamb encoders subclass VAE and call ``self._encode``,
+    # ``self.reparameterize`` and ``self._decode`` on their OWN concatenated inputs, inside their own autograd
+    # training loops (vamb/semisupervised_encode.py:189, 438).  These three methods are therefore ordinary
+    # differentiable module code over the registered layers -- whose parameters are views of the arena the kernels
+    # train, so both routes always see the same weights.  The hot path (trainmodel / encode) never goes through them.
+    def _encode(self, tensor: Tensor) -> Tensor:
+        "vamb/encode.py:259-273: BatchNorm(Dropout(LeakyReLU(Linear))) per hidden layer, then ``mu``."
+        tensor = tensor.to(self._arena.device)
+        for encoderlayer, encodernorm in zip(self.encoderlayers, self.encodernorms):
+            tensor = encodernorm(self.dropoutlayer(self.relu(encoderlayer(tensor))))
+        return self.mu(tensor)
+
     def reparameterize(self, mu: Tensor) -> Tensor:
-        "vamb/encode.py:276-286 (noise from the global torch generator, as in the reference)."
+        "vamb/encode.py:276-286 (noise from the global torch CPU generator, moved to the device, as in the reference)."
         epsilon = _torch.randn(mu.size(0), mu.size(1)).to(mu.device)
+        epsilon.requires_grad = True
         return mu + epsilon
 
+    def _decode(self, tensor: Tensor) -> tuple[Tensor, Tensor, Tensor]:
+        "vamb/encode.py:288-304: decoder blocks, output layer, softmax over the first ``nsamples`` outputs."
+        tensor = tensor.to(self._arena.device)
+        for decoderlayer, decodernorm in zip(self.decoderlayers, self.decodernorms):
+            tensor = decodernorm(self.dropoutlayer(self.relu(decoderlayer(tensor))))
+        reconstruction = self.outputlayer(tensor)
+        depths_out = _softmax(reconstruction.narrow(1, 0, self.nsamples), dim=1)
+        tnf_out = reconstruction.narrow(1, self.nsamples, self.ntnf)
+        abundance_out = reconstruction.narrow(1, self.nsamples + self.ntnf, 1)
+        return depths_out, tnf_out, abundance_out
+
     def forward(self, depths: Tensor, tnf: Tensor, abundance: Tensor) -> tuple[Tensor, Tensor, Tensor, Tensor]:
-        """(depths_out, tnf_out, abundance_out, mu) for explicit input tensors
-        (vamb/encode.py:306-314), in train or eval mode according to ``self.training``.
-        Runs the fused kernels; the outputs carry no autograd graph."""
+        """(depths_out, tnf_out, abundance_out, mu) for explicit input tensors (vamb/encode.py:306-314), in train or
+        eval mode according to ``self.training``.
+
+        In training mode with autograd enabled the call goes through the differentiable module route
+        (``_encode`` -> ``reparameterize`` -> ``_decode``) so that ``calc_loss(...)[0].backward()`` works for callers
+        that run their own optimiser; otherwise (eval mode or ``torch.no_grad()``) it runs the fused kernels and the
+        outputs carry no graph.  Outputs are returned on the device of the inputs."""
+        if self.training and _torch.is_grad_enabled():
+            src = depths.device
+            tensor = _torch.cat((depths, tnf, abundance.reshape(len(depths), -1)), 1)
+            mu = self._encode(tensor)
+            d_out, t_out, a_out = self._decode(self.reparameterize(mu))
+            return d_out.to(src), t_out.to(src), a_out.to(src), mu.to(src)
         out = self._forward_tensors(depths, tnf, abundance)
         return out[0], out[1], out[2], out[3]
 
