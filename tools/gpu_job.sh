@@ -1,0 +1,20 @@
+#!/bin/bash
+# The GPU-box job of the next gpurun slot (edited between slots; every leg has its own timeout and log).
+mkdir -p gpurun_out
+cd "$(dirname "$0")/.."
+leg() { # name timeout command...
+  local name="$1" t="$2"; shift 2
+  local t0=$(date +%s)
+  timeout "$t" "$@" > "gpurun_out/$name.log" 2>&1
+  echo "[$name] rc=$? $(( $(date +%s) - t0 ))s" | tee -a gpurun_out/job_summary.log
+}
+: > gpurun_out/job_summary.log
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader | tee -a gpurun_out/job_summary.log
+leg r02_pytest 900 python -m pytest tests -m gpu -q -x
+leg r02_bench 760 bash -c 'python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02_bench.json'
+leg r02_ref 300 bash -c 'python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02_ref.json'
+leg r02_tf32 120 python tools/measure_tf32_peak.py
+leg r02_graderr 300 python tools/grad_error_fp64.py
+leg r02_speed_tma0 200 env TC_MIN=128 VAMB_B200_TMA=0 python tools/train_speed.py
+leg r02_speed_tma1 200 env TC_MIN=128 VAMB_B200_TMA=1 python tools/train_speed.py
+tail -3 gpurun_out/r02_pytest.log; cat gpurun_out/job_summary.log; tail -c 1500 gpurun_out/r02_bench.log
