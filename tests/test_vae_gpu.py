@@ -31,6 +31,7 @@ def set_path(vae, tc):
     vae._net.tc_min_batch = 1 if tc else 0
     vae._net.staging = 1 if tc == "prep" else 0
     vae._net.use_tma = 1 if tc == "tma" else 0  # weight operand through TMA (cp.async.bulk.tensor) vs the cp.async ring
+    vae._net.wgrad_flush = 1 if tc == "flush" else 0  # wgrad accumulation chain cut every 128 batch rows
     return vae
 
 
@@ -79,10 +80,12 @@ def test_train_steps_and_encode_match_reference_golden(case, tc):
 
 @pytest.mark.parametrize("tc,B,S", [(False, 256, 50), (True, 256, 50), (True, 1024, 50), (True, 4096, 50),
                                     ("prep", 256, 50), ("prep", 4096, 50), (True, 1000, 50), (True, 256, 80),
-                                    (True, 8192, 50), ("tma", 256, 50), ("tma", 1000, 50), ("tma", 4096, 50)],
+                                    (True, 8192, 50), ("tma", 256, 50), ("tma", 1000, 50), ("tma", 4096, 50),
+                                    ("flush", 256, 50), ("flush", 1000, 50), ("flush", 4096, 50), ("flush", 8192, 50)],
                          ids=["ffma-256", "tcgen05-256", "tcgen05-1024-split2", "tcgen05-4096-split8", "tcgen05-prep-256",
                               "tcgen05-prep-4096", "tcgen05-1000-ragged", "tcgen05-256-wide-input",
-                              "tcgen05-8192-grid-fallback", "tcgen05-tma-256", "tcgen05-tma-1000-ragged", "tcgen05-tma-4096"])
+                              "tcgen05-8192-grid-fallback", "tcgen05-tma-256", "tcgen05-tma-1000-ragged", "tcgen05-tma-4096",
+                              "tcgen05-flush-256", "tcgen05-flush-1000-ragged", "tcgen05-flush-4096", "tcgen05-flush-8192"])
 def test_gradients_match_oracle_default_network(tc, B, S):
     """One fwd+bwd on the bin-default network (512-512-32): every gradient tensor.  S = 80 makes the
     reconstruction wider than the loss kernel stages itself (a prep launch takes over for that layer);

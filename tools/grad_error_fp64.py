@@ -45,9 +45,11 @@ def main():
         _, g32, eps, keeps = o.grads(d[idx], t[idx], a[idx], w[idx])
         g64 = grads_fp64(o, d[idx], t[idx], a[idx], w[idx], eps, keeps)
         row = {"oracle_fp32": {k: rel(g32[k].numpy(), g64[k].numpy()) for k in g64}}
-        for name, tcmin in (("cuda_tcgen05_3xtf32", 1), ("cuda_fp32_ffma", 0)):
+        for name, tcmin, flush in (("cuda_tcgen05_3xtf32", 1, 0), ("cuda_tcgen05_3xtf32_wgrad_flush128", 1, 1),
+                                   ("cuda_fp32_ffma", 0, 0)):
             vae = ve.VAE(S, seed=2)
             vae._net.tc_min_batch = tcmin
+            vae._net.wgrad_flush = flush
             vae._step_injected(dl.dataset.tensors, idx.numpy(), eps.numpy(), [k.numpy() for k in keeps], optimize=False)
             got = vae._grad_dict()
             row[name] = {k: rel(got[k].cpu().numpy(), g64[k].numpy()) for k in g64}

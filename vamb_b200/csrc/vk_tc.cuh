@@ -270,8 +270,18 @@ __host__ __device__ constexpr int ws_smem_bytes(int bn) { return WS_STAGES * 2 *
 
 struct WsShared {
     uint64_t full[WS_STAGES], empty[WS_STAGES], done;
+    uint64_t acc_full[2], acc_empty[2];  // FLUSH: hand-over of the two alternating accumulators
     uint32_t tmem_base;
 };
+
+// FLUSH (wgrad: the reduction runs over the batch, hundreds of rows): the tensor core's fp32 accumulator TRUNCATES on
+// every accumulation, so the error of a long chain grows linearly with its length and is biased.  With FLUSH the chain
+// is cut every WS_FLUSH_KT k-tiles (128 batch rows): the MMA warp alternates between two accumulators in tensor memory
+// (columns [0, 128) and [384, 512)), and the epilogue warps add each finished group into fp32 REGISTERS (round to
+// nearest) while the next group accumulates -- `racc[i][j]` = column 32 i + 16 (warp / 4) + j of this thread's row.
+constexpr int WS_FLUSH_KT = 4;
+constexpr int WS_DRAIN_LAG = 2;  // a group is drained once the producers are this many k-tiles into the next one
+constexpr uint32_t WS_ACC1_COL = 384u;
 
 // D[128 x bn] = sum over k-tiles [kt0, kt0 + nk) of A[m0.., k] * B[n0.., k]^T.  A: lane-major (m0 a multiple
 // of 128), B: plain K-major; both fp32, zero padded to whole tiles (ld = floats per row, multiple of 32).
@@ -282,10 +292,11 @@ struct WsShared {
 // prep_weights) through 128B-swizzled tensor maps whose box is 32 floats x `slot_rows` rows; the producer warps then
 // only feed A.  `slot_rows` (= the launch's tile width, >= bn) sizes the ring slots; tm_hi / tm_lo point to CUtensorMap
 // objects in kernel-parameter space (__grid_constant__).
-template <bool TMA_B = false>
+template <bool TMA_B = false, bool FLUSH = false>
 __device__ __forceinline__ bool ws_mainloop(const float *A, int lda, int m0, const float *B, int ldb, int n0, int bn,
                                             int kt0, int nk, uint8_t *smem, WsShared *sh, int slot_rows = 0,
-                                            const void *tm_hi = nullptr, const void *tm_lo = nullptr) {
+                                            const void *tm_hi = nullptr, const void *tm_lo = nullptr,
+                                            float (*racc)[16] = nullptr) {
     constexpr int S = WS_STAGES, P = 2;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int bbytes = b_tile_bytes(TMA_B ? slot_rows : bn), sbytes = 2 * bbytes;
@@ -345,6 +356,12 @@ __device__ __forceinline__ bool ws_mainloop(const float *A, int lda, int m0, con
             mbar_init(&sh->empty[s], 1);
         }
         mbar_init(&sh->done, 1);
+        if (FLUSH) {
+            mbar_init(&sh->acc_full[0], 1);
+            mbar_init(&sh->acc_full[1], 1);
+            mbar_init(&sh->acc_empty[0], 8);
+            mbar_init(&sh->acc_empty[1], 8);
+        }
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc(&sh->tmem_base, WS_TMEM_COLS);
@@ -366,6 +383,12 @@ __device__ __forceinline__ bool ws_mainloop(const float *A, int lda, int m0, con
             int slot = 0;
             uint32_t phase = 0;
             for (int kt = 0; kt < nk; ++kt) {
+                const int grp = FLUSH ? kt / WS_FLUSH_KT : 0;
+                const bool grp_first = FLUSH ? (kt % WS_FLUSH_KT == 0) : (kt == 0);
+                const bool grp_last = FLUSH ? ((kt + 1) % WS_FLUSH_KT == 0 || kt == nk - 1) : (kt == nk - 1);
+                const uint32_t tmem_acc = tmem_d + ((FLUSH && (grp & 1)) ? WS_ACC1_COL : 0u);
+                // the epilogue warps must have drained this accumulator's previous group (two groups ago)
+                if (FLUSH && grp_first && grp >= 2) mbar_wait(&sh->acc_empty[grp & 1], (uint32_t)(((grp >> 1) - 1) & 1));
                 mbar_wait(&sh->full[slot], phase);
                 tc_fence_after();
                 const uint32_t ah = tmem_d + 128u + 64u * slot, al = ah + 32u;
@@ -374,11 +397,12 @@ __device__ __forceinline__ bool ws_mainloop(const float *A, int lda, int m0, con
                 const uint64_t bl = bh + (uint64_t)((uint32_t)bbytes >> 4);
 #pragma unroll
                 for (int j = 0; j < KT / 8; ++j) {
-                    umma_tf32_ts(tmem_d, al + 8u * j, bh + kstep * j, idesc, (kt | j) ? 1u : 0u);  // small terms first
-                    umma_tf32_ts(tmem_d, ah + 8u * j, bl + kstep * j, idesc, 1u);
-                    umma_tf32_ts(tmem_d, ah + 8u * j, bh + kstep * j, idesc, 1u);
+                    umma_tf32_ts(tmem_acc, al + 8u * j, bh + kstep * j, idesc, (grp_first && j == 0) ? 0u : 1u);  // small terms first
+                    umma_tf32_ts(tmem_acc, ah + 8u * j, bl + kstep * j, idesc, 1u);
+                    umma_tf32_ts(tmem_acc, ah + 8u * j, bh + kstep * j, idesc, 1u);
                 }
                 umma_commit(&sh->empty[slot]);
+                if (FLUSH && grp_last && kt != nk - 1) umma_commit(&sh->acc_full[grp & 1]);
                 if (kt == nk - 1) umma_commit(&sh->done);
                 if (++slot == S) {
                     slot = 0;
@@ -420,9 +444,47 @@ __device__ __forceinline__ bool ws_mainloop(const float *A, int lda, int m0, con
         if (lane == 0) mbar_arrive(&sh->full[slot]);
         if (kt < 20) tl_mark(10 + kt);
     };
+    // FLUSH: add a finished group (all but the last, which the epilogue reads) into the register accumulators
+    int next_drain = 0;
+    auto drain_ready = [&](int kt_done) {  // after producing tile kt_done
+        if (!FLUSH) return;
+        while ((next_drain + 1) * WS_FLUSH_KT + WS_DRAIN_LAG <= kt_done + 1 && (next_drain + 1) * WS_FLUSH_KT < nk) {
+            const int a = next_drain & 1;
+            mbar_wait(&sh->acc_full[a], (uint32_t)((next_drain >> 1) & 1));
+            tc_fence_after();
+            const uint32_t base = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (a ? WS_ACC1_COL : 0u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c = (warp >> 2) * 16 + 32 * i;
+                if (c < bn) {
+                    float v[16];
+                    tmem_ld16(base + (uint32_t)c, v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) racc[i][j] += v[j];
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh->acc_empty[a]);
+            ++next_drain;
+        }
+    };
+    if (FLUSH) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) racc[i][j] = 0.0f;
+    }
     for (int kt = 0; kt < nk; kt += 2) {
         produce(kt, ra[0]);
-        if (kt + 1 < nk) produce(kt + 1, ra[1]);
+        drain_ready(kt);
+        if (kt + 1 < nk) {
+            produce(kt + 1, ra[1]);
+            drain_ready(kt + 1);
+        }
+    }
+    if (FLUSH) {  // groups that completed inside the last WS_DRAIN_LAG tiles
+        while ((next_drain + 1) * WS_FLUSH_KT < nk) drain_ready(1 << 28);
     }
     tl_mark(9);
     if (nk > 0) mbar_wait(&sh->done, 0);
@@ -432,15 +494,26 @@ __device__ __forceinline__ bool ws_mainloop(const float *A, int lda, int m0, con
 
 // Accumulator -> shared tile [128][ts] (raw values): warp w owns TMEM lanes 32*(w%4)..+31, the two warp
 // groups take alternate 16-column chunks.  nk == 0 (an empty split) yields zeros.
-__device__ __forceinline__ void ws_acc_to_tile(const WsShared *sh, int bn, int nk, float *tile, int ts) {
+// racc != nullptr (FLUSH): the last group sits in accumulator ((nk - 1) / WS_FLUSH_KT) & 1 and the earlier groups in
+// the register sums of ws_mainloop.
+__device__ __forceinline__ void ws_acc_to_tile(const WsShared *sh, int bn, int nk, float *tile, int ts,
+                                               const float (*racc)[16] = nullptr) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = (warp & 3) * 32 + lane;
-    for (int c = (warp >> 2) * 16; c < bn; c += 32) {
+    const uint32_t acc_col = (racc && nk > 0 && (((nk - 1) / WS_FLUSH_KT) & 1)) ? WS_ACC1_COL : 0u;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = (warp >> 2) * 16 + 32 * i;
+        if (c >= bn) break;
         float v[16];
-        if (nk > 0) tmem_ld16(sh->tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c, v);
+        if (nk > 0) tmem_ld16(sh->tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + acc_col + (uint32_t)c, v);
         else
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = 0.0f;
+        if (racc) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += racc[i][j];
+        }
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4)
             *reinterpret_cast<float4 *>(tile + row * ts + c + 4 * j4) =

@@ -819,6 +819,7 @@ __device__ __forceinline__ void stage_tile_transposed_lane(const float *tile, in
 struct BwdTcExtra {
     int nsplit, k_per_split;   // split-K over the batch for wgrad
     int64_t slab;              // floats between gradient slabs
+    int flush;                 // wgrad: cut the tensor-core accumulation chain every 128 batch rows (vk_tc.cuh: FLUSH)
 };
 
 // Forward layer: D = X' W^T on the tensor core, then one coalesced pass over the shared tile does bias,
@@ -1013,9 +1014,15 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(const _
         int nb = a.B - b0;
         nb = nb < 0 ? 0 : (nb > x.k_per_split ? x.k_per_split : nb);
         const int nk = (nb + tc::KT - 1) / tc::KT;  // b0 is a multiple of 32; the staged operands are zero padded
-        if (!tc::ws_mainloop(a.wg_a.hi, a.wg_a.ld, m0, a.wg_b.hi, a.wg_b.ld, n0, bn, b0 / tc::KT, nk, smem, &sh)) return;
+        float racc[4][16];
+        const bool alive_wg = x.flush
+            ? tc::ws_mainloop<false, true>(a.wg_a.hi, a.wg_a.ld, m0, a.wg_b.hi, a.wg_b.ld, n0, bn, b0 / tc::KT, nk, smem, &sh, 0,
+                                           nullptr, nullptr, racc)
+            : tc::ws_mainloop<false, false>(a.wg_a.hi, a.wg_a.ld, m0, a.wg_b.hi, a.wg_b.ld, n0, bn, b0 / tc::KT, nk, smem, &sh);
+        if (!alive_wg) return;
         tl_mark(2);
-        tc::ws_acc_to_tile(&sh, bn, nk, tile, TS);
+        if (x.flush) tc::ws_acc_to_tile(&sh, bn, nk, tile, TS, racc);
+        else tc::ws_acc_to_tile(&sh, bn, nk, tile, TS);
         tl_mark(3);
         tc::ws_tile_end(&sh);
         float *gW = a.gW + (int64_t)split * x.slab, *gb = a.gb + (int64_t)split * x.slab;
@@ -1843,6 +1850,7 @@ static int launch_backward(const vk_vae *net, int B, cudaStream_t s) {
             x.nsplit = tc_nsplit(net, B);
             x.k_per_split = (((B + x.nsplit - 1) / x.nsplit) + 31) & ~31;
             x.slab = net->grad_slab;
+            x.flush = net->wgrad_flush;
             a.tile_n = tc_tile_n(B);
             a.wg_tiles_m = (L.n_out + 127) / 128;
             a.wg_tile_n = tc_wg_tile_n(B);

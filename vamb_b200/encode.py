@@ -57,6 +57,7 @@ def _warn_once(msg: str) -> None:
 
 _MAX_BATCH = 8192  # rows of the activation workspaces (training batches double up to 4096)
 _GRAPH_CHUNKS = (128, 16, 4)  # optimiser steps per captured CUDA graph, largest first
+_WGRAD_FLUSH = 0  # default of vk_vae.wgrad_flush (opt-in until validated on the GPU box)
 _USE_TMA = 0  # default of vk_vae.use_tma (opt-in until validated on the GPU box)
 _TC_MIN_BATCH = 128  # batches >= this run their GEMMs on the tcgen05 tensor-core path (0 = never)
 
@@ -192,7 +193,7 @@ class _VkVae(_ct.Structure):
         ("layers", _VkLayer * _MAXL),
         ("data_ld", _ct.c_int32), ("tc_min_batch", _ct.c_int32), ("grad_slab", _ct.c_int64),
         ("n_grad_slabs", _ct.c_int32), ("staging", _ct.c_int32),
-        ("use_tma", _ct.c_int32), ("reserved0", _ct.c_int32),
+        ("use_tma", _ct.c_int32), ("wgrad_flush", _ct.c_int32),
     ]
 
 
@@ -371,6 +372,8 @@ class VAE(_nn.Module):
         net.staging = int(_os.environ.get("VAMB_B200_STAGING", "0"))
         # weight operand of the forward / dgrad GEMMs through TMA (cp.async.bulk.tensor) or the cp.async ring
         net.use_tma = int(_os.environ.get("VAMB_B200_TMA", str(_USE_TMA)))
+        # wgrad: cut the truncating tensor-core accumulation chain every 128 batch rows (fp32 register sums)
+        net.wgrad_flush = int(_os.environ.get("VAMB_B200_WGRAD_FLUSH", str(_WGRAD_FLUSH)))
         with _torch.cuda.device(dev):
             _lib.check(_L.vk_vae_init_device())  # side stream / events of the training step (once per device)
         for field, t in (("params", arena), ("grads", self._grads), ("exp_avg", self._exp_avg),
