@@ -307,9 +307,10 @@ int vk_vae_grad_step(const vk_vae *net, int batch, const vk_vae_inject *inject, 
  * (vk_lane_major_index), zero padded to whole 128-row panels; B: plain row-major [rows][ldb], zero padded to whole
  * tile_n-row tiles; lda, ldb multiples of 32; tile_n (output columns per CTA) a multiple of 16 in [16, 128].
  * B_lo != NULL selects the TMA-fed B operand (cp.async.bulk.tensor through 128B-swizzled tensor maps), B_lo holding the
- * tf32 remainders x - trunc13(x) of B -- the way the forward / dgrad GEMMs fetch the weights staged by prep_weights. */
+ * tf32 remainders x - trunc13(x) of B -- the way the forward / dgrad GEMMs fetch the weights staged by prep_weights.
+ * flush != 0 (B_lo == NULL) selects the wgrad variant: the accumulation chain is cut every 4 k-tiles (128 rows). */
 int vk_tc_gemm_test(const float *A_lane, int lda, const float *B, const float *B_lo, int ldb, float *C, int M, int N,
-                    int tile_n, int kt0, int nk, void *stream);
+                    int tile_n, int kt0, int nk, int flush, void *stream);
 
 /* Host-side: float offset of element (r, k) of an A-role operand in the "lane-major" staging layout
  * (128-row panels; each 32-wide k-tile of a panel is one 16 KB block [k/4][row][k%4]); ld = floats per row,

@@ -27,7 +27,7 @@ def lane_major(a: torch.Tensor, ld: int) -> torch.Tensor:
     return out
 
 
-def run(A, B, tile_n, kt0=0, nk=None, tma=False):
+def run(A, B, tile_n, kt0=0, nk=None, tma=False, flush=False):
     from vamb_b200 import _lib
 
     _lib.require_device()
@@ -47,7 +47,7 @@ def run(A, B, tile_n, kt0=0, nk=None, tma=False):
     if tma:  # the tf32 remainder the tensor core does not see: x - (x with the low 13 mantissa bits cleared)
         b_lo = Bp - (Bp.view(torch.int32) & -8192).view(torch.float32)
     _lib.check(_lib.lib.vk_tc_gemm_test(Al.data_ptr(), ld, Bp.data_ptr(), b_lo.data_ptr() if tma else None, ld, C.data_ptr(),
-                                        M, N, tile_n, kt0, nk, s))
+                                        M, N, tile_n, kt0, nk, 1 if flush else 0, s))
     torch.cuda.synchronize()
     return C
 
@@ -88,3 +88,18 @@ def test_lane_major_helper_matches_the_c_abi():
         a = torch.zeros((r // 128 + 1) * 128, ld)
         a[r, k] = 1.0
         assert int(lane_major(a, ld).argmax()) == int(_lib.lib.vk_lane_major_index(r, k, ld))
+
+
+@pytest.mark.parametrize("M,N,K,tile_n", [(512, 513, 512, 32), (154, 512, 4096, 64), (300, 100, 1000, 128), (128, 64, 96, 16),
+                                          (128, 48, 160, 48), (256, 128, 8192, 128)])
+def test_ws_mainloop_flush_variant_matches_fp64(M, N, K, tile_n):
+    """The wgrad variant: two alternating tensor-memory accumulators, every 4 k-tiles summed into fp32 registers.  The
+    error no longer grows with the chain length: below 1e-6 + 1.2e-8 * 128 for every K, and never above the plain loop."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    B = torch.randn(N, K, device="cuda", generator=g)
+    ref = A.double() @ B.double().t()
+    err_f = float((run(A, B, tile_n, flush=True).double() - ref).norm() / ref.norm())
+    err_p = float((run(A, B, tile_n).double() - ref).norm() / ref.norm())
+    assert err_f < 1e-6 + 1.2e-8 * 128 + 2e-8 * (K // 128), (err_f, err_p)
+    assert err_f <= err_p * 1.05 + 1e-7

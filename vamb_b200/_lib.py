@@ -67,7 +67,7 @@ _SIGNATURES = {
     "vk_mask_clear": [_p, _p, c_int32, _p],
     "vk_compact_rows_sync": [_p, _p, _p, _p, c_int64, c_int, _p, _p, _p, _p, _p, POINTER(c_int64), _p],
     "vk_distances": [_p, c_int64, c_int, c_int64, _p, _p],
-    "vk_tc_gemm_test": [_p, c_int, _p, _p, c_int, _p, c_int, c_int, c_int, c_int, c_int, _p],
+    "vk_tc_gemm_test": [_p, c_int, _p, _p, c_int, _p, c_int, c_int, c_int, c_int, c_int, c_int, _p],
     "vk_lane_major_index": [c_int, c_int, c_int],
 }
 

@@ -8,7 +8,7 @@ namespace {
 // bwd_layer_tc_kernel run): A in the lane-major layout (zero padded to 128-row panels and whole k-tiles),
 // B plain K-major (zero padded to whole tiles), k-tiles [kt0, kt0 + nk) only (split-K slices as in wgrad).
 struct WsTestMaps {
-    int use_tma;
+    int use_tma, flush;
     VkTmap hi, lo;
 };
 
@@ -21,12 +21,16 @@ ws_gemm_test_kernel(const float *A, int lda, const float *B, int ldb, float *C, 
     const int m0 = blockIdx.y * 128, n0 = blockIdx.x * tile_n;
     int bn = N - n0;
     bn = bn > tile_n ? tile_n : ((bn + 15) & ~15);
-    const bool alive = tm.use_tma ? tc::ws_mainloop<true>(A, lda, m0, B, ldb, n0, bn, kt0, nk, smem, &sh, tile_n, &tm.hi, &tm.lo)
-                                  : tc::ws_mainloop<false>(A, lda, m0, B, ldb, n0, bn, kt0, nk, smem, &sh);
+    float racc[4][16];
+    const bool alive =
+        tm.flush ? tc::ws_mainloop<false, true>(A, lda, m0, B, ldb, n0, bn, kt0, nk, smem, &sh, 0, nullptr, nullptr, racc)
+        : tm.use_tma ? tc::ws_mainloop<true>(A, lda, m0, B, ldb, n0, bn, kt0, nk, smem, &sh, tile_n, &tm.hi, &tm.lo)
+                     : tc::ws_mainloop<false>(A, lda, m0, B, ldb, n0, bn, kt0, nk, smem, &sh);
     if (!alive) return;
     constexpr int TS = 132;
     float *tile = reinterpret_cast<float *>(smem);
-    tc::ws_acc_to_tile(&sh, bn, nk, tile, TS);
+    if (tm.flush) tc::ws_acc_to_tile(&sh, bn, nk, tile, TS, racc);
+    else tc::ws_acc_to_tile(&sh, bn, nk, tile, TS);
     tc::ws_tile_end(&sh);
     for (int q = threadIdx.x; q < 128 * bn; q += tc::WS_EPI_THREADS) {
         const int r = q / bn, c = q - r * bn;
@@ -39,8 +43,9 @@ ws_gemm_test_kernel(const float *A, int lda, const float *B, int ldb, float *C, 
 // A_lane: [ceil(M / 128) * 128 rows, lda] in tc::lane_major_index order; B: [ceil(N / tile_n) * tile_n rows, ldb]
 // row-major; lda, ldb multiples of 32 covering k-tiles [0, kt0 + nk).  tile_n: multiple of 16 in [16, 128].
 // B_lo != NULL: B through TMA (B_lo = the tf32 remainders of B, same shape), as the forward / dgrad GEMMs fetch weights.
+// flush != 0 (with B_lo == NULL): the wgrad variant -- accumulation chain cut every 4 k-tiles (two accumulators).
 extern "C" int vk_tc_gemm_test(const float *A_lane, int lda, const float *B, const float *B_lo, int ldb, float *C, int M, int N,
-                               int tile_n, int kt0, int nk, void *stream) {
+                               int tile_n, int kt0, int nk, int flush, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (tile_n < 16 || tile_n > 128 || (tile_n & 15) || (lda & 31) || (ldb & 31)) {
         vk_set_error("vk_tc_gemm_test: bad tile / leading dimensions");
@@ -52,6 +57,7 @@ extern "C" int vk_tc_gemm_test(const float *A_lane, int lda, const float *B, con
     VK_CUDA(cudaFuncSetAttribute(ws_gemm_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     WsTestMaps tm;
     memset(&tm, 0, sizeof(tm));
+    tm.flush = (flush && !B_lo) ? 1 : 0;
     if (B_lo) {
         const int rows = (int)grid.x * tile_n;
         tm.use_tma = 1;
