@@ -236,6 +236,7 @@ def run_pass(ctx: Ctx, dl, lengths_cluster, nepochs, k_steps, resident: bool, ma
     ctx.barrier()
     step_ms, phases = [], {"train": 0.0, "encode": 0.0, "cluster": 0.0}
     n_clusters = n_members = probes = evals = 0
+    cluster_timing = {}
     latent_dev = None
     t_wall0 = time.perf_counter()
     edges = epoch_slices(nepochs, k_steps)
@@ -280,6 +281,7 @@ def run_pass(ctx: Ctx, dl, lengths_cluster, nepochs, k_steps, resident: bool, ma
                     if max_clusters and n_clusters >= max_clusters:
                         break
                 probes, evals = gen._n_probes, gen._n_evals
+                cluster_timing = gen._timing()
                 torch.cuda.synchronize()
             phases["cluster"] += time.perf_counter() - t2
         e1.record()
@@ -302,7 +304,8 @@ def run_pass(ctx: Ctx, dl, lengths_cluster, nepochs, k_steps, resident: bool, ma
     return {"step_ms": step_ms, "t_event": sum(step_ms) / 1e3, "t_wall": t_wall, "phases": phases,
             "n_clusters": n_clusters, "n_clustered": n_members, "probes": probes, "evals": evals,
             "train_steps": sum(s * e for _, s, e in sched), "launches": launches,
-            "final_loss": vae._last_epoch_losses[0], "vae": vae, "latent_dev": latent_dev}
+            "final_loss": vae._last_epoch_losses[0], "vae": vae, "latent_dev": latent_dev,
+            "cluster_timing": cluster_timing}
 
 
 def vae_roofline(vae, n, nepochs):
@@ -564,6 +567,7 @@ def main():
             "step_ms": [round(x, 2) for x in res["step_ms"]],
             "phases_s": res["phases"], "t_pass_wall_s": res["t_wall"],
             "clusters": res["n_clusters"], "final_loss": res["final_loss"],
+            "cluster_host_seconds": dict(res["cluster_timing"], probes=res["probes"], evals=res["evals"]),
             "roofline": roof, "roofline_cluster": roof_cluster, "cpu_baseline": base,
             "e2e": e2e if e2e is not None else {"value": None, "unit": "contigs/s", "h2d_bytes_per_step": 0,
                                                 "d2h_bytes_per_step": 0, "note": e2e_note},

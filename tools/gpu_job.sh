@@ -15,13 +15,13 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader | tee 
 leg r02_pt_cluster 400 python -m pytest tests/test_cluster_gpu.py tests/test_c2_scale_gpu.py -m gpu -q
 leg r02_pt_vae 500 python -m pytest tests/test_vae_gpu.py -m gpu -q -k "not tma and not flush"
 leg r02_pt_tc 300 python -m pytest tests/test_tc_gpu.py -m gpu -q -k "not tma and not flush"
+leg r02_bench 760 bash -c 'python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02_bench.json'
+leg r02_ref 300 bash -c 'python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02_ref.json'
 leg r02_pt_traj 400 python -m pytest tests/test_trajectory_gpu.py -m gpu -q
 leg r02_pt_tc_tma 300 python -m pytest tests/test_tc_gpu.py -m gpu -q -k "tma"
 leg r02_pt_tc_flush 300 python -m pytest tests/test_tc_gpu.py -m gpu -q -k "flush"
 leg r02_pt_vae_tma 400 python -m pytest tests/test_vae_gpu.py -m gpu -q -k "tma"
 leg r02_pt_vae_flush 400 python -m pytest tests/test_vae_gpu.py -m gpu -q -k "flush"
-leg r02_bench 760 bash -c 'python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02_bench.json'
-leg r02_ref 300 bash -c 'python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02_ref.json'
 leg r02_tf32 120 python tools/measure_tf32_peak.py
 leg r02_graderr 300 python tools/grad_error_fp64.py
 leg r02_speed_tma0 200 env TC_MIN=128 VAMB_B200_TMA=0 python tools/train_speed.py
