@@ -104,6 +104,19 @@ int vk_eval_candidates_mapped(const float *matrix, const float *lengths, int d, 
                               int n_cand, uint64_t *out_dev, uint64_t *out_pinned, int32_t *done_ticket,
                               int32_t *done_flag_pinned, int32_t seq, void *stream);
 
+/* Candidate evaluation that also returns what is needed to MOVE the medoid to a winning candidate without another
+ * full scan (native driver): the ids of the rows within 0.05 of candidate k (its `cluster`, vamb/cluster.py:626) are
+ * written to within_pinned[k * within_cap ...] (pinned host memory; entries beyond within_cap are dropped, the count
+ * still tells), and out_pinned (4 * VK_MAX_CAND uint64) = density_lo[k] | density_hi[k] | counts[k] | fp32 bits of
+ * d(candidate k, base_row).  `base_row` = the medoid whose neighbour list (radius nl_radius = 0.3) is passed in: the list
+ * covers the whole 0.05-neighbourhood of a candidate iff d(candidate, base) <= 0.12 (angles add: acos(0.76) +
+ * acos(0.9) = acos(0.4)), which the caller checks.  Mapped completion as vk_eval_candidates_mapped (out_dev: 4 *
+ * VK_MAX_CAND uint64, all zero on entry, left zeroed). */
+int vk_eval_candidates_lists(const float *matrix, const float *lengths, int d, const int32_t *nl_rows,
+                             const float *nl_dists, int32_t n_nl, float prune_radius, const int32_t *cand_rows_host,
+                             int n_cand, int32_t base_row, uint64_t *out_dev, uint64_t *out_pinned, int32_t *within_pinned,
+                             int32_t within_cap, int32_t *done_ticket, int32_t *done_flag_pinned, int32_t seq, void *stream);
+
 /* vamb/cluster.py:640-650 (_smaller_indices) + :308-309 (kept_mask[point] = 0):
  * appends orig_ids[row] of every neighbour-list entry with d <= threshold to `members`
  * (unordered), clears kept[row], returns the count through members_host[0] and the ids
@@ -175,7 +188,8 @@ int vk_cluster_create(void **handle, const vk_cluster_config *cfg);
 int vk_cluster_next(void *handle, vk_cluster_result *out); /* 0 = cluster, 2 = exhausted, 1 = error */
 int vk_cluster_stats(void *handle, int64_t *out8);         /* probes, evals, packs, physical rows, live buffer set (0/1),
                                                               successes, attempts in the window, order_index */
-int vk_cluster_timing(void *handle, double *out5);         /* host seconds in probes, evaluations, selections, packs, total */
+int vk_cluster_timing(void *handle, double *out7);         /* host seconds in probes, evaluations, selections, packs, total;
+                                                              medoid moves without a scan, re-basing probes */
 void vk_cluster_destroy(void *handle);
 int64_t vk_cluster_sizeof(int which);                      /* 0: vk_cluster_config, 1: vk_cluster_result */
 /* CPython-compatible random.Random(seed).sample(range(n_i), min(n_i, k)) for each i: writes k slots per

@@ -205,3 +205,86 @@ class TestReferenceClusterSuite:
 
         x = next(vc.ClusterGenerator(self.data, self.lens))
         assert isinstance(x.members, np.ndarray)
+
+
+def test_eval_candidates_lists_matches_oracle(vk):
+    """vk_eval_candidates_lists: per-candidate density / count / within-ids / distance to the base == the oracle's
+    sample_medoid on the kept rows, for candidates INSIDE the coverage radius 0.12 of the base."""
+    from oracle import cluster_oracle as co
+    from oracle import synth
+
+    n, d = 40000, 32
+    lat, lens = synth.make_latent(n, d, seed=5, spread=0.25)
+    host = lat.copy()
+    co.normalize(host)
+    lens32 = lens.astype(np.float32)
+    kept = (np.random.default_rng(1).random(n) > 0.2).astype(np.uint8)
+    dm, dl, dk = _dev(host), _dev(lens32), _dev(kept)
+    hdr = torch.zeros(vk.HDR_SIZE, dtype=torch.uint8, device="cuda")
+    hdr_host = torch.zeros(vk.HDR_SIZE, dtype=torch.uint8).pin_memory()
+    over = torch.empty(n, dtype=torch.int32, device="cuda")
+    nl_rows = torch.empty(n, dtype=torch.int32, device="cuda")
+    nl_d = torch.empty(n, dtype=torch.float32, device="cuda")
+    de = _dev(co.linspace_edges())
+    s = torch.cuda.current_stream().cuda_stream
+    base = int(np.flatnonzero(kept)[17])
+    vk.check(vk.lib.vk_probe_sync(dm.data_ptr(), dl.data_ptr(), dk.data_ptr(), n, d, base, 0.3, de.data_ptr(),
+                                  hdr.data_ptr(), over.data_ptr(), nl_rows.data_ptr(), nl_d.data_ptr(),
+                                  hdr_host.data_ptr(), s))
+    n_nl = int(hdr_host.numpy()[vk.HDR_NNL:vk.HDR_NNL + 4].view(np.int32)[0])
+    dist_base = co.calc_distances(host, base)
+    near = np.flatnonzero((dist_base <= np.float32(0.1199)) & (kept != 0))
+    far = np.flatnonzero((dist_base > np.float32(0.125)) & (dist_base <= np.float32(0.3)) & (kept != 0))
+    cands = list(near[:: max(1, len(near) // 20)][:20]) + list(far[:3])
+    C, cap = vk.VK_MAX_CAND, 512
+    out_dev = torch.zeros(4 * C, dtype=torch.int64, device="cuda")
+    out_pin = torch.zeros(4 * C, dtype=torch.int64).pin_memory()
+    within_pin = torch.zeros(C * cap, dtype=torch.int32).pin_memory()
+    ticket = torch.zeros(1, dtype=torch.int32, device="cuda")
+    flag = torch.zeros(1, dtype=torch.int32).pin_memory()
+    arr = (vk.c_int32 * len(cands))(*[int(c) for c in cands])
+    vk.check(vk.lib.vk_eval_candidates_lists(dm.data_ptr(), dl.data_ptr(), d, nl_rows.data_ptr(), nl_d.data_ptr(), n_nl,
+                                             0.3, arr, len(cands), base, out_dev.data_ptr(), out_pin.data_ptr(),
+                                             within_pin.data_ptr(), cap, ticket.data_ptr(), flag.data_ptr(), 7, s))
+    assert int(flag[0]) == 7 and int(out_dev.abs().sum()) == 0  # accumulators left zeroed for the next call
+    res = out_pin.numpy().view(np.uint64)
+    sel = np.flatnonzero(kept)
+    sub = np.ascontiguousarray(host[sel])
+    lib = co._load_lib()
+    for k, c in enumerate(cands):
+        dbase = np.array([res[3 * C + k]], dtype=np.uint64).astype(np.uint32).view(np.float32)[0]
+        assert dbase == dist_base[c]
+        if dist_base[c] > np.float32(0.1199):
+            continue  # outside the coverage radius the list may miss neighbours: the driver re-probes instead
+        dist = co.calc_distances(sub, int(np.searchsorted(sel, c)))
+        idx = np.empty(len(sel), dtype=np.int64)
+        od = (ctypes.c_uint64 * 2)()
+        cnt = lib.ok_sample(co._p(dist, ctypes.c_float), co._p(np.ascontiguousarray(lens32[sel]), ctypes.c_float),
+                            len(sel), ctypes.c_float(0.05), co._p(idx, ctypes.c_int64), od)
+        assert int(res[2 * C + k]) == cnt
+        assert (int(res[C + k]) << 12) + int(res[k]) == (int(od[1]) << 12) + int(od[0])
+        got = np.sort(within_pin.numpy()[k * cap:k * cap + cnt])
+        assert np.array_equal(got, sel[idx[:cnt]])
+
+
+@pytest.mark.parametrize("n,d,spread,seed", [(30000, 32, 0.3, 41), (30000, 32, 0.08, 42), (6000, 40, 0.2, 43)])
+def test_lazy_medoid_moves_emit_the_same_clusters(n, d, spread, seed, monkeypatch):
+    """Native driver with scan-free medoid moves (default) == a full scan per move (round-1 behaviour) == oracle;
+    and the scan-free path is actually taken."""
+    import vamb_b200.cluster as vc
+    from oracle import cluster_oracle as co
+    from oracle import synth
+
+    lat, lens = synth.make_latent(n, d, seed, spread)
+    gen = vc.ClusterGenerator(lat, lens, rng_seed=seed)
+    lazy = list(gen)
+    t = gen._timing()
+    monkeypatch.setenv("VAMB_B200_CLUSTER_LAZY", "0")
+    gen0 = vc.ClusterGenerator(lat, lens, rng_seed=seed)
+    eager = list(gen0)
+    t0 = gen0._timing()
+    monkeypatch.delenv("VAMB_B200_CLUSTER_LAZY")
+    _util.assert_clusters_equal(lazy, eager)
+    assert t0["lazy_moves"] == 0 and t["lazy_moves"] > 0
+    assert gen._n_probes < gen0._n_probes
+    _util.assert_clusters_equal(lazy, list(co.OracleClusterGenerator(lat, lens, rng_seed=seed)))

@@ -369,11 +369,11 @@ class ClusterGenerator:
         "Host seconds the native driver spent per call kind so far (diagnostics / bench)."
         from . import _cluster_native as _cn
 
-        out = (_lib.ctypes.c_double * 5)()
+        out = (_lib.ctypes.c_double * 7)()
         if self._native is None:
             return {}
         _cn._L.vk_cluster_timing(self._native, out)
-        return dict(zip(("probe", "eval", "select", "pack", "total"), (float(x) for x in out)))
+        return dict(zip(("probe", "eval", "select", "pack", "total", "lazy_moves", "rebases"), (float(x) for x in out)))
 
     # ------------------------------------------------------------------ API extras
     @property

@@ -636,6 +636,136 @@ extern "C" int vk_eval_candidates_mapped(const float *matrix, const float *lengt
     return wait_flag(done_flag_pinned, seq, s, "vk_eval_candidates_mapped");
 }
 
+// ------------------------------------------------------------------ candidate evaluation with within-lists
+// As eval_candidates_kernel, plus what lets the host MOVE the medoid to a winning candidate without another full
+// scan: the ids of the rows within 0.05 of every candidate (the candidate's `cluster` of sample_medoid,
+// vamb/cluster.py:626) go straight into pinned host memory, and the distance of every candidate to the medoid whose
+// neighbour list is being used (`base_row`) is reported so that the host can tell whether that list covers the
+// candidate's whole 0.05-neighbourhood (d(candidate, base) <= 0.12: angles add).
+// out / out_mapped: [0, C) density lo | [C, 2C) density hi | [2C, 3C) counts | [3C, 4C) d(candidate, base) as float bits.
+__global__ void __launch_bounds__(EC_THREADS)
+eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths, int d,
+                             const int32_t *__restrict__ nl_rows, const float *__restrict__ nl_dists, int n_nl,
+                             float prune_radius, CandRows cand, int n_cand, int32_t base_row, u64 *out, u64 *out_mapped,
+                             int32_t *within_mapped, int within_cap, int32_t *done_ticket, volatile int32_t *done_flag,
+                             int32_t seq) {
+    extern __shared__ __align__(16) float s_qs[];  // [n_cand][dpad]
+    __shared__ u64 s_dens[VK_MAX_CAND];
+    __shared__ u64 s_dens_hi[VK_MAX_CAND];
+    const int tid = threadIdx.x, lane8 = tid & 7, g = tid >> 3;
+    const unsigned gmask = group8_mask();
+    const int dpad = (d + 3) & ~3;
+    const bool vec4 = (d & 3) == 0;
+    const bool fast = (d == 32);
+    for (int i = tid; i < n_cand * dpad; i += EC_THREADS) {
+        const int k = i / dpad, c = i - k * dpad;
+        s_qs[i] = c < d ? matrix[(int64_t)cand.rows[k] * d + c] : 0.0f;
+    }
+    if (tid < VK_MAX_CAND) { s_dens[tid] = 0ull; s_dens_hi[tid] = 0ull; }
+    __syncthreads();
+
+    const float rad = 0.05f;
+    if (blockIdx.x == 0) {  // d(candidate, base) in the same arithmetic as every other distance
+        const float *x = matrix + (int64_t)base_row * d;
+        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (fast) xv = ldg_stream4(x + 4 * lane8);
+        for (int k = g; k < n_cand; k += EC_THREADS / 8) {
+            const float *q = s_qs + k * dpad;
+            float acc = fast ? chain4(xv, *reinterpret_cast<const float4 *>(q + 4 * lane8)) : lane_chain_generic(x, q, d, lane8, vec4);
+            acc = group8_sum(acc, gmask);
+            if (lane8 == 0) {
+                float dd = __fsub_rn(0.5f, acc);
+                if (cand.rows[k] == base_row) dd = 0.0f;
+                out[3 * VK_MAX_CAND + k] = (u64)__float_as_uint(dd);
+            }
+        }
+    }
+    const int groups_total = gridDim.x * (EC_THREADS / 8);
+    for (int j = blockIdx.x * (EC_THREADS / 8) + g; j < n_nl; j += groups_total) {
+        const float dj = nl_dists[j];
+        if (!(dj <= prune_radius)) continue;  // uniform within the 8-lane group
+        const int row = nl_rows[j];
+        const float *x = matrix + (int64_t)row * d;
+        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (fast) xv = ldg_stream4(x + 4 * lane8);
+        u64 lenq = 0ull;
+        if (lane8 == 0) lenq = __float2ull_rz(__ldg(lengths + row));
+        for (int k = 0; k < n_cand; ++k) {
+            const float *q = s_qs + k * dpad;
+            float acc;
+            if (fast) acc = chain4(xv, *reinterpret_cast<const float4 *>(q + 4 * lane8));
+            else acc = lane_chain_generic(x, q, d, lane8, vec4);
+            acc = group8_sum(acc, gmask);
+            if (lane8 == 0) {
+                float dd = __fsub_rn(0.5f, acc);
+                if (row == cand.rows[k]) dd = 0.0f;
+                if (dd <= rad) {
+                    const u64 cq = closeness_fx(rad, dd);
+                    atomicAdd(&s_dens[k], lenq * (cq & 4095ull));
+                    atomicAdd(&s_dens_hi[k], lenq * (cq >> 12));
+                    const u64 pos = atomicAdd(&out[2 * VK_MAX_CAND + k], 1ull);  // rare: a few dozen hits per candidate
+                    if (pos < (u64)within_cap) within_mapped[(size_t)k * within_cap + pos] = row;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < n_cand) {
+        if (s_dens[tid]) atomicAdd(&out[tid], s_dens[tid]);
+        if (s_dens_hi[tid]) atomicAdd(&out[VK_MAX_CAND + tid], s_dens_hi[tid]);
+    }
+    __shared__ int s_last;
+    __threadfence_system();  // this block's id-list writes (pinned host memory) and sums are visible before its ticket
+    __syncthreads();
+    if (tid == 0) {
+        const int t = atomicAdd(done_ticket, 1);
+        s_last = (t == (int)gridDim.x - 1);
+        if (s_last) *done_ticket = 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (tid < 4 * VK_MAX_CAND) {
+        out_mapped[tid] = __ldcg(out + tid);
+        out[tid] = 0ull;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) *done_flag = seq;
+}
+
+extern "C" int vk_eval_candidates_lists(const float *matrix, const float *lengths, int d, const int32_t *nl_rows,
+                                        const float *nl_dists, int32_t n_nl, float prune_radius,
+                                        const int32_t *cand_rows_host, int n_cand, int32_t base_row, uint64_t *out_dev,
+                                        uint64_t *out_pinned, int32_t *within_pinned, int32_t within_cap,
+                                        int32_t *done_ticket, int32_t *done_flag_pinned, int32_t seq, void *stream) {
+    if (n_cand < 1 || n_cand > VK_MAX_CAND || within_cap < 1) {
+        vk_set_error("vk_eval_candidates_lists: n_cand=%d outside [1, %d] or bad capacity", n_cand, VK_MAX_CAND);
+        return 1;
+    }
+    if (d < 1 || d > PB_MAX_D || n_nl <= 0) {
+        vk_set_error("vk_eval_candidates_lists: d=%d outside [1, %d] or empty neighbour list", d, PB_MAX_D);
+        return 1;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    CandRows cand;
+    memset(&cand, 0, sizeof(cand));
+    for (int k = 0; k < n_cand; ++k) cand.rows[k] = cand_rows_host[k];
+    const int dpad = (d + 3) & ~3;
+    const size_t smem = sizeof(float) * (size_t)n_cand * dpad;
+    if (smem > 48 * 1024)
+        VK_CUDA(cudaFuncSetAttribute(eval_candidates_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int per_block = EC_THREADS / 8;
+    int grid = (n_nl + per_block - 1) / per_block;
+    const int cap = vk_num_sms() * 4;
+    if (grid > cap) grid = cap;
+    eval_candidates_lists_kernel<<<grid, EC_THREADS, smem, s>>>(matrix, lengths, d, nl_rows, nl_dists, n_nl, prune_radius,
+                                                                cand, n_cand, base_row, (u64 *)out_dev, (u64 *)out_pinned,
+                                                                within_pinned, within_cap, done_ticket, done_flag_pinned, seq);
+    VK_LAUNCH_CHECK();
+    return wait_flag(done_flag_pinned, seq, s, "vk_eval_candidates_lists");
+}
+
 // ------------------------------------------------------------------ member selection
 __global__ void __launch_bounds__(256)
 select_members_kernel(const int32_t *__restrict__ nl_rows, const float *__restrict__ nl_dists, int n_nl,

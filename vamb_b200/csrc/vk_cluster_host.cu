@@ -11,6 +11,7 @@
 // 32-bit words of |seed|, getrandbits(k) = genrand_uint32() >> (32 - k), _randbelow by rejection,
 // and sample() with its pool / set-rejection switch at n <= 21 + 4^ceil(log4(3k)).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -125,6 +126,11 @@ struct State {
     int32_t *flags_pin = nullptr;   // [0] probe, [1] candidate evaluation
     int32_t *tickets_dev = nullptr; // [0] probe, [1] candidate evaluation
     int32_t seq = 0;
+    // lazy medoid moves (vk_eval_candidates_lists): device accumulators, pinned results and id lists
+    uint64_t *cand2_dev = nullptr, *cand2_pin = nullptr;
+    int32_t *within_pin = nullptr;
+    int64_t n_moves_lazy = 0, n_rebases = 0;
+    bool lazy_enabled = true;  // VAMB_B200_CLUSTER_LAZY=0: a full scan per move, as round 1 (same clusters)
     std::vector<int64_t> members;
     int64_t n_probes, n_evals, n_packs;
     double t_probe = 0.0, t_eval = 0.0, t_select = 0.0, t_pack = 0.0, t_total = 0.0;  // host wall seconds per call kind
@@ -271,37 +277,130 @@ void update_successes(State &st, bool success) {
     }
 }
 
-// vamb/cluster.py:415-450 with one device pass per round of candidates
+constexpr int WITHIN_CAP = 1024;     // ids per candidate in the pinned list buffer
+constexpr float R_EVAL = 0.1199f;    // d(candidate, base) up to which the base's 0.3-neighbour list covers the
+                                     // candidate's whole 0.05-neighbourhood: acos(1 - 2 * 0.1203) + acos(0.9) = acos(0.4)
+
+struct EvalLists {
+    std::vector<unsigned __int128> dens;
+    std::vector<int64_t> cnt;
+    std::vector<float> dbase;
+};
+
+int do_eval_lists(State &st, const Probe &base, float prune, const std::vector<int32_t> &rows, EvalLists &out) {
+    Stopwatch sw(st.t_eval);
+    const vk_cluster_config &c = st.c;
+    const int n = (int)rows.size();
+    ++st.n_evals;
+    if (vk_eval_candidates_lists(st.M(), st.LEN(), c.d, c.nl_rows, c.nl_dists, base.n_nl, prune, rows.data(), n, base.medoid,
+                                 st.cand2_dev, st.cand2_pin, st.within_pin, WITHIN_CAP, st.tickets_dev + 1,
+                                 st.flags_pin + 1, ++st.seq, c.stream))
+        return 1;
+    out.dens.resize((size_t)n);
+    out.cnt.resize((size_t)n);
+    out.dbase.resize((size_t)n);
+    for (int k = 0; k < n; ++k) {
+        out.dens[(size_t)k] = ((unsigned __int128)st.cand2_pin[VK_MAX_CAND + k] << 12) + st.cand2_pin[k];
+        out.cnt[(size_t)k] = (int64_t)st.cand2_pin[2 * VK_MAX_CAND + k];
+        const uint32_t bits = (uint32_t)st.cand2_pin[3 * VK_MAX_CAND + k];
+        memcpy(&out.dbase[(size_t)k], &bits, sizeof(float));
+    }
+    return 0;
+}
+
+// vamb/cluster.py:415-450.  The reference calls sample_medoid (a full scan) for every candidate and for every
+// move.  Here one full scan ("probe") at a BASE medoid leaves its neighbour list (rows within 0.3) on the device; the
+// candidates of a round are evaluated together over that list, and a move to a winning candidate needs no scan at all
+// as long as the list still covers the new candidates' 0.05-neighbourhoods (d(candidate, base) <= R_EVAL): the
+// winner's within-set and density come out of the evaluation.  Only when a sampled candidate lies too far from the base
+// is the current medoid probed (it becomes the base) and the SAME sample evaluated again; the final medoid is probed
+// once for its histogram / neighbour list.  Densities are pure functions of (medoid, live rows), so the decisions --
+// and the Python RNG call sequence -- are exactly the reference's.
 int wander(State &st, int32_t seed, Probe &probe, int32_t &seed_rank) {
     std::unordered_set<int32_t> tried;
     tried.insert(seed);
     if (do_probe(st, seed, probe)) return 1;
     seed_rank = probe.rank;
+    const bool list_is_everything = !(st.c.nl_radius < 1e30f);
+    const bool lazy = st.lazy_enabled && st.c.maxsteps <= VK_MAX_CAND && st.cand2_dev != nullptr &&
+                      (list_is_everything || st.c.nl_radius == 0.3f);
     unsigned __int128 local = probe.density;
+    int32_t cur = seed;                         // current medoid; probe describes the base (probe.medoid)
+    std::vector<int32_t> cur_within = probe.within;
     std::vector<int32_t> cand, sampled;
     std::vector<unsigned __int128> dens;
+    EvalLists ev;
+    auto rebase = [&]() -> int {                // full scan at the current medoid
+        const unsigned __int128 want = local;
+        if (do_probe(st, cur, probe)) return 1;
+        ++st.n_rebases;
+        if (probe.density != want || probe.within != cur_within) {
+            vk_set_error("vk_cluster: probe and candidate evaluation disagree");
+            return 1;
+        }
+        return 0;
+    };
     for (;;) {
         cand.clear();
-        for (int32_t r : probe.within)
+        for (int32_t r : cur_within)
             if (!tried.count(r)) cand.push_back(r);
         const int k = (int)std::min<size_t>(cand.size(), (size_t)st.c.maxsteps);
         st.rng.sample(cand, k, sampled);
         if (sampled.empty()) break;
-        if (do_eval(st, probe, sampled, dens)) return 1;
         int winner = -1;
-        for (size_t i = 0; i < sampled.size(); ++i) {
-            tried.insert(sampled[i]);
-            if (dens[i] > local) { winner = (int)i; break; }
+        if (!lazy) {
+            if (cur != probe.medoid && rebase()) return 1;
+            if (do_eval(st, probe, sampled, dens)) return 1;
+            for (size_t i = 0; i < sampled.size(); ++i) {
+                tried.insert(sampled[i]);
+                if (dens[i] > local) { winner = (int)i; break; }
+            }
+            if (winner < 0) break;
+            const unsigned __int128 want = dens[(size_t)winner];
+            if (do_probe(st, sampled[(size_t)winner], probe)) return 1;
+            if (probe.density != want) {
+                vk_set_error("vk_cluster: probe and candidate densities disagree");
+                return 1;
+            }
+            cur = sampled[(size_t)winner];
+            cur_within = probe.within;
+            local = probe.density;
+            continue;
+        }
+        for (;;) {
+            const bool at_base = cur == probe.medoid;
+            // candidates of the base itself lie within 0.05 of it: rows near them are within 0.19 (prune radius)
+            if (do_eval_lists(st, probe, at_base ? st.c.prune_radius : st.c.nl_radius, sampled, ev)) return 1;
+            bool need_rebase = false;
+            for (size_t i = 0; i < sampled.size(); ++i) {
+                if (!at_base && !list_is_everything && !(ev.dbase[i] <= R_EVAL)) { need_rebase = true; break; }
+                tried.insert(sampled[i]);
+                if (ev.dens[i] > local) { winner = (int)i; break; }
+            }
+            if (!need_rebase) break;
+            if (rebase()) return 1;  // then evaluate the same sample against the new base
+            winner = -1;
         }
         if (winner < 0) break;
-        const unsigned __int128 want = dens[(size_t)winner];
-        if (do_probe(st, sampled[(size_t)winner], probe)) return 1;
-        if (probe.density != want) {
-            vk_set_error("vk_cluster: probe and candidate densities disagree");
-            return 1;
+        const size_t w = (size_t)winner;
+        if (ev.cnt[w] > WITHIN_CAP) {  // id list truncated: take the winner's within-set from a full scan
+            const unsigned __int128 want = ev.dens[w];
+            if (do_probe(st, sampled[w], probe)) return 1;
+            if (probe.density != want) {
+                vk_set_error("vk_cluster: probe and candidate densities disagree");
+                return 1;
+            }
+            cur_within = probe.within;
+        } else {
+            const int32_t *ids = st.within_pin + w * WITHIN_CAP;
+            cur_within.assign(ids, ids + ev.cnt[w]);
+            std::sort(cur_within.begin(), cur_within.end());
+            ++st.n_moves_lazy;
         }
-        local = probe.density;
+        cur = sampled[w];
+        local = ev.dens[w];
     }
+    if (cur != probe.medoid && rebase()) return 1;  // the final medoid's histogram / neighbour list / loner count
     return 0;
 }
 
@@ -358,6 +457,7 @@ extern "C" int vk_cluster_create(void **handle, const vk_cluster_config *cfg) {
         return 1;
     }
     st->c = *cfg;
+    if (const char *v = getenv("VAMB_B200_CLUSTER_LAZY")) st->lazy_enabled = atoi(v) != 0;
     st->cur = 0;
     st->n_act = cfg->n;
     st->indices.resize((size_t)cfg->n);
@@ -378,6 +478,10 @@ extern "C" int vk_cluster_create(void **handle, const vk_cluster_config *cfg) {
         cudaHostAlloc((void **)&st->cand_pin, sizeof(uint64_t) * 3 * VK_MAX_CAND, cudaHostAllocMapped) != cudaSuccess ||
         cudaHostAlloc((void **)&st->flags_pin, sizeof(int32_t) * 2, cudaHostAllocMapped) != cudaSuccess ||
         cudaMalloc((void **)&st->tickets_dev, sizeof(int32_t) * 2) != cudaSuccess ||
+        cudaHostAlloc((void **)&st->cand2_pin, sizeof(uint64_t) * 4 * VK_MAX_CAND, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostAlloc((void **)&st->within_pin, sizeof(int32_t) * VK_MAX_CAND * WITHIN_CAP, cudaHostAllocMapped) != cudaSuccess ||
+        cudaMalloc((void **)&st->cand2_dev, sizeof(uint64_t) * 4 * VK_MAX_CAND) != cudaSuccess ||
+        cudaMemsetAsync(st->cand2_dev, 0, sizeof(uint64_t) * 4 * VK_MAX_CAND, s) != cudaSuccess ||
         cudaMemsetAsync(st->tickets_dev, 0, sizeof(int32_t) * 2, s) != cudaSuccess ||
         cudaMemsetAsync(cfg->hdr, 0, sizeof(vk_probe_header), s) != cudaSuccess ||
         cudaMemsetAsync(cfg->cand_out, 0, sizeof(uint64_t) * 3 * VK_MAX_CAND, s) != cudaSuccess ||
@@ -399,6 +503,9 @@ extern "C" void vk_cluster_destroy(void *handle) {
     if (st->cand_pin) cudaFreeHost(st->cand_pin);
     if (st->flags_pin) cudaFreeHost(st->flags_pin);
     if (st->tickets_dev) cudaFree(st->tickets_dev);
+    if (st->cand2_pin) cudaFreeHost(st->cand2_pin);
+    if (st->within_pin) cudaFreeHost(st->within_pin);
+    if (st->cand2_dev) cudaFree(st->cand2_dev);
     delete st;
 }
 
@@ -409,10 +516,12 @@ extern "C" int vk_cluster_stats(void *handle, int64_t *out8) {
     return 0;
 }
 
-// host wall-clock seconds spent so far in: probes, candidate evaluations, member selections, packs, all of vk_cluster_next
-extern "C" int vk_cluster_timing(void *handle, double *out5) {
+// host wall-clock seconds spent so far in: probes, candidate evaluations, member selections, packs, all of vk_cluster_next;
+// then the number of medoid moves made without a scan and the number of re-basing probes
+extern "C" int vk_cluster_timing(void *handle, double *out5 /* 7 doubles */) {
     State *st = static_cast<State *>(handle);
     out5[0] = st->t_probe; out5[1] = st->t_eval; out5[2] = st->t_select; out5[3] = st->t_pack; out5[4] = st->t_total;
+    out5[5] = (double)st->n_moves_lazy; out5[6] = (double)st->n_rebases;
     return 0;
 }
 
