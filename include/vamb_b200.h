@@ -184,14 +184,31 @@ typedef struct vk_cluster_result {
     int32_t successes, attempts;
 } vk_cluster_result;
 
+/* A block of consecutive clusters in caller-provided HOST arrays (struct-of-arrays; `members` holds the ascending
+ * original ids of cluster 0, then cluster 1, ... -- capacity n is always enough).  Fields as in vk_cluster_result. */
+typedef struct vk_cluster_block {
+    int64_t max_clusters;        /* in: capacity of the per-cluster arrays                                */
+    int64_t n_clusters;          /* out                                                                   */
+    int64_t n_members_total;     /* out: entries used in `members`                                        */
+    int64_t n_remaining;         /* out: unclustered observations after the block                         */
+    int64_t *medoid, *seed, *n_members; /* [max_clusters]                                                 */
+    int64_t *members;            /* [n]                                                                   */
+    double *maximal_pvr, *observed_pvr, *radius; /* [max_clusters], NaN = None                            */
+    int32_t *kind, *successes, *attempts;        /* [max_clusters]                                        */
+    double peak_valley_ratio;    /* out: the generator's pvr after the block                              */
+} vk_cluster_block;
+
 int vk_cluster_create(void **handle, const vk_cluster_config *cfg);
+/* Up to blk->max_clusters calls of vk_cluster_next in ONE foreign call (vamb/__main__.py:1289-1377 consumes the
+ * clusters as a stream; per-cluster Python becomes per-block NumPy).  0 = ok (n_clusters may be 0: exhausted), 1 = error. */
+int vk_cluster_next_block(void *handle, vk_cluster_block *blk);
 int vk_cluster_next(void *handle, vk_cluster_result *out); /* 0 = cluster, 2 = exhausted, 1 = error */
 int vk_cluster_stats(void *handle, int64_t *out8);         /* probes, evals, packs, physical rows, live buffer set (0/1),
                                                               successes, attempts in the window, order_index */
 int vk_cluster_timing(void *handle, double *out7);         /* host seconds in probes, evaluations, selections, packs, total;
                                                               medoid moves without a scan, re-basing probes */
 void vk_cluster_destroy(void *handle);
-int64_t vk_cluster_sizeof(int which);                      /* 0: vk_cluster_config, 1: vk_cluster_result */
+int64_t vk_cluster_sizeof(int which);                      /* 0: vk_cluster_config, 1: vk_cluster_result, 2: vk_cluster_block */
 /* CPython-compatible random.Random(seed).sample(range(n_i), min(n_i, k)) for each i: writes k slots per
  * call into out (unused slots = -1).  Host only; used by the CPU test-suite. */
 int vk_cluster_rng_selftest(const uint32_t *key, int key_len, const int32_t *ns, int n_calls, int k, int32_t *out);

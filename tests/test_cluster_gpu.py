@@ -288,3 +288,31 @@ def test_lazy_medoid_moves_emit_the_same_clusters(n, d, spread, seed, monkeypatc
     assert t0["lazy_moves"] == 0 and t["lazy_moves"] > 0
     assert gen._n_probes < gen0._n_probes
     _util.assert_clusters_equal(lazy, list(co.OracleClusterGenerator(lat, lens, rng_seed=seed)))
+
+
+def test_next_block_equals_iteration_and_writes_reference_text(tmp_path):
+    """Block emission (one foreign call per block): same clusters as iterating, mixing ``next()`` and
+    ``next_block`` is allowed, and the block writer's files equal the per-cluster restatement of the reference's loop."""
+    import os
+
+    import vamb_b200.cluster as vc
+    from oracle import synth
+    from tests.test_cluster_writer_cpu import reference_style
+
+    lat, lens = synth.make_latent(12000, 32, 51, 0.25)
+    want = list(vc.ClusterGenerator(lat, lens, rng_seed=9))
+    gen = vc.ClusterGenerator(lat, lens, rng_seed=9)
+    got = [next(gen), next(gen)]
+    for blk in gen.iter_blocks(97):
+        assert len(blk) <= 97 and blk.offsets[-1] == len(blk.members)
+        got.extend(blk.clusters())
+    _util.assert_clusters_equal(got, want)
+    assert gen.n_remaining_points == 0 and gen.n_emitted_clusters == len(want)
+    with pytest.raises(StopIteration):
+        next(gen)
+    names = [f"S{i % 3}C{i}" for i in range(len(lat))]
+    base = os.path.join(tmp_path, "vae")
+    n_cl, n_ct = vc.write_clusters_tsv(vc.ClusterGenerator(lat, lens, rng_seed=9), names, lens, base, bin_prefix="bin_")
+    u, m = reference_style(want, names, lens, "bin_")
+    assert (n_cl, n_ct) == (len(want), len(lat))
+    assert open(base + "_unsplit.tsv").read() == u and open(base + "_metadata.tsv").read() == m

@@ -39,7 +39,20 @@ class VkClusterResult(_ct.Structure):
     ]
 
 
+class VkClusterBlock(_ct.Structure):
+    _fields_ = [
+        ("max_clusters", _ct.c_int64), ("n_clusters", _ct.c_int64), ("n_members_total", _ct.c_int64),
+        ("n_remaining", _ct.c_int64),
+        ("medoid", _p), ("seed", _p), ("n_members", _p), ("members", _p),
+        ("maximal_pvr", _p), ("observed_pvr", _p), ("radius", _p),
+        ("kind", _p), ("successes", _p), ("attempts", _p),
+        ("peak_valley_ratio", _ct.c_double),
+    ]
+
+
 _L = _lib.lib
+_L.vk_cluster_next_block.argtypes = [_ct.c_void_p, _ct.POINTER(VkClusterBlock)]
+_L.vk_cluster_next_block.restype = _ct.c_int
 _L.vk_cluster_create.argtypes = [_ct.POINTER(_ct.c_void_p), _ct.POINTER(VkClusterConfig)]
 _L.vk_cluster_create.restype = _ct.c_int
 _L.vk_cluster_next.argtypes = [_ct.c_void_p, _ct.POINTER(VkClusterResult)]
@@ -55,7 +68,8 @@ _L.vk_cluster_rng_selftest.argtypes = [_ct.POINTER(_ct.c_uint32), _ct.c_int, _ct
 _L.vk_cluster_rng_selftest.restype = _ct.c_int
 _L.vk_cluster_sizeof.argtypes = [_ct.c_int]
 _L.vk_cluster_sizeof.restype = _ct.c_int64
-if _L.vk_cluster_sizeof(0) != _ct.sizeof(VkClusterConfig) or _L.vk_cluster_sizeof(1) != _ct.sizeof(VkClusterResult):
+if (_L.vk_cluster_sizeof(0) != _ct.sizeof(VkClusterConfig) or _L.vk_cluster_sizeof(1) != _ct.sizeof(VkClusterResult)
+        or _L.vk_cluster_sizeof(2) != _ct.sizeof(VkClusterBlock)):
     raise ImportError("vamb_b200: cluster driver structs are out of sync with include/vamb_b200.h")
 
 

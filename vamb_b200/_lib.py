@@ -90,7 +90,7 @@ _VAE_SYMBOLS = [
     "vk_vae_sizeof", "vk_vae_train_step", "vk_vae_grad_step", "vk_vae_forward", "vk_vae_encode",
     "vk_vae_prepare_eval", "vk_vae_dadapt_step", "vk_vae_profile_step", "vk_vae_init_device",
     # bound in vamb_b200/_cluster_native.py
-    "vk_cluster_create", "vk_cluster_next", "vk_cluster_stats", "vk_cluster_timing", "vk_cluster_destroy", "vk_cluster_rng_selftest", "vk_cluster_sizeof",
+    "vk_cluster_create", "vk_cluster_next", "vk_cluster_next_block", "vk_cluster_stats", "vk_cluster_timing", "vk_cluster_destroy", "vk_cluster_rng_selftest", "vk_cluster_sizeof",
 ]
 for _name in _VAE_SYMBOLS:
     getattr(lib, _name)  # AttributeError = stale .so

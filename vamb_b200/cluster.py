@@ -110,6 +110,34 @@ class Cluster:
         return "loner" if self.radius is None else "fallback"
 
 
+class ClusterBlock:
+    """A run of consecutive clusters as arrays (``ClusterGenerator.next_block``): what
+    ``cluster_and_write_files`` (vamb/__main__.py:1325-1377) needs per cluster, without a Python object per
+    cluster.  ``members`` holds the ascending original ids of cluster 0, then cluster 1, ...; cluster i owns
+    ``members[offsets[i]:offsets[i + 1]]``.  ``radius`` / ``observed_pvr`` are NaN where the reference has None."""
+
+    __slots__ = ["medoid", "seed", "offsets", "members", "maximal_pvr", "observed_pvr", "radius", "kind",
+                 "successes", "attempts"]
+
+    _KIND_STR = ("loner", "fallback", "normal")
+
+    def __len__(self) -> int:
+        return len(self.medoid)
+
+    def kind_strs(self) -> list:
+        return [self._KIND_STR[k] for k in self.kind.tolist()]
+
+    def clusters(self):
+        "The same clusters as ``Cluster`` objects (compatibility path)."
+        for i in range(len(self)):
+            k = int(self.kind[i])
+            yield Cluster(
+                int(self.medoid[i]), int(self.seed[i]), self.members[self.offsets[i]:self.offsets[i + 1]].copy(),
+                float(self.maximal_pvr[i]), float(self.observed_pvr[i]) if k == 2 else None,
+                None if k == 0 else float(self.radius[i]), int(self.successes[i]), int(self.attempts[i]),
+            )
+
+
 class _Probe:
     """Host view of one vk_probe_header."""
 
@@ -348,6 +376,12 @@ class ClusterGenerator:
         self.n_emitted_clusters += 1
         self.n_remaining_points = int(res.n_remaining)
         self.peak_valley_ratio = res.peak_valley_ratio
+        self._sync_native_stats()
+        return cluster
+
+    def _sync_native_stats(self) -> None:
+        from . import _cluster_native as _cn
+
         stats = (_lib.ctypes.c_int64 * 8)()
         _cn._L.vk_cluster_stats(self._native, stats)
         self._n_probes, self._n_evals, self._n_act = int(stats[0]), int(stats[1]), int(stats[3])
@@ -363,7 +397,62 @@ class ClusterGenerator:
         self.successes, self.order_index = int(stats[5]), int(stats[7])
         if len(self.attempts) != int(stats[6]):
             self.attempts = _deque([False] * int(stats[6]), maxlen=self.attempts.maxlen)
-        return cluster
+
+    def next_block(self, max_clusters: int = 1024) -> ClusterBlock:
+        """Up to ``max_clusters`` further clusters in ONE foreign call, as arrays (empty block = exhausted).
+        Interleaves freely with ``next()``; the Python driver falls back to a per-cluster loop."""
+        blk = ClusterBlock()
+        m = max(1, int(max_clusters))
+        if self._native is None:
+            got = []
+            for _ in range(m):
+                try:
+                    got.append(next(self))
+                except StopIteration:
+                    break
+            blk.medoid = _np.array([c.medoid for c in got], dtype=_np.int64)
+            blk.seed = _np.array([c.seed for c in got], dtype=_np.int64)
+            sizes = _np.array([len(c.members) for c in got], dtype=_np.int64)
+            blk.offsets = _np.concatenate([[0], _np.cumsum(sizes)]).astype(_np.int64)
+            blk.members = _np.concatenate([_np.asarray(c.members, dtype=_np.int64) for c in got]) if got else _np.empty(0, _np.int64)
+            blk.maximal_pvr = _np.array([c.maximal_pvr for c in got], dtype=_np.float64)
+            blk.observed_pvr = _np.array([_np.nan if c.observed_pvr is None else c.observed_pvr for c in got], dtype=_np.float64)
+            blk.radius = _np.array([_np.nan if c.radius is None else c.radius for c in got], dtype=_np.float64)
+            blk.kind = _np.array([{"loner": 0, "fallback": 1, "normal": 2}[c.kind_str] for c in got], dtype=_np.int32)
+            blk.successes = _np.array([c.successes for c in got], dtype=_np.int32)
+            blk.attempts = _np.array([c.attempts for c in got], dtype=_np.int32)
+            return blk
+        from . import _cluster_native as _cn
+
+        arrs = {name: _np.empty(m, dtype=dt) for name, dt in (
+            ("medoid", _np.int64), ("seed", _np.int64), ("n_members", _np.int64), ("maximal_pvr", _np.float64),
+            ("observed_pvr", _np.float64), ("radius", _np.float64), ("kind", _np.int32), ("successes", _np.int32),
+            ("attempts", _np.int32))}
+        members = _np.empty(max(1, self.n_remaining_points), dtype=_np.int64)
+        c = _cn.VkClusterBlock()
+        c.max_clusters = m
+        for name, a in arrs.items():
+            setattr(c, name, a.ctypes.data)
+        c.members = members.ctypes.data
+        _lib.check(_cn._L.vk_cluster_next_block(self._native, _lib.ctypes.byref(c)))
+        k = int(c.n_clusters)
+        for name in ("medoid", "seed", "maximal_pvr", "observed_pvr", "radius", "kind", "successes", "attempts"):
+            setattr(blk, name, arrs[name][:k])
+        blk.offsets = _np.concatenate([[0], _np.cumsum(arrs["n_members"][:k])]).astype(_np.int64)
+        blk.members = members[: int(c.n_members_total)]
+        self.n_emitted_clusters += k
+        self.n_remaining_points = int(c.n_remaining)
+        self.peak_valley_ratio = float(c.peak_valley_ratio)
+        self._sync_native_stats()
+        return blk
+
+    def iter_blocks(self, max_clusters: int = 1024):
+        "Iterate the remaining clusters block by block."
+        while True:
+            blk = self.next_block(max_clusters)
+            if len(blk) == 0:
+                return
+            yield blk
 
     def _timing(self) -> dict:
         "Host seconds the native driver spent per call kind so far (diagnostics / bench)."
@@ -627,3 +716,44 @@ class ClusterGenerator:
         if self.n_remaining_points and self.n_remaining_points < self._pack_fraction * self._n_act:
             self.pack()
         return cluster
+
+
+def write_clusters_tsv(generator: ClusterGenerator, sequence_names, sequence_lens, base_clusters_name: str,
+                       bin_prefix: Optional[str] = None, max_clusters: Optional[int] = None,
+                       block: int = 2048) -> tuple:
+    """Stream the clusters of ``generator`` into ``<base>_unsplit.tsv`` and ``<base>_metadata.tsv`` with the exact
+    text the reference's per-cluster loop prints (vamb/__main__.py:1310-1377, binsplitter disabled): cluster names
+    ``bin_prefix + str(index + 1)``, one ``name\tcontig`` line per member, and the metadata columns name / radius
+    (3 decimals) / peak valley ratio (2 decimals) / kind / bp / ncontigs / medoid.  Works block-wise on arrays:
+    name lookups, base-pair sums and line assembly are NumPy operations per block of clusters, not Python per member.
+    Returns (n_clusters, n_contigs)."""
+    names = _np.asarray(sequence_names, dtype=object)
+    lens = _np.asarray(sequence_lens)
+    prefix = "" if bin_prefix is None else bin_prefix
+    n_clusters = n_contigs = 0
+    with open(base_clusters_name + "_metadata.tsv", "w") as meta, open(base_clusters_name + "_unsplit.tsv", "w") as unsplit:
+        print("name\tradius\tpeak valley ratio\tkind\tbp\tncontigs\tmedoid", file=meta)
+        print("clustername\tcontigname", file=unsplit)  # vamb.vambtools.CLUSTERS_HEADER
+        while max_clusters is None or n_clusters < max_clusters:
+            want = block if max_clusters is None else min(block, max_clusters - n_clusters)
+            blk = generator.next_block(want)
+            k = len(blk)
+            if k == 0:
+                break
+            sizes = _np.diff(blk.offsets)
+            cl_names = _np.array([prefix + str(i) for i in range(n_clusters + 1, n_clusters + k + 1)], dtype=object)
+            member_names = names[blk.members]
+            unsplit.write("\n".join((_np.repeat(cl_names, sizes) + "\t" + member_names).tolist()))
+            unsplit.write("\n")
+            bp = _np.add.reduceat(lens[blk.members], blk.offsets[:-1]) if len(blk.members) else _np.zeros(k, dtype=lens.dtype)
+            kinds = blk.kind_strs()
+            rows = []
+            for i in range(k):  # per cluster (not per member): seven short fields
+                radius = None if blk.kind[i] == 0 else round(float(blk.radius[i]), 3)
+                pvr = round(float(blk.observed_pvr[i]), 2) if blk.kind[i] == 2 else None
+                rows.append(f"{cl_names[i]}\t{radius}\t{pvr}\t{kinds[i]}\t{bp[i]}\t{sizes[i]}\t{names[blk.medoid[i]]}")
+            meta.write("\n".join(rows))
+            meta.write("\n")
+            n_clusters += k
+            n_contigs += int(sizes.sum())
+    return n_clusters, n_contigs

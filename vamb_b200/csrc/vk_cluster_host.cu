@@ -580,6 +580,27 @@ extern "C" int vk_cluster_next(void *handle, vk_cluster_result *out) {
     return 0;
 }
 
+extern "C" int vk_cluster_next_block(void *handle, vk_cluster_block *blk) {
+    blk->n_clusters = 0;
+    blk->n_members_total = 0;
+    State &st = *static_cast<State *>(handle);
+    vk_cluster_result r;
+    while (blk->n_clusters < blk->max_clusters) {
+        const int rc = vk_cluster_next(handle, &r);
+        if (rc == 2) break;
+        if (rc) return 1;
+        const int64_t i = blk->n_clusters++;
+        blk->medoid[i] = r.medoid; blk->seed[i] = r.seed; blk->n_members[i] = r.n_members;
+        blk->maximal_pvr[i] = r.maximal_pvr; blk->observed_pvr[i] = r.observed_pvr; blk->radius[i] = r.radius;
+        blk->kind[i] = r.kind; blk->successes[i] = r.successes; blk->attempts[i] = r.attempts;
+        memcpy(blk->members + blk->n_members_total, r.members_host, sizeof(int64_t) * (size_t)r.n_members);
+        blk->n_members_total += r.n_members;
+    }
+    blk->n_remaining = st.n_remaining;
+    blk->peak_valley_ratio = st.pvr;
+    return 0;
+}
+
 extern "C" int vk_cluster_rng_selftest(const uint32_t *key, int key_len, const int32_t *ns, int n_calls, int k,
                                        int32_t *out) {
     MT19937 rng;
@@ -596,5 +617,6 @@ extern "C" int vk_cluster_rng_selftest(const uint32_t *key, int key_len, const i
 }
 
 extern "C" int64_t vk_cluster_sizeof(int which) {
-    return which == 0 ? (int64_t)sizeof(vk_cluster_config) : (int64_t)sizeof(vk_cluster_result);
+    return which == 0 ? (int64_t)sizeof(vk_cluster_config)
+                      : (which == 1 ? (int64_t)sizeof(vk_cluster_result) : (int64_t)sizeof(vk_cluster_block));
 }
