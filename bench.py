@@ -346,14 +346,12 @@ def probe_roofline(latent_dev, lengths):
     import vamb_b200.cluster as vc
     from vamb_b200 import _lib
 
-    gen = vc.ClusterGenerator(latent_dev, lengths, rng_seed=0)
+    gen = vc.ClusterGenerator(latent_dev, lengths, rng_seed=0, _driver="python")
     n = gen._n_act
-    s = torch.cuda.current_stream().cuda_stream
+    state = {}
 
-    def call(i):
-        _lib.check(_lib.lib.vk_probe(gen._m.data_ptr(), gen._len.data_ptr(), gen._kept.data_ptr(), n, gen._d,
-                                     (i * 7919) % n, 0.3, gen._edges.data_ptr(), gen._hdr.data_ptr(),
-                                     gen._within_over.data_ptr(), gen._nl_rows.data_ptr(), gen._nl_d.data_ptr(), s))
+    def call(i):  # ONE launch, as the native driver issues it (mapped completion; the rank count is part of the kernel)
+        gen._probe_mapped_once((i * 7919) % n, state)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for i in range(3):

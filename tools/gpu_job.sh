@@ -27,3 +27,6 @@ leg r02_graderr 300 python tools/grad_error_fp64.py
 leg r02_speed_tma0 200 env TC_MIN=128 VAMB_B200_TMA=0 python tools/train_speed.py
 leg r02_speed_tma1 200 env TC_MIN=128 VAMB_B200_TMA=1 python tools/train_speed.py
 for f in gpurun_out/r02_pt_*.log; do echo "== $f"; tail -4 $f; done; cat gpurun_out/job_summary.log; tail -c 1500 gpurun_out/r02_bench.log
+: > gpurun_out/r02_probe_sweep.txt
+for cfg in "4 4" "4 2" "4 6" "4 8" "8 3" "8 2" "8 4"; do set -- $cfg; VK_PROBE_R=$1 VK_PROBE_BPS=$2 timeout 120 python tools/probe_speed.py >> gpurun_out/r02_probe_sweep.txt 2>&1; done
+cat gpurun_out/r02_probe_sweep.txt | grep "N=" 

@@ -1,19 +1,17 @@
-"""Probe kernel timing (CUDA events around vk_probe; cold = L2 flushed before every launch)."""
+"""Probe kernel timing: CUDA events around the single launch the native driver issues (vk_probe_mapped);
+cold = L2 flushed before every launch.  VK_PROBE_R (4 | 8 rows in flight per lane) and VK_PROBE_BPS (persistent blocks
+per SM) select the launch shape; run once per setting (they are read once per process)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import vamb_b200.cluster as vc
-from vamb_b200 import _lib
 from oracle import synth
 
 for n in (1_000_000, 5_000_000):
     lat, ln = synth.make_latent(n, 32, seed=0, spread=0.1)
     gen = vc.ClusterGenerator(lat, ln, rng_seed=0, _driver="python")
-    s = torch.cuda.current_stream().cuda_stream
-    def call(i):
-        _lib.check(_lib.lib.vk_probe(gen._m.data_ptr(), gen._len.data_ptr(), gen._kept.data_ptr(), n, gen._d,
-                                     (i * 7919) % n, 0.3, gen._edges.data_ptr(), gen._hdr.data_ptr(),
-                                     gen._within_over.data_ptr(), gen._nl_rows.data_ptr(), gen._nl_d.data_ptr(), s))
+    state = {}
+    call = lambda i: gen._probe_mapped_once((i * 7919) % n, state)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     res = {}
     for mode in ("warm", "cold"):
@@ -28,6 +26,7 @@ for n in (1_000_000, 5_000_000):
             ts.append(a.elapsed_time(b))
         res[mode] = float(np.median(ts))
     nbytes = n * 133
-    print(f"VK_PROBE_BULK={os.environ.get('VK_PROBE_BULK', '0')} N={n}: warm {res['warm']*1e3:.1f} us ({nbytes/res['warm']/1e6:.0f} GB/s), "
-          f"cold {res['cold']*1e3:.1f} us ({nbytes/res['cold']/1e6:.0f} GB/s)   [memset + rank + probe launches]")
+    print(f"VK_PROBE_R={os.environ.get('VK_PROBE_R', '4')} VK_PROBE_BPS={os.environ.get('VK_PROBE_BPS', '4')} N={n}: "
+          f"warm {res['warm']*1e3:.1f} us ({nbytes/res['warm']/1e6:.0f} GB/s), cold {res['cold']*1e3:.1f} us "
+          f"({nbytes/res['cold']/1e6:.0f} GB/s)   [one launch]")
     del gen, lat

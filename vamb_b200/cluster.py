@@ -454,6 +454,24 @@ class ClusterGenerator:
                 return
             yield blk
 
+    def _probe_mapped_once(self, row: int, state: dict) -> None:
+        """One probe exactly as the native driver issues it -- a single launch with the mapped completion
+        (vk_probe_mapped) -- for timing tools (bench.py, tools/probe_speed.py).  ``state`` carries the pinned
+        buffers between calls."""
+        if not state:
+            self._hdr.zero_()
+            state["hdr"] = _torch.zeros(_lib.HDR_SIZE, dtype=_torch.uint8).pin_memory()
+            state["ticket"] = _torch.zeros(1, dtype=_torch.int32, device=self._m.device)
+            state["flag"] = _torch.zeros(1, dtype=_torch.int32).pin_memory()
+            state["seq"] = 0
+            _torch.cuda.synchronize()
+        state["seq"] += 1
+        _lib.check(_lib.lib.vk_probe_mapped(
+            self._m.data_ptr(), self._len.data_ptr(), self._kept.data_ptr(), self._n_act, self._d, int(row),
+            self._nl_radius, self._edges.data_ptr(), self._hdr.data_ptr(), self._within_over.data_ptr(),
+            self._nl_rows.data_ptr(), self._nl_d.data_ptr(), state["hdr"].data_ptr(), state["ticket"].data_ptr(),
+            state["flag"].data_ptr(), state["seq"], self._stream))
+
     def _timing(self) -> dict:
         "Host seconds the native driver spent per call kind so far (diagnostics / bench)."
         from . import _cluster_native as _cn

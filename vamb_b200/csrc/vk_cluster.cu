@@ -142,8 +142,10 @@ struct ProbeAcc {
 // no block barrier) and flushed with one global reservation per ~48 entries.
 constexpr int PB_WBUF = 64;  // staged entries per warp (<= 16 appended per iteration)
 
-template <int DFIX>
-__global__ void __launch_bounds__(PB_THREADS, 4)
+// R = independent rows (float4 loads) in flight per lane and per buffer (two buffers for D = 32); BPS = resident blocks
+// per SM the register budget is held to.
+template <int DFIX, int R, int BPS>
+__global__ void __launch_bounds__(PB_THREADS, BPS)
 probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths,
              const uint8_t *__restrict__ kept, int64_t n, int d_rt, int64_t mrow, float nl_radius,
              const float *__restrict__ edges_g, vk_probe_header *hdr, int32_t *within_overflow,
@@ -168,6 +170,18 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
     if (tid < VK_NBINS) s_hist[tid] = 0ull;
     if (tid == 0) { s_acc.dens = 0ull; s_acc.dens_hi = 0ull; s_acc.nlt = 0u; s_acc.rank = 0u; }
     for (int k = tid; k < d; k += PB_THREADS) s_q[k] = matrix[mrow * (int64_t)d + k];
+    // rank = number of kept rows before the medoid row (the reference's packed index of the seed,
+    // vamb/cluster.py:370): a grid-strided pass over kept[0, mrow) (1 byte per row) instead of a launch of its own
+    {
+        unsigned cnt = 0;
+        const int64_t words = mrow >> 2;  // kept is at least 4-byte aligned (a tensor of its own)
+        const uint32_t *k4 = reinterpret_cast<const uint32_t *>(kept);
+        for (int64_t i = (int64_t)blockIdx.x * PB_THREADS + tid; i < words; i += (int64_t)gridDim.x * PB_THREADS)
+            cnt += __popc(__ldg(k4 + i) & 0x01010101u);  // the mask holds 0 / 1 bytes
+        if (blockIdx.x == 0 && tid < (int)(mrow & 3)) cnt += kept[(words << 2) + tid] != 0;
+        for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0 && cnt) atomicAdd(&hdr->rank, (int)cnt);
+    }
     __syncthreads();
 
     float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -196,6 +210,7 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
     // chunks of 128 consecutive rows (4 per lane group), grid-strided; for D = 32 the next chunk's loads
     // are issued before the current chunk is processed (register double buffering) so that every resident
     // warp keeps 128 bytes per lane in flight.
+    constexpr int PB_R = R;
     constexpr int CHUNK = PB_GROUPS * PB_R;
     const int n32 = (int)n;
     const int n_chunks = (n32 + CHUNK - 1) / CHUNK;
@@ -265,7 +280,7 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
                 }
             }
         }
-        if (wcnt > PB_WBUF - PB_GROUPS / 8 * PB_R) flush_warp();
+        if (wcnt > PB_WBUF - 4 * PB_R) flush_warp();  // a warp appends at most 4 entries per row slot
     }
     flush_warp();
 
@@ -311,18 +326,24 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
     if (tid == 0) *done_flag = seq;
 }
 
-// rank = number of kept rows before the medoid row (the reference's packed index of the seed,
-// vamb/cluster.py:370); only the seed probe of a cluster asks for it.
-__global__ void __launch_bounds__(256) rank_kernel(const uint8_t *__restrict__ kept, int64_t mrow, vk_probe_header *hdr) {
-    unsigned cnt = 0;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < mrow; i += (int64_t)gridDim.x * 256) cnt += kept[i] != 0;
-    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&hdr->rank, (int)cnt);
+// Launch shape of the probe: rows in flight per lane (VK_PROBE_R = 4 | 8) and persistent blocks per SM
+// (VK_PROBE_BPS = 2..8); defaults chosen on B200 with tools/probe_speed.py (profiles/r02_probe_sweep.txt).
+static int probe_env(const char *name, int dflt, int lo, int hi) {
+    const char *v = getenv(name);
+    const int x = v ? atoi(v) : dflt;
+    return x < lo ? lo : (x > hi ? hi : x);
 }
-
-static int probe_grid(int n_tiles) {
-    const int cap = vk_num_sms() * 4;
-    return n_tiles < cap ? n_tiles : cap;
+static int probe_r() {
+    static const int r = probe_env("VK_PROBE_R", 4, 4, 8) >= 8 ? 8 : 4;
+    return r;
+}
+static int probe_bps() {
+    static const int b = probe_env("VK_PROBE_BPS", 4, 1, 8);
+    return b;
+}
+static int probe_grid(int n_chunks) {
+    const int cap = vk_num_sms() * probe_bps();
+    return n_chunks < cap ? n_chunks : cap;
 }
 
 static int probe_launch(const float *matrix, const float *lengths, const uint8_t *kept, int64_t n, int d,
@@ -343,22 +364,25 @@ static int probe_launch(const float *matrix, const float *lengths, const uint8_t
     }
     // only the accumulators need zeroing, not the inline id list (the mapped variant leaves them zeroed itself)
     if (!hdr_mapped) VK_CUDA(cudaMemsetAsync(hdr, 0, offsetof(vk_probe_header, within), s));
-    if (medoid_row > 0) {  // before the probe: its last block publishes the whole header
-        int rb = (int)((medoid_row + 256 * 64 - 1) / (256 * 64));
-        if (rb > 2 * vk_num_sms()) rb = 2 * vk_num_sms();
-        rank_kernel<<<rb, 256, 0, s>>>(kept, medoid_row, hdr);
-        VK_LAUNCH_CHECK();
+    if ((reinterpret_cast<uintptr_t>(kept) & 3) != 0) {
+        vk_set_error("vk_probe: the kept mask must be 4-byte aligned");
+        return 1;
     }
-    const int n_tiles = (int)((n + PB_TILE - 1) / PB_TILE);
-    const int grid = probe_grid(n_tiles);
-    if (d == 32)
-        probe_kernel<32><<<grid, PB_THREADS, 0, s>>>(matrix, lengths, kept, n, d, medoid_row, nl_radius, edges,
-                                                     hdr, within_overflow, nl_rows, nl_dists, n_tiles, hdr_mapped,
-                                                     done_ticket, done_flag, seq);
-    else
-        probe_kernel<0><<<grid, PB_THREADS, 0, s>>>(matrix, lengths, kept, n, d, medoid_row, nl_radius, edges,
-                                                    hdr, within_overflow, nl_rows, nl_dists, n_tiles, hdr_mapped,
-                                                    done_ticket, done_flag, seq);
+    const int r = probe_r();
+    const int n_chunks = (int)((n + PB_GROUPS * r - 1) / (PB_GROUPS * r));
+    const int grid = probe_grid(n_chunks);
+#define VK_PROBE_LAUNCH(DF, RR, BB)                                                                                  \
+    probe_kernel<DF, RR, BB><<<grid, PB_THREADS, 0, s>>>(matrix, lengths, kept, n, d, medoid_row, nl_radius, edges, hdr, \
+                                                         within_overflow, nl_rows, nl_dists, n_chunks, hdr_mapped,       \
+                                                         done_ticket, done_flag, seq)
+    if (d == 32) {
+        if (r == 8) VK_PROBE_LAUNCH(32, 8, 3);
+        else if (probe_bps() > 4) VK_PROBE_LAUNCH(32, 4, 6);
+        else VK_PROBE_LAUNCH(32, 4, 4);
+    } else {
+        VK_PROBE_LAUNCH(0, 4, 4);
+    }
+#undef VK_PROBE_LAUNCH
     VK_LAUNCH_CHECK();
     return 0;
 }
