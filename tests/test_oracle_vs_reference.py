@@ -106,3 +106,47 @@ def test_vae_oracle_equals_live_reference_over_training_steps():
         assert torch.equal(v, o.state[k]), k
     vae.eval()
     assert np.array_equal(vae.encode(dl), o.encode(d, t, a, batch=batch)[0])
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree only exists in the build container")
+def test_strict_rng_emulation_follows_the_live_reference_trainmodel():
+    """``vamb_b200.encode.reference_epoch_noise`` (the strict-RNG parity mode of the CUDA path) consumes torch's global
+    generator exactly like the reference's DataLoader + forward pass: driving the (bit-exact) oracle with it reproduces
+    the per-epoch losses that the unmodified ``VAE.trainmodel`` logs, including a batch-size doubling."""
+    import re
+
+    pytest.importorskip("vamb_b200._lib")
+    from loguru import logger
+
+    import vamb_b200.encode as ve
+    from oracle import normalize as onorm
+    from oracle import synth
+
+    ref = ref_loader.load()
+    S, n, seed, nepochs, bsteps = 4, 1500, 3, 4, [2]
+    ab, tnf, lens = synth.make_contigs(n, S, seed=8)
+    rows = []
+    pat = re.compile(r"Epoch:\s*(\d+)\s+Loss:\s*(\S+)")
+    logger.enable("vamb")
+    sink = logger.add(lambda m: rows.append(pat.search(str(m))), level="INFO")
+    dl = ref.encode.make_dataloader(ab.copy(), tnf.copy(), lens, batchsize=128)
+    vae = ref.encode.VAE(S, nhiddens=[64, 32], nlatent=8, seed=seed)
+    vae.trainmodel(dl, nepochs=nepochs, batchsteps=bsteps)
+    logger.remove(sink)
+    logger.disable("vamb")
+    want = [float(m.group(2)) for m in rows if m]
+    assert len(want) == nepochs
+
+    d, t, a, w = (torch.from_numpy(x) for x in onorm.normalize(ab, tnf, lens))
+    o = vo.OracleVAE(S, nhiddens=[64, 32], nlatent=8, seed=seed)  # torch.manual_seed(seed) + the reference's init draws
+    batch, got = 128, []
+    for epoch in range(nepochs):
+        if epoch in bsteps:
+            batch *= 2
+        tot, k = 0.0, 0
+        for idx, eps, keeps in ve.reference_epoch_noise(n, batch, n > batch, o.nhiddens, o.nlatent, o.dropout):
+            lo, _, _ = o.train_step(d[idx], t[idx], a[idx], w[idx], eps=eps, keeps=keeps)
+            tot += lo[0]
+            k += 1
+        got.append(tot / k)
+    assert [f"{x:.5e}" for x in got] == [f"{x:.5e}" for x in want], (got, want)

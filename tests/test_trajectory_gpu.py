@@ -65,3 +65,38 @@ def test_c1_full_schedule_matches_reference_band():
     assert ari >= 0.99, ari
     sizes = np.array(sorted((len(c.members) for c in clusters), reverse=True))[:10]
     assert np.abs(sizes - g["top_sizes"][0, :10]).max() <= 3, (sizes, g["top_sizes"][0, :10])
+
+
+def test_strict_rng_mode_follows_the_reference_trajectory():
+    """Parity mode ``VAE.strict_rng`` (vamb/encode.py:210, 264, 277, 292: batch order, dropout masks and noise from
+    torch's global CPU generator, in the reference's call order): 6 epochs of ``trainmodel`` on the C1 dataset with two
+    batch-size doublings reproduce the losses the LIVE reference logged (tests/golden/strict_rng_c1.npz, written by
+    oracle/make_golden_strict.py) -- the same trajectory, step for step, up to fp32 rounding (3xTF32 GEMMs vs MKL)
+    -- and the encoded latent of the trained model."""
+    import vamb_b200.encode as ve
+    from oracle import synth
+
+    g = np.load(os.path.join(os.path.dirname(GOLDEN), "strict_rng_c1.npz"))
+    n, s, nepochs, seed = (int(x) for x in g["params"][:4])
+    batchsteps = [int(x) for x in g["params"][4:]]
+    ab, tnf, lens = synth.make_contigs(n, s, seed=0)
+    dl = ve.make_dataloader(ab.copy(), tnf.copy(), lens, batchsize=256)
+    vae = ve.VAE(s, seed=seed)  # torch.manual_seed(seed) + the reference's init draws: the global stream is now aligned
+    vae.strict_rng = True
+    got = []
+    vae._ensure_capacity(256 * 2 ** len(batchsteps))
+    vae._reset_optimizer()
+    loader = dl
+    for epoch in range(nepochs):
+        loader = vae.trainepoch(loader, epoch, None, batchsteps)
+        lo = vae._last_epoch_losses
+        got.append((lo[0], lo[2], lo[1], lo[3], lo[4]))
+    got = np.array(got)
+    want = g["traj"]
+    rel = np.abs(got - want) / np.abs(want)
+    assert rel[:, 0].max() < 5e-4, (got[:, 0], want[:, 0])
+    assert rel.max() < 5e-3, rel.max(0)
+    latent = vae.encode(dl)[:512]
+    err = np.abs(latent - g["latent_head"]).max()
+    assert err < 2e-2 * np.abs(g["latent_head"]).max(), err
+    assert abs(float(vae.state_dict()["mu.weight"].norm()) - float(g["mu_weight_norm"])) < 1e-3 * float(g["mu_weight_norm"])

@@ -150,6 +150,33 @@ def make_dataloader(
     )
 
 
+def reference_epoch_noise(n_seq: int, batch: int, drop_last: bool, nhiddens, nlatent: int, dropout: float):
+    """Yield (batch_idx, eps, keeps) for one epoch, consuming torch's global CPU generator exactly as one epoch of
+    the reference does: ``iter(DataLoader)`` draws the worker base seed and then the RandomSampler seed
+    (torch/utils/data/dataloader.py ``_BaseDataLoaderIter.__init__``, sampler.py ``RandomSampler.__iter__``), the
+    permutation comes from a private generator seeded with the latter, and every step draws its dropout masks
+    (``empty_like(h).bernoulli_(1 - p)``, one per hidden block in forward order) and ``randn(B, nlatent)`` between
+    the encoder and the decoder (vamb/encode.py:264, 277, 292).  Pinned against the live reference by
+    tests/test_oracle_vs_reference.py."""
+    _torch.empty((), dtype=_torch.int64).random_()
+    sampler_seed = int(_torch.empty((), dtype=_torch.int64).random_().item())
+    g = _torch.Generator()
+    g.manual_seed(sampler_seed)
+    perm = _torch.randperm(n_seq, generator=g)
+    nb = n_seq // batch if drop_last else (n_seq + batch - 1) // batch
+    p = float(dropout)
+    for i in range(nb):
+        idx = perm[i * batch:(i + 1) * batch]
+        b = len(idx)
+        keeps = []
+        for h in nhiddens:
+            keeps.append(_torch.empty(b, h).bernoulli_(1 - p) if p > 0 else None)
+        eps = _torch.randn(b, nlatent)
+        for h in list(nhiddens)[::-1]:
+            keeps.append(_torch.empty(b, h).bernoulli_(1 - p) if p > 0 else None)
+        yield idx, eps, keeps
+
+
 # ---------------------------------------------------------------------- ctypes mirrors
 _MAXL = 10
 
@@ -305,6 +332,11 @@ class VAE(_nn.Module):
         self.dropout = dropout
         self._seed = int(seed)
         self._bmax = _MAX_BATCH  # rows of the activation workspaces; grown on demand by _ensure_capacity
+        # Parity mode: draw batch order, dropout masks and reparameterisation noise from torch's GLOBAL CPU generator
+        # with the reference's own calls in the reference's order (vamb/encode.py:210, 264, 277, 292 + the two draws of
+        # iter(DataLoader)) and inject them, so that a training run follows the CPU reference's trajectory for the same
+        # ``seed``.  Slow (host RNG + H2D per step); the default draws everything on the device (Philox).
+        self.strict_rng = _os.environ.get("VAMB_B200_STRICT_RNG", "0") not in ("", "0")
 
         self.encoderlayers = _nn.ModuleList()
         self.encodernorms = _nn.ModuleList()
@@ -733,6 +765,20 @@ class VAE(_nn.Module):
             return
         _par.average_running_stats_(list(self.encodernorms) + list(self.decodernorms), self._dp_group)
 
+    def _run_epoch_strict(self, n_seq: int, batch: int, drop_last: bool) -> None:
+        dev = self._arena.device
+        for idx, eps, keeps in reference_epoch_noise(n_seq, batch, drop_last, self.nhiddens, self.nlatent, self.dropout):
+            hold = [idx.to(dev), eps.to(dev).contiguous()]
+            inj = _VkInject()
+            inj.batch_idx, inj.eps = hold[0].data_ptr(), hold[1].data_ptr()
+            for j, k in zip(self._hidden_layer_ids(), keeps):
+                if k is not None:
+                    t = k.to(_torch.uint8).to(dev).contiguous()
+                    hold.append(t)
+                    inj.keep[j] = t.data_ptr()
+            _lib.check(_L.vk_vae_train_step(_ct.byref(self._net), len(idx), _ct.byref(inj), self._stream()))
+            _torch.cuda.current_stream().synchronize()  # `hold` must outlive the step
+
     def trainepoch(self, data_loader: _DataLoader, epoch: int, optimizer, batchsteps: list[int]) -> _DataLoader:
         """One pass over the data (vamb/encode.py:359-440).  ``optimizer`` is accepted for
         signature compatibility; the D-Adaptation state lives on the device."""
@@ -762,7 +808,10 @@ class VAE(_nn.Module):
         so = _VkCtl.step.offset // 8
         self._ctl_i64[_VkCtl.epoch_step0.offset // 8] = self._ctl_i64[so]
         self._reset_loss_sums()
-        self._run_steps(batch, nsteps)
+        if self.strict_rng and self._dp_group is None:
+            self._run_epoch_strict(n_seq, batch, bool(data_loader.drop_last))
+        else:
+            self._run_steps(batch, nsteps)
         sums, n = self._read_loss_sums()  # the only host synchronisation of the epoch
         n = max(n, 1)
         logger.info(
