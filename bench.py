@@ -178,7 +178,7 @@ def ncu_traffic(kernel: str):
         with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as fh:
             t = json.load(fh)
         for k, v in t.items():
-            if kernel.startswith(k):
+            if kernel.startswith(k) or k.startswith(kernel):
                 return v
     except Exception:
         pass
