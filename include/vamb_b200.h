@@ -142,6 +142,12 @@ int vk_compact_rows_sync(const float *matrix, const float *lengths, const int32_
 int vk_distances(const float *matrix, int64_t n, int d, int64_t medoid_row, float *dists, void *stream);
 
 
+/* The step before the path: vamb/parsecontigs.py:141-150 Composition._project -- per contig the 256
+ * four-mer counts become frequencies (row / rowsum; all-zero rows stay zero), shifted by -1/256 and multiplied by the
+ * 256 x n_out projection kernel (n_out = 103; the caller passes the reference's kernel matrix, row-major [256][n_out]).
+ * counts: device [n, 256] fp32 (not modified, unlike the reference's in-place version); out: device [n, n_out]. */
+int vk_tnf_project(const float *counts, const float *kernel, float *out, int64_t n, int n_out, void *stream);
+
 /* ------------------------------------------------------------------ native clusterer driver
  * The decision logic of vamb/cluster.py (ClusterGenerator.__next__ :298-316 and everything it
  * calls) in C++ on top of the kernels above: one foreign call per emitted cluster.  All device and

@@ -71,6 +71,7 @@ _SIGNATURES = {
     "vk_distances": [_p, c_int64, c_int, c_int64, _p, _p],
     "vk_tc_gemm_test": [_p, c_int, _p, _p, c_int, _p, c_int, c_int, c_int, c_int, c_int, c_int, _p],
     "vk_lane_major_index": [c_int, c_int, c_int],
+    "vk_tnf_project": [_p, _p, _p, c_int64, c_int, _p],
 }
 
 
