@@ -14,7 +14,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader | tee 
 # poisons only its own CUDA context
 leg r02_pt_cluster 400 python -m pytest tests/test_cluster_gpu.py tests/test_c2_scale_gpu.py -m gpu -q
 leg r02_pt_vae 500 python -m pytest tests/test_vae_gpu.py -m gpu -q -k "not tma and not flush"
-leg r02_pt_tc 300 python -m pytest tests/test_tc_gpu.py -m gpu -q -k "not tma and not flush"
+leg r02_pt_tc 300 python -m pytest tests/test_tc_gpu.py tests/test_inputs.py -m gpu -q -k "not tma and not flush"
 leg r02_bench 760 bash -c 'python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02_bench.json'
 leg r02_ref 300 bash -c 'python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02_ref.json'
 leg r02_pt_traj 400 python -m pytest tests/test_trajectory_gpu.py -m gpu -q
