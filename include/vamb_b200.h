@@ -211,8 +211,8 @@ int vk_cluster_next_block(void *handle, vk_cluster_block *blk);
 int vk_cluster_next(void *handle, vk_cluster_result *out); /* 0 = cluster, 2 = exhausted, 1 = error */
 int vk_cluster_stats(void *handle, int64_t *out8);         /* probes, evals, packs, physical rows, live buffer set (0/1),
                                                               successes, attempts in the window, order_index */
-int vk_cluster_timing(void *handle, double *out7);         /* host seconds in probes, evaluations, selections, packs, total;
-                                                              medoid moves without a scan, re-basing probes */
+int vk_cluster_timing(void *handle, double *out8);         /* host seconds in probes, evaluations, selections, packs, total;
+                                                              medoid moves without a scan, re-basing probes, sum of neighbour-list sizes over evaluations */
 void vk_cluster_destroy(void *handle);
 int64_t vk_cluster_sizeof(int which);                      /* 0: vk_cluster_config, 1: vk_cluster_result, 2: vk_cluster_block */
 /* CPython-compatible random.Random(seed).sample(range(n_i), min(n_i, k)) for each i: writes k slots per

@@ -105,11 +105,10 @@ def test_gradients_match_oracle_default_network(tc, B, S):
     losses = vae._step_injected(dl.dataset.tensors, idx.numpy(), eps.numpy(), [k.numpy() for k in keeps], optimize=False)
     assert np.allclose(losses, lo, rtol=2e-5, atol=1e-7)
     got = vae._grad_dict()
-    # Intermediates (P, dH, BN statistics, dMU) match an fp64 oracle to 1e-6 at every batch size
-    # (tools/vae_bwd_diag.py); the weight gradients are B-term sums of products of random sign, so their
-    # relative error grows with the length of the fp32 accumulation chain: 3e-5 up to B = 256, and up to
-    # ~1e-3 on the most cancelling tensors at B = 4096 (tensor-core accumulators truncate).
-    tol = 3e-5 if B <= 256 else (2e-4 if B <= 1024 else (3e-3 if B <= 4096 else 6e-3))
+    # Measured against an fp64 evaluation of the same step (tools/grad_error_fp64.py, profiles/r02_grad_error_fp64.txt):
+    # fp32 CPU oracle 0.9-1.7e-6, CUDA 3xTF32 path 7.5-8.8e-6 (worst tensor, B = 256 ... 4096; 7.0-7.3e-6 with the
+    # 128-row wgrad flush), CUDA fp32 path 1.3-1.9e-6 -- the tensor-core path is fp32-grade at every batch size.
+    tol = 3e-5 if B <= 4096 else 6e-5
     for k, gref in grads.items():
         assert rel(got[k].cpu().numpy(), gref.numpy()) < tol, k
 

@@ -476,11 +476,12 @@ class ClusterGenerator:
         "Host seconds the native driver spent per call kind so far (diagnostics / bench)."
         from . import _cluster_native as _cn
 
-        out = (_lib.ctypes.c_double * 7)()
+        out = (_lib.ctypes.c_double * 8)()
         if self._native is None:
             return {}
         _cn._L.vk_cluster_timing(self._native, out)
-        return dict(zip(("probe", "eval", "select", "pack", "total", "lazy_moves", "rebases"), (float(x) for x in out)))
+        return dict(zip(("probe", "eval", "select", "pack", "total", "lazy_moves", "rebases", "sum_nl_per_eval"),
+                        (float(x) for x in out)))
 
     # ------------------------------------------------------------------ API extras
     @property

@@ -689,7 +689,13 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
     __syncthreads();
 
     const float rad = 0.05f;
-    if (blockIdx.x == 0) {  // d(candidate, base) in the same arithmetic as every other distance
+    // d(candidate, base) in the same arithmetic as every other distance -- every block computes all of them (n_cand dot
+    // products): block 0 reports them, and each gives the candidate's REACH: a row within 0.05 of candidate k lies within
+    // angle(d_k) + acos(0.9) of the base, i.e. at a base distance of at most
+    //     reach_k = 0.5 * (1 - ((1 - 2 d_k) * 0.9 - sqrt(1 - (1 - 2 d_k)^2) * sqrt(0.19)))      (+ 1e-4 of slack).
+    // Neighbour-list entries beyond max_k reach_k (and beyond `prune_radius`) cannot matter and are not gathered.
+    __shared__ float s_reach[VK_MAX_CAND];
+    {
         const float *x = matrix + (int64_t)base_row * d;
         float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (fast) xv = ldg_stream4(x + 4 * lane8);
@@ -700,14 +706,24 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
             if (lane8 == 0) {
                 float dd = __fsub_rn(0.5f, acc);
                 if (cand.rows[k] == base_row) dd = 0.0f;
-                out[3 * VK_MAX_CAND + k] = (u64)__float_as_uint(dd);
+                if (blockIdx.x == 0) out[3 * VK_MAX_CAND + k] = (u64)__float_as_uint(dd);
+                const float ca = 1.0f - 2.0f * fmaxf(dd, 0.0f);
+                const float sa = sqrtf(fmaxf(1.0f - ca * ca, 0.0f));
+                const float cs = ca * 0.9f - sa * 0.43588990f;  // cos(angle(d_k) + acos(0.9))
+                s_reach[k] = (ca <= -0.9f) ? 1e30f : 0.5f * (1.0f - cs) + 1e-4f;  // beyond 180 degrees: everything
             }
         }
     }
+    __syncthreads();
+    // the bound is geometry on unit-norm rows: an infinite prune_radius (rows not verified as normalised) switches it off
+    const bool geo = prune_radius < 1e29f;
+    float reach = 0.0f;
+    for (int k = 0; k < n_cand; ++k) reach = fmaxf(reach, s_reach[k]);
+    const float visit_radius = geo ? fminf(prune_radius, reach) : prune_radius;
     const int groups_total = gridDim.x * (EC_THREADS / 8);
     for (int j = blockIdx.x * (EC_THREADS / 8) + g; j < n_nl; j += groups_total) {
         const float dj = nl_dists[j];
-        if (!(dj <= prune_radius)) continue;  // uniform within the 8-lane group
+        if (!(dj <= visit_radius)) continue;  // uniform within the 8-lane group
         const int row = nl_rows[j];
         const float *x = matrix + (int64_t)row * d;
         float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -715,6 +731,7 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
         u64 lenq = 0ull;
         if (lane8 == 0) lenq = __float2ull_rz(__ldg(lengths + row));
         for (int k = 0; k < n_cand; ++k) {
+            if (geo && !(dj <= s_reach[k])) continue;  // this row cannot be within 0.05 of candidate k
             const float *q = s_qs + k * dpad;
             float acc;
             if (fast) acc = chain4(xv, *reinterpret_cast<const float4 *>(q + 4 * lane8));

@@ -129,7 +129,7 @@ struct State {
     // lazy medoid moves (vk_eval_candidates_lists): device accumulators, pinned results and id lists
     uint64_t *cand2_dev = nullptr, *cand2_pin = nullptr;
     int32_t *within_pin = nullptr;
-    int64_t n_moves_lazy = 0, n_rebases = 0;
+    int64_t n_moves_lazy = 0, n_rebases = 0, sum_nnl = 0;  // sum_nnl: neighbour-list sizes over all candidate evaluations
     bool lazy_enabled = true;  // VAMB_B200_CLUSTER_LAZY=0: a full scan per move, as round 1 (same clusters)
     std::vector<int64_t> members;
     int64_t n_probes, n_evals, n_packs;
@@ -292,6 +292,7 @@ int do_eval_lists(State &st, const Probe &base, float prune, const std::vector<i
     const vk_cluster_config &c = st.c;
     const int n = (int)rows.size();
     ++st.n_evals;
+    st.sum_nnl += base.n_nl;
     if (vk_eval_candidates_lists(st.M(), st.LEN(), c.d, c.nl_rows, c.nl_dists, base.n_nl, prune, rows.data(), n, base.medoid,
                                  st.cand2_dev, st.cand2_pin, st.within_pin, WITHIN_CAP, st.tickets_dev + 1,
                                  st.flags_pin + 1, ++st.seq, c.stream))
@@ -518,10 +519,10 @@ extern "C" int vk_cluster_stats(void *handle, int64_t *out8) {
 
 // host wall-clock seconds spent so far in: probes, candidate evaluations, member selections, packs, all of vk_cluster_next;
 // then the number of medoid moves made without a scan and the number of re-basing probes
-extern "C" int vk_cluster_timing(void *handle, double *out5 /* 7 doubles */) {
+extern "C" int vk_cluster_timing(void *handle, double *out5 /* 8 doubles */) {
     State *st = static_cast<State *>(handle);
     out5[0] = st->t_probe; out5[1] = st->t_eval; out5[2] = st->t_select; out5[3] = st->t_pack; out5[4] = st->t_total;
-    out5[5] = (double)st->n_moves_lazy; out5[6] = (double)st->n_rebases;
+    out5[5] = (double)st->n_moves_lazy; out5[6] = (double)st->n_rebases; out5[7] = (double)st->sum_nnl;
     return 0;
 }
 
