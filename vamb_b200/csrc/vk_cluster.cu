@@ -142,9 +142,21 @@ struct ProbeAcc {
 // no block barrier) and flushed with one global reservation per ~48 entries.
 constexpr int PB_WBUF = 64;  // staged entries per warp (<= 16 appended per iteration)
 
-// R = independent rows (float4 loads) in flight per lane and per buffer (two buffers for D = 32); BPS = resident blocks
-// per SM the register budget is held to.
-template <int DFIX, int R, int BPS>
+// R = independent rows (float4 loads) in flight per lane and per buffer; BPS = resident blocks per SM the register
+// budget is held to.  RING = 0: two register buffers per lane (the chunk being processed and the next one).
+// RING > 0 (D = 32): each LANE owns a private queue of RING chunks in shared memory filled by cp.async (LDGSTS, 16 bytes
+// per row and lane) -- a lane only ever reads back what it copied itself, so there is no barrier of any kind in the loop
+// (cp.async.wait_group is per thread) and RING x R x 16 bytes per lane are in flight instead of 2 x R x 16: the loop at
+// N = 1M is bound by memory latency per iteration, not by bandwidth (profiles/r02_probe_sweep_v1.txt: 24 us of the
+// 44 us do not scale with N).
+__device__ __forceinline__ void probe_cp_async16(uint32_t saddr, const void *gptr) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void probe_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void probe_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int DFIX, int R, int BPS, int RING>
 __global__ void __launch_bounds__(PB_THREADS, BPS)
 probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths,
              const uint8_t *__restrict__ kept, int64_t n, int d_rt, int64_t mrow, float nl_radius,
@@ -223,14 +235,41 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
             if (row < n32) v[k] = ldg_stream4(matrix + (int64_t)row * 32 + 4 * lane8);
         }
     };
-    if (DFIX == 32 && (int)blockIdx.x < n_chunks) load_chunk(blockIdx.x, vnext);
+    // RING: slot s of this lane = ring[(s * PB_R + k) * PB_THREADS + tid] (consecutive lanes -> consecutive 16 bytes)
+    extern __shared__ __align__(16) float4 s_ring[];
+    auto issue_chunk = [&](int c, int slot) {
+        if (c < n_chunks) {
+#pragma unroll
+            for (int k = 0; k < PB_R; ++k) {
+                const int row = c * CHUNK + k * PB_GROUPS + g;
+                if (row < n32)
+                    probe_cp_async16((uint32_t)__cvta_generic_to_shared(&s_ring[(slot * PB_R + k) * PB_THREADS + tid]),
+                                     matrix + (int64_t)row * 32 + 4 * lane8);
+            }
+        }
+        probe_cp_commit();  // one group per slot, possibly empty: the wait below counts groups
+    };
+    if (DFIX == 32 && RING > 0) {
+#pragma unroll
+        for (int s0 = 0; s0 < RING - 1; ++s0) issue_chunk((int)blockIdx.x + s0 * (int)gridDim.x, s0);
+    } else if (DFIX == 32 && (int)blockIdx.x < n_chunks) {
+        load_chunk(blockIdx.x, vnext);
+    }
+    int ring_it = 0;
 #pragma unroll 1
     for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
         float acc[PB_R];
         int rows[PB_R];
 #pragma unroll
         for (int k = 0; k < PB_R; ++k) rows[k] = c * CHUNK + k * PB_GROUPS + g;
-        if (DFIX == 32) {
+        if (DFIX == 32 && RING > 0) {
+            const int slot = ring_it % RING;
+            issue_chunk(c + (RING - 1) * (int)gridDim.x, (ring_it + RING - 1) % RING);
+            probe_cp_wait<RING - 1>();  // all but the newest RING - 1 groups have landed: this chunk is in
+            ++ring_it;
+#pragma unroll
+            for (int k = 0; k < PB_R; ++k) acc[k] = chain4(s_ring[(slot * PB_R + k) * PB_THREADS + tid], qv);
+        } else if (DFIX == 32) {
             float4 v[PB_R];
 #pragma unroll
             for (int k = 0; k < PB_R; ++k) v[k] = vnext[k];
@@ -337,6 +376,10 @@ static int probe_r() {
     static const int r = probe_env("VK_PROBE_R", 4, 4, 8) >= 8 ? 8 : 4;
     return r;
 }
+static int probe_ring() {  // VK_PROBE_RING = 0 (registers) | 4 | 6 | 8 | 12 chunks queued per lane in shared memory
+    static const int g = probe_env("VK_PROBE_RING", 0, 0, 12);
+    return g;
+}
 static int probe_bps() {
     static const int b = probe_env("VK_PROBE_BPS", 4, 1, 8);
     return b;
@@ -371,16 +414,30 @@ static int probe_launch(const float *matrix, const float *lengths, const uint8_t
     const int r = probe_r();
     const int n_chunks = (int)((n + PB_GROUPS * r - 1) / (PB_GROUPS * r));
     const int grid = probe_grid(n_chunks);
-#define VK_PROBE_LAUNCH(DF, RR, BB)                                                                                  \
-    probe_kernel<DF, RR, BB><<<grid, PB_THREADS, 0, s>>>(matrix, lengths, kept, n, d, medoid_row, nl_radius, edges, hdr, \
-                                                         within_overflow, nl_rows, nl_dists, n_chunks, hdr_mapped,       \
-                                                         done_ticket, done_flag, seq)
+#define VK_PROBE_LAUNCH(DF, RR, BB, RG)                                                                              \
+    do {                                                                                                             \
+        const size_t ring_bytes = (size_t)(RG) * (RR) * PB_THREADS * sizeof(float4);                                  \
+        static bool attr_done = false;                                                                               \
+        if (ring_bytes > 40 * 1024 && !attr_done) {                                                                  \
+            VK_CUDA(cudaFuncSetAttribute(probe_kernel<DF, RR, BB, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                         (int)ring_bytes));                                                          \
+            attr_done = true;                                                                                        \
+        }                                                                                                            \
+        probe_kernel<DF, RR, BB, RG><<<grid, PB_THREADS, ring_bytes, s>>>(                                            \
+            matrix, lengths, kept, n, d, medoid_row, nl_radius, edges, hdr, within_overflow, nl_rows, nl_dists,       \
+            n_chunks, hdr_mapped, done_ticket, done_flag, seq);                                                      \
+    } while (0)
     if (d == 32) {
-        if (r == 8) VK_PROBE_LAUNCH(32, 8, 3);
-        else if (probe_bps() > 4) VK_PROBE_LAUNCH(32, 4, 6);
-        else VK_PROBE_LAUNCH(32, 4, 4);
+        const int ring = probe_ring();
+        if (ring == 4) VK_PROBE_LAUNCH(32, 4, 3, 4);        // 64 KB ring: 3 blocks / SM
+        else if (ring == 6) VK_PROBE_LAUNCH(32, 4, 2, 6);   // 96 KB ring: 2 blocks / SM
+        else if (ring == 8) VK_PROBE_LAUNCH(32, 4, 1, 8);   // 128 KB ring: 1 block / SM
+        else if (ring == 12) VK_PROBE_LAUNCH(32, 4, 1, 12); // 192 KB ring: 1 block / SM
+        else if (r == 8) VK_PROBE_LAUNCH(32, 8, 3, 0);
+        else if (probe_bps() > 4) VK_PROBE_LAUNCH(32, 4, 6, 0);
+        else VK_PROBE_LAUNCH(32, 4, 4, 0);
     } else {
-        VK_PROBE_LAUNCH(0, 4, 4);
+        VK_PROBE_LAUNCH(0, 4, 4, 0);
     }
 #undef VK_PROBE_LAUNCH
     VK_LAUNCH_CHECK();
