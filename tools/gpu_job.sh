@@ -24,6 +24,8 @@ d = json.load(open("gpurun_out/r02b_bench.json"))
 print({k: d[k] for k in ("value", "phases_s", "cluster_host_seconds", "clusters", "final_loss")})
 print(d["e2e"]); print(d["roofline"]["achieved"], d["roofline"]["frac"], d["roofline_cluster"]["achieved"], d["roofline_cluster"]["frac"])
 PY
+leg r02b_pt_cluster_ring6 400 env VK_PROBE_RING=6 python -m pytest tests/test_cluster_gpu.py -m gpu -q
+leg r02b_pt_cluster_ring12 400 env VK_PROBE_RING=12 python -m pytest tests/test_cluster_gpu.py -m gpu -q -k 'golden or probe'
 : > gpurun_out/r02b_probe_sweep.txt
 for ring in 0 4 6 8 12; do VK_PROBE_RING=$ring timeout 120 python tools/probe_speed.py 2>&1 | grep "N=" | sed "s/^/RING=$ring /" >> gpurun_out/r02b_probe_sweep.txt; done
 cat gpurun_out/r02b_probe_sweep.txt
