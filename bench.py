@@ -172,17 +172,23 @@ def measured_peaks():
         return hbm, bf16 / 2.0, f"half of the {which} bf16 dense sustained figure (no TF32 measurement on file)", which
 
 
-def ncu_traffic(kernel: str):
-    """dram bytes (read + write) per launch of `kernel` from the committed ncu capture summary, or None."""
+def ncu_record(kernel: str):
+    """The committed ncu capture of `kernel` (tools/ncu_extract.py -> profiles/r02_ncu_traffic.json): dram bytes per
+    launch, tensor-pipe activity, duration under the profiler -- or None when no capture is on file."""
     try:
         with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as fh:
             t = json.load(fh)
         for k, v in t.items():
             if kernel.startswith(k) or k.startswith(kernel):
-                return v
+                return v if isinstance(v, dict) else {"dram_bytes": v}
     except Exception:
         pass
     return None
+
+
+def ncu_traffic(kernel: str):
+    r = ncu_record(kernel)
+    return None if r is None else r.get("dram_bytes")
 
 
 # ---------------------------------------------------------------------------------- the GPU pass
@@ -529,6 +535,7 @@ def main():
         roof = {"bound": "tensor", "kernel": best["kernel"], "achieved": best["tflops"], "peak": tf_peak,
                 "unit": "TFLOP/s", "frac": best["tflops"] / tf_peak, "traffic": ncu_traffic(best["kernel"].split("[")[0]),
                 "peak_source": tf_label, "time_share": share, "ms_per_launch": best["ms"],
+                "ncu": ncu_record(best["kernel"].split("[")[0]),  # committed capture: tensor-pipe % / dram bytes of this kernel
                 "note": "algorithmic FLOP of the launch (wgrad + dgrad, SURVEY 8d) / CUDA-event time of the launch; the tensor "
                         "pipe executes 3x these FLOP (3xTF32 error compensation)"}
         roof_cluster = None

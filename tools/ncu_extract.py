@@ -66,7 +66,9 @@ def main():
         lines.append(f"| `{k}` | {len(ds)} | {int(ds[0].get('grid', 0))} x {int(ds[0].get('block', 0))} | {int(ds[0].get('regs', 0))} | "
                      f"{min(dur):.1f} / {med(dur):.1f} | {rd / 1e6:.2f} / {wr / 1e6:.2f} | {gbs:.0f} | "
                      f"{med([d.get('dram_pct', 0.0) for d in ds]):.0f} | {tens:.1f} | {med([d.get('warps_pct', 0.0) for d in ds]):.0f} |")
-        traffic[k.split("<")[0]] = rd + wr
+        traffic[k.split("<")[0]] = {"dram_bytes": rd + wr, "dram_read": rd, "dram_write": wr, "duration_us_median": med(dur),
+                                    "tensor_pipe_pct_max": tens, "launches_captured": len(ds),
+                                    "dram_pct_median": med([d.get("dram_pct", 0.0) for d in ds])}
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json"), "w") as fh:
         json.dump(traffic, fh, indent=1)
