@@ -302,7 +302,8 @@ def run_pass(ctx: Ctx, dl, lengths_cluster, nepochs, k_steps, resident: bool, ma
         base = 2 * nl + 3
         if not (tcm and b >= tcm):
             return base
-        return base + (3 if vae._net.staging == 0 else 2 * nl + 1)
+        # tensor-core path: the first layer's gather draws the batch (no batch_rows launch), + weight staging + loss fold
+        return base - 1 + (3 if vae._net.staging == 0 else 2 * nl + 1)
 
     launches = (sum(s * e * per_step(b) for b, s, e in sched)
                 + ((n_local + vae._net.bmax - 1) // vae._net.bmax) * (nl + 2)

@@ -279,7 +279,7 @@ typedef struct vk_vae {
     float *params, *grads, *exp_avg, *exp_avg_sq, *s; /* flat arenas, module.parameters() order */
     float *z;                           /* [bmax, nlatent] mu + eps                            */
     int64_t *batch_rows;                /* [bmax] dataset row of every batch row               */
-    double *opt_part;                   /* [2 * ceil(n_params / 1024) + bmax / 256 + 8] optimiser block partials, then the batch-weight partials */
+    double *opt_part;                   /* [2 * ceil(n_params / 1024) + bmax / 32 + 8] optimiser block partials, then the batch-weight partials */
     double *loss_part;                  /* [4 * ceil(bmax / 32) * 4 + 64] loss block partials (4 per 8 rows) */
     vk_vae_ctl *ctl;
     vk_vae_layer layers[VK_VAE_MAX_LAYERS];

@@ -94,6 +94,22 @@ __device__ __forceinline__ bool last_block_done(int32_t *ticket, int total) {
     return s_last != 0;
 }
 
+// Dataset row of batch position b.  mode 0: host-injected indices; 1: epoch permutation (Feistel network keyed by
+// seed / epoch, position = step within the epoch * B + b); 2: contiguous [row0, row0 + B).
+__device__ __forceinline__ int64_t batch_row_index(int mode, int b, int B, const int64_t *batch_idx, const vk_vae_ctl *ctl,
+                                                   int64_t n_rows, int64_t row0, int steps_per_epoch) {
+    if (mode == 0) return batch_idx[b];
+    if (mode == 1) {
+        int half_bits = 1;
+        while ((1ull << (2 * half_bits)) < (uint64_t)n_rows) ++half_bits;
+        const uint64_t key = mix64(ctl->seed ^ (0x5851F42D4C957F2Dull * (uint64_t)(ctl->epoch + 1)));
+        int64_t t = ctl->step - ctl->epoch_step0;
+        if (steps_per_epoch > 0) t %= steps_per_epoch;
+        return (int64_t)feistel_perm((uint64_t)(t * (int64_t)B + b), (uint64_t)n_rows, half_bits, key);
+    }
+    return row0 + b;
+}
+
 // One thread per batch row (grid = ceil(B / 256) blocks); the batch-mean weight is folded by the last
 // block from per-block partial sums in block order (fixed order -> reproducible).
 __global__ void __launch_bounds__(256)
@@ -106,16 +122,7 @@ batch_rows_kernel(int64_t *batch_rows, const int64_t *batch_idx, const float *we
     const int b = blockIdx.x * 256 + tid;
     double acc = 0.0;
     if (b < B) {
-        int64_t r;
-        if (mode == 0) r = batch_idx[b];
-        else if (mode == 1) {
-            int half_bits = 1;
-            while ((1ull << (2 * half_bits)) < (uint64_t)n_rows) ++half_bits;
-            const uint64_t key = mix64(ctl->seed ^ (0x5851F42D4C957F2Dull * (uint64_t)(ctl->epoch + 1)));
-            int64_t t = ctl->step - ctl->epoch_step0;
-            if (steps_per_epoch > 0) t %= steps_per_epoch;
-            r = (int64_t)feistel_perm((uint64_t)(t * (int64_t)B + b), (uint64_t)n_rows, half_bits, key);
-        } else r = row0 + b;
+        const int64_t r = batch_row_index(mode, b, B, batch_idx, ctl, n_rows, row0, steps_per_epoch);
         batch_rows[b] = r;
         acc = (double)weights[r];
     }
@@ -1202,11 +1209,18 @@ struct PrepArgs {
     const float *gamma, *beta, *mean_in, *rstd_in;
     float *bn_mean, *bn_rstd, *bn_a, *bn_c, *running_mean, *running_var; int64_t *nbt;
     float *g_gamma, *g_beta, *m1, *m2, *bA, *bB, *bC; float inv_keep;
+    // mode 3 with rows_mode >= 0: the gather draws the batch itself (what batch_rows_kernel did in a launch of its own):
+    // every block computes the dataset rows of its 32 batch positions; the first column of blocks also publishes them
+    // (batch_rows, read by the loss kernel) and folds the batch-mean weight into ctl->wbar.
+    int rows_mode; const int64_t *inject_idx; const float *weights; vk_vae_ctl *ctl; int64_t n_rows_total, row0;
+    int steps_per_epoch; int64_t *rows_out; double *wpart; int ticket_id;
 };
 
 // k0/k1/k2: the per-column constants of column c (from shared memory)
-__device__ __forceinline__ float prep_value(const PrepArgs &a, int r, int c, float k0, float k1, float k2) {
+__device__ __forceinline__ float prep_value(const PrepArgs &a, int r, int c, float k0, float k1, float k2,
+                                            const int64_t *rows_local = nullptr, int r_local = 0) {
     if (r >= a.rows || c >= a.cols) return 0.0f;
+    if (rows_local) return __ldg(a.data + rows_local[r_local] * (int64_t)a.data_ld + c);
     switch (a.mode) {
         case 0: return __ldg(a.src + (int64_t)r * a.ld_src + c);
         case 1: return __fmaf_rn(__ldg(a.src + (int64_t)r * a.ld_src + c), k0, k1);
@@ -1294,13 +1308,14 @@ __device__ __forceinline__ void prep_consts(const PrepArgs &a, int c0, bool firs
     __syncthreads();
 }
 
-__device__ __forceinline__ void prep_tile(const PrepArgs &a, int r0, int c0, float (*tile)[33], float (*s_k)[32]) {
+__device__ __forceinline__ void prep_tile(const PrepArgs &a, int r0, int c0, float (*tile)[33], float (*s_k)[32],
+                                          const int64_t *rows_local = nullptr) {
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads
     const float k0 = s_k[0][tx], k1 = s_k[1][tx], k2 = s_k[2][tx];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int r = r0 + ty * 4 + i, c = c0 + tx;
-        float v = prep_value(a, r, c, k0, k1, k2);
+        float v = prep_value(a, r, c, k0, k1, k2, rows_local, ty * 4 + i);
         if (a.hi && !a.hi_lane && r < a.rows_w && c < a.cols_w) {
             a.hi[(int64_t)r * a.ld + c] = v;
             if (a.lo) a.lo[(int64_t)r * a.ld + c] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
@@ -1342,6 +1357,33 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a) {
     __shared__ float s_k[3][32];
     __shared__ double s_f[2][8][32];
     if (a.mode == 1 || a.mode == 2) prep_consts(a, blockIdx.x * 32, blockIdx.y == 0, s_k, s_f);
+    if (a.mode == 3 && a.rows_mode >= 0) {
+        // the batch is drawn here: rows of this block's 32 batch positions (uniform branch for the whole block)
+        __shared__ int64_t s_rows[32];
+        const int tid = threadIdx.x, b = blockIdx.y * 32 + tid;
+        if (tid < 32) {
+            const int64_t r = b < a.rows ? batch_row_index(a.rows_mode, b, a.rows, a.inject_idx, a.ctl, a.n_rows_total, a.row0,
+                                                           a.steps_per_epoch) : 0;
+            s_rows[tid] = r;
+            if (blockIdx.x == 0) {
+                if (b < a.rows) a.rows_out[b] = r;
+                double w = b < a.rows ? (double)a.weights[r] : 0.0;
+                for (int o = 16; o; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+                if (tid == 0) a.wpart[blockIdx.y] = w;
+            }
+        }
+        __syncthreads();
+        prep_tile(a, blockIdx.y * 32, blockIdx.x * 32, tile, s_k, s_rows);
+        tk_end(tk);
+        if (blockIdx.x != 0) return;
+        if (!last_block_done(&a.ctl->tickets[a.ticket_id], gridDim.y)) return;
+        if (tid == 0) {  // batch-mean weight: the per-32-row sums in block order (fixed order -> reproducible)
+            double tot = 0.0;
+            for (unsigned i = 0; i < gridDim.y; ++i) tot += __ldcg(a.wpart + i);
+            a.ctl->wbar = tot / (double)a.rows;
+        }
+        return;
+    }
     prep_tile(a, blockIdx.y * 32, blockIdx.x * 32, tile, s_k);
     tk_end(tk);
 }
@@ -1598,15 +1640,33 @@ static int launch_prep(const PrepArgs &a, cudaStream_t s) {
 }
 
 // stage the input of layer j (A of its forward GEMM; its transpose is B of its wgrad)
-static int launch_prep_input(const vk_vae *net, int j, int B, int training, cudaStream_t s) {
+// How the batch of the current step is drawn (consumed by the gather of layer 0 on the tensor-core path, which replaces
+// the batch_rows launch): mode < 0 = batch_rows already holds the rows.
+struct BatchDraw {
+    int mode = -1;
+    int64_t row0 = 0;
+    const vk_vae_inject *inj = nullptr;
+};
+
+static int launch_prep_input(const vk_vae *net, int j, int B, int training, cudaStream_t s, const BatchDraw *draw = nullptr) {
     const vk_vae_layer &L = net->layers[j];
     PrepArgs a;
     memset(&a, 0, sizeof(a));
+    a.rows_mode = -1;
     a.rows = B; a.cols = L.k_in; a.rows_w = r128(B); a.cols_w = L.k_in;
     a.hi = L.xop_hi; a.lo = nullptr; a.ld = r32(L.k_in); a.hi_lane = 1;  // A of the forward GEMM
     if (training) { a.hiT = L.xt_hi; a.loT = nullptr; a.ldT = net->bmax; a.ones_row = 1; }
     if (L.in_kind == VK_IN_DATA) {
         a.mode = 3; a.data = net->data; a.rows_idx = net->batch_rows; a.data_ld = net->data_ld;
+        if (draw && draw->mode >= 0) {
+            const int64_t n = net->n_rows;
+            a.rows_mode = draw->mode; a.inject_idx = draw->inj ? draw->inj->batch_idx : nullptr;
+            a.weights = net->weights; a.ctl = net->ctl; a.n_rows_total = n; a.row0 = draw->row0;
+            a.steps_per_epoch = n > B ? (int)(n / B) : 1;
+            a.rows_out = net->batch_rows;
+            a.wpart = net->opt_part + 2 * ((net->n_params + OPT_ELEMS - 1) / OPT_ELEMS);  // bmax / 32 + 8 doubles
+            a.ticket_id = 2 * VK_VAE_MAX_LAYERS + 3;
+        }
     } else if (L.in_kind == VK_IN_BN) {
         const vk_vae_layer &P = net->layers[j - 1];
         a.mode = 1; a.src = P.act; a.ld_src = P.n_out; a.c0 = P.bn_a; a.c1 = P.bn_c;
@@ -1695,7 +1755,7 @@ static int launch_batch_rows(const vk_vae *net, int B, int mode, int64_t row0, c
 
 static int launch_forward(const vk_vae *net, int B, int training, int upto /*exclusive layer index*/,
                           const vk_vae_inject *inj, int mask_bits, float *latent_out, cudaStream_t s,
-                          cudaEvent_t weights_ready = nullptr) {
+                          cudaEvent_t weights_ready = nullptr, const BatchDraw *draw = nullptr) {
     for (int j = 0; j < upto; ++j) {
         const vk_vae_layer &L = net->layers[j];
         FwdArgs a;
@@ -1723,7 +1783,7 @@ static int launch_forward(const vk_vae *net, int B, int training, int upto /*exc
         const bool tcp = use_tc(net, B);
         const bool fused = tcp && fused_staging(net, B);
         if (tcp && (!fused || j == 0))  // fused: layer j - 1 staged this layer's operands from its output tile
-            if (launch_prep_input(net, j, B, training, s)) return 1;
+            if (launch_prep_input(net, j, B, training, s, j == 0 ? draw : nullptr)) return 1;
         if (fused && j + 1 < upto && L.kind != VK_LAYER_OUT) {
             const vk_vae_layer &Nx = net->layers[j + 1];
             a.stage = (L.kind == VK_LAYER_HIDDEN && training) ? 1 : 2;
@@ -1909,9 +1969,12 @@ static int grad_step_impl(const vk_vae *net, int batch, const vk_vae_inject *inj
         if (launch_prep_weights(net, sc->side)) return 1;
         VK_CUDA(cudaEventRecord(sc->weights_done, sc->side));
     }
-    if (launch_batch_rows(net, batch, mode, 0, inject, s)) return 1;
+    // tensor-core path: the gather of the first layer draws the batch itself (one launch less on the critical path)
+    BatchDraw draw;
+    if (use_tc(net, batch)) { draw.mode = mode; draw.row0 = 0; draw.inj = inject; }
+    else if (launch_batch_rows(net, batch, mode, 0, inject, s)) return 1;
     if (!sc && use_tc(net, batch) && launch_prep_weights(net, s)) return 1;
-    if (launch_forward(net, batch, 1, net->n_layers, inject, 0, nullptr, s, sc ? sc->weights_done : nullptr)) return 1;
+    if (launch_forward(net, batch, 1, net->n_layers, inject, 0, nullptr, s, sc ? sc->weights_done : nullptr, &draw)) return 1;
     if (launch_loss(net, batch, 1, s, sc)) return 1;
     if (launch_backward(net, batch, s)) return 1;
     if (sc) VK_CUDA(cudaStreamWaitEvent(s, sc->fold_done, 0));  // join before the optimiser / the end of a capture
@@ -1944,9 +2007,11 @@ extern "C" int vk_vae_forward(const vk_vae *net, int64_t row0, int batch, int tr
     if (check_net(net, batch)) return 1;
     cudaStream_t s = (cudaStream_t)stream;
     const int mode = (inject && inject->batch_idx) ? 0 : 2;
-    if (launch_batch_rows(net, batch, mode, row0, inject, s)) return 1;
+    BatchDraw draw;
+    if (use_tc(net, batch)) { draw.mode = mode; draw.row0 = row0; draw.inj = inject; }
+    else if (launch_batch_rows(net, batch, mode, row0, inject, s)) return 1;
     if (use_tc(net, batch) && launch_prep_weights(net, s)) return 1;
-    if (launch_forward(net, batch, training, net->n_layers, inject, 0, nullptr, s)) return 1;
+    if (launch_forward(net, batch, training, net->n_layers, inject, 0, nullptr, s, nullptr, &draw)) return 1;
     if (with_loss && launch_loss(net, batch, 0, s)) return 1;
     return 0;
 }
@@ -1978,8 +2043,10 @@ extern "C" int vk_vae_encode(const vk_vae *net, int64_t row0, int64_t n, int mas
     if (use_tc(net, (int)(n < net->bmax ? n : net->bmax)) && launch_prep_weights(net, s)) return 1;
     for (int64_t off = 0; off < n; off += net->bmax) {
         const int B = (int)((n - off) < net->bmax ? (n - off) : net->bmax);
-        if (launch_batch_rows(net, B, 2, row0 + off, nullptr, s)) return 1;
-        if (launch_forward(net, B, 0, mu_j + 1, nullptr, mask_bits, latent_out + off * net->nlatent, s)) return 1;
+        BatchDraw draw;
+        if (use_tc(net, B)) { draw.mode = 2; draw.row0 = row0 + off; }
+        else if (launch_batch_rows(net, B, 2, row0 + off, nullptr, s)) return 1;
+        if (launch_forward(net, B, 0, mu_j + 1, nullptr, mask_bits, latent_out + off * net->nlatent, s, nullptr, &draw)) return 1;
     }
     return 0;
 }

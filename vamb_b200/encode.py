@@ -419,9 +419,9 @@ class VAE(_nn.Module):
 
         net.z = buf("z", bmax, self.nlatent)
         net.batch_rows = buf("batch_rows", bmax, dtype=_torch.int64)
-        # partial sums: two doubles per 1024-parameter block of the optimiser + one per 256 batch rows (weight fold); four
+        # partial sums: two doubles per 1024-parameter block of the optimiser + one per 32 batch rows (weight fold); four
         # doubles per 8-row block of the loss kernel (include/vamb_b200.h: vk_vae.opt_part / loss_part)
-        net.opt_part = buf("opt_part", 2 * ((total + 1023) // 1024) + bmax // 256 + 8, dtype=_torch.float64)
+        net.opt_part = buf("opt_part", 2 * ((total + 1023) // 1024) + bmax // 32 + 8, dtype=_torch.float64)
         net.loss_part = buf("loss_part", 4 * ((bmax + 31) // 32 * 32 // 8) + 64, dtype=_torch.float64)
         self._ctl = _torch.zeros(_ct.sizeof(_VkCtl), dtype=_torch.uint8, device=dev)
         net.ctl = self._ctl.data_ptr()
