@@ -81,13 +81,16 @@ def test_train_steps_and_encode_match_reference_golden(case, tc):
 @pytest.mark.parametrize("tc,B,S", [(False, 256, 50), (True, 256, 50), (True, 1024, 50), (True, 4096, 50),
                                     ("prep", 256, 50), ("prep", 4096, 50), (True, 1000, 50), (True, 256, 80),
                                     (True, 8192, 50), ("tma", 256, 50), ("tma", 1000, 50), ("tma", 4096, 50),
-                                    ("flush", 256, 50), ("flush", 1000, 50), ("flush", 4096, 50), ("flush", 8192, 50)],
+                                    ("flush", 256, 50), ("flush", 1000, 50), ("flush", 4096, 50), ("flush", 8192, 50),
+                                    (True, 512, 100), ("tma", 2048, 100)],
                          ids=["ffma-256", "tcgen05-256", "tcgen05-1024-split2", "tcgen05-4096-split8", "tcgen05-prep-256",
                               "tcgen05-prep-4096", "tcgen05-1000-ragged", "tcgen05-256-wide-input",
                               "tcgen05-8192-grid-fallback", "tcgen05-tma-256", "tcgen05-tma-1000-ragged", "tcgen05-tma-4096",
-                              "tcgen05-flush-256", "tcgen05-flush-1000-ragged", "tcgen05-flush-4096", "tcgen05-flush-8192"])
+                              "tcgen05-flush-256", "tcgen05-flush-1000-ragged", "tcgen05-flush-4096", "tcgen05-flush-8192",
+                              "tcgen05-512-C3-shape-S100", "tcgen05-tma-2048-C3-shape-S100"])
 def test_gradients_match_oracle_default_network(tc, B, S):
-    """One fwd+bwd on the bin-default network (512-512-32): every gradient tensor.  S = 80 makes the
+    """One fwd+bwd on the bin-default network (512-512-32): every gradient tensor.  S = 100 is BASELINE's C3 shape
+    (D_in = 204); S = 80 / 100 make the
     reconstruction wider than the loss kernel stages itself (a prep launch takes over for that layer);
     B = 8192 exceeds the SM count with its forward grid, so operand staging falls back to prep launches."""
     import vamb_b200.encode as ve
