@@ -28,6 +28,7 @@ extern "C" {
 #define VK_ABI_VERSION 1
 #define VK_NBINS 60          /* ceil(0.3 / 0.005), vamb/cluster.py:231 */
 #define VK_MAX_CAND 32       /* candidates evaluated per vk_eval_candidates launch */
+#define VK_LIST_CAND 64      /* candidates evaluated per vk_eval_candidates_lists launch */
 #define VK_PROBE_INLINE 2040 /* `within` ids returned inline with the probe header */
 
 const char *vk_last_error(void);
@@ -107,11 +108,11 @@ int vk_eval_candidates_mapped(const float *matrix, const float *lengths, int d, 
 /* Candidate evaluation that also returns what is needed to MOVE the medoid to a winning candidate without another
  * full scan (native driver): the ids of the rows within 0.05 of candidate k (its `cluster`, vamb/cluster.py:626) are
  * written to within_pinned[k * within_cap ...] (pinned host memory; entries beyond within_cap are dropped, the count
- * still tells), and out_pinned (4 * VK_MAX_CAND uint64) = density_lo[k] | density_hi[k] | counts[k] | fp32 bits of
+ * still tells), and out_pinned (4 * VK_LIST_CAND uint64) = density_lo[k] | density_hi[k] | counts[k] | fp32 bits of
  * d(candidate k, base_row).  `base_row` = the medoid whose neighbour list (radius nl_radius = 0.3) is passed in: the list
  * covers the whole 0.05-neighbourhood of a candidate iff d(candidate, base) <= 0.12 (angles add: acos(0.76) +
  * acos(0.9) = acos(0.4)), which the caller checks.  Mapped completion as vk_eval_candidates_mapped (out_dev: 4 *
- * VK_MAX_CAND uint64, all zero on entry, left zeroed). */
+ * VK_LIST_CAND uint64, all zero on entry, left zeroed; n_cand <= VK_LIST_CAND). */
 int vk_eval_candidates_lists(const float *matrix, const float *lengths, int d, const int32_t *nl_rows,
                              const float *nl_dists, int32_t n_nl, float prune_radius, const int32_t *cand_rows_host,
                              int n_cand, int32_t base_row, uint64_t *out_dev, uint64_t *out_pinned, int32_t *within_pinned,

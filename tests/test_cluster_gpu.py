@@ -235,8 +235,8 @@ def test_eval_candidates_lists_matches_oracle(vk):
     dist_base = co.calc_distances(host, base)
     near = np.flatnonzero((dist_base <= np.float32(0.1199)) & (kept != 0))
     far = np.flatnonzero((dist_base > np.float32(0.125)) & (dist_base <= np.float32(0.3)) & (kept != 0))
-    cands = list(near[:: max(1, len(near) // 20)][:20]) + list(far[:3])
-    C, cap = vk.VK_MAX_CAND, 512
+    cands = list(near[:: max(1, len(near) // 50)][:50]) + list(far[:3])  # more than VK_MAX_CAND: the lists kernel takes 64
+    C, cap = vk.VK_LIST_CAND, 512
     out_dev = torch.zeros(4 * C, dtype=torch.int64, device="cuda")
     out_pin = torch.zeros(4 * C, dtype=torch.int64).pin_memory()
     within_pin = torch.zeros(C * cap, dtype=torch.int32).pin_memory()

@@ -16,6 +16,7 @@ _SO = os.environ.get("VAMB_B200_SO") or os.path.join(_HERE, "_vk.so")
 VK_ABI_VERSION = 1
 VK_NBINS = 60
 VK_MAX_CAND = 32
+VK_LIST_CAND = 64
 VK_PROBE_INLINE = 2040
 
 # byte offsets inside vk_probe_header (include/vamb_b200.h)

@@ -718,6 +718,10 @@ extern "C" int vk_eval_candidates_mapped(const float *matrix, const float *lengt
 }
 
 // ------------------------------------------------------------------ candidate evaluation with within-lists
+struct CandRowsL {
+    int32_t rows[VK_LIST_CAND];
+};
+
 // As eval_candidates_kernel, plus what lets the host MOVE the medoid to a winning candidate without another full
 // scan: the ids of the rows within 0.05 of every candidate (the candidate's `cluster` of sample_medoid,
 // vamb/cluster.py:626) go straight into pinned host memory, and the distance of every candidate to the medoid whose
@@ -727,12 +731,12 @@ extern "C" int vk_eval_candidates_mapped(const float *matrix, const float *lengt
 __global__ void __launch_bounds__(EC_THREADS)
 eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths, int d,
                              const int32_t *__restrict__ nl_rows, const float *__restrict__ nl_dists, int n_nl,
-                             float prune_radius, CandRows cand, int n_cand, int32_t base_row, u64 *out, u64 *out_mapped,
+                             float prune_radius, CandRowsL cand, int n_cand, int32_t base_row, u64 *out, u64 *out_mapped,
                              int32_t *within_mapped, int within_cap, int32_t *done_ticket, volatile int32_t *done_flag,
                              int32_t seq) {
     extern __shared__ __align__(16) float s_qs[];  // [n_cand][dpad]
-    __shared__ u64 s_dens[VK_MAX_CAND];
-    __shared__ u64 s_dens_hi[VK_MAX_CAND];
+    __shared__ u64 s_dens[VK_LIST_CAND];
+    __shared__ u64 s_dens_hi[VK_LIST_CAND];
     const int tid = threadIdx.x, lane8 = tid & 7, g = tid >> 3;
     const unsigned gmask = group8_mask();
     const int dpad = (d + 3) & ~3;
@@ -742,7 +746,7 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
         const int k = i / dpad, c = i - k * dpad;
         s_qs[i] = c < d ? matrix[(int64_t)cand.rows[k] * d + c] : 0.0f;
     }
-    if (tid < VK_MAX_CAND) { s_dens[tid] = 0ull; s_dens_hi[tid] = 0ull; }
+    if (tid < VK_LIST_CAND) { s_dens[tid] = 0ull; s_dens_hi[tid] = 0ull; }
     __syncthreads();
 
     const float rad = 0.05f;
@@ -751,7 +755,7 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
     // angle(d_k) + acos(0.9) of the base, i.e. at a base distance of at most
     //     reach_k = 0.5 * (1 - ((1 - 2 d_k) * 0.9 - sqrt(1 - (1 - 2 d_k)^2) * sqrt(0.19)))      (+ 1e-4 of slack).
     // Neighbour-list entries beyond max_k reach_k (and beyond `prune_radius`) cannot matter and are not gathered.
-    __shared__ float s_reach[VK_MAX_CAND];
+    __shared__ float s_reach[VK_LIST_CAND];
     {
         const float *x = matrix + (int64_t)base_row * d;
         float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -763,7 +767,7 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
             if (lane8 == 0) {
                 float dd = __fsub_rn(0.5f, acc);
                 if (cand.rows[k] == base_row) dd = 0.0f;
-                if (blockIdx.x == 0) out[3 * VK_MAX_CAND + k] = (u64)__float_as_uint(dd);
+                if (blockIdx.x == 0) out[3 * VK_LIST_CAND + k] = (u64)__float_as_uint(dd);
                 const float ca = 1.0f - 2.0f * fmaxf(dd, 0.0f);
                 const float sa = sqrtf(fmaxf(1.0f - ca * ca, 0.0f));
                 const float cs = ca * 0.9f - sa * 0.43588990f;  // cos(angle(d_k) + acos(0.9))
@@ -801,7 +805,7 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
                     const u64 cq = closeness_fx(rad, dd);
                     atomicAdd(&s_dens[k], lenq * (cq & 4095ull));
                     atomicAdd(&s_dens_hi[k], lenq * (cq >> 12));
-                    const u64 pos = atomicAdd(&out[2 * VK_MAX_CAND + k], 1ull);  // rare: a few dozen hits per candidate
+                    const u64 pos = atomicAdd(&out[2 * VK_LIST_CAND + k], 1ull);  // rare: a few dozen hits per candidate
                     if (pos < (u64)within_cap) within_mapped[(size_t)k * within_cap + pos] = row;
                 }
             }
@@ -810,7 +814,7 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
     __syncthreads();
     if (tid < n_cand) {
         if (s_dens[tid]) atomicAdd(&out[tid], s_dens[tid]);
-        if (s_dens_hi[tid]) atomicAdd(&out[VK_MAX_CAND + tid], s_dens_hi[tid]);
+        if (s_dens_hi[tid]) atomicAdd(&out[VK_LIST_CAND + tid], s_dens_hi[tid]);
     }
     __shared__ int s_last;
     __threadfence_system();  // this block's id-list writes (pinned host memory) and sums are visible before its ticket
@@ -823,7 +827,7 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    if (tid < 4 * VK_MAX_CAND) {
+    if (tid < 4 * VK_LIST_CAND) {
         out_mapped[tid] = __ldcg(out + tid);
         out[tid] = 0ull;
     }
@@ -837,8 +841,8 @@ extern "C" int vk_eval_candidates_lists(const float *matrix, const float *length
                                         const int32_t *cand_rows_host, int n_cand, int32_t base_row, uint64_t *out_dev,
                                         uint64_t *out_pinned, int32_t *within_pinned, int32_t within_cap,
                                         int32_t *done_ticket, int32_t *done_flag_pinned, int32_t seq, void *stream) {
-    if (n_cand < 1 || n_cand > VK_MAX_CAND || within_cap < 1) {
-        vk_set_error("vk_eval_candidates_lists: n_cand=%d outside [1, %d] or bad capacity", n_cand, VK_MAX_CAND);
+    if (n_cand < 1 || n_cand > VK_LIST_CAND || within_cap < 1) {
+        vk_set_error("vk_eval_candidates_lists: n_cand=%d outside [1, %d] or bad capacity", n_cand, VK_LIST_CAND);
         return 1;
     }
     if (d < 1 || d > PB_MAX_D || n_nl <= 0) {
@@ -846,7 +850,7 @@ extern "C" int vk_eval_candidates_lists(const float *matrix, const float *length
         return 1;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    CandRows cand;
+    CandRowsL cand;
     memset(&cand, 0, sizeof(cand));
     for (int k = 0; k < n_cand; ++k) cand.rows[k] = cand_rows_host[k];
     const int dpad = (d + 3) & ~3;

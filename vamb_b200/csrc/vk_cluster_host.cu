@@ -18,6 +18,7 @@
 #include <chrono>
 #include <deque>
 #include <new>
+#include <unordered_map>
 #include <unordered_set>
 #include <vector>
 
@@ -301,9 +302,9 @@ int do_eval_lists(State &st, const Probe &base, float prune, const std::vector<i
     out.cnt.resize((size_t)n);
     out.dbase.resize((size_t)n);
     for (int k = 0; k < n; ++k) {
-        out.dens[(size_t)k] = ((unsigned __int128)st.cand2_pin[VK_MAX_CAND + k] << 12) + st.cand2_pin[k];
-        out.cnt[(size_t)k] = (int64_t)st.cand2_pin[2 * VK_MAX_CAND + k];
-        const uint32_t bits = (uint32_t)st.cand2_pin[3 * VK_MAX_CAND + k];
+        out.dens[(size_t)k] = ((unsigned __int128)st.cand2_pin[VK_LIST_CAND + k] << 12) + st.cand2_pin[k];
+        out.cnt[(size_t)k] = (int64_t)st.cand2_pin[2 * VK_LIST_CAND + k];
+        const uint32_t bits = (uint32_t)st.cand2_pin[3 * VK_LIST_CAND + k];
         memcpy(&out.dbase[(size_t)k], &bits, sizeof(float));
     }
     return 0;
@@ -323,7 +324,7 @@ int wander(State &st, int32_t seed, Probe &probe, int32_t &seed_rank) {
     if (do_probe(st, seed, probe)) return 1;
     seed_rank = probe.rank;
     const bool list_is_everything = !(st.c.nl_radius < 1e30f);
-    const bool lazy = st.lazy_enabled && st.c.maxsteps <= VK_MAX_CAND && st.cand2_dev != nullptr &&
+    const bool lazy = st.lazy_enabled && st.c.maxsteps <= VK_LIST_CAND && st.cand2_dev != nullptr &&
                       (list_is_everything || st.c.nl_radius == 0.3f);
     unsigned __int128 local = probe.density;
     int32_t cur = seed;                         // current medoid; probe describes the base (probe.medoid)
@@ -331,6 +332,13 @@ int wander(State &st, int32_t seed, Probe &probe, int32_t &seed_rank) {
     std::vector<int32_t> cand, sampled;
     std::vector<unsigned __int128> dens;
     EvalLists ev;
+    struct Cached {
+        unsigned __int128 dens;
+        std::vector<int32_t> within;
+        bool lists_ok;
+    };
+    std::unordered_map<int32_t, Cached> cache;  // row -> what a candidate evaluation of this wander returned
+    std::vector<int32_t> batch;
     auto rebase = [&]() -> int {                // full scan at the current medoid
         const unsigned __int128 want = local;
         if (do_probe(st, cur, probe)) return 1;
@@ -368,24 +376,55 @@ int wander(State &st, int32_t seed, Probe &probe, int32_t &seed_rank) {
             local = probe.density;
             continue;
         }
+        // Densities (and within-sets) are pure functions of (row, live rows), and no row changes during one wander: what
+        // a launch computes stays valid for the rest of this wander.  Every launch therefore evaluates the sampled
+        // candidates that are not known yet PLUS as many further members of the current within-set as fit (the next
+        // rounds sample from exactly those), so most rounds -- and most moves between overlapping within-sets -- need
+        // no device call at all.  Only sampled candidates enter `tried`, in the reference's order.
         for (;;) {
-            const bool at_base = cur == probe.medoid;
-            // candidates of the base itself lie within 0.05 of it: rows near them are within 0.19 (prune radius)
-            if (do_eval_lists(st, probe, at_base ? st.c.prune_radius : st.c.nl_radius, sampled, ev)) return 1;
+            batch.clear();
+            for (int32_t c : sampled)
+                if (!cache.count(c)) batch.push_back(c);
+            if (!batch.empty()) {
+                const size_t n_need = batch.size();
+                for (int32_t c : cur_within) {
+                    if (batch.size() >= (size_t)VK_LIST_CAND) break;
+                    if (!tried.count(c) && !cache.count(c) && std::find(batch.begin(), batch.end(), c) == batch.end())
+                        batch.push_back(c);
+                }
+                const bool at_base = cur == probe.medoid;
+                // candidates of the base itself lie within 0.05 of it: rows near them are within 0.19 (prune radius)
+                if (do_eval_lists(st, probe, at_base ? st.c.prune_radius : st.c.nl_radius, batch, ev)) return 1;
+                for (size_t i = 0; i < batch.size(); ++i) {
+                    const bool ok = at_base || list_is_everything || ev.dbase[i] <= R_EVAL;
+                    if (!ok) continue;  // the list may not cover this candidate's neighbourhood: not usable
+                    Cached &cc = cache[batch[i]];
+                    cc.dens = ev.dens[i];
+                    cc.lists_ok = ev.cnt[i] <= WITHIN_CAP;
+                    if (cc.lists_ok) {
+                        const int32_t *ids = st.within_pin + i * WITHIN_CAP;
+                        cc.within.assign(ids, ids + ev.cnt[i]);
+                        std::sort(cc.within.begin(), cc.within.end());
+                    }
+                }
+                (void)n_need;
+            }
             bool need_rebase = false;
+            winner = -1;
             for (size_t i = 0; i < sampled.size(); ++i) {
-                if (!at_base && !list_is_everything && !(ev.dbase[i] <= R_EVAL)) { need_rebase = true; break; }
+                const auto it = cache.find(sampled[i]);
+                if (it == cache.end()) { need_rebase = true; break; }  // beyond the coverage radius of the base
                 tried.insert(sampled[i]);
-                if (ev.dens[i] > local) { winner = (int)i; break; }
+                if (it->second.dens > local) { winner = (int)i; break; }
             }
             if (!need_rebase) break;
-            if (rebase()) return 1;  // then evaluate the same sample against the new base
-            winner = -1;
+            if (rebase()) return 1;  // then evaluate what is still unknown of the same sample against the new base
         }
         if (winner < 0) break;
         const size_t w = (size_t)winner;
-        if (ev.cnt[w] > WITHIN_CAP) {  // id list truncated: take the winner's within-set from a full scan
-            const unsigned __int128 want = ev.dens[w];
+        const Cached &cw = cache[sampled[w]];
+        if (!cw.lists_ok) {  // id list truncated: take the winner's within-set from a full scan
+            const unsigned __int128 want = cw.dens;
             if (do_probe(st, sampled[w], probe)) return 1;
             if (probe.density != want) {
                 vk_set_error("vk_cluster: probe and candidate densities disagree");
@@ -393,13 +432,11 @@ int wander(State &st, int32_t seed, Probe &probe, int32_t &seed_rank) {
             }
             cur_within = probe.within;
         } else {
-            const int32_t *ids = st.within_pin + w * WITHIN_CAP;
-            cur_within.assign(ids, ids + ev.cnt[w]);
-            std::sort(cur_within.begin(), cur_within.end());
+            cur_within = cw.within;
             ++st.n_moves_lazy;
         }
         cur = sampled[w];
-        local = ev.dens[w];
+        local = cw.dens;
     }
     if (cur != probe.medoid && rebase()) return 1;  // the final medoid's histogram / neighbour list / loner count
     return 0;
@@ -479,10 +516,10 @@ extern "C" int vk_cluster_create(void **handle, const vk_cluster_config *cfg) {
         cudaHostAlloc((void **)&st->cand_pin, sizeof(uint64_t) * 3 * VK_MAX_CAND, cudaHostAllocMapped) != cudaSuccess ||
         cudaHostAlloc((void **)&st->flags_pin, sizeof(int32_t) * 2, cudaHostAllocMapped) != cudaSuccess ||
         cudaMalloc((void **)&st->tickets_dev, sizeof(int32_t) * 2) != cudaSuccess ||
-        cudaHostAlloc((void **)&st->cand2_pin, sizeof(uint64_t) * 4 * VK_MAX_CAND, cudaHostAllocMapped) != cudaSuccess ||
-        cudaHostAlloc((void **)&st->within_pin, sizeof(int32_t) * VK_MAX_CAND * WITHIN_CAP, cudaHostAllocMapped) != cudaSuccess ||
-        cudaMalloc((void **)&st->cand2_dev, sizeof(uint64_t) * 4 * VK_MAX_CAND) != cudaSuccess ||
-        cudaMemsetAsync(st->cand2_dev, 0, sizeof(uint64_t) * 4 * VK_MAX_CAND, s) != cudaSuccess ||
+        cudaHostAlloc((void **)&st->cand2_pin, sizeof(uint64_t) * 4 * VK_LIST_CAND, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostAlloc((void **)&st->within_pin, sizeof(int32_t) * VK_LIST_CAND * WITHIN_CAP, cudaHostAllocMapped) != cudaSuccess ||
+        cudaMalloc((void **)&st->cand2_dev, sizeof(uint64_t) * 4 * VK_LIST_CAND) != cudaSuccess ||
+        cudaMemsetAsync(st->cand2_dev, 0, sizeof(uint64_t) * 4 * VK_LIST_CAND, s) != cudaSuccess ||
         cudaMemsetAsync(st->tickets_dev, 0, sizeof(int32_t) * 2, s) != cudaSuccess ||
         cudaMemsetAsync(cfg->hdr, 0, sizeof(vk_probe_header), s) != cudaSuccess ||
         cudaMemsetAsync(cfg->cand_out, 0, sizeof(uint64_t) * 3 * VK_MAX_CAND, s) != cudaSuccess ||
