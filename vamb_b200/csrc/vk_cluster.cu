@@ -737,6 +737,9 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
     extern __shared__ __align__(16) float s_qs[];  // [n_cand][dpad]
     __shared__ u64 s_dens[VK_LIST_CAND];
     __shared__ u64 s_dens_hi[VK_LIST_CAND];
+    __shared__ int32_t s_crow[VK_LIST_CAND];  // candidate rows (indexing the by-value parameter array dynamically would
+                                              // send every access through local memory)
+    __shared__ int s_wrote;                   // this block appended ids to the pinned lists
     const int tid = threadIdx.x, lane8 = tid & 7, g = tid >> 3;
     const unsigned gmask = group8_mask();
     const int dpad = (d + 3) & ~3;
@@ -746,7 +749,8 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
         const int k = i / dpad, c = i - k * dpad;
         s_qs[i] = c < d ? matrix[(int64_t)cand.rows[k] * d + c] : 0.0f;
     }
-    if (tid < VK_LIST_CAND) { s_dens[tid] = 0ull; s_dens_hi[tid] = 0ull; }
+    if (tid < VK_LIST_CAND) { s_dens[tid] = 0ull; s_dens_hi[tid] = 0ull; s_crow[tid] = tid < n_cand ? cand.rows[tid] : -1; }
+    if (tid == 0) s_wrote = 0;
     __syncthreads();
 
     const float rad = 0.05f;
@@ -766,7 +770,7 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
             acc = group8_sum(acc, gmask);
             if (lane8 == 0) {
                 float dd = __fsub_rn(0.5f, acc);
-                if (cand.rows[k] == base_row) dd = 0.0f;
+                if (s_crow[k] == base_row) dd = 0.0f;
                 if (blockIdx.x == 0) out[3 * VK_LIST_CAND + k] = (u64)__float_as_uint(dd);
                 const float ca = 1.0f - 2.0f * fmaxf(dd, 0.0f);
                 const float sa = sqrtf(fmaxf(1.0f - ca * ca, 0.0f));
@@ -800,13 +804,16 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
             acc = group8_sum(acc, gmask);
             if (lane8 == 0) {
                 float dd = __fsub_rn(0.5f, acc);
-                if (row == cand.rows[k]) dd = 0.0f;
+                if (row == s_crow[k]) dd = 0.0f;
                 if (dd <= rad) {
                     const u64 cq = closeness_fx(rad, dd);
                     atomicAdd(&s_dens[k], lenq * (cq & 4095ull));
                     atomicAdd(&s_dens_hi[k], lenq * (cq >> 12));
                     const u64 pos = atomicAdd(&out[2 * VK_LIST_CAND + k], 1ull);  // rare: a few dozen hits per candidate
-                    if (pos < (u64)within_cap) within_mapped[(size_t)k * within_cap + pos] = row;
+                    if (pos < (u64)within_cap) {
+                        within_mapped[(size_t)k * within_cap + pos] = row;
+                        s_wrote = 1;
+                    }
                 }
             }
         }
@@ -817,7 +824,11 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
         if (s_dens_hi[tid]) atomicAdd(&out[VK_LIST_CAND + tid], s_dens_hi[tid]);
     }
     __shared__ int s_last;
-    __threadfence_system();  // this block's id-list writes (pinned host memory) and sums are visible before its ticket
+    __syncthreads();
+    // this block's sums (device memory) and id-list writes (pinned host memory: system scope, only if it made any) are
+    // visible before its ticket
+    if (s_wrote) __threadfence_system();
+    else __threadfence();
     __syncthreads();
     if (tid == 0) {
         const int t = atomicAdd(done_ticket, 1);
