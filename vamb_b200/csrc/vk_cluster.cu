@@ -112,6 +112,36 @@ extern "C" int vk_check_normalized(const float *matrix, int64_t n, int d, float 
     return 0;
 }
 
+// ------------------------------------------------------------------ mapped completion
+// "Last block done" with ONE fencing thread per block: after the block barrier, thread 0's device-scope fence is
+// cumulative over everything the block wrote before the barrier (the release pattern of the PTX memory model, as in
+// cutlass/semaphore.h); having all 256 threads of every block execute MEMBAR (let alone the system-scope one, which
+// also invalidates L1) cost 30-50 us per launch on B200 (profiles/r02_ncu_summary.md: ERRBAR / barrier stalls).
+// Returns true in every thread of the block that finishes last; that block has acquired the other blocks' writes.
+__device__ __forceinline__ bool vk_last_block(int32_t *ticket, int *s_last) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const int t = atomicAdd(ticket, 1);
+        *s_last = (t == (int)gridDim.x - 1);
+        if (*s_last) {
+            *ticket = 0;
+            __threadfence();
+        }
+    }
+    __syncthreads();
+    return *s_last != 0;
+}
+// Publish: after the last block's writes to the pinned result buffers, one thread orders them (system scope) before
+// the flag the host spins on.
+__device__ __forceinline__ void vk_raise_flag(volatile int32_t *flag, int32_t seq) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        *flag = seq;
+    }
+}
+
 // ------------------------------------------------------------------ probe
 constexpr int PB_THREADS = 256;
 constexpr int PB_GROUPS = PB_THREADS / 8;  // rows per pass
@@ -343,16 +373,7 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
     // leaves the device accumulators zeroed for the next probe and raises the flag the host is spinning on --
     // one launch per probe instead of memset + kernel + copy + stream synchronisation.
     __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const int t = atomicAdd(done_ticket, 1);
-        s_last = (t == (int)gridDim.x - 1);
-        if (s_last) *done_ticket = 0;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
+    if (!vk_last_block(done_ticket, &s_last)) return;
     constexpr int HEAD_WORDS = (int)(offsetof(vk_probe_header, within) / sizeof(u64));  // accumulators + counters
     if (tid < HEAD_WORDS) reinterpret_cast<u64 *>(hdr_mapped)[tid] = __ldcg(reinterpret_cast<const u64 *>(hdr) + tid);
     int nw = __ldcg(&hdr->n_within);
@@ -360,9 +381,7 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
     for (int i = tid; i < nw; i += PB_THREADS) hdr_mapped->within[i] = __ldcg(&hdr->within[i]);
     __syncthreads();
     if (tid < HEAD_WORDS) reinterpret_cast<u64 *>(hdr)[tid] = 0ull;
-    __threadfence_system();
-    __syncthreads();
-    if (tid == 0) *done_flag = seq;
+    vk_raise_flag(done_flag, seq);
 }
 
 // Launch shape of the probe: rows in flight per lane (VK_PROBE_R = 4 | 8) and persistent blocks per SM
@@ -623,23 +642,12 @@ eval_candidates_kernel(const float *__restrict__ matrix, const float *__restrict
     if (out_mapped == nullptr) return;
     // mapped completion, as in probe_kernel: results to pinned host memory, accumulators left zeroed, flag raised
     __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const int t = atomicAdd(done_ticket, 1);
-        s_last = (t == (int)gridDim.x - 1);
-        if (s_last) *done_ticket = 0;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
+    if (!vk_last_block(done_ticket, &s_last)) return;
     if (tid < 3 * VK_MAX_CAND) {
         out_mapped[tid] = __ldcg(out + tid);
         out[tid] = 0ull;
     }
-    __threadfence_system();
-    __syncthreads();
-    if (tid == 0) *done_flag = seq;
+    vk_raise_flag(done_flag, seq);
 }
 
 extern "C" int vk_eval_candidates_sync(const float *matrix, const float *lengths, int d, const int32_t *nl_rows,
@@ -739,7 +747,6 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
     __shared__ u64 s_dens_hi[VK_LIST_CAND];
     __shared__ int32_t s_crow[VK_LIST_CAND];  // candidate rows (indexing the by-value parameter array dynamically would
                                               // send every access through local memory)
-    __shared__ int s_wrote;                   // this block appended ids to the pinned lists
     const int tid = threadIdx.x, lane8 = tid & 7, g = tid >> 3;
     const unsigned gmask = group8_mask();
     const int dpad = (d + 3) & ~3;
@@ -750,7 +757,6 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
         s_qs[i] = c < d ? matrix[(int64_t)cand.rows[k] * d + c] : 0.0f;
     }
     if (tid < VK_LIST_CAND) { s_dens[tid] = 0ull; s_dens_hi[tid] = 0ull; s_crow[tid] = tid < n_cand ? cand.rows[tid] : -1; }
-    if (tid == 0) s_wrote = 0;
     __syncthreads();
 
     const float rad = 0.05f;
@@ -811,8 +817,8 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
                     atomicAdd(&s_dens_hi[k], lenq * (cq >> 12));
                     const u64 pos = atomicAdd(&out[2 * VK_LIST_CAND + k], 1ull);  // rare: a few dozen hits per candidate
                     if (pos < (u64)within_cap) {
-                        within_mapped[(size_t)k * within_cap + pos] = row;
-                        s_wrote = 1;
+                        within_mapped[(size_t)k * within_cap + pos] = row;  // pinned host memory
+                        __threadfence_system();  // by the writing thread only: a few dozen ids per candidate
                     }
                 }
             }
@@ -824,27 +830,12 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
         if (s_dens_hi[tid]) atomicAdd(&out[VK_LIST_CAND + tid], s_dens_hi[tid]);
     }
     __shared__ int s_last;
-    __syncthreads();
-    // this block's sums (device memory) and id-list writes (pinned host memory: system scope, only if it made any) are
-    // visible before its ticket
-    if (s_wrote) __threadfence_system();
-    else __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const int t = atomicAdd(done_ticket, 1);
-        s_last = (t == (int)gridDim.x - 1);
-        if (s_last) *done_ticket = 0;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
+    if (!vk_last_block(done_ticket, &s_last)) return;
     if (tid < 4 * VK_LIST_CAND) {
         out_mapped[tid] = __ldcg(out + tid);
         out[tid] = 0ull;
     }
-    __threadfence_system();
-    __syncthreads();
-    if (tid == 0) *done_flag = seq;
+    vk_raise_flag(done_flag, seq);
 }
 
 extern "C" int vk_eval_candidates_lists(const float *matrix, const float *lengths, int d, const int32_t *nl_rows,

@@ -80,17 +80,22 @@ __device__ __forceinline__ double block_sum256(double v, double *s8) {
 // ------------------------------------------------------------------ batch rows + mean weight
 // mode 0: rows from inject->batch_idx; 1: epoch permutation; 2: contiguous [row0, row0+B)
 // "last block done": returns true in every thread of the block that finishes last.
+// One fencing thread per block: after the block barrier, thread 0's device-scope fence is cumulative over what the
+// block wrote before the barrier (release), and its second fence orders the last block's reads after the ticket
+// (acquire) -- the pattern of cutlass/semaphore.h.  A MEMBAR by every thread of every block cost microseconds per launch.
 __device__ __forceinline__ bool last_block_done(int32_t *ticket, int total) {
     __shared__ int s_last;
-    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence();
         const int t = atomicAdd(ticket, 1);
         s_last = (t == total - 1);
-        if (s_last) *ticket = 0;  // self-reset for the next launch
+        if (s_last) {
+            *ticket = 0;  // self-reset for the next launch
+            __threadfence();
+        }
     }
     __syncthreads();
-    if (s_last) __threadfence();
     return s_last != 0;
 }
 
