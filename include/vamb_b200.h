@@ -293,7 +293,8 @@ typedef struct vk_vae {
     int32_t use_tma;                    /* 1 = the weight operand (B) of the forward / dgrad GEMMs is fetched by TMA
                                            (cp.async.bulk.tensor, 128B swizzle; needs w_lo / wt_lo), 0 = cp.async ring  */
     int32_t wgrad_flush;                /* 1 = wgrad sums every 128 batch rows into fp32 registers (two alternating tensor-memory
-                                           accumulators) instead of one truncating accumulation chain per 512-row split    */
+                                           accumulators) instead of one truncating accumulation chain per 512-row split;
+                                           2 = also the forward GEMMs in training (evaluation always uses the flushed form) */
 } vk_vae;
 
 /* Optional host-injected randomness for parity tests (all device pointers, NULL = on-device RNG). */

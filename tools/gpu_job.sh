@@ -10,17 +10,19 @@ leg() { # name timeout command...
 }
 : > gpurun_out/job_summary.log
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader | tee -a gpurun_out/job_summary.log
-leg r02c_pt_cluster 400 python -m pytest tests/test_cluster_gpu.py tests/test_c2_scale_gpu.py -m gpu -q -s
-leg r02c_pt_vae 500 python -m pytest tests/test_vae_gpu.py -m gpu -q
-leg r02c_pt_traj 400 python -m pytest tests/test_trajectory_gpu.py -m gpu -q -s
-# same box: round-1 tree (git aeaa032, built in .r1/) against the current tree, step time per batch size
-leg r02c_speed_r1 200 bash -c 'cd .r1 && TC_MIN=128 python tools/train_speed.py'
-leg r02c_speed_now 200 env TC_MIN=128 python tools/train_speed.py
-leg r02c_speed_now_tma0 200 env TC_MIN=128 VAMB_B200_TMA=0 python tools/train_speed.py
-leg r02c_clusterbench 300 python tools/cluster_speed.py
-leg r02c_pt_cluster_ring6 400 env VK_PROBE_RING=6 python -m pytest tests/test_cluster_gpu.py -m gpu -q -k "golden or probe or lazy"
-: > gpurun_out/r02c_probe_sweep.txt
-for ring in 0 4 6 8 12; do VK_PROBE_RING=$ring timeout 120 python tools/probe_speed.py 2>&1 | grep "N=" | sed "s/^/RING=$ring /" >> gpurun_out/r02c_probe_sweep.txt; done
-leg r02c_ncu 1500 bash tools/ncu_job.sh
-for f in gpurun_out/r02c_pt_*.log; do echo "== $f"; grep -E "^FAILED|^ERROR|passed|failed|encode 1M|strict-RNG" $f | tail -8; done
-cat gpurun_out/job_summary.log; cat gpurun_out/r02c_probe_sweep.txt; grep "B=" gpurun_out/r02c_speed_*.log | cut -c1-90; cat gpurun_out/r02c_clusterbench.log | tail -12
+leg r02d_pt_cluster 400 python -m pytest tests/test_cluster_gpu.py tests/test_c2_scale_gpu.py -m gpu -q -s
+leg r02d_pt_vae 500 python -m pytest tests/test_vae_gpu.py tests/test_tc_gpu.py tests/test_inputs.py -m gpu -q
+leg r02d_pt_traj 400 python -m pytest tests/test_trajectory_gpu.py -m gpu -q -s
+leg r02d_speed_r1 200 bash -c 'cd .r1 && TC_MIN=128 python tools/train_speed.py'
+leg r02d_speed_now 200 env TC_MIN=128 python tools/train_speed.py
+leg r02d_clusterbench 300 python tools/cluster_speed.py
+leg r02d_graderr 400 env GRAD_CASES=50:4096,50:8192,100:512,100:2048 GRAD_OUT=gpurun_out/r02d_grad_error.json python tools/grad_error_fp64.py
+leg r02d_bench 760 bash -c 'python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02d_bench.json'
+for f in gpurun_out/r02d_pt_*.log; do echo "== $f"; grep -E "^FAILED|^ERROR|passed|failed|encode 1M|strict-RNG" $f | tail -8; done
+cat gpurun_out/job_summary.log; grep "B=" gpurun_out/r02d_speed_*.log | cut -c1-90; tail -3 gpurun_out/r02d_clusterbench.log; grep -v WARNING gpurun_out/r02d_graderr.log | tail -30
+python - <<'PY'
+import json
+d = json.load(open("gpurun_out/r02d_bench.json"))
+print({k: d[k] for k in ("value", "phases_s", "cluster_host_seconds", "clusters", "final_loss")})
+print(d["e2e"]); print(d["roofline"]["achieved"], d["roofline"]["frac"], d["roofline_cluster"]["achieved"], d["roofline_cluster"]["frac"])
+PY

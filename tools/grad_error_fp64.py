@@ -33,8 +33,12 @@ def grads_fp64(o32, d, t, a, w, eps, keeps):
 
 
 def main():
-    S, out = 50, {}
-    for B in (256, 1024, 4096):
+    # GRAD_CASES="S:B,S:B,..." overrides the default sweep (S = 50 at B = 256, 1024, 4096)
+    cases = [(50, 256), (50, 1024), (50, 4096)]
+    if os.environ.get("GRAD_CASES"):
+        cases = [tuple(int(x) for x in c.split(":")) for c in os.environ["GRAD_CASES"].split(",")]
+    out = {}
+    for S, B in cases:
         n = max(5000, B + 1000)
         rpkm, tnfs, lens = vae_inputs(S, n, 7)
         dl = ve.make_dataloader(rpkm.copy(), tnfs.copy(), lens, batchsize=B)
@@ -45,21 +49,24 @@ def main():
         _, g32, eps, keeps = o.grads(d[idx], t[idx], a[idx], w[idx])
         g64 = grads_fp64(o, d[idx], t[idx], a[idx], w[idx], eps, keeps)
         row = {"oracle_fp32": {k: rel(g32[k].numpy(), g64[k].numpy()) for k in g64}}
-        for name, tcmin, flush in (("cuda_tcgen05_3xtf32", 1, 0), ("cuda_tcgen05_3xtf32_wgrad_flush128", 1, 1),
-                                   ("cuda_fp32_ffma", 0, 0)):
+        for name, tcmin, flush, staging in (("cuda_tcgen05_3xtf32", 1, 0, 0), ("cuda_tcgen05_3xtf32_wgrad_flush128", 1, 1, 0),
+                                            ("cuda_tcgen05_3xtf32_prep_staging", 1, 0, 1), ("cuda_fp32_ffma", 0, 0, 0)):
             vae = ve.VAE(S, seed=2)
             vae._net.tc_min_batch = tcmin
             vae._net.wgrad_flush = flush
+            vae._net.staging = staging
             vae._step_injected(dl.dataset.tensors, idx.numpy(), eps.numpy(), [k.numpy() for k in keeps], optimize=False)
             got = vae._grad_dict()
             row[name] = {k: rel(got[k].cpu().numpy(), g64[k].numpy()) for k in g64}
-        out[str(B)] = row
-        print(f"B = {B}: worst tensor / median over tensors of ||g - g64|| / ||g64||")
+        out[f"S{S}_B{B}"] = row
+        print(f"S = {S}, B = {B}: worst tensor / median over tensors of ||g - g64|| / ||g64||")
         for name, errs in row.items():
             worst = max(errs, key=errs.get)
-            print(f"  {name:22s} worst {errs[worst]:.2e} ({worst})  median {np.median(list(errs.values())):.2e}")
+            print(f"  {name:36s} worst {errs[worst]:.2e} ({worst})  median {np.median(list(errs.values())):.2e}")
+            if errs[worst] > 5e-5:
+                print("      tensors above 5e-5:", {k: float(f"{v:.2e}") for k, v in errs.items() if v > 5e-5})
     os.makedirs("gpurun_out", exist_ok=True)
-    with open("gpurun_out/r02_grad_error_fp64.json", "w") as fh:
+    with open(os.environ.get("GRAD_OUT", "gpurun_out/r02_grad_error_fp64.json"), "w") as fh:
         json.dump(out, fh, indent=1)
 
 

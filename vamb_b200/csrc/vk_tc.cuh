@@ -22,32 +22,24 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void mbar_fence_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-// A wait that never completes (a lost arrival, a bulk copy that never lands) traps after ~2 s instead of hanging the
-// GPU.  The clock is only consulted after a long run of failed polls: the hot path is the bare try_wait loop.
-__device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
-    uint32_t ok;
+// The bare try_wait loop (the hardware suspends the thread inside try_wait for a bounded time), plus a poll counter: a
+// wait that never completes (a lost arrival, a bulk copy that never lands) traps after 2^26 failed polls (seconds)
+// instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    return ok != 0;
-}
-static __device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity) {
-    const long long t0 = clock64();
-    for (;;) {
-        for (int i = 0; i < 1024; ++i)
-            if (mbar_try_wait(addr, parity)) return;
-        if (clock64() - t0 > 4000000000LL) __trap();
-    }
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-#pragma unroll 1
-    for (int i = 0; i < 4096; ++i)
-        if (mbar_try_wait(addr, parity)) return;
-    mbar_wait_slow(addr, parity);
+        ".reg .pred p, q;\n\t"
+        ".reg .u32 n;\n\t"
+        "mov.u32 n, 0;\n\t"
+        "LAB_WAIT%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra LAB_DONE%=;\n\t"
+        "add.u32 n, n, 1;\n\t"
+        "setp.lt.u32 q, n, 0x4000000;\n\t"
+        "@q bra LAB_WAIT%=;\n\t"
+        "trap;\n\t"
+        "LAB_DONE%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
 // ---- fences ----

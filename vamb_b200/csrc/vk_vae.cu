@@ -837,6 +837,12 @@ struct BwdTcExtra {
 // Forward layer: D = X' W^T on the tensor core, then one coalesced pass over the shared tile does bias,
 // LeakyReLU, dropout (one Philox call per four outputs) / the reparameterisation, and the global stores;
 // hidden layers in training add the BatchNorm column sums and the last CTA folds them.
+// TMA: the weight operand through cp.async.bulk.tensor; FLUSH: accumulation chain cut every 128 K-elements (fp32 register
+// sums, vk_tc.cuh) -- used for evaluation (`encode`), where the latent must stay within 1e-4 of fp32: the tensor core's
+// truncating accumulator alone leaves ~1e-5 of the accumulator magnitude per 512-deep layer (1.5e-4 on |mu| <= 11.5,
+// profiles/r02_encode_error.txt).  One instantiation per combination keeps every kernel's code (and its cold
+// instruction-cache footprint at launch) to the path it runs.
+template <bool TMA, bool FLUSH>
 __global__ void __launch_bounds__(tc::WS_THREADS, 1) fwd_layer_tc_kernel(const __grid_constant__ FwdArgs a) {
     tl_begin(a.layer_id);
     const int tk = tk_begin(20 + a.layer_id);
@@ -855,13 +861,13 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) fwd_layer_tc_kernel(const _
     const uint32_t k0 = (uint32_t)a.ctl->seed, k1 = (uint32_t)(a.ctl->seed >> 32);
     const uint32_t step_lo = (uint32_t)a.ctl->step, step_hi = (uint32_t)(a.ctl->step >> 32);
     const int nk = (a.K + tc::KT - 1) / tc::KT;
-    const bool alive = a.use_tma
-        ? tc::ws_mainloop<true>(a.a_op.hi, a.a_op.ld, m0, a.b_op.hi, a.b_op.ld, n0, bn, 0, nk, smem, &sh, a.tile_n, &a.tm_b_hi, &a.tm_b_lo)
-        : tc::ws_mainloop<false>(a.a_op.hi, a.a_op.ld, m0, a.b_op.hi, a.b_op.ld, n0, bn, 0, nk, smem, &sh);
-    if (!alive) return;
+    float racc[FLUSH ? 4 : 1][16];
+    if (!tc::ws_mainloop<TMA, FLUSH>(a.a_op.hi, a.a_op.ld, m0, a.b_op.hi, a.b_op.ld, n0, bn, 0, nk, smem, &sh, a.tile_n,
+                                     &a.tm_b_hi, &a.tm_b_lo, FLUSH ? racc : nullptr))
+        return;
     tl_mark(2);
     float *tile = reinterpret_cast<float *>(smem);  // [128][TS]; the operand stages are dead now
-    tc::ws_acc_to_tile(&sh, bn, nk, tile, TS);
+    tc::ws_acc_to_tile(&sh, bn, nk, tile, TS, FLUSH ? racc : nullptr);
     tl_mark(3);
     tc::ws_tile_end(&sh);
     tl_mark(44);
@@ -1003,6 +1009,7 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) fwd_layer_tc_kernel(const _
 
 // Backward layer: wgrad slices (split-K over the batch, one gradient slab per split) and dgrad tiles in
 // one launch.
+template <bool TMA, bool FLUSH>
 __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(const __grid_constant__ BwdArgs a, BwdTcExtra x) {
     tl_begin(8 + a.ticket_id);
     const int tk = tk_begin(40 + a.ticket_id);
@@ -1026,15 +1033,12 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(const _
         int nb = a.B - b0;
         nb = nb < 0 ? 0 : (nb > x.k_per_split ? x.k_per_split : nb);
         const int nk = (nb + tc::KT - 1) / tc::KT;  // b0 is a multiple of 32; the staged operands are zero padded
-        float racc[4][16];
-        const bool alive_wg = x.flush
-            ? tc::ws_mainloop<false, true>(a.wg_a.hi, a.wg_a.ld, m0, a.wg_b.hi, a.wg_b.ld, n0, bn, b0 / tc::KT, nk, smem, &sh, 0,
-                                           nullptr, nullptr, racc)
-            : tc::ws_mainloop<false, false>(a.wg_a.hi, a.wg_a.ld, m0, a.wg_b.hi, a.wg_b.ld, n0, bn, b0 / tc::KT, nk, smem, &sh);
-        if (!alive_wg) return;
+        float racc[FLUSH ? 4 : 1][16];
+        if (!tc::ws_mainloop<false, FLUSH>(a.wg_a.hi, a.wg_a.ld, m0, a.wg_b.hi, a.wg_b.ld, n0, bn, b0 / tc::KT, nk, smem, &sh, 0,
+                                           nullptr, nullptr, FLUSH ? racc : nullptr))
+            return;
         tl_mark(2);
-        if (x.flush) tc::ws_acc_to_tile(&sh, bn, nk, tile, TS, racc);
-        else tc::ws_acc_to_tile(&sh, bn, nk, tile, TS);
+        tc::ws_acc_to_tile(&sh, bn, nk, tile, TS, FLUSH ? racc : nullptr);
         tl_mark(3);
         tc::ws_tile_end(&sh);
         float *gW = a.gW + (int64_t)split * x.slab, *gb = a.gb + (int64_t)split * x.slab;
@@ -1057,10 +1061,9 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(const _
     bn = bn > a.tile_n ? a.tile_n : ((bn + 15) & ~15);
     const float gsc = (float)(a.ctl->wbar / (double)a.B);
     const int nk = (a.N + tc::KT - 1) / tc::KT;
-    const bool alive = a.use_tma
-        ? tc::ws_mainloop<true>(a.dg_a.hi, a.dg_a.ld, m0, a.dg_b.hi, a.dg_b.ld, n0, bn, 0, nk, smem, &sh, a.tile_n, &a.tm_dg_hi, &a.tm_dg_lo)
-        : tc::ws_mainloop<false>(a.dg_a.hi, a.dg_a.ld, m0, a.dg_b.hi, a.dg_b.ld, n0, bn, 0, nk, smem, &sh);
-    if (!alive) return;
+    if (!tc::ws_mainloop<TMA, false>(a.dg_a.hi, a.dg_a.ld, m0, a.dg_b.hi, a.dg_b.ld, n0, bn, 0, nk, smem, &sh, a.tile_n,
+                                     &a.tm_dg_hi, &a.tm_dg_lo))
+        return;
     const int q_per_row = bn >> 2;
     float *ptile = tile + 128 * TS;  // the previous layer's output P for the same rows / columns (zeros outside)
     if (a.in_kind == VK_IN_BN) {
@@ -1611,8 +1614,14 @@ static bool use_tma(const vk_vae *net, const vk_vae_layer &L) {
 static int tc_prepare() {
     static bool done = false;
     if (done) return 0;
-    VK_CUDA(cudaFuncSetAttribute(fwd_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_for(128, 1)));
-    VK_CUDA(cudaFuncSetAttribute(bwd_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_for(128, 2)));
+#define VK_TC_ATTR(T, F)                                                                                                          \
+    VK_CUDA(cudaFuncSetAttribute(fwd_layer_tc_kernel<T, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_for(128, 1))); \
+    VK_CUDA(cudaFuncSetAttribute(bwd_layer_tc_kernel<T, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_for(128, 2)))
+    VK_TC_ATTR(false, false);
+    VK_TC_ATTR(false, true);
+    VK_TC_ATTR(true, false);
+    VK_TC_ATTR(true, true);
+#undef VK_TC_ATTR
     done = true;
     return 0;
 }
@@ -1807,7 +1816,17 @@ static int launch_forward(const vk_vae *net, int B, int training, int upto /*exc
                               vk_make_tmap_2d(&a.tm_b_lo, L.w_lo, r32(L.k_in), r128(L.n_out), a.tile_n)))
                 return 1;
             dim3 grid((L.n_out + a.tile_n - 1) / a.tile_n, (B + 127) / 128);
-            VK_CUDA(vk_launch(fwd_layer_tc_kernel, dim3(grid), dim3(tc::WS_THREADS), (size_t)tc_smem_for(a.tile_n, 1), s, a));
+            // evaluation (encode): the flushed accumulation keeps the latent within 1e-4 of fp32 (net->wgrad_flush == 2
+            // forces it in training too, for measurements)
+            const bool flush = !training || net->wgrad_flush == 2;
+            const size_t smem = (size_t)tc_smem_for(a.tile_n, 1);
+            if (a.use_tma) {
+                if (flush) VK_CUDA(vk_launch(fwd_layer_tc_kernel<true, true>, dim3(grid), dim3(tc::WS_THREADS), smem, s, a));
+                else VK_CUDA(vk_launch(fwd_layer_tc_kernel<true, false>, dim3(grid), dim3(tc::WS_THREADS), smem, s, a));
+            } else {
+                if (flush) VK_CUDA(vk_launch(fwd_layer_tc_kernel<false, true>, dim3(grid), dim3(tc::WS_THREADS), smem, s, a));
+                else VK_CUDA(vk_launch(fwd_layer_tc_kernel<false, false>, dim3(grid), dim3(tc::WS_THREADS), smem, s, a));
+            }
         } else {
             dim3 grid((L.n_out + 63) / 64, (B + 63) / 64);
             VK_CUDA(vk_launch(fwd_layer_kernel, dim3(grid), dim3(GT), (size_t)(0), s, a));
@@ -1915,7 +1934,7 @@ static int launch_backward(const vk_vae *net, int B, cudaStream_t s) {
             x.nsplit = tc_nsplit(net, B);
             x.k_per_split = (((B + x.nsplit - 1) / x.nsplit) + 31) & ~31;
             x.slab = net->grad_slab;
-            x.flush = net->wgrad_flush;
+            x.flush = net->wgrad_flush != 0;
             a.tile_n = tc_tile_n(B);
             a.wg_tiles_m = (L.n_out + 127) / 128;
             a.wg_tile_n = tc_wg_tile_n(B);
@@ -1933,7 +1952,14 @@ static int launch_backward(const vk_vae *net, int B, cudaStream_t s) {
                               vk_make_tmap_2d(&a.tm_dg_lo, L.wt_lo, r32(L.n_out), r128(L.k_in), a.tile_n)))
                 return 1;
             const int blocks = a.wg_tiles_m * a.wg_tiles_n * x.nsplit + a.dg_tiles_m * a.dg_tiles_n;
-            VK_CUDA(vk_launch(bwd_layer_tc_kernel, dim3(blocks), dim3(tc::WS_THREADS), (size_t)tc_smem_for(a.tile_n > a.wg_tile_n ? a.tile_n : a.wg_tile_n, 2), s, a, x));
+            const size_t smem = (size_t)tc_smem_for(a.tile_n > a.wg_tile_n ? a.tile_n : a.wg_tile_n, 2);
+            if (a.use_tma) {
+                if (x.flush) VK_CUDA(vk_launch(bwd_layer_tc_kernel<true, true>, dim3(blocks), dim3(tc::WS_THREADS), smem, s, a, x));
+                else VK_CUDA(vk_launch(bwd_layer_tc_kernel<true, false>, dim3(blocks), dim3(tc::WS_THREADS), smem, s, a, x));
+            } else {
+                if (x.flush) VK_CUDA(vk_launch(bwd_layer_tc_kernel<false, true>, dim3(blocks), dim3(tc::WS_THREADS), smem, s, a, x));
+                else VK_CUDA(vk_launch(bwd_layer_tc_kernel<false, false>, dim3(blocks), dim3(tc::WS_THREADS), smem, s, a, x));
+            }
         } else {
             const int blocks = a.wg_tiles_m * a.wg_tiles_n + a.dg_tiles_m * a.dg_tiles_n;
             VK_CUDA(vk_launch(bwd_layer_kernel, dim3(blocks), dim3(GT), (size_t)(0), s, a));
