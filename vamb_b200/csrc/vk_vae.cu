@@ -953,6 +953,7 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) fwd_layer_tc_kernel(const _
         if (a.stage != 1) return;  // the consumer (prep_kernel of the next layer) folds the column sums
         // every CTA's column sums are needed: wait for the whole grid, then fold the own columns
         grid_barrier(&a.ctl->tickets[a.layer_id], &a.ctl->barrier_gen[a.layer_id], gridDim.x * gridDim.y);
+        tl_mark(6);
         if (tid < bn) {
             const int n = n0 + tid;
             float k0 = 0.0f, k1 = 0.0f;
@@ -994,6 +995,7 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) fwd_layer_tc_kernel(const _
         return;
     }
     __syncthreads();
+    tl_mark(45);
     // the next layer's input X' = BatchNorm(P) (or z): the tile holds P with zeros outside [B, N]
     auto bn_apply = [&](int r, int c, float v) {
         return (m0 + r < a.B && n0 + c < a.N) ? __fmaf_rn(v, s_k[0][c], s_k[1][c]) : 0.0f;
@@ -1004,6 +1006,7 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) fwd_layer_tc_kernel(const _
         // the row of ones that turns the bias gradient into one more column of the wgrad GEMM
         if (blockIdx.x == 0 && tid < 128) a.stage_t[(int64_t)a.N * a.stage_t_ld + m0 + tid] = m0 + tid < a.B ? 1.0f : 0.0f;
     }
+    tl_mark(7);
     tk_end(tk);
 }
 
