@@ -115,7 +115,8 @@ int vk_eval_candidates_mapped(const float *matrix, const float *lengths, int d, 
  * VK_LIST_CAND uint64, all zero on entry, left zeroed; n_cand <= VK_LIST_CAND). */
 int vk_eval_candidates_lists(const float *matrix, const float *lengths, int d, const int32_t *nl_rows,
                              const float *nl_dists, int32_t n_nl, float prune_radius, const int32_t *cand_rows_host,
-                             int n_cand, int32_t base_row, uint64_t *out_dev, uint64_t *out_pinned, int32_t *within_pinned,
+                             int n_cand, int32_t base_row, uint64_t *out_dev, uint64_t *out_pinned,
+                             int32_t *within_dev /* device scratch [VK_LIST_CAND * within_cap] */, int32_t *within_pinned,
                              int32_t within_cap, int32_t *done_ticket, int32_t *done_flag_pinned, int32_t seq, void *stream);
 
 /* vamb/cluster.py:640-650 (_smaller_indices) + :308-309 (kept_mask[point] = 0):

@@ -240,12 +240,14 @@ def test_eval_candidates_lists_matches_oracle(vk):
     out_dev = torch.zeros(4 * C, dtype=torch.int64, device="cuda")
     out_pin = torch.zeros(4 * C, dtype=torch.int64).pin_memory()
     within_pin = torch.zeros(C * cap, dtype=torch.int32).pin_memory()
+    within_dev = torch.zeros(C * cap, dtype=torch.int32, device="cuda")
     ticket = torch.zeros(1, dtype=torch.int32, device="cuda")
     flag = torch.zeros(1, dtype=torch.int32).pin_memory()
     arr = (vk.c_int32 * len(cands))(*[int(c) for c in cands])
     vk.check(vk.lib.vk_eval_candidates_lists(dm.data_ptr(), dl.data_ptr(), d, nl_rows.data_ptr(), nl_d.data_ptr(), n_nl,
                                              0.3, arr, len(cands), base, out_dev.data_ptr(), out_pin.data_ptr(),
-                                             within_pin.data_ptr(), cap, ticket.data_ptr(), flag.data_ptr(), 7, s))
+                                             within_dev.data_ptr(), within_pin.data_ptr(), cap, ticket.data_ptr(),
+                                             flag.data_ptr(), 7, s))
     assert int(flag[0]) == 7 and int(out_dev.abs().sum()) == 0  # accumulators left zeroed for the next call
     res = out_pin.numpy().view(np.uint64)
     sel = np.flatnonzero(kept)

@@ -596,11 +596,16 @@ eval_candidates_kernel(const float *__restrict__ matrix, const float *__restrict
     const unsigned gmask = group8_mask();
     const int dpad = (d + 3) & ~3;
     const bool vec4 = (d & 3) == 0;
+    __shared__ int32_t s_crow[VK_MAX_CAND];  // static-index copy of the by-value parameter (no local-memory spill)
+#pragma unroll
+    for (int k = 0; k < VK_MAX_CAND; ++k)
+        if (tid == k) s_crow[k] = k < n_cand ? cand.rows[k] : -1;
+    if (tid < VK_MAX_CAND) { s_dens[tid] = 0ull; s_dens_hi[tid] = 0ull; s_cnt[tid] = 0u; }
+    __syncthreads();
     for (int i = tid; i < n_cand * dpad; i += EC_THREADS) {
         const int k = i / dpad, c = i - k * dpad;
-        s_qs[i] = c < d ? matrix[(int64_t)cand.rows[k] * d + c] : 0.0f;
+        s_qs[i] = c < d ? matrix[(int64_t)s_crow[k] * d + c] : 0.0f;
     }
-    if (tid < VK_MAX_CAND) { s_dens[tid] = 0ull; s_dens_hi[tid] = 0ull; s_cnt[tid] = 0u; }
     __syncthreads();
 
     const float rad = 0.05f;
@@ -623,7 +628,7 @@ eval_candidates_kernel(const float *__restrict__ matrix, const float *__restrict
             acc = group8_sum(acc, gmask);
             if (lane8 == 0) {
                 float dd = __fsub_rn(0.5f, acc);
-                if (row == cand.rows[k]) dd = 0.0f;
+                if (row == s_crow[k]) dd = 0.0f;
                 if (dd <= rad) {
                     const u64 cq = closeness_fx(rad, dd);
                     atomicAdd(&s_dens[k], lenq * (cq & 4095ull));
@@ -740,23 +745,27 @@ __global__ void __launch_bounds__(EC_THREADS)
 eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths, int d,
                              const int32_t *__restrict__ nl_rows, const float *__restrict__ nl_dists, int n_nl,
                              float prune_radius, CandRowsL cand, int n_cand, int32_t base_row, u64 *out, u64 *out_mapped,
-                             int32_t *within_mapped, int within_cap, int32_t *done_ticket, volatile int32_t *done_flag,
-                             int32_t seq) {
+                             int32_t *within_dev, int32_t *within_mapped, int within_cap, int32_t *done_ticket,
+                             volatile int32_t *done_flag, int32_t seq) {
     extern __shared__ __align__(16) float s_qs[];  // [n_cand][dpad]
     __shared__ u64 s_dens[VK_LIST_CAND];
     __shared__ u64 s_dens_hi[VK_LIST_CAND];
-    __shared__ int32_t s_crow[VK_LIST_CAND];  // candidate rows (indexing the by-value parameter array dynamically would
-                                              // send every access through local memory)
+    __shared__ int32_t s_crow[VK_LIST_CAND];  // candidate rows: copied out of the by-value parameter with STATIC indices
+                                              // (a dynamic index would make every thread spill the array to local memory)
     const int tid = threadIdx.x, lane8 = tid & 7, g = tid >> 3;
     const unsigned gmask = group8_mask();
     const int dpad = (d + 3) & ~3;
     const bool vec4 = (d & 3) == 0;
     const bool fast = (d == 32);
+#pragma unroll
+    for (int k = 0; k < VK_LIST_CAND; ++k)
+        if (tid == k) s_crow[k] = k < n_cand ? cand.rows[k] : -1;
+    if (tid < VK_LIST_CAND) { s_dens[tid] = 0ull; s_dens_hi[tid] = 0ull; }
+    __syncthreads();
     for (int i = tid; i < n_cand * dpad; i += EC_THREADS) {
         const int k = i / dpad, c = i - k * dpad;
-        s_qs[i] = c < d ? matrix[(int64_t)cand.rows[k] * d + c] : 0.0f;
+        s_qs[i] = c < d ? matrix[(int64_t)s_crow[k] * d + c] : 0.0f;
     }
-    if (tid < VK_LIST_CAND) { s_dens[tid] = 0ull; s_dens_hi[tid] = 0ull; s_crow[tid] = tid < n_cand ? cand.rows[tid] : -1; }
     __syncthreads();
 
     const float rad = 0.05f;
@@ -816,10 +825,7 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
                     atomicAdd(&s_dens[k], lenq * (cq & 4095ull));
                     atomicAdd(&s_dens_hi[k], lenq * (cq >> 12));
                     const u64 pos = atomicAdd(&out[2 * VK_LIST_CAND + k], 1ull);  // rare: a few dozen hits per candidate
-                    if (pos < (u64)within_cap) {
-                        within_mapped[(size_t)k * within_cap + pos] = row;  // pinned host memory
-                        __threadfence_system();  // by the writing thread only: a few dozen ids per candidate
-                    }
+                    if (pos < (u64)within_cap) within_dev[(size_t)k * within_cap + pos] = row;
                 }
             }
         }
@@ -831,6 +837,17 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
     }
     __shared__ int s_last;
     if (!vk_last_block(done_ticket, &s_last)) return;
+    // the last block publishes: the id lists (device -> pinned host memory, one warp per candidate, coalesced), then the
+    // sums and counts; ONE system-scope fence (vk_raise_flag) orders all of it before the flag
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int kk = warp; kk < n_cand; kk += EC_THREADS / 32) {
+            u64 cnt = __ldcg(out + 2 * VK_LIST_CAND + kk);
+            if (cnt > (u64)within_cap) cnt = (u64)within_cap;
+            for (int i = lane; i < (int)cnt; i += 32)
+                within_mapped[(size_t)kk * within_cap + i] = __ldcg(within_dev + (size_t)kk * within_cap + i);
+        }
+    }
     if (tid < 4 * VK_LIST_CAND) {
         out_mapped[tid] = __ldcg(out + tid);
         out[tid] = 0ull;
@@ -841,8 +858,9 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
 extern "C" int vk_eval_candidates_lists(const float *matrix, const float *lengths, int d, const int32_t *nl_rows,
                                         const float *nl_dists, int32_t n_nl, float prune_radius,
                                         const int32_t *cand_rows_host, int n_cand, int32_t base_row, uint64_t *out_dev,
-                                        uint64_t *out_pinned, int32_t *within_pinned, int32_t within_cap,
-                                        int32_t *done_ticket, int32_t *done_flag_pinned, int32_t seq, void *stream) {
+                                        uint64_t *out_pinned, int32_t *within_dev, int32_t *within_pinned,
+                                        int32_t within_cap, int32_t *done_ticket, int32_t *done_flag_pinned, int32_t seq,
+                                        void *stream) {
     if (n_cand < 1 || n_cand > VK_LIST_CAND || within_cap < 1) {
         vk_set_error("vk_eval_candidates_lists: n_cand=%d outside [1, %d] or bad capacity", n_cand, VK_LIST_CAND);
         return 1;
@@ -865,7 +883,8 @@ extern "C" int vk_eval_candidates_lists(const float *matrix, const float *length
     if (grid > cap) grid = cap;
     eval_candidates_lists_kernel<<<grid, EC_THREADS, smem, s>>>(matrix, lengths, d, nl_rows, nl_dists, n_nl, prune_radius,
                                                                 cand, n_cand, base_row, (u64 *)out_dev, (u64 *)out_pinned,
-                                                                within_pinned, within_cap, done_ticket, done_flag_pinned, seq);
+                                                                within_dev, within_pinned, within_cap, done_ticket,
+                                                                done_flag_pinned, seq);
     VK_LAUNCH_CHECK();
     return wait_flag(done_flag_pinned, seq, s, "vk_eval_candidates_lists");
 }

@@ -129,7 +129,7 @@ struct State {
     int32_t seq = 0;
     // lazy medoid moves (vk_eval_candidates_lists): device accumulators, pinned results and id lists
     uint64_t *cand2_dev = nullptr, *cand2_pin = nullptr;
-    int32_t *within_pin = nullptr;
+    int32_t *within_pin = nullptr, *within_dev = nullptr;
     int64_t n_moves_lazy = 0, n_rebases = 0, sum_nnl = 0;  // sum_nnl: neighbour-list sizes over all candidate evaluations
     bool lazy_enabled = true;  // VAMB_B200_CLUSTER_LAZY=0: a full scan per move, as round 1 (same clusters)
     std::vector<int64_t> members;
@@ -295,7 +295,7 @@ int do_eval_lists(State &st, const Probe &base, float prune, const std::vector<i
     ++st.n_evals;
     st.sum_nnl += base.n_nl;
     if (vk_eval_candidates_lists(st.M(), st.LEN(), c.d, c.nl_rows, c.nl_dists, base.n_nl, prune, rows.data(), n, base.medoid,
-                                 st.cand2_dev, st.cand2_pin, st.within_pin, WITHIN_CAP, st.tickets_dev + 1,
+                                 st.cand2_dev, st.cand2_pin, st.within_dev, st.within_pin, WITHIN_CAP, st.tickets_dev + 1,
                                  st.flags_pin + 1, ++st.seq, c.stream))
         return 1;
     out.dens.resize((size_t)n);
@@ -519,6 +519,7 @@ extern "C" int vk_cluster_create(void **handle, const vk_cluster_config *cfg) {
         cudaHostAlloc((void **)&st->cand2_pin, sizeof(uint64_t) * 4 * VK_LIST_CAND, cudaHostAllocMapped) != cudaSuccess ||
         cudaHostAlloc((void **)&st->within_pin, sizeof(int32_t) * VK_LIST_CAND * WITHIN_CAP, cudaHostAllocMapped) != cudaSuccess ||
         cudaMalloc((void **)&st->cand2_dev, sizeof(uint64_t) * 4 * VK_LIST_CAND) != cudaSuccess ||
+        cudaMalloc((void **)&st->within_dev, sizeof(int32_t) * VK_LIST_CAND * WITHIN_CAP) != cudaSuccess ||
         cudaMemsetAsync(st->cand2_dev, 0, sizeof(uint64_t) * 4 * VK_LIST_CAND, s) != cudaSuccess ||
         cudaMemsetAsync(st->tickets_dev, 0, sizeof(int32_t) * 2, s) != cudaSuccess ||
         cudaMemsetAsync(cfg->hdr, 0, sizeof(vk_probe_header), s) != cudaSuccess ||
@@ -544,6 +545,7 @@ extern "C" void vk_cluster_destroy(void *handle) {
     if (st->cand2_pin) cudaFreeHost(st->cand2_pin);
     if (st->within_pin) cudaFreeHost(st->within_pin);
     if (st->cand2_dev) cudaFree(st->cand2_dev);
+    if (st->within_dev) cudaFree(st->within_dev);
     delete st;
 }
 
