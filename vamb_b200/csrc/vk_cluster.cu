@@ -194,6 +194,7 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
              int32_t *nl_rows, float *nl_dists, int n_tiles, vk_probe_header *hdr_mapped, int32_t *done_ticket,
              volatile int32_t *done_flag, int32_t seq) {
     const int d = DFIX ? DFIX : d_rt;
+    tl_begin(0);
     __shared__ float s_edges[VK_NBINS + 1];
     __shared__ u64 s_hist[VK_NBINS];
     __shared__ int32_t s_wrows[PB_THREADS / 32][PB_WBUF];
@@ -226,6 +227,7 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
     }
     __syncthreads();
 
+    tl_mark(1);
     float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
     if (DFIX == 32) qv = *reinterpret_cast<const float4 *>(s_q + 4 * lane8);
     const float e_lo = s_edges[0], e_hi = s_edges[VK_NBINS];
@@ -351,6 +353,7 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
         }
         if (wcnt > PB_WBUF - 4 * PB_R) flush_warp();  // a warp appends at most 4 entries per row slot
     }
+    tl_mark(2);
     flush_warp();
 
     if (lane8 == 0 && (t_dens | t_dens_hi | t_nlt)) {
@@ -368,12 +371,15 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
         if (s_acc.dens_hi) atomicAdd(reinterpret_cast<u64 *>(&hdr->density_hi), s_acc.dens_hi);
         if (s_acc.nlt) atomicAdd(&hdr->n_lt, (int)s_acc.nlt);
     }
+    tl_mark(3);
     if (hdr_mapped == nullptr) return;
     // Mapped completion (vk_probe_mapped): the last block to finish copies the header into pinned host memory,
     // leaves the device accumulators zeroed for the next probe and raises the flag the host is spinning on --
     // one launch per probe instead of memset + kernel + copy + stream synchronisation.
     __shared__ int s_last;
+    tl_mark(4);
     if (!vk_last_block(done_ticket, &s_last)) return;
+    tl_mark_any(5);
     constexpr int HEAD_WORDS = (int)(offsetof(vk_probe_header, within) / sizeof(u64));  // accumulators + counters
     if (tid < HEAD_WORDS) reinterpret_cast<u64 *>(hdr_mapped)[tid] = __ldcg(reinterpret_cast<const u64 *>(hdr) + tid);
     int nw = __ldcg(&hdr->n_within);
@@ -381,7 +387,9 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
     for (int i = tid; i < nw; i += PB_THREADS) hdr_mapped->within[i] = __ldcg(&hdr->within[i]);
     __syncthreads();
     if (tid < HEAD_WORDS) reinterpret_cast<u64 *>(hdr)[tid] = 0ull;
+    tl_mark_any(6);
     vk_raise_flag(done_flag, seq);
+    tl_mark_any(7);
 }
 
 // Launch shape of the probe: rows in flight per lane (VK_PROBE_R = 4 | 8) and persistent blocks per SM
@@ -1033,3 +1041,13 @@ extern "C" int vk_compact_rows_sync(const float *matrix, const float *lengths, c
     *n_out_host = total;
     return 0;
 }
+
+#ifdef VK_TIMELINE
+// stamps of the probe kernel (slots 0 entry, 1 prologue done, 2 scan done, 3 block sums merged, 4 before the ticket
+// [block 0]; 5 last block elected, 6 results written to pinned memory, 7 flag raised [last block])
+extern "C" int vk_cluster_timeline_read(unsigned long long *out_host) {
+    VK_CUDA(cudaDeviceSynchronize());
+    VK_CUDA(cudaMemcpyFromSymbol(out_host, vk_tl, sizeof(unsigned long long) * 4096));
+    return 0;
+}
+#endif

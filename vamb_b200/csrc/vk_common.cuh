@@ -120,6 +120,15 @@ __device__ __forceinline__ void tl_mark(int slot) {
         vk_tl[((vk_tl_base + slot) & 4095) ^ 2048] = (unsigned long long)clock64();
     }
 }
+// stamp from thread 0 of WHICHEVER block calls it (e.g. the last block of a mapped-completion kernel)
+__device__ __forceinline__ void tl_mark_any(int slot) {
+    if (threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        vk_tl[(vk_tl_base + slot) & 4095] = t;
+        vk_tl[((vk_tl_base + slot) & 4095) ^ 2048] = (unsigned long long)clock64();
+    }
+}
 __device__ __forceinline__ void tl_begin(int kernel_id) {
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) vk_tl_base = kernel_id * 64;
     tl_mark(0);
@@ -147,6 +156,7 @@ __device__ __forceinline__ void tk_end(int idx) {
 }
 #else
 #define tl_mark(slot) ((void)0)
+#define tl_mark_any(slot) ((void)0)
 #define tl_begin(id) ((void)0)
 #define tk_begin(kind) (-1)
 #define tk_end(idx) ((void)(idx))
