@@ -856,6 +856,7 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
                 within_mapped[(size_t)kk * within_cap + i] = __ldcg(within_dev + (size_t)kk * within_cap + i);
         }
     }
+    __syncthreads();  // every warp has read its counts before they are zeroed below
     if (tid < 4 * VK_LIST_CAND) {
         out_mapped[tid] = __ldcg(out + tid);
         out[tid] = 0ull;
