@@ -731,29 +731,78 @@ __device__ __forceinline__ uint8_t *align1024(uint8_t *p) {
     return reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
 }
 
-// Column sums of two per-element quantities over the 128 rows of the shared tile(s), fixed order.
-// f(r, c) -> (v0, v1).  Writes out0/out1[n0 + c] for c < bn with n0 + c < N.
+// Column sums of two per-element quantities over the 128 rows of the shared tile(s), in a fixed order, by ALL 256
+// epilogue threads: the tile's bn columns (a multiple of 16) are covered by G = 256 / bnp row groups (bnp = bn rounded
+// up to a power of two), thread (g, col) sums rows [g * 128 / G, (g + 1) * 128 / G) in double, and thread col folds the
+// G partials in order.  (One thread per column and half -- 64 serial double additions -- cost 1.65 us per layer at
+// B = 256, where only 32 of the 256 threads had a column: tools/kernel_timeline.py.)
+// f(r, c) -> (v0, v1).  Writes out0/out1[n0 + c] for c < bn with n0 + c < N.  s_cs: 512 doubles of shared memory.
 template <class F>
 __device__ __forceinline__ void tc_colsum2(int bn, int n0, int N, double (*s_cs)[2][128], double *out0, double *out1,
                                            const F &f) {
-    const int tid = threadIdx.x, col = tid & 127, half = tid >> 7;
+    double *part = &s_cs[0][0][0];  // [G][2][bnp] with G * bnp = 256
+    const int tid = threadIdx.x;
+    int bnp = 16;
+    while (bnp < bn) bnp <<= 1;
+    const int G = 256 / bnp, rows_per = 128 / G;
+    const int col = tid & (bnp - 1), g = tid / bnp;
     if (col < bn) {
         double a0 = 0.0, a1 = 0.0;
-        for (int r = half * 64; r < half * 64 + 64; ++r) {
+        const int r0 = g * rows_per;
+#pragma unroll 4
+        for (int r = r0; r < r0 + rows_per; ++r) {
             float v0, v1;
             f(r, col, v0, v1);
             a0 += (double)v0;
             a1 += (double)v1;
         }
-        s_cs[half][0][col] = a0;
-        s_cs[half][1][col] = a1;
+        part[(g * 2 + 0) * bnp + col] = a0;
+        part[(g * 2 + 1) * bnp + col] = a1;
     }
     __syncthreads();
     if (tid < bn && n0 + tid < N) {
-        out0[n0 + tid] = s_cs[0][0][tid] + s_cs[1][0][tid];
-        out1[n0 + tid] = s_cs[0][1][tid] + s_cs[1][1][tid];
+        double t0 = 0.0, t1 = 0.0;
+        for (int gg = 0; gg < G; ++gg) {
+            t0 += part[(gg * 2 + 0) * bnp + tid];
+            t1 += part[(gg * 2 + 1) * bnp + tid];
+        }
+        out0[n0 + tid] = t0;
+        out1[n0 + tid] = t1;
     }
     __syncthreads();
+}
+
+// Fold the per-row-tile column partials of this CTA's columns over all n_rt row tiles with ALL 256 epilogue threads
+// (thread (g, col) takes row tiles g, g + G, ...; thread col adds the G partials in order): u / v are valid for
+// tid < bn.  A single thread per column walking 32 row tiles of L2-resident partials cost 4.8 us at B = 4096.
+__device__ __forceinline__ void fold_rowtile_sums(const double *part, int n_rt, int N, int n0, int bn,
+                                                  double (*s_cs)[2][128], double &u, double &v) {
+    double *sp = &s_cs[0][0][0];  // [G][2][bnp], G * bnp = 256
+    const int tid = threadIdx.x;
+    int bnp = 16;
+    while (bnp < bn) bnp <<= 1;
+    const int G = 256 / bnp;
+    const int col = tid & (bnp - 1), g = tid / bnp;
+    double a0 = 0.0, a1 = 0.0;
+    if (col < bn && n0 + col < N) {
+#pragma unroll 4
+        for (int rt = g; rt < n_rt; rt += G) {
+            a0 += __ldcg(part + ((int64_t)rt * 2 + 0) * N + n0 + col);
+            a1 += __ldcg(part + ((int64_t)rt * 2 + 1) * N + n0 + col);
+        }
+    }
+    if (col < bn) {
+        sp[(g * 2 + 0) * bnp + col] = a0;
+        sp[(g * 2 + 1) * bnp + col] = a1;
+    }
+    __syncthreads();
+    u = 0.0;
+    v = 0.0;
+    if (tid < bn)
+        for (int gg = 0; gg < G; ++gg) {
+            u += sp[(gg * 2 + 0) * bnp + tid];
+            v += sp[(gg * 2 + 1) * bnp + tid];
+        }
 }
 
 // ---- fused staging: the producing kernel writes the consumer GEMM's operands from its shared tile ----
@@ -771,9 +820,8 @@ __device__ __forceinline__ void grid_barrier(int32_t *cnt, int32_t *gen, int tot
             atomicExch(gen, g + 1);
         } else {
             unsigned spins = 0;
-            while (*reinterpret_cast<volatile int32_t *>(gen) == g) {
-                __nanosleep(32);
-                if (++spins > (1u << 24)) __trap();
+            while (*reinterpret_cast<volatile int32_t *>(gen) == g) {  // one thread per CTA polls: no back-off needed
+                if (++spins > (1u << 26)) __trap();
             }
         }
         __threadfence();
@@ -954,15 +1002,12 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) fwd_layer_tc_kernel(const _
         // every CTA's column sums are needed: wait for the whole grid, then fold the own columns
         grid_barrier(&a.ctl->tickets[a.layer_id], &a.ctl->barrier_gen[a.layer_id], gridDim.x * gridDim.y);
         tl_mark(6);
+        double sm, q;
+        fold_rowtile_sums(a.part, (int)gridDim.y, a.N, n0, bn, s_cs, sm, q);
         if (tid < bn) {
             const int n = n0 + tid;
             float k0 = 0.0f, k1 = 0.0f;
             if (n < a.N) {
-                double sm = 0.0, q = 0.0;
-                for (int rt = 0; rt < (int)gridDim.y; ++rt) {
-                    sm += __ldcg(a.part + ((int64_t)rt * 2 + 0) * a.N + n);
-                    q += __ldcg(a.part + ((int64_t)rt * 2 + 1) * a.N + n);
-                }
                 // torch.nn.BatchNorm1d in training mode (as bn_forward_finalize)
                 const double mean = sm / a.B;
                 double var = q / a.B - mean * mean;
@@ -1131,15 +1176,12 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(const _
         });
         if (a.stage != 1) return;  // the consumer (prep_kernel staging dL/dY of the previous layer) folds the sums
         grid_barrier(&a.ctl->tickets[a.ticket_id], &a.ctl->barrier_gen[a.ticket_id - 1], a.dg_tiles_m * a.dg_tiles_n);
+        double u, v;
+        fold_rowtile_sums(a.part_prev, a.dg_tiles_m, a.K, n0, bn, s_cs, u, v);
         if (tid < bn) {
             const int n = n0 + tid;
             float k0 = 0.0f, k1 = 0.0f, k2 = 0.0f;
             if (n < a.K) {
-                double u = 0.0, v = 0.0;
-                for (int rt = 0; rt < a.dg_tiles_m; ++rt) {
-                    u += __ldcg(a.part_prev + ((int64_t)rt * 2 + 0) * a.K + n);
-                    v += __ldcg(a.part_prev + ((int64_t)rt * 2 + 1) * a.K + n);
-                }
                 // BatchNorm weight / bias gradients and the folded dL/dY constants (as bn_backward_finalize)
                 const float rs = a.rstd_prev[n], mu = a.mean_prev[n];
                 const float m1 = (float)(u / a.B), m2 = (float)(v / a.B);
