@@ -25,4 +25,32 @@ for n in (1_000_000, 5_000_000):
     print(f"N={n}: event time {a.elapsed_time(b) * 1e3:.1f} us; global timer [us after block-0 entry]: prologue {rel[1]:.1f}, "
           f"scan done {rel[2]:.1f}, sums merged {rel[3]:.1f}, before ticket {rel[4]:.1f} | last block elected {rel[5]:.1f}, "
           f"pinned writes done {rel[6]:.1f}, flag raised {rel[7]:.1f}")
+    # one candidate evaluation over the neighbour list the probe left behind (kernel id 1 -> slots 64..)
+    hdr = state["hdr"].numpy()
+    n_nl = int(hdr[_lib.HDR_NNL:_lib.HDR_NNL + 4].view(np.int32)[0])
+    n_within = int(hdr[_lib.HDR_NWITHIN:_lib.HDR_NWITHIN + 4].view(np.int32)[0])
+    cands = hdr[_lib.HDR_WITHIN:_lib.HDR_WITHIN + 4 * min(n_within, 40)].view(np.int32).tolist()
+    C, cap = _lib.VK_LIST_CAND, 1024
+    out_dev = torch.zeros(4 * C, dtype=torch.int64, device="cuda")
+    out_pin = torch.zeros(4 * C, dtype=torch.int64).pin_memory()
+    wdev = torch.zeros(C * cap, dtype=torch.int32, device="cuda")
+    wpin = torch.zeros(C * cap, dtype=torch.int32).pin_memory()
+    ticket = torch.zeros(1, dtype=torch.int32, device="cuda")
+    flag = torch.zeros(1, dtype=torch.int32).pin_memory()
+    arr = (_lib.c_int32 * len(cands))(*cands)
+    base = (7 * 7919 + n // 2) % n
+    for seq in (1, 2, 3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _lib.check(_lib.lib.vk_eval_candidates_lists(gen._m.data_ptr(), gen._len.data_ptr(), 32, gen._nl_rows.data_ptr(),
+                                                     gen._nl_d.data_ptr(), n_nl, 0.2, arr, len(cands), base, out_dev.data_ptr(),
+                                                     out_pin.data_ptr(), wdev.data_ptr(), wpin.data_ptr(), cap, ticket.data_ptr(),
+                                                     flag.data_ptr(), seq, gen._stream))
+        b.record(); torch.cuda.synchronize()
+    rd(buf.ctypes.data)
+    g = buf[64:128].astype(np.int64)
+    rel = [(int(g[i]) - int(g[0])) / 1e3 if g[i] else float("nan") for i in range(8)]
+    print(f"   eval of {len(cands)} candidates over a {n_nl}-row list: event time {a.elapsed_time(b) * 1e3:.1f} us; [us after block-0 entry] "
+          f"prologue {rel[1]:.1f}, rows done {rel[2]:.1f}, block barrier {rel[3]:.1f}, before ticket {rel[4]:.1f} | last block elected "
+          f"{rel[5]:.1f}, published {rel[6]:.1f}, flag raised {rel[7]:.1f}")
     del gen, lat

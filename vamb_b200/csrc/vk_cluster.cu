@@ -755,6 +755,7 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
                              float prune_radius, CandRowsL cand, int n_cand, int32_t base_row, u64 *out, u64 *out_mapped,
                              int32_t *within_dev, int32_t *within_mapped, int within_cap, int32_t *done_ticket,
                              volatile int32_t *done_flag, int32_t seq) {
+    tl_begin(1);
     extern __shared__ __align__(16) float s_qs[];  // [n_cand][dpad]
     __shared__ u64 s_dens[VK_LIST_CAND];
     __shared__ u64 s_dens_hi[VK_LIST_CAND];
@@ -803,6 +804,7 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
         }
     }
     __syncthreads();
+    tl_mark(1);
     // the bound is geometry on unit-norm rows: an infinite prune_radius (rows not verified as normalised) switches it off
     const bool geo = prune_radius < 1e29f;
     float reach = 0.0f;
@@ -838,13 +840,17 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
             }
         }
     }
+    tl_mark(2);
     __syncthreads();
+    tl_mark(3);
     if (tid < n_cand) {
         if (s_dens[tid]) atomicAdd(&out[tid], s_dens[tid]);
         if (s_dens_hi[tid]) atomicAdd(&out[VK_LIST_CAND + tid], s_dens_hi[tid]);
     }
     __shared__ int s_last;
+    tl_mark(4);
     if (!vk_last_block(done_ticket, &s_last)) return;
+    tl_mark_any(5);
     // the last block publishes: the id lists (device -> pinned host memory, one warp per candidate, coalesced), then the
     // sums and counts; ONE system-scope fence (vk_raise_flag) orders all of it before the flag
     {
@@ -861,7 +867,9 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
         out_mapped[tid] = __ldcg(out + tid);
         out[tid] = 0ull;
     }
+    tl_mark_any(6);
     vk_raise_flag(done_flag, seq);
+    tl_mark_any(7);
 }
 
 extern "C" int vk_eval_candidates_lists(const float *matrix, const float *lengths, int d, const int32_t *nl_rows,

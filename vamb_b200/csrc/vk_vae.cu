@@ -927,6 +927,44 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) fwd_layer_tc_kernel(const _
     const float keep_scale = 1.0f / (1.0f - a.dropout);
     const bool vec = ((a.N & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
     const int q_per_row = bn >> 2;
+    // Lean pass for the case that carries the training run -- a hidden layer in training mode with on-device dropout, a
+    // tile that lies fully inside [.., N) and a power-of-two tile width: the general loop below spends ~700 SASS
+    // instructions per four outputs (64-bit address arithmetic for five optional outputs, per-element bounds, two inlined
+    // Philox bodies, an integer division; ncu: 11 of the 33 us of a 512 -> 512 layer at B = 4096), this one ~150.  Same
+    // values, same Philox stream: the keep test (float)(x >> 8) + 1) * 2^-24 > p is the integer test (x >> 8) >= floor(p 2^24).
+    const bool lean = hidden && a.training && a.keep == nullptr && vec && (n0 + bn <= a.N) && ((q_per_row & (q_per_row - 1)) == 0);
+    if (lean) {
+        const int sh = __ffs(q_per_row) - 1;
+        const uint32_t thr = (uint32_t)floor((double)a.dropout * 16777216.0);
+        const uint32_t c3 = step_hi ^ ((uint32_t)(a.layer_id + 1) << 24);
+        const float slope = a.slope;
+        float *out_tile = a.out + (int64_t)m0 * a.N + n0;
+        const int rows_in = a.B - m0;  // rows of this tile inside the batch (may exceed 128)
+        const int N = a.N;
+#pragma unroll 2
+        for (int q = tid; q < (128 << sh); q += tc::WS_EPI_THREADS) {
+            const int r = q >> sh, c = (q & (q_per_row - 1)) << 2;
+            const float4 t = *reinterpret_cast<const float4 *>(tile + r * TS + c);
+            const float4 bz = *reinterpret_cast<const float4 *>(s_bias + c);
+            float p0 = t.x + bz.x, p1 = t.y + bz.y, p2 = t.z + bz.z, p3 = t.w + bz.w;
+            p0 = p0 > 0.0f ? p0 : p0 * slope;
+            p1 = p1 > 0.0f ? p1 : p1 * slope;
+            p2 = p2 > 0.0f ? p2 : p2 * slope;
+            p3 = p3 > 0.0f ? p3 : p3 * slope;
+            if (drop) {
+                uint32_t rnd[4];
+                philox4x32((uint32_t)(m0 + r), (uint32_t)((n0 + c) >> 2), step_lo, c3, k0, k1, rnd);
+                p0 = (rnd[0] >> 8) >= thr ? p0 * keep_scale : 0.0f;
+                p1 = (rnd[1] >> 8) >= thr ? p1 * keep_scale : 0.0f;
+                p2 = (rnd[2] >> 8) >= thr ? p2 * keep_scale : 0.0f;
+                p3 = (rnd[3] >> 8) >= thr ? p3 * keep_scale : 0.0f;
+            }
+            const bool in_batch = r < rows_in;
+            const float4 o = in_batch ? make_float4(p0, p1, p2, p3) : make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4 *>(tile + r * TS + c) = o;
+            if (in_batch) *reinterpret_cast<float4 *>(out_tile + r * N + c) = o;
+        }
+    } else
     for (int q = tid; q < 128 * q_per_row; q += tc::WS_EPI_THREADS) {
         const int r = q / q_per_row, c = (q - r * q_per_row) << 2;
         const int m = m0 + r, nb = n0 + c;
