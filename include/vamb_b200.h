@@ -82,11 +82,13 @@ int vk_probe_sync(const float *matrix, const float *lengths, const uint8_t *kept
  * (`hdr_pinned`, device-visible), leaves the device accumulators of `hdr` zeroed for the next call and sets
  * `*done_flag_pinned = seq`; the call returns once the host has seen the flag.  `hdr` must be all zero before
  * the first call, `*done_ticket` (device) zero.  One launch per probe instead of memset + kernel + copy +
- * stream synchronisation.  Used by the native cluster driver (vk_cluster_next). */
+ * stream synchronisation.  `work_counter` (device int32, zero before the first call, left zero; NULL = static
+ * striding): the blocks draw their 256-row work units from it, so faster SMs scan more of the matrix.
+ * Used by the native cluster driver (vk_cluster_next). */
 int vk_probe_mapped(const float *matrix, const float *lengths, const uint8_t *kept, int64_t n, int d,
                     int64_t medoid_row, float nl_radius, const float *edges, vk_probe_header *hdr,
                     int32_t *within_overflow, int32_t *nl_rows, float *nl_dists, vk_probe_header *hdr_pinned,
-                    int32_t *done_ticket, int32_t *done_flag_pinned, int32_t seq, void *stream);
+                    int32_t *done_ticket, int32_t *done_flag_pinned, int32_t seq, int32_t *work_counter, void *stream);
 
 /* Local densities of up to VK_MAX_CAND candidate medoids in one pass over the neighbour
  * list (the <= maxsteps sample_medoid calls of one wander_medoid round,

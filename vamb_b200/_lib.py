@@ -60,7 +60,7 @@ _SIGNATURES = {
     "vk_check_normalized": [_p, c_int64, c_int, c_float, _p, _p],
     "vk_probe": [_p, _p, _p, c_int64, c_int, c_int64, c_float, _p, _p, _p, _p, _p, _p],
     "vk_probe_sync": [_p, _p, _p, c_int64, c_int, c_int64, c_float, _p, _p, _p, _p, _p, _p, _p],
-    "vk_probe_mapped": [_p, _p, _p, c_int64, c_int, c_int64, c_float, _p, _p, _p, _p, _p, _p, _p, _p, c_int32, _p],
+    "vk_probe_mapped": [_p, _p, _p, c_int64, c_int, c_int64, c_float, _p, _p, _p, _p, _p, _p, _p, _p, c_int32, _p, _p],
     "vk_eval_candidates_sync": [_p, _p, c_int, _p, _p, c_int32, c_float, POINTER(c_int32), c_int, _p, _p, _p],
     "vk_eval_candidates_mapped": [_p, _p, c_int, _p, _p, c_int32, c_float, POINTER(c_int32), c_int, _p, _p, _p, _p,
                                   c_int32, _p],

@@ -461,7 +461,7 @@ class ClusterGenerator:
         if not state:
             self._hdr.zero_()
             state["hdr"] = _torch.zeros(_lib.HDR_SIZE, dtype=_torch.uint8).pin_memory()
-            state["ticket"] = _torch.zeros(1, dtype=_torch.int32, device=self._m.device)
+            state["ticket"] = _torch.zeros(2, dtype=_torch.int32, device=self._m.device)  # [ticket, work counter]
             state["flag"] = _torch.zeros(1, dtype=_torch.int32).pin_memory()
             state["seq"] = 0
             _torch.cuda.synchronize()
@@ -470,7 +470,7 @@ class ClusterGenerator:
             self._m.data_ptr(), self._len.data_ptr(), self._kept.data_ptr(), self._n_act, self._d, int(row),
             self._nl_radius, self._edges.data_ptr(), self._hdr.data_ptr(), self._within_over.data_ptr(),
             self._nl_rows.data_ptr(), self._nl_d.data_ptr(), state["hdr"].data_ptr(), state["ticket"].data_ptr(),
-            state["flag"].data_ptr(), state["seq"], self._stream))
+            state["flag"].data_ptr(), state["seq"], state["ticket"].data_ptr() + 4, self._stream))
 
     def _timing(self) -> dict:
         "Host seconds the native driver spent per call kind so far (diagnostics / bench)."

@@ -172,27 +172,16 @@ struct ProbeAcc {
 // no block barrier) and flushed with one global reservation per ~48 entries.
 constexpr int PB_WBUF = 64;  // staged entries per warp (<= 16 appended per iteration)
 
-// R = independent rows (float4 loads) in flight per lane and per buffer; BPS = resident blocks per SM the register
-// budget is held to.  RING = 0: two register buffers per lane (the chunk being processed and the next one).
-// RING > 0 (D = 32): each LANE owns a private queue of RING chunks in shared memory filled by cp.async (LDGSTS, 16 bytes
-// per row and lane) -- a lane only ever reads back what it copied itself, so there is no barrier of any kind in the loop
-// (cp.async.wait_group is per thread) and RING x R x 16 bytes per lane are in flight instead of 2 x R x 16: the loop at
-// N = 1M is bound by memory latency per iteration, not by bandwidth (profiles/r02_probe_sweep_v1.txt: 24 us of the
-// 44 us do not scale with N).
-__device__ __forceinline__ void probe_cp_async16(uint32_t saddr, const void *gptr) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
-}
-__device__ __forceinline__ void probe_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void probe_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-template <int DFIX, int R, int BPS, int RING>
+// R = independent rows (float4 loads) in flight per lane and per buffer (the chunk being processed and the next one);
+// BPS = resident blocks per SM the register budget is held to.  (A per-lane cp.async queue of 4-12 chunks in shared
+// memory was measured and dropped: 63-92 us against 45 us at N = 1M, profiles/r02_probe_sweep_v2.txt.)
+template <int DFIX, int R, int BPS>
 __global__ void __launch_bounds__(PB_THREADS, BPS)
 probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths,
              const uint8_t *__restrict__ kept, int64_t n, int d_rt, int64_t mrow, float nl_radius,
              const float *__restrict__ edges_g, vk_probe_header *hdr, int32_t *within_overflow,
              int32_t *nl_rows, float *nl_dists, int n_tiles, vk_probe_header *hdr_mapped, int32_t *done_ticket,
-             volatile int32_t *done_flag, int32_t seq) {
+             volatile int32_t *done_flag, int32_t seq, int32_t *work_counter) {
     const int d = DFIX ? DFIX : d_rt;
     tl_begin(0);
     __shared__ float s_edges[VK_NBINS + 1];
@@ -267,45 +256,47 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
             if (row < n32) v[k] = ldg_stream4(matrix + (int64_t)row * 32 + 4 * lane8);
         }
     };
-    // RING: slot s of this lane = ring[(s * PB_R + k) * PB_THREADS + tid] (consecutive lanes -> consecutive 16 bytes)
-    extern __shared__ __align__(16) float4 s_ring[];
-    auto issue_chunk = [&](int c, int slot) {
-        if (c < n_chunks) {
-#pragma unroll
-            for (int k = 0; k < PB_R; ++k) {
-                const int row = c * CHUNK + k * PB_GROUPS + g;
-                if (row < n32)
-                    probe_cp_async16((uint32_t)__cvta_generic_to_shared(&s_ring[(slot * PB_R + k) * PB_THREADS + tid]),
-                                     matrix + (int64_t)row * 32 + 4 * lane8);
-            }
-        }
-        probe_cp_commit();  // one group per slot, possibly empty: the wait below counts groups
+    // Work distribution: units of PB_UNIT chunks (256 rows).  With a work counter (mapped completion: the native
+    // driver) every block draws its next unit from one atomic counter, two units ahead, so that the SMs that stream
+    // faster take more of the matrix -- with the static stride the slowest of the 592 blocks finished 7 us after the
+    // first at N = 1M (tools/probe_timeline.py), a quarter of the kernel.  Without a counter the units are strided.
+    constexpr int PB_UNIT = 2;
+    const int n_units = (n_chunks + PB_UNIT - 1) / PB_UNIT;
+    __shared__ int s_unit[2];
+    int static_unit = blockIdx.x;  // thread 0 only
+    auto fetch_unit = [&]() -> int {
+        if (work_counter) return atomicAdd(work_counter, 1);
+        const int u = static_unit;
+        static_unit += gridDim.x;
+        return u;
     };
-    if (DFIX == 32 && RING > 0) {
-#pragma unroll
-        for (int s0 = 0; s0 < RING - 1; ++s0) issue_chunk((int)blockIdx.x + s0 * (int)gridDim.x, s0);
-    } else if (DFIX == 32 && (int)blockIdx.x < n_chunks) {
-        load_chunk(blockIdx.x, vnext);
+    if (tid == 0) {
+        s_unit[0] = fetch_unit();
+        s_unit[1] = fetch_unit();
     }
-    int ring_it = 0;
+    __syncthreads();
+    int cur = s_unit[0], nxt = s_unit[1], par = 0;
+    __syncthreads();  // both slots read by everyone before slot 0 is rewritten
+    if (DFIX == 32 && cur < n_units) load_chunk(cur * PB_UNIT, vnext);
 #pragma unroll 1
-    for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    while (cur < n_units) {
+        if (tid == 0) s_unit[par] = fetch_unit();  // the unit after next; consumed after the barrier below
+#pragma unroll 1
+        for (int it = 0; it < PB_UNIT; ++it) {
+        const int c = cur * PB_UNIT + it;
+        if (c >= n_chunks) break;
         float acc[PB_R];
         int rows[PB_R];
 #pragma unroll
         for (int k = 0; k < PB_R; ++k) rows[k] = c * CHUNK + k * PB_GROUPS + g;
-        if (DFIX == 32 && RING > 0) {
-            const int slot = ring_it % RING;
-            issue_chunk(c + (RING - 1) * (int)gridDim.x, (ring_it + RING - 1) % RING);
-            probe_cp_wait<RING - 1>();  // all but the newest RING - 1 groups have landed: this chunk is in
-            ++ring_it;
-#pragma unroll
-            for (int k = 0; k < PB_R; ++k) acc[k] = chain4(s_ring[(slot * PB_R + k) * PB_THREADS + tid], qv);
-        } else if (DFIX == 32) {
+        if (DFIX == 32) {
             float4 v[PB_R];
 #pragma unroll
             for (int k = 0; k < PB_R; ++k) v[k] = vnext[k];
-            if (c + (int)gridDim.x < n_chunks) load_chunk(c + gridDim.x, vnext);
+            // the next chunk of this block: the following one of the unit, else the first one of the next unit
+            const bool unit_end = (it + 1 == PB_UNIT) || (c + 1 >= n_chunks);
+            if (!unit_end) load_chunk(c + 1, vnext);
+            else if (nxt < n_units) load_chunk(nxt * PB_UNIT, vnext);
 #pragma unroll
             for (int k = 0; k < PB_R; ++k) acc[k] = chain4(v[k], qv);
         } else {
@@ -352,6 +343,11 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
             }
         }
         if (wcnt > PB_WBUF - 4 * PB_R) flush_warp();  // a warp appends at most 4 entries per row slot
+        }
+        __syncthreads();
+        cur = nxt;
+        nxt = s_unit[par];
+        par ^= 1;
     }
     tl_mark(2);
     flush_warp();
@@ -380,6 +376,7 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
     tl_mark(4);
     if (!vk_last_block(done_ticket, &s_last)) return;
     tl_mark_any(5);
+    if (tid == 0 && work_counter) *work_counter = 0;  // every block has drawn its last unit before its ticket
     constexpr int HEAD_WORDS = (int)(offsetof(vk_probe_header, within) / sizeof(u64));  // accumulators + counters
     if (tid < HEAD_WORDS) reinterpret_cast<u64 *>(hdr_mapped)[tid] = __ldcg(reinterpret_cast<const u64 *>(hdr) + tid);
     int nw = __ldcg(&hdr->n_within);
@@ -403,10 +400,6 @@ static int probe_r() {
     static const int r = probe_env("VK_PROBE_R", 4, 4, 8) >= 8 ? 8 : 4;
     return r;
 }
-static int probe_ring() {  // VK_PROBE_RING = 0 (registers) | 4 | 6 | 8 | 12 chunks queued per lane in shared memory
-    static const int g = probe_env("VK_PROBE_RING", 0, 0, 12);
-    return g;
-}
 static int probe_bps() {
     static const int b = probe_env("VK_PROBE_BPS", 4, 1, 8);
     return b;
@@ -419,7 +412,7 @@ static int probe_grid(int n_chunks) {
 static int probe_launch(const float *matrix, const float *lengths, const uint8_t *kept, int64_t n, int d,
                         int64_t medoid_row, float nl_radius, const float *edges, vk_probe_header *hdr,
                         int32_t *within_overflow, int32_t *nl_rows, float *nl_dists, vk_probe_header *hdr_mapped,
-                        int32_t *done_ticket, int32_t *done_flag, int32_t seq, cudaStream_t s) {
+                        int32_t *done_ticket, int32_t *done_flag, int32_t seq, int32_t *work_counter, cudaStream_t s) {
     if (n <= 0 || medoid_row < 0 || medoid_row >= n) {
         vk_set_error("vk_probe: bad arguments (n=%lld, medoid_row=%lld)", (long long)n, (long long)medoid_row);
         return 1;
@@ -441,30 +434,16 @@ static int probe_launch(const float *matrix, const float *lengths, const uint8_t
     const int r = probe_r();
     const int n_chunks = (int)((n + PB_GROUPS * r - 1) / (PB_GROUPS * r));
     const int grid = probe_grid(n_chunks);
-#define VK_PROBE_LAUNCH(DF, RR, BB, RG)                                                                              \
-    do {                                                                                                             \
-        const size_t ring_bytes = (size_t)(RG) * (RR) * PB_THREADS * sizeof(float4);                                  \
-        static bool attr_done = false;                                                                               \
-        if (ring_bytes > 40 * 1024 && !attr_done) {                                                                  \
-            VK_CUDA(cudaFuncSetAttribute(probe_kernel<DF, RR, BB, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                         (int)ring_bytes));                                                          \
-            attr_done = true;                                                                                        \
-        }                                                                                                            \
-        probe_kernel<DF, RR, BB, RG><<<grid, PB_THREADS, ring_bytes, s>>>(                                            \
-            matrix, lengths, kept, n, d, medoid_row, nl_radius, edges, hdr, within_overflow, nl_rows, nl_dists,       \
-            n_chunks, hdr_mapped, done_ticket, done_flag, seq);                                                      \
-    } while (0)
+#define VK_PROBE_LAUNCH(DF, RR, BB)                                                                                  \
+    probe_kernel<DF, RR, BB><<<grid, PB_THREADS, 0, s>>>(matrix, lengths, kept, n, d, medoid_row, nl_radius, edges, hdr, \
+                                                         within_overflow, nl_rows, nl_dists, n_chunks, hdr_mapped,       \
+                                                         done_ticket, done_flag, seq, work_counter)
     if (d == 32) {
-        const int ring = probe_ring();
-        if (ring == 4) VK_PROBE_LAUNCH(32, 4, 3, 4);        // 64 KB ring: 3 blocks / SM
-        else if (ring == 6) VK_PROBE_LAUNCH(32, 4, 2, 6);   // 96 KB ring: 2 blocks / SM
-        else if (ring == 8) VK_PROBE_LAUNCH(32, 4, 1, 8);   // 128 KB ring: 1 block / SM
-        else if (ring == 12) VK_PROBE_LAUNCH(32, 4, 1, 12); // 192 KB ring: 1 block / SM
-        else if (r == 8) VK_PROBE_LAUNCH(32, 8, 3, 0);
-        else if (probe_bps() > 4) VK_PROBE_LAUNCH(32, 4, 6, 0);
-        else VK_PROBE_LAUNCH(32, 4, 4, 0);
+        if (r == 8) VK_PROBE_LAUNCH(32, 8, 3);
+        else if (probe_bps() > 4) VK_PROBE_LAUNCH(32, 4, 6);
+        else VK_PROBE_LAUNCH(32, 4, 4);
     } else {
-        VK_PROBE_LAUNCH(0, 4, 4, 0);
+        VK_PROBE_LAUNCH(0, 4, 4);
     }
 #undef VK_PROBE_LAUNCH
     VK_LAUNCH_CHECK();
@@ -475,7 +454,7 @@ extern "C" int vk_probe(const float *matrix, const float *lengths, const uint8_t
                         int64_t medoid_row, float nl_radius, const float *edges, vk_probe_header *hdr,
                         int32_t *within_overflow, int32_t *nl_rows, float *nl_dists, void *stream) {
     return probe_launch(matrix, lengths, kept, n, d, medoid_row, nl_radius, edges, hdr, within_overflow, nl_rows,
-                        nl_dists, nullptr, nullptr, nullptr, 0, (cudaStream_t)stream);
+                        nl_dists, nullptr, nullptr, nullptr, 0, nullptr, (cudaStream_t)stream);
 }
 
 // Spin on a flag in pinned host memory that the last block of a kernel sets to `seq`; the stream is only
@@ -502,10 +481,10 @@ extern "C" int vk_probe_mapped(const float *matrix, const float *lengths, const 
                                int64_t medoid_row, float nl_radius, const float *edges, vk_probe_header *hdr,
                                int32_t *within_overflow, int32_t *nl_rows, float *nl_dists,
                                vk_probe_header *hdr_pinned, int32_t *done_ticket, int32_t *done_flag_pinned, int32_t seq,
-                               void *stream) {
+                               int32_t *work_counter, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (probe_launch(matrix, lengths, kept, n, d, medoid_row, nl_radius, edges, hdr, within_overflow, nl_rows, nl_dists,
-                     hdr_pinned, done_ticket, done_flag_pinned, seq, s))
+                     hdr_pinned, done_ticket, done_flag_pinned, seq, work_counter, s))
         return 1;
     return wait_flag(done_flag_pinned, seq, s, "vk_probe_mapped");
 }

@@ -125,7 +125,7 @@ struct State {
     vk_probe_header *hdr_pin = nullptr;
     uint64_t *cand_pin = nullptr;
     int32_t *flags_pin = nullptr;   // [0] probe, [1] candidate evaluation
-    int32_t *tickets_dev = nullptr; // [0] probe, [1] candidate evaluation
+    int32_t *tickets_dev = nullptr; // [0] probe, [1] candidate evaluation, [2] work counter of the probe
     int32_t seq = 0;
     // lazy medoid moves (vk_eval_candidates_lists): device accumulators, pinned results and id lists
     uint64_t *cand2_dev = nullptr, *cand2_pin = nullptr;
@@ -154,7 +154,7 @@ int do_probe(State &st, int32_t row, Probe &p) {
     ++st.n_probes;
     const vk_cluster_config &c = st.c;
     if (vk_probe_mapped(st.M(), st.LEN(), st.KEPT(), st.n_act, c.d, row, c.nl_radius, c.edges, c.hdr, c.within_overflow,
-                        c.nl_rows, c.nl_dists, st.hdr_pin, st.tickets_dev, st.flags_pin, ++st.seq, c.stream))
+                        c.nl_rows, c.nl_dists, st.hdr_pin, st.tickets_dev, st.flags_pin, ++st.seq, st.tickets_dev + 2, c.stream))
         return 1;
     const vk_probe_header *h = st.hdr_pin;
     p.medoid = row;
@@ -515,13 +515,13 @@ extern "C" int vk_cluster_create(void **handle, const vk_cluster_config *cfg) {
     if (cudaHostAlloc((void **)&st->hdr_pin, sizeof(vk_probe_header), cudaHostAllocMapped) != cudaSuccess ||
         cudaHostAlloc((void **)&st->cand_pin, sizeof(uint64_t) * 3 * VK_MAX_CAND, cudaHostAllocMapped) != cudaSuccess ||
         cudaHostAlloc((void **)&st->flags_pin, sizeof(int32_t) * 2, cudaHostAllocMapped) != cudaSuccess ||
-        cudaMalloc((void **)&st->tickets_dev, sizeof(int32_t) * 2) != cudaSuccess ||
+        cudaMalloc((void **)&st->tickets_dev, sizeof(int32_t) * 4) != cudaSuccess ||
         cudaHostAlloc((void **)&st->cand2_pin, sizeof(uint64_t) * 4 * VK_LIST_CAND, cudaHostAllocMapped) != cudaSuccess ||
         cudaHostAlloc((void **)&st->within_pin, sizeof(int32_t) * VK_LIST_CAND * WITHIN_CAP, cudaHostAllocMapped) != cudaSuccess ||
         cudaMalloc((void **)&st->cand2_dev, sizeof(uint64_t) * 4 * VK_LIST_CAND) != cudaSuccess ||
         cudaMalloc((void **)&st->within_dev, sizeof(int32_t) * VK_LIST_CAND * WITHIN_CAP) != cudaSuccess ||
         cudaMemsetAsync(st->cand2_dev, 0, sizeof(uint64_t) * 4 * VK_LIST_CAND, s) != cudaSuccess ||
-        cudaMemsetAsync(st->tickets_dev, 0, sizeof(int32_t) * 2, s) != cudaSuccess ||
+        cudaMemsetAsync(st->tickets_dev, 0, sizeof(int32_t) * 4, s) != cudaSuccess ||
         cudaMemsetAsync(cfg->hdr, 0, sizeof(vk_probe_header), s) != cudaSuccess ||
         cudaMemsetAsync(cfg->cand_out, 0, sizeof(uint64_t) * 3 * VK_MAX_CAND, s) != cudaSuccess ||
         cudaStreamSynchronize(s) != cudaSuccess) {
