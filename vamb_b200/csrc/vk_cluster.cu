@@ -738,6 +738,15 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
     extern __shared__ __align__(16) float s_qs[];  // [n_cand][dpad]
     __shared__ u64 s_dens[VK_LIST_CAND];
     __shared__ u64 s_dens_hi[VK_LIST_CAND];
+    // Hits (row within 0.05 of candidate k) are collected per block in shared memory and appended to the global id
+    // lists with ONE range reservation per (block, candidate): a returning global atomic per hit serialised ~40 of them
+    // (0.7-1 us each) in the lane that scans a row of a dense core -- the last block finished 38 us after the first
+    // (tools/probe_timeline.py).
+    constexpr int HIT_CAP = (EC_THREADS / 8) * VK_LIST_CAND;  // one round: 32 rows x 64 candidates
+    __shared__ int32_t s_hit_row[HIT_CAP];
+    __shared__ uint8_t s_hit_k[HIT_CAP];
+    __shared__ unsigned s_nhit, s_cnt[VK_LIST_CAND], s_cnt2[VK_LIST_CAND];
+    __shared__ u64 s_base[VK_LIST_CAND];
     __shared__ int32_t s_crow[VK_LIST_CAND];  // candidate rows: copied out of the by-value parameter with STATIC indices
                                               // (a dynamic index would make every thread spill the array to local memory)
     const int tid = threadIdx.x, lane8 = tid & 7, g = tid >> 3;
@@ -748,7 +757,8 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
 #pragma unroll
     for (int k = 0; k < VK_LIST_CAND; ++k)
         if (tid == k) s_crow[k] = k < n_cand ? cand.rows[k] : -1;
-    if (tid < VK_LIST_CAND) { s_dens[tid] = 0ull; s_dens_hi[tid] = 0ull; }
+    if (tid < VK_LIST_CAND) { s_dens[tid] = 0ull; s_dens_hi[tid] = 0ull; s_cnt[tid] = 0u; s_cnt2[tid] = 0u; }
+    if (tid == 0) s_nhit = 0u;
     __syncthreads();
     for (int i = tid; i < n_cand * dpad; i += EC_THREADS) {
         const int k = i / dpad, c = i - k * dpad;
@@ -790,34 +800,52 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
     for (int k = 0; k < n_cand; ++k) reach = fmaxf(reach, s_reach[k]);
     const float visit_radius = geo ? fminf(prune_radius, reach) : prune_radius;
     const int groups_total = gridDim.x * (EC_THREADS / 8);
-    for (int j = blockIdx.x * (EC_THREADS / 8) + g; j < n_nl; j += groups_total) {
-        const float dj = nl_dists[j];
-        if (!(dj <= visit_radius)) continue;  // uniform within the 8-lane group
-        const int row = nl_rows[j];
-        const float *x = matrix + (int64_t)row * d;
-        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (fast) xv = ldg_stream4(x + 4 * lane8);
-        u64 lenq = 0ull;
-        if (lane8 == 0) lenq = __float2ull_rz(__ldg(lengths + row));
-        for (int k = 0; k < n_cand; ++k) {
-            if (geo && !(dj <= s_reach[k])) continue;  // this row cannot be within 0.05 of candidate k
-            const float *q = s_qs + k * dpad;
-            float acc;
-            if (fast) acc = chain4(xv, *reinterpret_cast<const float4 *>(q + 4 * lane8));
-            else acc = lane_chain_generic(x, q, d, lane8, vec4);
-            acc = group8_sum(acc, gmask);
-            if (lane8 == 0) {
-                float dd = __fsub_rn(0.5f, acc);
-                if (row == s_crow[k]) dd = 0.0f;
-                if (dd <= rad) {
-                    const u64 cq = closeness_fx(rad, dd);
-                    atomicAdd(&s_dens[k], lenq * (cq & 4095ull));
-                    atomicAdd(&s_dens_hi[k], lenq * (cq >> 12));
-                    const u64 pos = atomicAdd(&out[2 * VK_LIST_CAND + k], 1ull);  // rare: a few dozen hits per candidate
-                    if (pos < (u64)within_cap) within_dev[(size_t)k * within_cap + pos] = row;
+    const int n_rounds = (n_nl + groups_total - 1) / groups_total;  // block-uniform
+    for (int round = 0; round < n_rounds; ++round) {
+        const int j = round * groups_total + blockIdx.x * (EC_THREADS / 8) + g;
+        const float dj = j < n_nl ? nl_dists[j] : 1e30f;
+        if (dj <= visit_radius) {  // uniform within the 8-lane group
+            const int row = nl_rows[j];
+            const float *x = matrix + (int64_t)row * d;
+            float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (fast) xv = ldg_stream4(x + 4 * lane8);
+            u64 lenq = 0ull;
+            if (lane8 == 0) lenq = __float2ull_rz(__ldg(lengths + row));
+            for (int k = 0; k < n_cand; ++k) {
+                if (geo && !(dj <= s_reach[k])) continue;  // this row cannot be within 0.05 of candidate k
+                const float *q = s_qs + k * dpad;
+                float acc;
+                if (fast) acc = chain4(xv, *reinterpret_cast<const float4 *>(q + 4 * lane8));
+                else acc = lane_chain_generic(x, q, d, lane8, vec4);
+                acc = group8_sum(acc, gmask);
+                if (lane8 == 0) {
+                    float dd = __fsub_rn(0.5f, acc);
+                    if (row == s_crow[k]) dd = 0.0f;
+                    if (dd <= rad) {
+                        const u64 cq = closeness_fx(rad, dd);
+                        atomicAdd(&s_dens[k], lenq * (cq & 4095ull));
+                        atomicAdd(&s_dens_hi[k], lenq * (cq >> 12));
+                        const unsigned h = atomicAdd(&s_nhit, 1u);  // shared memory: at most HIT_CAP hits per round
+                        s_hit_row[h] = row;
+                        s_hit_k[h] = (uint8_t)k;
+                        atomicAdd(&s_cnt[k], 1u);
+                    }
                 }
             }
         }
+        __syncthreads();
+        // publish the round's hits: one range per (block, candidate), then every hit takes a slot of its range
+        if (tid < n_cand && s_cnt[tid]) s_base[tid] = atomicAdd(&out[2 * VK_LIST_CAND + tid], (u64)s_cnt[tid]);
+        __syncthreads();
+        for (unsigned h = tid; h < s_nhit; h += EC_THREADS) {
+            const int kk = s_hit_k[h];
+            const u64 pos = s_base[kk] + atomicAdd(&s_cnt2[kk], 1u);
+            if (pos < (u64)within_cap) within_dev[(size_t)kk * within_cap + pos] = s_hit_row[h];
+        }
+        __syncthreads();
+        if (tid < VK_LIST_CAND) { s_cnt[tid] = 0u; s_cnt2[tid] = 0u; }
+        if (tid == 0) s_nhit = 0u;
+        __syncthreads();
     }
     tl_mark(2);
     __syncthreads();
