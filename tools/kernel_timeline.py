@@ -43,3 +43,12 @@ for B in [int(b) for b in os.environ.get("BATCHES", "256,1024,4096").split(",")]
         print(f"  L{k}: wait {d(0, 1):5.2f} setup {d(1, 8):5.2f} produce {d(8, 9):6.2f} drain {d(9, 2):5.2f} acc->tile {d(2, 3):5.2f} "
               f"tmem free {d(3, 44):5.2f} epilogue pass {d(44, 4):5.2f} colsum {d(4, 5):5.2f} grid barrier {d(5, 6):5.2f} "
               f"bn fold {d(6, 45):5.2f} staging {d(45, 7):5.2f} | total {d(0, 7):6.2f} | k-tiles {kt}")
+    print(f"   backward kernels (launch order: layer 5 .. 0), FIRST DGRAD CTA, [us]: main loop = entry -> accumulator complete, then the epilogue phases")
+    for k in range(19, 26):  # kernel id = 8 + ticket_id = 19 + layer
+        c = ck[k]
+        if c[1] == 0:
+            continue
+        def d(a, b):
+            return (c[b] - c[a]) / 1965.0 if c[a] and c[b] else float("nan")
+        print(f"  layer {k - 19}: main loop {d(1, 2):6.2f} P tile + acc->tile {d(2, 3):5.2f} pass (store dX) {d(3, 4):5.2f} colsum {d(4, 5):5.2f} "
+              f"grid barrier {d(5, 6):5.2f} fold {d(6, 45):5.2f} dY pass {d(45, 46):5.2f} staging {d(46, 7):5.2f} | total {d(1, 7):6.2f}")

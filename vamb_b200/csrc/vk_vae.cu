@@ -1142,6 +1142,8 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(const _
     }
     // ---- dgrad: dX[b, k] = sum_n dY[b, n] * W[n, k] ----
     const int t = blockIdx.x - n_wg;
+#define TLD(slot) do { if (t == 0) tl_mark_any(slot); } while (0)
+    TLD(1);
     const int m0 = (t / a.dg_tiles_n) * 128, n0 = (t % a.dg_tiles_n) * a.tile_n;
     int bn = a.K - n0;
     bn = bn > a.tile_n ? a.tile_n : ((bn + 15) & ~15);
@@ -1150,6 +1152,7 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(const _
     if (!tc::ws_mainloop<TMA, false>(a.dg_a.hi, a.dg_a.ld, m0, a.dg_b.hi, a.dg_b.ld, n0, bn, 0, nk, smem, &sh, a.tile_n,
                                      &a.tm_dg_hi, &a.tm_dg_lo))
         return;
+    TLD(2);
     const int q_per_row = bn >> 2;
     float *ptile = tile + 128 * TS;  // the previous layer's output P for the same rows / columns (zeros outside)
     if (a.in_kind == VK_IN_BN) {
@@ -1174,6 +1177,7 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(const _
     }
     tc::ws_acc_to_tile(&sh, bn, nk, tile, TS);
     tc::ws_tile_end(&sh);
+    TLD(3);
     const bool vec = ((a.K & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.d_in) & 15) == 0);
     const bool add_kld = a.in_kind == VK_IN_Z;
     for (int q = tid; q < 128 * q_per_row; q += tc::WS_EPI_THREADS) {
@@ -1198,6 +1202,7 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(const _
             }
         }
     }
+    TLD(4);
     __shared__ float s_k[3][128];
     if (a.in_kind == VK_IN_BN) {
         __syncthreads();
@@ -1212,8 +1217,10 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(const _
             v0 = dv;
             v1 = dv * ph;
         });
+        TLD(5);
         if (a.stage != 1) return;  // the consumer (prep_kernel staging dL/dY of the previous layer) folds the sums
         grid_barrier(&a.ctl->tickets[a.ticket_id], &a.ctl->barrier_gen[a.ticket_id - 1], a.dg_tiles_m * a.dg_tiles_n);
+        TLD(6);
         double u, v;
         fold_rowtile_sums(a.part_prev, a.dg_tiles_m, a.K, n0, bn, s_cs, u, v);
         if (tid < bn) {
@@ -1241,6 +1248,7 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(const _
             s_k[2][tid] = k2;
         }
         __syncthreads();
+        TLD(45);
         // dL/dY of the previous layer = sgn(P) * (bA dH + bB P + bC), 0 for dropped units, replaces dH in the tile
 #pragma unroll 4
         for (int q = tid; q < 128 * q_per_row; q += tc::WS_EPI_THREADS) {
@@ -1264,9 +1272,12 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(const _
         return;
     }
     __syncthreads();
+    TLD(46);
     auto ident = [](int, int, float v) { return v; };
     stage_tile_lane(tile, bn, a.stage_a, a.stage_a_ld, m0, n0, ident);
     stage_tile_transposed_lane(tile, bn, a.stage_t, a.stage_t_ld, m0, n0, a.K, ident);
+    TLD(7);
+#undef TLD
 }
 
 
