@@ -240,63 +240,65 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
         wcnt = 0;
     };
 
-    // chunks of 128 consecutive rows (4 per lane group), grid-strided; for D = 32 the next chunk's loads
-    // are issued before the current chunk is processed (register double buffering) so that every resident
-    // warp keeps 128 bytes per lane in flight.
+    // for D = 32 the next chunk's loads are issued before the current chunk is processed (register double buffering)
+    // so that every resident warp keeps 128 bytes per lane in flight.
     constexpr int PB_R = R;
-    constexpr int CHUNK = PB_GROUPS * PB_R;
     const int n32 = (int)n;
-    const int n_chunks = (n32 + CHUNK - 1) / CHUNK;
     float4 vnext[PB_R];
-    auto load_chunk = [&](int c, float4 (&v)[PB_R]) {
+    // Work distribution, PER WARP and without any block barrier: a warp-chunk is 4 x R consecutive rows (one 512-byte
+    // load per k for the warp), a unit is PB_WUNIT warp-chunks (256 rows at R = 4).  With a work counter (mapped
+    // completion: the native driver) every warp draws its next unit from one atomic counter, two units ahead -- lane 0
+    // issues the atomic at the start of a unit and the warp reads the result only at its end -- so that the SMs that
+    // stream faster take more of the matrix: with a static stride the slowest of the 592 blocks finished 7 us after the
+    // first at N = 1M (tools/probe_timeline.py), a quarter of the kernel; a block-level scheme with a barrier per
+    // unit balanced the tail but cost 30-45 % of the streaming rate.  Without a counter the units are strided.
+    constexpr int WCHUNK = 4 * PB_R, PB_WUNIT = 16;
+    const int n_wchunks = (n32 + WCHUNK - 1) / WCHUNK;
+    const int n_units = (n_wchunks + PB_WUNIT - 1) / PB_WUNIT;
+    const int gw = lane >> 3;  // group of the lane inside its warp
+    int static_unit = (int)blockIdx.x * (PB_THREADS / 32) + warp;  // lane 0 only
+    auto fetch_lane0 = [&]() -> int {  // called by lane 0; the result is consumed later (no immediate dependency)
+        if (work_counter) return atomicAdd(work_counter, 1);
+        const int u = static_unit;
+        static_unit += (int)gridDim.x * (PB_THREADS / 32);
+        return u;
+    };
+    auto load_wchunk = [&](int wc, float4 (&v)[PB_R]) {
 #pragma unroll
         for (int k = 0; k < PB_R; ++k) {
-            const int row = c * CHUNK + k * PB_GROUPS + g;
+            const int row = wc * WCHUNK + k * 4 + gw;
             v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (row < n32) v[k] = ldg_stream4(matrix + (int64_t)row * 32 + 4 * lane8);
         }
     };
-    // Work distribution: units of PB_UNIT chunks (256 rows).  With a work counter (mapped completion: the native
-    // driver) every block draws its next unit from one atomic counter, two units ahead, so that the SMs that stream
-    // faster take more of the matrix -- with the static stride the slowest of the 592 blocks finished 7 us after the
-    // first at N = 1M (tools/probe_timeline.py), a quarter of the kernel.  Without a counter the units are strided.
-    constexpr int PB_UNIT = 2;
-    const int n_units = (n_chunks + PB_UNIT - 1) / PB_UNIT;
-    __shared__ int s_unit[2];
-    int static_unit = blockIdx.x;  // thread 0 only
-    auto fetch_unit = [&]() -> int {
-        if (work_counter) return atomicAdd(work_counter, 1);
-        const int u = static_unit;
-        static_unit += gridDim.x;
-        return u;
-    };
-    if (tid == 0) {
-        s_unit[0] = fetch_unit();
-        s_unit[1] = fetch_unit();
+    int cur = 0, nxt = 0;
+    {
+        int a0 = 0, a1 = 0;
+        if (lane == 0) { a0 = fetch_lane0(); a1 = fetch_lane0(); }
+        cur = __shfl_sync(0xffffffffu, a0, 0);
+        nxt = __shfl_sync(0xffffffffu, a1, 0);
     }
-    __syncthreads();
-    int cur = s_unit[0], nxt = s_unit[1], par = 0;
-    __syncthreads();  // both slots read by everyone before slot 0 is rewritten
-    if (DFIX == 32 && cur < n_units) load_chunk(cur * PB_UNIT, vnext);
+    if (DFIX == 32 && cur < n_units) load_wchunk(cur * PB_WUNIT, vnext);
 #pragma unroll 1
     while (cur < n_units) {
-        if (tid == 0) s_unit[par] = fetch_unit();  // the unit after next; consumed after the barrier below
+        int pending = 0;
+        if (lane == 0) pending = fetch_lane0();  // the unit after next
 #pragma unroll 1
-        for (int it = 0; it < PB_UNIT; ++it) {
-        const int c = cur * PB_UNIT + it;
-        if (c >= n_chunks) break;
+        for (int it = 0; it < PB_WUNIT; ++it) {
+        const int c = cur * PB_WUNIT + it;
+        if (c >= n_wchunks) break;
         float acc[PB_R];
         int rows[PB_R];
 #pragma unroll
-        for (int k = 0; k < PB_R; ++k) rows[k] = c * CHUNK + k * PB_GROUPS + g;
+        for (int k = 0; k < PB_R; ++k) rows[k] = c * WCHUNK + k * 4 + gw;
         if (DFIX == 32) {
             float4 v[PB_R];
 #pragma unroll
             for (int k = 0; k < PB_R; ++k) v[k] = vnext[k];
-            // the next chunk of this block: the following one of the unit, else the first one of the next unit
-            const bool unit_end = (it + 1 == PB_UNIT) || (c + 1 >= n_chunks);
-            if (!unit_end) load_chunk(c + 1, vnext);
-            else if (nxt < n_units) load_chunk(nxt * PB_UNIT, vnext);
+            // the warp's next chunk: the following one of the unit, else the first one of its next unit
+            const bool unit_end = (it + 1 == PB_WUNIT) || (c + 1 >= n_wchunks);
+            if (!unit_end) load_wchunk(c + 1, vnext);
+            else if (nxt < n_units) load_wchunk(nxt * PB_WUNIT, vnext);
 #pragma unroll
             for (int k = 0; k < PB_R; ++k) acc[k] = chain4(v[k], qv);
         } else {
@@ -344,10 +346,8 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
         }
         if (wcnt > PB_WBUF - 4 * PB_R) flush_warp();  // a warp appends at most 4 entries per row slot
         }
-        __syncthreads();
         cur = nxt;
-        nxt = s_unit[par];
-        par ^= 1;
+        nxt = __shfl_sync(0xffffffffu, pending, 0);
     }
     tl_mark(2);
     flush_warp();
@@ -736,19 +736,21 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
                              volatile int32_t *done_flag, int32_t seq) {
     tl_begin(1);
     extern __shared__ __align__(16) float s_qs[];  // [n_cand][dpad]
-    __shared__ u64 s_dens[VK_LIST_CAND];
-    __shared__ u64 s_dens_hi[VK_LIST_CAND];
-    // Hits (row within 0.05 of candidate k) are collected per block in shared memory and appended to the global id
-    // lists with ONE range reservation per (block, candidate): a returning global atomic per hit serialised ~40 of them
-    // (0.7-1 us each) in the lane that scans a row of a dense core -- the last block finished 38 us after the first
-    // (tools/probe_timeline.py).
+    // A hit = (row within 0.05 of candidate k).  The lane that scans a row of a dense core finds a hit for almost every
+    // candidate; doing the bookkeeping there (three shared atomics + a returning global atomic per hit) serialised
+    // 40 x ~1 us in that one lane and the last block finished 25-38 us after the first (tools/probe_timeline.py).  So
+    // the scan only RECORDS hits (one 32-bit shared atomic each); all 256 threads then fold them into the per-candidate
+    // sums, reserve ONE range per (block, candidate) in the global id lists and scatter the ids.
     constexpr int HIT_CAP = (EC_THREADS / 8) * VK_LIST_CAND;  // one round: 32 rows x 64 candidates
     __shared__ int32_t s_hit_row[HIT_CAP];
+    __shared__ uint32_t s_hit_cq[HIT_CAP], s_hit_len[HIT_CAP];
+    __shared__ uint16_t s_hit_rank[HIT_CAP];
     __shared__ uint8_t s_hit_k[HIT_CAP];
-    __shared__ unsigned s_nhit, s_cnt[VK_LIST_CAND], s_cnt2[VK_LIST_CAND];
-    __shared__ u64 s_base[VK_LIST_CAND];
+    __shared__ unsigned s_nhit, s_cnt[VK_LIST_CAND];
+    __shared__ u64 s_base[VK_LIST_CAND], s_dens[VK_LIST_CAND], s_dens_hi[VK_LIST_CAND];
     __shared__ int32_t s_crow[VK_LIST_CAND];  // candidate rows: copied out of the by-value parameter with STATIC indices
                                               // (a dynamic index would make every thread spill the array to local memory)
+    __shared__ float s_reach[VK_LIST_CAND];
     const int tid = threadIdx.x, lane8 = tid & 7, g = tid >> 3;
     const unsigned gmask = group8_mask();
     const int dpad = (d + 3) & ~3;
@@ -757,13 +759,22 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
 #pragma unroll
     for (int k = 0; k < VK_LIST_CAND; ++k)
         if (tid == k) s_crow[k] = k < n_cand ? cand.rows[k] : -1;
-    if (tid < VK_LIST_CAND) { s_dens[tid] = 0ull; s_dens_hi[tid] = 0ull; s_cnt[tid] = 0u; s_cnt2[tid] = 0u; }
+    if (tid < VK_LIST_CAND) { s_dens[tid] = 0ull; s_dens_hi[tid] = 0ull; s_cnt[tid] = 0u; }
     if (tid == 0) s_nhit = 0u;
     __syncthreads();
-    for (int i = tid; i < n_cand * dpad; i += EC_THREADS) {
-        const int k = i / dpad, c = i - k * dpad;
-        s_qs[i] = c < d ? matrix[(int64_t)s_crow[k] * d + c] : 0.0f;
+    if (fast) {  // 8 float4 per candidate row, all loads independent
+        for (int i = tid; i < n_cand * 8; i += EC_THREADS)
+            *reinterpret_cast<float4 *>(s_qs + (i >> 3) * 32 + (i & 7) * 4) = ldg_stream4(matrix + (int64_t)s_crow[i >> 3] * 32 + (i & 7) * 4);
+    } else {
+        for (int i = tid; i < n_cand * dpad; i += EC_THREADS) {
+            const int k = i / dpad, c = i - k * dpad;
+            s_qs[i] = c < d ? matrix[(int64_t)s_crow[k] * d + c] : 0.0f;
+        }
     }
+    // the base row (for the candidates' distances to it) is loaded alongside
+    const float *xb = matrix + (int64_t)base_row * d;
+    float4 xbv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (fast) xbv = ldg_stream4(xb + 4 * lane8);
     __syncthreads();
 
     const float rad = 0.05f;
@@ -772,24 +783,18 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
     // angle(d_k) + acos(0.9) of the base, i.e. at a base distance of at most
     //     reach_k = 0.5 * (1 - ((1 - 2 d_k) * 0.9 - sqrt(1 - (1 - 2 d_k)^2) * sqrt(0.19)))      (+ 1e-4 of slack).
     // Neighbour-list entries beyond max_k reach_k (and beyond `prune_radius`) cannot matter and are not gathered.
-    __shared__ float s_reach[VK_LIST_CAND];
-    {
-        const float *x = matrix + (int64_t)base_row * d;
-        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (fast) xv = ldg_stream4(x + 4 * lane8);
-        for (int k = g; k < n_cand; k += EC_THREADS / 8) {
-            const float *q = s_qs + k * dpad;
-            float acc = fast ? chain4(xv, *reinterpret_cast<const float4 *>(q + 4 * lane8)) : lane_chain_generic(x, q, d, lane8, vec4);
-            acc = group8_sum(acc, gmask);
-            if (lane8 == 0) {
-                float dd = __fsub_rn(0.5f, acc);
-                if (s_crow[k] == base_row) dd = 0.0f;
-                if (blockIdx.x == 0) out[3 * VK_LIST_CAND + k] = (u64)__float_as_uint(dd);
-                const float ca = 1.0f - 2.0f * fmaxf(dd, 0.0f);
-                const float sa = sqrtf(fmaxf(1.0f - ca * ca, 0.0f));
-                const float cs = ca * 0.9f - sa * 0.43588990f;  // cos(angle(d_k) + acos(0.9))
-                s_reach[k] = (ca <= -0.9f) ? 1e30f : 0.5f * (1.0f - cs) + 1e-4f;  // beyond 180 degrees: everything
-            }
+    for (int k = g; k < n_cand; k += EC_THREADS / 8) {
+        const float *q = s_qs + k * dpad;
+        float acc = fast ? chain4(xbv, *reinterpret_cast<const float4 *>(q + 4 * lane8)) : lane_chain_generic(xb, q, d, lane8, vec4);
+        acc = group8_sum(acc, gmask);
+        if (lane8 == 0) {
+            float dd = __fsub_rn(0.5f, acc);
+            if (s_crow[k] == base_row) dd = 0.0f;
+            if (blockIdx.x == 0) out[3 * VK_LIST_CAND + k] = (u64)__float_as_uint(dd);
+            const float ca = 1.0f - 2.0f * fmaxf(dd, 0.0f);
+            const float sa = sqrtf(fmaxf(1.0f - ca * ca, 0.0f));
+            const float cs = ca * 0.9f - sa * 0.43588990f;  // cos(angle(d_k) + acos(0.9))
+            s_reach[k] = (ca <= -0.9f) ? 1e30f : 0.5f * (1.0f - cs) + 1e-4f;  // beyond 180 degrees: everything
         }
     }
     __syncthreads();
@@ -809,8 +814,8 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
             const float *x = matrix + (int64_t)row * d;
             float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
             if (fast) xv = ldg_stream4(x + 4 * lane8);
-            u64 lenq = 0ull;
-            if (lane8 == 0) lenq = __float2ull_rz(__ldg(lengths + row));
+            uint32_t lenq = 0u;
+            if (lane8 == 0) lenq = (uint32_t)__float2ull_rz(__ldg(lengths + row));  // integral, < 2^24 per contig
             for (int k = 0; k < n_cand; ++k) {
                 if (geo && !(dj <= s_reach[k])) continue;  // this row cannot be within 0.05 of candidate k
                 const float *q = s_qs + k * dpad;
@@ -822,33 +827,38 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
                     float dd = __fsub_rn(0.5f, acc);
                     if (row == s_crow[k]) dd = 0.0f;
                     if (dd <= rad) {
-                        const u64 cq = closeness_fx(rad, dd);
-                        atomicAdd(&s_dens[k], lenq * (cq & 4095ull));
-                        atomicAdd(&s_dens_hi[k], lenq * (cq >> 12));
-                        const unsigned h = atomicAdd(&s_nhit, 1u);  // shared memory: at most HIT_CAP hits per round
+                        const unsigned h = atomicAdd(&s_nhit, 1u);  // at most HIT_CAP hits per round
                         s_hit_row[h] = row;
                         s_hit_k[h] = (uint8_t)k;
-                        atomicAdd(&s_cnt[k], 1u);
+                        s_hit_cq[h] = (uint32_t)closeness_fx(rad, dd);  // <= 0.05 * 2^29 < 2^25
+                        s_hit_len[h] = lenq;
                     }
                 }
             }
         }
         __syncthreads();
-        // publish the round's hits: one range per (block, candidate), then every hit takes a slot of its range
+        const unsigned nh = s_nhit;
+        for (unsigned h = tid; h < nh; h += EC_THREADS) {  // fold: all threads, a few hits each
+            const int kk = s_hit_k[h];
+            const u64 cq = s_hit_cq[h], len = s_hit_len[h];
+            atomicAdd(&s_dens[kk], len * (cq & 4095ull));
+            atomicAdd(&s_dens_hi[kk], len * (cq >> 12));
+            s_hit_rank[h] = (uint16_t)atomicAdd(&s_cnt[kk], 1u);
+        }
+        __syncthreads();
         if (tid < n_cand && s_cnt[tid]) s_base[tid] = atomicAdd(&out[2 * VK_LIST_CAND + tid], (u64)s_cnt[tid]);
         __syncthreads();
-        for (unsigned h = tid; h < s_nhit; h += EC_THREADS) {
+        for (unsigned h = tid; h < nh; h += EC_THREADS) {
             const int kk = s_hit_k[h];
-            const u64 pos = s_base[kk] + atomicAdd(&s_cnt2[kk], 1u);
+            const u64 pos = s_base[kk] + s_hit_rank[h];
             if (pos < (u64)within_cap) within_dev[(size_t)kk * within_cap + pos] = s_hit_row[h];
         }
         __syncthreads();
-        if (tid < VK_LIST_CAND) { s_cnt[tid] = 0u; s_cnt2[tid] = 0u; }
+        if (tid < VK_LIST_CAND) s_cnt[tid] = 0u;
         if (tid == 0) s_nhit = 0u;
         __syncthreads();
     }
     tl_mark(2);
-    __syncthreads();
     tl_mark(3);
     if (tid < n_cand) {
         if (s_dens[tid]) atomicAdd(&out[tid], s_dens[tid]);
@@ -858,18 +868,32 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
     tl_mark(4);
     if (!vk_last_block(done_ticket, &s_last)) return;
     tl_mark_any(5);
-    // the last block publishes: the id lists (device -> pinned host memory, one warp per candidate, coalesced), then the
-    // sums and counts; ONE system-scope fence (vk_raise_flag) orders all of it before the flag
-    {
-        const int warp = tid >> 5, lane = tid & 31;
-        for (int kk = warp; kk < n_cand; kk += EC_THREADS / 32) {
+    // The last block publishes: the id lists (device -> pinned host memory), then the sums and counts; ONE system-scope
+    // fence (vk_raise_flag) orders all of it before the flag.  The lists are flattened so that every thread copies a few
+    // ids with independent loads (a warp per candidate walked them one after the other: 6 us).
+    __shared__ int s_off[VK_LIST_CAND + 1];
+    if (tid == 0) {
+        int run = 0;
+        for (int kk = 0; kk < n_cand; ++kk) {
             u64 cnt = __ldcg(out + 2 * VK_LIST_CAND + kk);
             if (cnt > (u64)within_cap) cnt = (u64)within_cap;
-            for (int i = lane; i < (int)cnt; i += 32)
-                within_mapped[(size_t)kk * within_cap + i] = __ldcg(within_dev + (size_t)kk * within_cap + i);
+            s_off[kk] = run;
+            run += (int)cnt;
         }
+        s_off[n_cand] = run;
     }
-    __syncthreads();  // every warp has read its counts before they are zeroed below
+    __syncthreads();
+    for (int e = tid; e < s_off[n_cand]; e += EC_THREADS) {
+        int lo = 0, hi = n_cand;  // the candidate whose range holds e: s_off[kk] <= e < s_off[kk + 1]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_off[mid] <= e) lo = mid;
+            else hi = mid;
+        }
+        const size_t idx = (size_t)lo * within_cap + (e - s_off[lo]);
+        within_mapped[idx] = __ldcg(within_dev + idx);
+    }
+    __syncthreads();  // every count has been read before the accumulators are zeroed below
     if (tid < 4 * VK_LIST_CAND) {
         out_mapped[tid] = __ldcg(out + tid);
         out[tid] = 0ull;
