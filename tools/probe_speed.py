@@ -1,13 +1,13 @@
 """Probe kernel timing: CUDA events around the single launch the native driver issues (vk_probe_mapped);
 cold = L2 flushed before every launch.  VK_PROBE_R (4 | 8 rows in flight per lane) and VK_PROBE_BPS (persistent blocks
-per SM) select the launch shape; run once per setting (they are read once per process)."""
+per SM) select the launch shape, VK_PROBE_UNIT / VK_PROBE_DYNAMIC the work distribution; run once per setting (they are read once per process)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import vamb_b200.cluster as vc
 from oracle import synth
 
-for n in (1_000_000, 5_000_000):
+for n in [int(x) for x in os.environ.get("PROBE_N", "1000000,5000000").split(",")]:
     lat, ln = synth.make_latent(n, 32, seed=0, spread=0.1)
     gen = vc.ClusterGenerator(lat, ln, rng_seed=0, _driver="python")
     state = {}
@@ -26,7 +26,8 @@ for n in (1_000_000, 5_000_000):
             ts.append(a.elapsed_time(b))
         res[mode] = float(np.median(ts))
     nbytes = n * 133
-    print(f"VK_PROBE_R={os.environ.get('VK_PROBE_R', '4')} VK_PROBE_BPS={os.environ.get('VK_PROBE_BPS', '4')} N={n}: "
+    print(f"VK_PROBE_R={os.environ.get('VK_PROBE_R', '4')} VK_PROBE_BPS={os.environ.get('VK_PROBE_BPS', '4')} "
+          f"UNIT={os.environ.get('VK_PROBE_UNIT', '1')} DYNAMIC={os.environ.get('VK_PROBE_DYNAMIC', '0')} N={n}: "
           f"warm {res['warm']*1e3:.1f} us ({nbytes/res['warm']/1e6:.0f} GB/s), cold {res['cold']*1e3:.1f} us "
           f"({nbytes/res['cold']/1e6:.0f} GB/s)   [one launch]")
     del gen, lat

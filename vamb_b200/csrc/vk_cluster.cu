@@ -181,7 +181,7 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
              const uint8_t *__restrict__ kept, int64_t n, int d_rt, int64_t mrow, float nl_radius,
              const float *__restrict__ edges_g, vk_probe_header *hdr, int32_t *within_overflow,
              int32_t *nl_rows, float *nl_dists, int n_tiles, vk_probe_header *hdr_mapped, int32_t *done_ticket,
-             volatile int32_t *done_flag, int32_t seq, int32_t *work_counter) {
+             volatile int32_t *done_flag, int32_t seq, int32_t *work_counter, int unit_chunks) {
     const int d = DFIX ? DFIX : d_rt;
     tl_begin(0);
     __shared__ float s_edges[VK_NBINS + 1];
@@ -246,13 +246,14 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
     const int n32 = (int)n;
     float4 vnext[PB_R];
     // Work distribution, PER WARP and without any block barrier: a warp-chunk is 4 x R consecutive rows (one 512-byte
-    // load per k for the warp), a unit is PB_WUNIT warp-chunks (256 rows at R = 4).  With a work counter (mapped
-    // completion: the native driver) every warp draws its next unit from one atomic counter, two units ahead -- lane 0
-    // issues the atomic at the start of a unit and the warp reads the result only at its end -- so that the SMs that
-    // stream faster take more of the matrix: with a static stride the slowest of the 592 blocks finished 7 us after the
-    // first at N = 1M (tools/probe_timeline.py), a quarter of the kernel; a block-level scheme with a barrier per
-    // unit balanced the tail but cost 30-45 % of the streaming rate.  Without a counter the units are strided.
-    constexpr int WCHUNK = 4 * PB_R, PB_WUNIT = 16;
+    // load per k for the warp, 2 KB at R = 4), a unit is `unit_chunks` warp-chunks.  Default: units strided over the
+    // warps of the grid, one chunk per unit -- at any moment the grid streams one contiguous window of the matrix and
+    // every warp gets the same number of chunks to within one.  Measured alternatives (tools/probe_speed.py,
+    // profiles/r02_probe_sweep_v3.txt): units drawn from one atomic counter, two ahead (VK_PROBE_DYNAMIC=1), so that
+    // faster SMs scan more rows: 75 us against 45 us at N = 1M (the warps scheduled first claim all the units and the
+    // others idle) and 147 against 126 us at N = 5M; a block-level scheme with a barrier per unit: 54 / 164 us.
+    constexpr int WCHUNK = 4 * PB_R;
+    const int PB_WUNIT = unit_chunks;
     const int n_wchunks = (n32 + WCHUNK - 1) / WCHUNK;
     const int n_units = (n_wchunks + PB_WUNIT - 1) / PB_WUNIT;
     const int gw = lane >> 3;  // group of the lane inside its warp
@@ -432,12 +433,15 @@ static int probe_launch(const float *matrix, const float *lengths, const uint8_t
         return 1;
     }
     const int r = probe_r();
+    static const int unit = probe_env("VK_PROBE_UNIT", 1, 1, 64);
+    static const int dynamic_units = probe_env("VK_PROBE_DYNAMIC", 0, 0, 1);
+    if (!dynamic_units) work_counter = nullptr;
     const int n_chunks = (int)((n + PB_GROUPS * r - 1) / (PB_GROUPS * r));
     const int grid = probe_grid(n_chunks);
 #define VK_PROBE_LAUNCH(DF, RR, BB)                                                                                  \
     probe_kernel<DF, RR, BB><<<grid, PB_THREADS, 0, s>>>(matrix, lengths, kept, n, d, medoid_row, nl_radius, edges, hdr, \
                                                          within_overflow, nl_rows, nl_dists, n_chunks, hdr_mapped,       \
-                                                         done_ticket, done_flag, seq, work_counter)
+                                                         done_ticket, done_flag, seq, work_counter, unit)
     if (d == 32) {
         if (r == 8) VK_PROBE_LAUNCH(32, 8, 3);
         else if (probe_bps() > 4) VK_PROBE_LAUNCH(32, 4, 6);
@@ -737,17 +741,22 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
     tl_begin(1);
     extern __shared__ __align__(16) float s_qs[];  // [n_cand][dpad]
     // A hit = (row within 0.05 of candidate k).  The lane that scans a row of a dense core finds a hit for almost every
-    // candidate; doing the bookkeeping there (three shared atomics + a returning global atomic per hit) serialised
-    // 40 x ~1 us in that one lane and the last block finished 25-38 us after the first (tools/probe_timeline.py).  So
-    // the scan only RECORDS hits (one 32-bit shared atomic each); all 256 threads then fold them into the per-candidate
-    // sums, reserve ONE range per (block, candidate) in the global id lists and scatter the ids.
-    constexpr int HIT_CAP = (EC_THREADS / 8) * VK_LIST_CAND;  // one round: 32 rows x 64 candidates
-    __shared__ int32_t s_hit_row[HIT_CAP];
-    __shared__ uint32_t s_hit_cq[HIT_CAP], s_hit_len[HIT_CAP];
-    __shared__ uint16_t s_hit_rank[HIT_CAP];
-    __shared__ uint8_t s_hit_k[HIT_CAP];
-    __shared__ unsigned s_nhit, s_cnt[VK_LIST_CAND];
-    __shared__ u64 s_base[VK_LIST_CAND], s_dens[VK_LIST_CAND], s_dens_hi[VK_LIST_CAND];
+    // candidate; doing the bookkeeping there (shared atomics + a returning global atomic per hit) serialised 40 x ~1 us
+    // in that one lane, and folding recorded hits with 64-bit shared atomics (CAS loops, 32 hits of one candidate in
+    // consecutive threads) still left the last block 16 us behind the first (tools/probe_timeline.py).  So the scan only
+    // WRITES each hit into its own cell of a dense [row slot][candidate] table -- no atomic at all -- and the fold is a
+    // fixed ownership: thread (candidate k, quarter p) reads the 8 row slots of its quarter, keeps the candidate's sums
+    // in REGISTERS over all rounds, one thread per candidate reserves ONE range in the global id list per round, and the
+    // owners scatter the ids (and clear their cells).
+    constexpr int EC_SLOTS = EC_THREADS / 8;             // rows per block and round
+    constexpr int EC_PARTS = EC_THREADS / VK_LIST_CAND;  // owners per candidate
+    constexpr int EC_PER = EC_SLOTS / EC_PARTS;          // row slots per owner
+    static_assert(EC_THREADS % VK_LIST_CAND == 0 && EC_SLOTS % EC_PARTS == 0, "eval ownership");
+    __shared__ uint32_t s_cell[EC_SLOTS][VK_LIST_CAND];  // closeness + 1 of (row slot, candidate), 0 = no hit
+    __shared__ int32_t s_slot_row[EC_SLOTS];
+    __shared__ uint32_t s_slot_len[EC_SLOTS];
+    __shared__ unsigned s_pcnt[EC_PARTS][VK_LIST_CAND];
+    __shared__ u64 s_base[VK_LIST_CAND];
     __shared__ int32_t s_crow[VK_LIST_CAND];  // candidate rows: copied out of the by-value parameter with STATIC indices
                                               // (a dynamic index would make every thread spill the array to local memory)
     __shared__ float s_reach[VK_LIST_CAND];
@@ -759,8 +768,7 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
 #pragma unroll
     for (int k = 0; k < VK_LIST_CAND; ++k)
         if (tid == k) s_crow[k] = k < n_cand ? cand.rows[k] : -1;
-    if (tid < VK_LIST_CAND) { s_dens[tid] = 0ull; s_dens_hi[tid] = 0ull; s_cnt[tid] = 0u; }
-    if (tid == 0) s_nhit = 0u;
+    for (int i = tid; i < EC_SLOTS * VK_LIST_CAND; i += EC_THREADS) (&s_cell[0][0])[i] = 0u;
     __syncthreads();
     if (fast) {  // 8 float4 per candidate row, all loads independent
         for (int i = tid; i < n_cand * 8; i += EC_THREADS)
@@ -804,18 +812,23 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
     float reach = 0.0f;
     for (int k = 0; k < n_cand; ++k) reach = fmaxf(reach, s_reach[k]);
     const float visit_radius = geo ? fminf(prune_radius, reach) : prune_radius;
-    const int groups_total = gridDim.x * (EC_THREADS / 8);
+    const int groups_total = gridDim.x * EC_SLOTS;
     const int n_rounds = (n_nl + groups_total - 1) / groups_total;  // block-uniform
+    const int own_k = tid & (VK_LIST_CAND - 1), own_p = tid / VK_LIST_CAND;
+    u64 r_dens = 0ull, r_dens_hi = 0ull;  // sums of candidate own_k over this owner's row slots, all rounds
     for (int round = 0; round < n_rounds; ++round) {
-        const int j = round * groups_total + blockIdx.x * (EC_THREADS / 8) + g;
+        const int j = round * groups_total + blockIdx.x * EC_SLOTS + g;
         const float dj = j < n_nl ? nl_dists[j] : 1e30f;
+        bool any = false;
         if (dj <= visit_radius) {  // uniform within the 8-lane group
             const int row = nl_rows[j];
             const float *x = matrix + (int64_t)row * d;
             float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
             if (fast) xv = ldg_stream4(x + 4 * lane8);
-            uint32_t lenq = 0u;
-            if (lane8 == 0) lenq = (uint32_t)__float2ull_rz(__ldg(lengths + row));  // integral, < 2^24 per contig
+            if (lane8 == 0) {
+                s_slot_row[g] = row;
+                s_slot_len[g] = (uint32_t)__float2ull_rz(__ldg(lengths + row));  // integral, < 2^24 per contig
+            }
             for (int k = 0; k < n_cand; ++k) {
                 if (geo && !(dj <= s_reach[k])) continue;  // this row cannot be within 0.05 of candidate k
                 const float *q = s_qs + k * dpad;
@@ -827,43 +840,53 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
                     float dd = __fsub_rn(0.5f, acc);
                     if (row == s_crow[k]) dd = 0.0f;
                     if (dd <= rad) {
-                        const unsigned h = atomicAdd(&s_nhit, 1u);  // at most HIT_CAP hits per round
-                        s_hit_row[h] = row;
-                        s_hit_k[h] = (uint8_t)k;
-                        s_hit_cq[h] = (uint32_t)closeness_fx(rad, dd);  // <= 0.05 * 2^29 < 2^25
-                        s_hit_len[h] = lenq;
+                        s_cell[g][k] = (uint32_t)closeness_fx(rad, dd) + 1u;  // closeness <= 0.05 * 2^29 < 2^25
+                        any = true;
                     }
                 }
             }
         }
+        if (!__syncthreads_or(any)) continue;  // no hit in this block and round (the common case away from the core)
+        unsigned cnt = 0;
+#pragma unroll
+        for (int i = 0; i < EC_PER; ++i) {
+            const int slot = own_p * EC_PER + i;
+            const uint32_t c1 = s_cell[slot][own_k];
+            if (c1) {
+                const u64 cq = c1 - 1u, len = s_slot_len[slot];
+                r_dens += len * (cq & 4095ull);
+                r_dens_hi += len * (cq >> 12);
+                ++cnt;
+            }
+        }
+        s_pcnt[own_p][own_k] = cnt;
         __syncthreads();
-        const unsigned nh = s_nhit;
-        for (unsigned h = tid; h < nh; h += EC_THREADS) {  // fold: all threads, a few hits each
-            const int kk = s_hit_k[h];
-            const u64 cq = s_hit_cq[h], len = s_hit_len[h];
-            atomicAdd(&s_dens[kk], len * (cq & 4095ull));
-            atomicAdd(&s_dens_hi[kk], len * (cq >> 12));
-            s_hit_rank[h] = (uint16_t)atomicAdd(&s_cnt[kk], 1u);
+        if (tid < n_cand) {
+            unsigned tot = 0;
+#pragma unroll
+            for (int p = 0; p < EC_PARTS; ++p) tot += s_pcnt[p][tid];
+            if (tot) s_base[tid] = atomicAdd(&out[2 * VK_LIST_CAND + tid], (u64)tot);
         }
         __syncthreads();
-        if (tid < n_cand && s_cnt[tid]) s_base[tid] = atomicAdd(&out[2 * VK_LIST_CAND + tid], (u64)s_cnt[tid]);
-        __syncthreads();
-        for (unsigned h = tid; h < nh; h += EC_THREADS) {
-            const int kk = s_hit_k[h];
-            const u64 pos = s_base[kk] + s_hit_rank[h];
-            if (pos < (u64)within_cap) within_dev[(size_t)kk * within_cap + pos] = s_hit_row[h];
+        if (cnt) {
+            u64 pos = s_base[own_k];
+            for (int p = 0; p < own_p; ++p) pos += s_pcnt[p][own_k];
+#pragma unroll
+            for (int i = 0; i < EC_PER; ++i) {
+                const int slot = own_p * EC_PER + i;
+                if (s_cell[slot][own_k]) {
+                    if (pos < (u64)within_cap) within_dev[(size_t)own_k * within_cap + pos] = s_slot_row[slot];
+                    ++pos;
+                    s_cell[slot][own_k] = 0u;
+                }
+            }
         }
-        __syncthreads();
-        if (tid < VK_LIST_CAND) s_cnt[tid] = 0u;
-        if (tid == 0) s_nhit = 0u;
         __syncthreads();
     }
     tl_mark(2);
     tl_mark(3);
-    if (tid < n_cand) {
-        if (s_dens[tid]) atomicAdd(&out[tid], s_dens[tid]);
-        if (s_dens_hi[tid]) atomicAdd(&out[VK_LIST_CAND + tid], s_dens_hi[tid]);
-    }
+    if (r_dens) atomicAdd(&out[own_k], r_dens);
+    if (r_dens_hi) atomicAdd(&out[VK_LIST_CAND + own_k], r_dens_hi);
     __shared__ int s_last;
     tl_mark(4);
     if (!vk_last_block(done_ticket, &s_last)) return;
@@ -872,13 +895,18 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
     // fence (vk_raise_flag) orders all of it before the flag.  The lists are flattened so that every thread copies a few
     // ids with independent loads (a warp per candidate walked them one after the other: 6 us).
     __shared__ int s_off[VK_LIST_CAND + 1];
+    __shared__ int s_len_k[VK_LIST_CAND];
+    if (tid < VK_LIST_CAND) {  // the counts: independent loads, then a serial prefix in shared memory
+        u64 cnt = tid < n_cand ? __ldcg(out + 2 * VK_LIST_CAND + tid) : 0ull;
+        if (cnt > (u64)within_cap) cnt = (u64)within_cap;
+        s_len_k[tid] = (int)cnt;
+    }
+    __syncthreads();
     if (tid == 0) {
         int run = 0;
         for (int kk = 0; kk < n_cand; ++kk) {
-            u64 cnt = __ldcg(out + 2 * VK_LIST_CAND + kk);
-            if (cnt > (u64)within_cap) cnt = (u64)within_cap;
             s_off[kk] = run;
-            run += (int)cnt;
+            run += s_len_k[kk];
         }
         s_off[n_cand] = run;
     }

@@ -785,7 +785,7 @@ __device__ __forceinline__ void fold_rowtile_sums(const double *part, int n_rt, 
     const int col = tid & (bnp - 1), g = tid / bnp;
     double a0 = 0.0, a1 = 0.0;
     if (col < bn && n0 + col < N) {
-#pragma unroll 4
+#pragma unroll 8
         for (int rt = g; rt < n_rt; rt += G) {
             a0 += __ldcg(part + ((int64_t)rt * 2 + 0) * N + n0 + col);
             a1 += __ldcg(part + ((int64_t)rt * 2 + 1) * N + n0 + col);
@@ -963,6 +963,19 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) fwd_layer_tc_kernel(const _
             const float4 o = in_batch ? make_float4(p0, p1, p2, p3) : make_float4(0.f, 0.f, 0.f, 0.f);
             *reinterpret_cast<float4 *>(tile + r * TS + c) = o;
             if (in_batch) *reinterpret_cast<float4 *>(out_tile + r * N + c) = o;
+        }
+    } else if (a.kind == VK_LAYER_OUT && vec && (n0 + bn <= a.N) && ((q_per_row & (q_per_row - 1)) == 0)) {
+        // output layer, full tile: bias and store
+        const int sh = __ffs(q_per_row) - 1;
+        float *out_tile = a.out + (int64_t)m0 * a.N + n0;
+        const int rows_in = a.B - m0, N = a.N;
+#pragma unroll 4
+        for (int q = tid; q < (128 << sh); q += tc::WS_EPI_THREADS) {
+            const int r = q >> sh, c = (q & (q_per_row - 1)) << 2;
+            if (r >= rows_in) continue;
+            const float4 t = *reinterpret_cast<const float4 *>(tile + r * TS + c);
+            const float4 bz = *reinterpret_cast<const float4 *>(s_bias + c);
+            *reinterpret_cast<float4 *>(out_tile + r * N + c) = make_float4(t.x + bz.x, t.y + bz.y, t.z + bz.z, t.w + bz.w);
         }
     } else
     for (int q = tid; q < 128 * q_per_row; q += tc::WS_EPI_THREADS) {
@@ -1155,7 +1168,23 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(const _
     TLD(2);
     const int q_per_row = bn >> 2;
     float *ptile = tile + 128 * TS;  // the previous layer's output P for the same rows / columns (zeros outside)
-    if (a.in_kind == VK_IN_BN) {
+    // Lean epilogue passes (hidden layer below, full tile, power-of-two width, aligned rows): shifts instead of
+    // divisions, one row predicate instead of per-element bounds, 32-bit offsets from a tile pointer -- same values.
+    const bool lean_d = a.in_kind == VK_IN_BN && ((a.K & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.p_prev) & 15) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(a.d_in) & 15) == 0) && (n0 + bn <= a.K) &&
+                        ((q_per_row & (q_per_row - 1)) == 0);
+    const int sh_d = __ffs(q_per_row) - 1, rows_in_d = a.B - m0;
+    if (lean_d) {
+        const float *p_tile = a.p_prev + (int64_t)m0 * a.K + n0;
+        const int K = a.K;
+#pragma unroll 4
+        for (int q = tid; q < (128 << sh_d); q += tc::WS_EPI_THREADS) {
+            const int r = q >> sh_d, c = (q & (q_per_row - 1)) << 2;
+            float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < rows_in_d) pv = __ldg(reinterpret_cast<const float4 *>(p_tile + r * K + c));
+            *reinterpret_cast<float4 *>(ptile + r * TS + c) = pv;
+        }
+    } else if (a.in_kind == VK_IN_BN) {
         const bool pvec = ((a.K & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.p_prev) & 15) == 0);
 #pragma unroll 4
         for (int q = tid; q < 128 * q_per_row; q += tc::WS_EPI_THREADS) {
@@ -1180,6 +1209,16 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(const _
     TLD(3);
     const bool vec = ((a.K & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.d_in) & 15) == 0);
     const bool add_kld = a.in_kind == VK_IN_Z;
+    if (lean_d) {
+        float *d_tile = a.d_in + (int64_t)m0 * a.K + n0;
+        const int K = a.K;
+#pragma unroll 4
+        for (int q = tid; q < (128 << sh_d); q += tc::WS_EPI_THREADS) {
+            const int r = q >> sh_d, c = (q & (q_per_row - 1)) << 2;
+            if (r < rows_in_d) *reinterpret_cast<float4 *>(d_tile + r * K + c) = *reinterpret_cast<const float4 *>(tile + r * TS + c);
+            else *reinterpret_cast<float4 *>(tile + r * TS + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    } else
     for (int q = tid; q < 128 * q_per_row; q += tc::WS_EPI_THREADS) {
         const int r = q / q_per_row, c = (q - r * q_per_row) << 2;
         const int m = m0 + r, nb = n0 + c;
@@ -1203,7 +1242,7 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(const _
         }
     }
     TLD(4);
-    __shared__ float s_k[3][128];
+    __shared__ __align__(16) float s_k[3][128];
     if (a.in_kind == VK_IN_BN) {
         __syncthreads();
         const int row_tile = t / a.dg_tiles_n;
@@ -1250,6 +1289,28 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(const _
         __syncthreads();
         TLD(45);
         // dL/dY of the previous layer = sgn(P) * (bA dH + bB P + bC), 0 for dropped units, replaces dH in the tile
+        if (lean_d) {
+            const float slope = a.slope;
+            const bool hd = a.has_dropout != 0;
+#pragma unroll 4
+            for (int q = tid; q < (128 << sh_d); q += tc::WS_EPI_THREADS) {
+                const int r = q >> sh_d, c = (q & (q_per_row - 1)) << 2;
+                const float4 p4 = *reinterpret_cast<const float4 *>(ptile + r * TS + c);
+                const float4 dh = *reinterpret_cast<const float4 *>(tile + r * TS + c);
+                const float4 k0 = *reinterpret_cast<const float4 *>(&s_k[0][c]), k1 = *reinterpret_cast<const float4 *>(&s_k[1][c]),
+                             k2 = *reinterpret_cast<const float4 *>(&s_k[2][c]);
+                float v0 = __fmaf_rn(k0.x, dh.x, __fmaf_rn(k1.x, p4.x, k2.x)), v1 = __fmaf_rn(k0.y, dh.y, __fmaf_rn(k1.y, p4.y, k2.y));
+                float v2 = __fmaf_rn(k0.z, dh.z, __fmaf_rn(k1.z, p4.z, k2.z)), v3 = __fmaf_rn(k0.w, dh.w, __fmaf_rn(k1.w, p4.w, k2.w));
+                v0 = p4.x > 0.0f ? v0 : v0 * slope;
+                v1 = p4.y > 0.0f ? v1 : v1 * slope;
+                v2 = p4.z > 0.0f ? v2 : v2 * slope;
+                v3 = p4.w > 0.0f ? v3 : v3 * slope;
+                const bool in_b = r < rows_in_d;
+                *reinterpret_cast<float4 *>(tile + r * TS + c) =
+                    make_float4((in_b && !(hd && p4.x == 0.0f)) ? v0 : 0.0f, (in_b && !(hd && p4.y == 0.0f)) ? v1 : 0.0f,
+                                (in_b && !(hd && p4.z == 0.0f)) ? v2 : 0.0f, (in_b && !(hd && p4.w == 0.0f)) ? v3 : 0.0f);
+            }
+        } else
 #pragma unroll 4
         for (int q = tid; q < 128 * q_per_row; q += tc::WS_EPI_THREADS) {
             const int r = q / q_per_row, c = (q - r * q_per_row) << 2;
