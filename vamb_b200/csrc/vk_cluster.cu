@@ -247,8 +247,8 @@ probe_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths
     float4 vnext[PB_R];
     // Work distribution, PER WARP and without any block barrier: a warp-chunk is 4 x R consecutive rows (one 512-byte
     // load per k for the warp, 2 KB at R = 4), a unit is `unit_chunks` warp-chunks.  Default: units strided over the
-    // warps of the grid, one chunk per unit -- at any moment the grid streams one contiguous window of the matrix and
-    // every warp gets the same number of chunks to within one.  Measured alternatives (tools/probe_speed.py,
+    // warps of the grid, four chunks (8 KB) per unit (VK_PROBE_UNIT; 1 / 4 / 16 chunks: 49.9 / 49.4 / 49.5 us at N = 1M,
+    // 146 / 133 / 142 us at N = 5M) -- at any moment the grid streams one contiguous window of the matrix.  Measured alternatives (tools/probe_speed.py,
     // profiles/r02_probe_sweep_v3.txt): units drawn from one atomic counter, two ahead (VK_PROBE_DYNAMIC=1), so that
     // faster SMs scan more rows: 75 us against 45 us at N = 1M (the warps scheduled first claim all the units and the
     // others idle) and 147 against 126 us at N = 5M; a block-level scheme with a barrier per unit: 54 / 164 us.
@@ -433,7 +433,7 @@ static int probe_launch(const float *matrix, const float *lengths, const uint8_t
         return 1;
     }
     const int r = probe_r();
-    static const int unit = probe_env("VK_PROBE_UNIT", 1, 1, 64);
+    static const int unit = probe_env("VK_PROBE_UNIT", 4, 1, 64);
     static const int dynamic_units = probe_env("VK_PROBE_DYNAMIC", 0, 0, 1);
     if (!dynamic_units) work_counter = nullptr;
     const int n_chunks = (int)((n + PB_GROUPS * r - 1) / (PB_GROUPS * r));
@@ -885,8 +885,20 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
     }
     tl_mark(2);
     tl_mark(3);
-    if (r_dens) atomicAdd(&out[own_k], r_dens);
-    if (r_dens_hi) atomicAdd(&out[VK_LIST_CAND + own_k], r_dens_hi);
+    // the owners of a candidate are combined in shared memory first: one pair of global atomics per (block, candidate)
+    // -- with four times as many, on the same 2 x n_cand addresses from every block, the last block finished ~15 us
+    // after the first (tools/probe_timeline.py)
+    __shared__ u64 s_own[EC_PARTS][2][VK_LIST_CAND];
+    s_own[own_p][0][own_k] = r_dens;
+    s_own[own_p][1][own_k] = r_dens_hi;
+    __syncthreads();
+    if (tid < 2 * VK_LIST_CAND) {
+        const int kk = tid & (VK_LIST_CAND - 1), which = tid / VK_LIST_CAND;
+        u64 tot = 0ull;
+#pragma unroll
+        for (int p = 0; p < EC_PARTS; ++p) tot += s_own[p][which][kk];
+        if (tot) atomicAdd(&out[which * VK_LIST_CAND + kk], tot);
+    }
     __shared__ int s_last;
     tl_mark(4);
     if (!vk_last_block(done_ticket, &s_last)) return;

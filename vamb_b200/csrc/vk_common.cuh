@@ -184,3 +184,24 @@ static inline cudaError_t vk_launch(void (*kernel)(KArgs...), dim3 grid, dim3 bl
     cfg.numAttrs = vk_pdl_enabled() ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
+
+// as vk_launch, as thread-block clusters of `cluster` CTAs (grid dimensions are multiples of the cluster's)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t vk_launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                            dim3 cluster, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster.x;
+    attr[0].val.clusterDim.y = cluster.y;
+    attr[0].val.clusterDim.z = cluster.z;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = vk_pdl_enabled() ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}

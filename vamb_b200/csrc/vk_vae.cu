@@ -369,6 +369,7 @@ struct FwdArgs {
     int stage; float *stage_a; int stage_a_ld; float *stage_t; int stage_t_ld;
     // B operand (W and its tf32 remainder) through TMA: 128B-swizzled tensor maps, box = 32 floats x tile_n rows
     int use_tma; VkTmap tm_b_hi, tm_b_lo;
+    int cluster_rt;       // > 0: the row tiles of one column tile form a thread-block cluster of this size (cluster fold)
 };
 
 // Fold the per-row-tile column sums of P and P^2 into the BatchNorm affine, the saved batch statistics
@@ -633,6 +634,7 @@ struct BwdArgs {
     // 2 plain copy (dL/dmu)
     int stage; float *stage_a; int stage_a_ld; float *stage_t; int stage_t_ld; float slope; int has_dropout;
     int use_tma; VkTmap tm_dg_hi, tm_dg_lo;  // dgrad B operand (W^T and its tf32 remainder) through TMA
+    int cluster_rt, n_wg_pad;  // cluster fold: dgrad row tiles of one column tile = one cluster; wgrad CTAs padded to whole clusters
 };
 
 // Fold the per-row-tile column sums of dH and dH*Phat: BatchNorm weight/bias gradients and the two
@@ -770,6 +772,52 @@ __device__ __forceinline__ void tc_colsum2(int bn, int n0, int N, double (*s_cs)
         out1[n0 + tid] = t1;
     }
     __syncthreads();
+}
+
+// ---- cluster fold: BatchNorm sums exchanged through distributed shared memory ----
+// When the row tiles of one column tile fit a portable thread-block cluster (B <= 1024: <= 8 CTAs), the per-row-tile
+// column sums never leave the SMs: every CTA leaves its two sums per column in shared memory, one hardware cluster
+// barrier replaces the software grid barrier (global atomics + polling: 2-3 us per layer, tools/kernel_timeline.py),
+// and every CTA reads its peers' sums with ld.shared::cluster in the SAME order as the global fold below (identical
+// doubles, identical results).  A second barrier before exit keeps the shared memory alive while peers read it.
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ double dsmem_ld_f64(const double *own, unsigned rank) {
+    const uint32_t la = (uint32_t)__cvta_generic_to_shared(own);
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+    double v;
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+    return v;
+}
+// as fold_rowtile_sums, the partials of row tile rt being s_mine[.][col] of the cluster's CTA of rank rt
+__device__ __forceinline__ void fold_cluster_sums(const double (*s_mine)[128], int n_rt, int N, int n0, int bn,
+                                                  double (*s_cs)[2][128], double &u, double &v) {
+    double *sp = &s_cs[0][0][0];  // [G][2][bnp], G * bnp = 256
+    const int tid = threadIdx.x;
+    int bnp = 16;
+    while (bnp < bn) bnp <<= 1;
+    const int G = 256 / bnp;
+    const int col = tid & (bnp - 1), g = tid / bnp;
+    double a0 = 0.0, a1 = 0.0;
+    if (col < bn && n0 + col < N) {
+        for (int rt = g; rt < n_rt; rt += G) {
+            a0 += dsmem_ld_f64(&s_mine[0][col], (unsigned)rt);
+            a1 += dsmem_ld_f64(&s_mine[1][col], (unsigned)rt);
+        }
+    }
+    if (col < bn) {
+        sp[(g * 2 + 0) * bnp + col] = a0;
+        sp[(g * 2 + 1) * bnp + col] = a1;
+    }
+    __syncthreads();
+    u = 0.0;
+    v = 0.0;
+    if (tid < bn)
+        for (int gg = 0; gg < G; ++gg) {
+            u += sp[(gg * 2 + 0) * bnp + tid];
+            v += sp[(gg * 2 + 1) * bnp + tid];
+        }
 }
 
 // Fold the per-row-tile column partials of this CTA's columns over all n_rt row tiles with ALL 256 epilogue threads
@@ -1039,10 +1087,13 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) fwd_layer_tc_kernel(const _
     tl_mark(4);
     tk_end(tk);
     __shared__ float s_k[2][128];
+    __shared__ double s_mine[2][128];  // cluster fold: this CTA's column sums, read by its cluster peers
+    const bool cl_exit = hidden && a.training && a.stage == 1 && a.cluster_rt > 0;
     if (hidden && a.training) {
         __syncthreads();
-        double *p0 = a.part + ((int64_t)blockIdx.y * 2 + 0) * a.N;
-        double *p1 = a.part + ((int64_t)blockIdx.y * 2 + 1) * a.N;
+        const bool cl = a.cluster_rt > 0;  // cluster fold: the sums stay in shared memory (indexed by tile column)
+        double *p0 = cl ? &s_mine[0][0] - n0 : a.part + ((int64_t)blockIdx.y * 2 + 0) * a.N;
+        double *p1 = cl ? &s_mine[1][0] - n0 : a.part + ((int64_t)blockIdx.y * 2 + 1) * a.N;
         tc_colsum2(bn, n0, a.N, s_cs, p0, p1, [&](int r, int c, float &v0, float &v1) {
             const float p = tile[r * TS + c];  // rows >= B and columns >= N hold zeros
             v0 = p;
@@ -1050,11 +1101,20 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) fwd_layer_tc_kernel(const _
         });
         tl_mark(5);
         if (a.stage != 1) return;  // the consumer (prep_kernel of the next layer) folds the column sums
-        // every CTA's column sums are needed: wait for the whole grid, then fold the own columns
-        grid_barrier(&a.ctl->tickets[a.layer_id], &a.ctl->barrier_gen[a.layer_id], gridDim.x * gridDim.y);
-        tl_mark(6);
         double sm, q;
-        fold_rowtile_sums(a.part, (int)gridDim.y, a.N, n0, bn, s_cs, sm, q);
+        if (cl) {
+            // the row tiles of this column tile are one cluster (cluster dims (1, gridDim.y, 1): rank = blockIdx.y)
+            cluster_arrive();
+            cluster_wait();
+            tl_mark(6);
+            fold_cluster_sums(s_mine, (int)gridDim.y, a.N, n0, bn, s_cs, sm, q);
+            cluster_arrive();  // this CTA has read its peers' sums; matched by the wait before exit
+        } else {
+            // every CTA's column sums are needed: wait for the whole grid, then fold the own columns
+            grid_barrier(&a.ctl->tickets[a.layer_id], &a.ctl->barrier_gen[a.layer_id], gridDim.x * gridDim.y);
+            tl_mark(6);
+            fold_rowtile_sums(a.part, (int)gridDim.y, a.N, n0, bn, s_cs, sm, q);
+        }
         if (tid < bn) {
             const int n = n0 + tid;
             float k0 = 0.0f, k1 = 0.0f;
@@ -1104,6 +1164,7 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) fwd_layer_tc_kernel(const _
     }
     tl_mark(7);
     tk_end(tk);
+    if (cl_exit) cluster_wait();  // peers may still be reading s_mine
 }
 
 // Backward layer: wgrad slices (split-K over the batch, one gradient slab per split) and dgrad tiles in
@@ -1121,6 +1182,8 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(const _
     const int tid = threadIdx.x;
     float *tile = reinterpret_cast<float *>(smem);
     const int n_wg = a.wg_tiles_m * a.wg_tiles_n * x.nsplit;
+    const bool cl = a.cluster_rt > 0;
+    if (cl && (int)blockIdx.x >= n_wg && (int)blockIdx.x < a.n_wg_pad) return;  // padding up to whole clusters
     if ((int)blockIdx.x < n_wg) {
         // ---- wgrad slice: gW[n, k] (+ bias column) over batch rows [b0, b0 + nb) ----
         const int split = blockIdx.x / (a.wg_tiles_m * a.wg_tiles_n);
@@ -1154,10 +1217,12 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(const _
         return;
     }
     // ---- dgrad: dX[b, k] = sum_n dY[b, n] * W[n, k] ----
-    const int t = blockIdx.x - n_wg;
+    // cluster fold: clusters of cluster_rt consecutive CTAs = the row tiles of one column tile (rank = row tile)
+    const int t = blockIdx.x - (cl ? a.n_wg_pad : n_wg);
+    const int row_tile = cl ? t % a.cluster_rt : t / a.dg_tiles_n, col_tile = cl ? t / a.cluster_rt : t % a.dg_tiles_n;
 #define TLD(slot) do { if (t == 0) tl_mark_any(slot); } while (0)
     TLD(1);
-    const int m0 = (t / a.dg_tiles_n) * 128, n0 = (t % a.dg_tiles_n) * a.tile_n;
+    const int m0 = row_tile * 128, n0 = col_tile * a.tile_n;
     int bn = a.K - n0;
     bn = bn > a.tile_n ? a.tile_n : ((bn + 15) & ~15);
     const float gsc = (float)(a.ctl->wbar / (double)a.B);
@@ -1243,11 +1308,11 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(const _
     }
     TLD(4);
     __shared__ __align__(16) float s_k[3][128];
+    __shared__ double s_mine[2][128];  // cluster fold: this CTA's column sums, read by its cluster peers
     if (a.in_kind == VK_IN_BN) {
         __syncthreads();
-        const int row_tile = t / a.dg_tiles_n;
-        double *p0 = a.part_prev + ((int64_t)row_tile * 2 + 0) * a.K;
-        double *p1 = a.part_prev + ((int64_t)row_tile * 2 + 1) * a.K;
+        double *p0 = cl ? &s_mine[0][0] - n0 : a.part_prev + ((int64_t)row_tile * 2 + 0) * a.K;
+        double *p1 = cl ? &s_mine[1][0] - n0 : a.part_prev + ((int64_t)row_tile * 2 + 1) * a.K;
         tc_colsum2(bn, n0, a.K, s_cs, p0, p1, [&](int r, int c, float &v0, float &v1) {
             const float dv = tile[r * TS + c];
             float ph = 0.0f;
@@ -1258,10 +1323,18 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(const _
         });
         TLD(5);
         if (a.stage != 1) return;  // the consumer (prep_kernel staging dL/dY of the previous layer) folds the sums
-        grid_barrier(&a.ctl->tickets[a.ticket_id], &a.ctl->barrier_gen[a.ticket_id - 1], a.dg_tiles_m * a.dg_tiles_n);
-        TLD(6);
         double u, v;
-        fold_rowtile_sums(a.part_prev, a.dg_tiles_m, a.K, n0, bn, s_cs, u, v);
+        if (cl) {
+            cluster_arrive();
+            cluster_wait();
+            TLD(6);
+            fold_cluster_sums(s_mine, a.dg_tiles_m, a.K, n0, bn, s_cs, u, v);
+            cluster_arrive();  // matched by the wait before exit
+        } else {
+            grid_barrier(&a.ctl->tickets[a.ticket_id], &a.ctl->barrier_gen[a.ticket_id - 1], a.dg_tiles_m * a.dg_tiles_n);
+            TLD(6);
+            fold_rowtile_sums(a.part_prev, a.dg_tiles_m, a.K, n0, bn, s_cs, u, v);
+        }
         if (tid < bn) {
             const int n = n0 + tid;
             float k0 = 0.0f, k1 = 0.0f, k2 = 0.0f;
@@ -1338,6 +1411,7 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(const _
     stage_tile_lane(tile, bn, a.stage_a, a.stage_a_ld, m0, n0, ident);
     stage_tile_transposed_lane(tile, bn, a.stage_t, a.stage_t_ld, m0, n0, a.K, ident);
     TLD(7);
+    if (cl && a.in_kind == VK_IN_BN && a.stage == 1) cluster_wait();  // peers may still be reading s_mine
 #undef TLD
 }
 
@@ -1799,6 +1873,16 @@ static bool fused_staging(const vk_vae *net, int B) {
     return true;
 }
 
+// Cluster fold (see fold_cluster_sums): on for 2..8 row tiles (B <= 1024) unless VK_CLUSTER_FOLD=0
+static int cluster_fold_rt(int B) {
+    static const int on = [] {
+        const char *v = getenv("VK_CLUSTER_FOLD");
+        return v ? atoi(v) : 1;
+    }();
+    const int rt = (B + 127) / 128;
+    return (on && rt >= 2 && rt <= 8) ? rt : 0;
+}
+
 static int launch_prep(const PrepArgs &a, cudaStream_t s) {
     const int cx = a.cols + (a.ones_row ? 1 : 0);
     dim3 grid((cx + 31) / 32, (a.rows_w + 31) / 32);
@@ -1975,7 +2059,17 @@ static int launch_forward(const vk_vae *net, int B, int training, int upto /*exc
             // forces it in training too, for measurements)
             const bool flush = !training || net->wgrad_flush == 2;
             const size_t smem = (size_t)tc_smem_for(a.tile_n, 1);
-            if (a.use_tma) {
+            a.cluster_rt = (a.stage == 1 && L.kind == VK_LAYER_HIDDEN && training) ? cluster_fold_rt(B) : 0;
+            if (a.cluster_rt) {
+                const dim3 cluster(1, a.cluster_rt, 1);
+                if (a.use_tma) {
+                    if (flush) VK_CUDA(vk_launch_cluster(fwd_layer_tc_kernel<true, true>, dim3(grid), dim3(tc::WS_THREADS), smem, s, cluster, a));
+                    else VK_CUDA(vk_launch_cluster(fwd_layer_tc_kernel<true, false>, dim3(grid), dim3(tc::WS_THREADS), smem, s, cluster, a));
+                } else {
+                    if (flush) VK_CUDA(vk_launch_cluster(fwd_layer_tc_kernel<false, true>, dim3(grid), dim3(tc::WS_THREADS), smem, s, cluster, a));
+                    else VK_CUDA(vk_launch_cluster(fwd_layer_tc_kernel<false, false>, dim3(grid), dim3(tc::WS_THREADS), smem, s, cluster, a));
+                }
+            } else if (a.use_tma) {
                 if (flush) VK_CUDA(vk_launch(fwd_layer_tc_kernel<true, true>, dim3(grid), dim3(tc::WS_THREADS), smem, s, a));
                 else VK_CUDA(vk_launch(fwd_layer_tc_kernel<true, false>, dim3(grid), dim3(tc::WS_THREADS), smem, s, a));
             } else {
@@ -2106,9 +2200,22 @@ static int launch_backward(const vk_vae *net, int B, cudaStream_t s) {
             if (a.use_tma && (vk_make_tmap_2d(&a.tm_dg_hi, L.wt_hi, r32(L.n_out), r128(L.k_in), a.tile_n) ||
                               vk_make_tmap_2d(&a.tm_dg_lo, L.wt_lo, r32(L.n_out), r128(L.k_in), a.tile_n)))
                 return 1;
-            const int blocks = a.wg_tiles_m * a.wg_tiles_n * x.nsplit + a.dg_tiles_m * a.dg_tiles_n;
+            int blocks = a.wg_tiles_m * a.wg_tiles_n * x.nsplit + a.dg_tiles_m * a.dg_tiles_n;
             const size_t smem = (size_t)tc_smem_for(a.tile_n > a.wg_tile_n ? a.tile_n : a.wg_tile_n, 2);
-            if (a.use_tma) {
+            a.cluster_rt = (a.stage == 1 && L.in_kind == VK_IN_BN && a.dg_tiles_m) ? cluster_fold_rt(B) : 0;
+            if (a.cluster_rt) {
+                const int n_wg = a.wg_tiles_m * a.wg_tiles_n * x.nsplit;
+                a.n_wg_pad = ((n_wg + a.cluster_rt - 1) / a.cluster_rt) * a.cluster_rt;
+                blocks = a.n_wg_pad + a.dg_tiles_m * a.dg_tiles_n;  // dg_tiles_m == cluster_rt
+                const dim3 cluster(a.cluster_rt, 1, 1);
+                if (a.use_tma) {
+                    if (x.flush) VK_CUDA(vk_launch_cluster(bwd_layer_tc_kernel<true, true>, dim3(blocks), dim3(tc::WS_THREADS), smem, s, cluster, a, x));
+                    else VK_CUDA(vk_launch_cluster(bwd_layer_tc_kernel<true, false>, dim3(blocks), dim3(tc::WS_THREADS), smem, s, cluster, a, x));
+                } else {
+                    if (x.flush) VK_CUDA(vk_launch_cluster(bwd_layer_tc_kernel<false, true>, dim3(blocks), dim3(tc::WS_THREADS), smem, s, cluster, a, x));
+                    else VK_CUDA(vk_launch_cluster(bwd_layer_tc_kernel<false, false>, dim3(blocks), dim3(tc::WS_THREADS), smem, s, cluster, a, x));
+                }
+            } else if (a.use_tma) {
                 if (x.flush) VK_CUDA(vk_launch(bwd_layer_tc_kernel<true, true>, dim3(blocks), dim3(tc::WS_THREADS), smem, s, a, x));
                 else VK_CUDA(vk_launch(bwd_layer_tc_kernel<true, false>, dim3(blocks), dim3(tc::WS_THREADS), smem, s, a, x));
             } else {
