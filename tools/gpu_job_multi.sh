@@ -9,7 +9,10 @@ leg() { local name="$1" t="$2"; shift 2; local t0=$(date +%s); timeout "$t" "$@"
 nvidia-smi --query-gpu=index,name --format=csv,noheader | tee -a gpurun_out/job_multi_summary.log
 leg r02_pt_multigpu 400 python -m pytest tests/test_multigpu.py -m gpu -q
 leg r02_bench_dp${N} 800 bash -c "python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r02_bench_dp${N}.json"
+if [ "${REF:-1}" = "1" ]; then
+leg r02_bench_ref_dp${N} 600 bash -c "python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --impl reference --gpus $N --steps 20 --warmup 5 > gpurun_out/r02_bench_ref_dp${N}.json"
+fi
 if [ "${WEAK:-0}" = "1" ]; then
 leg r02_bench_dp${N}_weak 800 bash -c "python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 20 --warmup 3 --scaling weak --no-e2e > gpurun_out/r02_bench_dp${N}_weak.json"
 fi
-tail -3 gpurun_out/r02_pt_multigpu.log; tail -c 1200 gpurun_out/r02_bench_dp${N}.log; cat gpurun_out/job_multi_summary.log; head -c 600 gpurun_out/r02_bench_dp${N}.json
+tail -3 gpurun_out/r02_pt_multigpu.log; tail -c 1200 gpurun_out/r02_bench_dp${N}.log; cat gpurun_out/job_multi_summary.log; head -c 600 gpurun_out/r02_bench_dp${N}.json; echo; head -c 400 gpurun_out/r02_bench_ref_dp${N}.json

@@ -775,7 +775,7 @@ __device__ __forceinline__ void tc_colsum2(int bn, int n0, int N, double (*s_cs)
 }
 
 // ---- cluster fold: BatchNorm sums exchanged through distributed shared memory ----
-// When the row tiles of one column tile fit a portable thread-block cluster (B <= 1024: <= 8 CTAs), the per-row-tile
+// When the row tiles of one column tile are a small thread-block cluster (B <= 512: 2 or 4 CTAs), the per-row-tile
 // column sums never leave the SMs: every CTA leaves its two sums per column in shared memory, one hardware cluster
 // barrier replaces the software grid barrier (global atomics + polling: 2-3 us per layer, tools/kernel_timeline.py),
 // and every CTA reads its peers' sums with ld.shared::cluster in the SAME order as the global fold below (identical
@@ -790,34 +790,28 @@ __device__ __forceinline__ double dsmem_ld_f64(const double *own, unsigned rank)
     asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
     return v;
 }
-// as fold_rowtile_sums, the partials of row tile rt being s_mine[.][col] of the cluster's CTA of rank rt
-__device__ __forceinline__ void fold_cluster_sums(const double (*s_mine)[128], int n_rt, int N, int n0, int bn,
-                                                  double (*s_cs)[2][128], double &u, double &v) {
-    double *sp = &s_cs[0][0][0];  // [G][2][bnp], G * bnp = 256
+// as fold_rowtile_sums, the partials of row tile rt being s_mine[.][col] of the cluster's CTA of rank rt.  With at most
+// four row tiles every (g, col) thread of the global fold holds at most one partial (n_rt <= G), so its result is the
+// plain left-to-right sum p_0 + p_1 + ...: thread col reads the 2 n_rt doubles itself (independent remote loads) -- no
+// second trip through shared memory, no block barrier.  u / v are valid for tid < bn.
+__device__ __forceinline__ void fold_cluster_sums(const double (*s_mine)[128], int n_rt, int N, int n0, int bn, double &u,
+                                                  double &v) {
     const int tid = threadIdx.x;
-    int bnp = 16;
-    while (bnp < bn) bnp <<= 1;
-    const int G = 256 / bnp;
-    const int col = tid & (bnp - 1), g = tid / bnp;
-    double a0 = 0.0, a1 = 0.0;
-    if (col < bn && n0 + col < N) {
-        for (int rt = g; rt < n_rt; rt += G) {
-            a0 += dsmem_ld_f64(&s_mine[0][col], (unsigned)rt);
-            a1 += dsmem_ld_f64(&s_mine[1][col], (unsigned)rt);
-        }
-    }
-    if (col < bn) {
-        sp[(g * 2 + 0) * bnp + col] = a0;
-        sp[(g * 2 + 1) * bnp + col] = a1;
-    }
-    __syncthreads();
     u = 0.0;
     v = 0.0;
-    if (tid < bn)
-        for (int gg = 0; gg < G; ++gg) {
-            u += sp[(gg * 2 + 0) * bnp + tid];
-            v += sp[(gg * 2 + 1) * bnp + tid];
+    if (tid < bn && n0 + tid < N) {
+        double p[2][4];
+#pragma unroll
+        for (int rt = 0; rt < 4; ++rt) {
+            p[0][rt] = rt < n_rt ? dsmem_ld_f64(&s_mine[0][tid], (unsigned)rt) : 0.0;
+            p[1][rt] = rt < n_rt ? dsmem_ld_f64(&s_mine[1][tid], (unsigned)rt) : 0.0;
         }
+#pragma unroll
+        for (int rt = 0; rt < 4; ++rt) {
+            u += p[0][rt];
+            v += p[1][rt];
+        }
+    }
 }
 
 // Fold the per-row-tile column partials of this CTA's columns over all n_rt row tiles with ALL 256 epilogue threads
@@ -1107,7 +1101,7 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) fwd_layer_tc_kernel(const _
             cluster_arrive();
             cluster_wait();
             tl_mark(6);
-            fold_cluster_sums(s_mine, (int)gridDim.y, a.N, n0, bn, s_cs, sm, q);
+            fold_cluster_sums(s_mine, (int)gridDim.y, a.N, n0, bn, sm, q);
             cluster_arrive();  // this CTA has read its peers' sums; matched by the wait before exit
         } else {
             // every CTA's column sums are needed: wait for the whole grid, then fold the own columns
@@ -1328,7 +1322,7 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(const _
             cluster_arrive();
             cluster_wait();
             TLD(6);
-            fold_cluster_sums(s_mine, a.dg_tiles_m, a.K, n0, bn, s_cs, u, v);
+            fold_cluster_sums(s_mine, a.dg_tiles_m, a.K, n0, bn, u, v);
             cluster_arrive();  // matched by the wait before exit
         } else {
             grid_barrier(&a.ctl->tickets[a.ticket_id], &a.ctl->barrier_gen[a.ticket_id - 1], a.dg_tiles_m * a.dg_tiles_n);
@@ -1873,14 +1867,16 @@ static bool fused_staging(const vk_vae *net, int B) {
     return true;
 }
 
-// Cluster fold (see fold_cluster_sums): on for 2..8 row tiles (B <= 1024) unless VK_CLUSTER_FOLD=0
+// Cluster fold (see fold_cluster_sums): on for 2..4 row tiles (B <= 512) unless VK_CLUSTER_FOLD=0.  Measured step times
+// (tools/train_speed.py, us, cluster fold / grid barrier): B = 256: 180.5 / 199.0, 512: 203.8 / 219.0, and with clusters
+// of 8 at B = 1024: 307.3 / 274.8 -- eight co-scheduled 1-CTA-per-SM blocks per GPC cost more than the barrier saves.
 static int cluster_fold_rt(int B) {
     static const int on = [] {
         const char *v = getenv("VK_CLUSTER_FOLD");
         return v ? atoi(v) : 1;
     }();
     const int rt = (B + 127) / 128;
-    return (on && rt >= 2 && rt <= 8) ? rt : 0;
+    return (on && rt >= 2 && rt <= 4) ? rt : 0;
 }
 
 static int launch_prep(const PrepArgs &a, cudaStream_t s) {
