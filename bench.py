@@ -473,6 +473,9 @@ def main():
         import torch.distributed as dist
 
         torch.cuda.set_device(ctx.local_rank)
+        # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION) would precede it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", ctx.local_rank))
     else:
         torch.cuda.set_device(0)

@@ -29,6 +29,8 @@ extern "C" {
 #define VK_NBINS 60          /* ceil(0.3 / 0.005), vamb/cluster.py:231 */
 #define VK_MAX_CAND 32       /* candidates evaluated per vk_eval_candidates launch */
 #define VK_LIST_CAND 64      /* candidates evaluated per vk_eval_candidates_lists launch */
+#define VK_EVAL_SUBS 4       /* copies of its device accumulators / id lists (spread by block: L2 atomic contention) */
+#define VK_EVAL_SCRATCH_U64 (VK_EVAL_SUBS * VK_LIST_CAND * 16) /* uint64 words of its device accumulator scratch */
 #define VK_PROBE_INLINE 2040 /* `within` ids returned inline with the probe header */
 
 const char *vk_last_error(void);
@@ -113,12 +115,12 @@ int vk_eval_candidates_mapped(const float *matrix, const float *lengths, int d, 
  * still tells), and out_pinned (4 * VK_LIST_CAND uint64) = density_lo[k] | density_hi[k] | counts[k] | fp32 bits of
  * d(candidate k, base_row).  `base_row` = the medoid whose neighbour list (radius nl_radius = 0.3) is passed in: the list
  * covers the whole 0.05-neighbourhood of a candidate iff d(candidate, base) <= 0.12 (angles add: acos(0.76) +
- * acos(0.9) = acos(0.4)), which the caller checks.  Mapped completion as vk_eval_candidates_mapped (out_dev: 4 *
- * VK_LIST_CAND uint64, all zero on entry, left zeroed; n_cand <= VK_LIST_CAND). */
+ * acos(0.9) = acos(0.4)), which the caller checks.  Mapped completion as vk_eval_candidates_mapped (out_dev:
+ * VK_EVAL_SCRATCH_U64 uint64 of device scratch, all zero on entry, left zeroed; n_cand <= VK_LIST_CAND). */
 int vk_eval_candidates_lists(const float *matrix, const float *lengths, int d, const int32_t *nl_rows,
                              const float *nl_dists, int32_t n_nl, float prune_radius, const int32_t *cand_rows_host,
                              int n_cand, int32_t base_row, uint64_t *out_dev, uint64_t *out_pinned,
-                             int32_t *within_dev /* device scratch [VK_LIST_CAND * within_cap] */, int32_t *within_pinned,
+                             int32_t *within_dev /* device scratch [VK_EVAL_SUBS * VK_LIST_CAND * within_cap] */, int32_t *within_pinned,
                              int32_t within_cap, int32_t *done_ticket, int32_t *done_flag_pinned, int32_t seq, void *stream);
 
 /* vamb/cluster.py:640-650 (_smaller_indices) + :308-309 (kept_mask[point] = 0):

@@ -237,10 +237,10 @@ def test_eval_candidates_lists_matches_oracle(vk):
     far = np.flatnonzero((dist_base > np.float32(0.125)) & (dist_base <= np.float32(0.3)) & (kept != 0))
     cands = list(near[:: max(1, len(near) // 50)][:50]) + list(far[:3])  # more than VK_MAX_CAND: the lists kernel takes 64
     C, cap = vk.VK_LIST_CAND, 512
-    out_dev = torch.zeros(4 * C, dtype=torch.int64, device="cuda")
+    out_dev = torch.zeros(vk.VK_EVAL_SCRATCH_U64, dtype=torch.int64, device="cuda")
     out_pin = torch.zeros(4 * C, dtype=torch.int64).pin_memory()
     within_pin = torch.zeros(C * cap, dtype=torch.int32).pin_memory()
-    within_dev = torch.zeros(C * cap, dtype=torch.int32, device="cuda")
+    within_dev = torch.zeros(vk.VK_EVAL_SUBS * C * cap, dtype=torch.int32, device="cuda")
     ticket = torch.zeros(1, dtype=torch.int32, device="cuda")
     flag = torch.zeros(1, dtype=torch.int32).pin_memory()
     arr = (vk.c_int32 * len(cands))(*[int(c) for c in cands])

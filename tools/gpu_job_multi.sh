@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 leg() { local name="$1" t="$2"; shift 2; local t0=$(date +%s); timeout "$t" "$@" > "gpurun_out/$name.log" 2>&1
         echo "[$name] rc=$? $(( $(date +%s) - t0 ))s" | tee -a gpurun_out/job_multi_summary.log; }
 nvidia-smi --query-gpu=index,name --format=csv,noheader | tee -a gpurun_out/job_multi_summary.log
-leg r02_pt_multigpu 400 python -m pytest tests/test_multigpu.py -m gpu -q
+if [ "${TESTS:-1}" = "1" ]; then leg r02_pt_multigpu 400 python -m pytest tests/test_multigpu.py -m gpu -q; fi
 leg r02_bench_dp${N} 800 bash -c "python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r02_bench_dp${N}.json"
 if [ "${REF:-1}" = "1" ]; then
 leg r02_bench_ref_dp${N} 600 bash -c "python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --impl reference --gpus $N --steps 20 --warmup 5 > gpurun_out/r02_bench_ref_dp${N}.json"

@@ -31,9 +31,9 @@ for n in (1_000_000, 5_000_000):
     n_within = int(hdr[_lib.HDR_NWITHIN:_lib.HDR_NWITHIN + 4].view(np.int32)[0])
     cands = hdr[_lib.HDR_WITHIN:_lib.HDR_WITHIN + 4 * min(n_within, 40)].view(np.int32).tolist()
     C, cap = _lib.VK_LIST_CAND, 1024
-    out_dev = torch.zeros(4 * C, dtype=torch.int64, device="cuda")
+    out_dev = torch.zeros(_lib.VK_EVAL_SCRATCH_U64, dtype=torch.int64, device="cuda")
     out_pin = torch.zeros(4 * C, dtype=torch.int64).pin_memory()
-    wdev = torch.zeros(C * cap, dtype=torch.int32, device="cuda")
+    wdev = torch.zeros(_lib.VK_EVAL_SUBS * C * cap, dtype=torch.int32, device="cuda")
     wpin = torch.zeros(C * cap, dtype=torch.int32).pin_memory()
     ticket = torch.zeros(1, dtype=torch.int32, device="cuda")
     flag = torch.zeros(1, dtype=torch.int32).pin_memory()

@@ -17,6 +17,8 @@ VK_ABI_VERSION = 1
 VK_NBINS = 60
 VK_MAX_CAND = 32
 VK_LIST_CAND = 64
+VK_EVAL_SUBS = 4
+VK_EVAL_SCRATCH_U64 = VK_EVAL_SUBS * VK_LIST_CAND * 16  # device accumulator words of vk_eval_candidates_lists
 VK_PROBE_INLINE = 2040
 
 # byte offsets inside vk_probe_header (include/vamb_b200.h)

@@ -725,6 +725,16 @@ extern "C" int vk_eval_candidates_mapped(const float *matrix, const float *lengt
 struct CandRowsL {
     int32_t rows[VK_LIST_CAND];
 };
+// Device accumulators of eval_candidates_lists_kernel: VK_EVAL_SUBS copies ("subs", picked by blockIdx) of one 128-byte
+// line per candidate (u64 words: 0 density lo, 1 density hi, 2 count, 3 float bits of d(candidate, base)).  With the
+// compact [field][candidate] layout all counts of a launch shared 3-4 lines and every block's atomics queued up behind
+// each other in the same L2 slices: the last block finished ~15 us after the first whatever was done inside the blocks
+// (tools/probe_timeline.py); one line per (sub, candidate) spreads them over 4 x n_cand lines.
+constexpr int EV_LINE = 16;  // u64 words per (sub, candidate)
+__device__ __forceinline__ u64 *ev_slot(u64 *out, int sub, int k, int field) {
+    return out + ((size_t)(sub * VK_LIST_CAND + k) * EV_LINE + field);
+}
+static_assert(VK_EVAL_SUBS * VK_LIST_CAND * EV_LINE == VK_EVAL_SCRATCH_U64, "eval scratch size");
 
 // As eval_candidates_kernel, plus what lets the host MOVE the medoid to a winning candidate without another full
 // scan: the ids of the rows within 0.05 of every candidate (the candidate's `cluster` of sample_medoid,
@@ -798,7 +808,7 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
         if (lane8 == 0) {
             float dd = __fsub_rn(0.5f, acc);
             if (s_crow[k] == base_row) dd = 0.0f;
-            if (blockIdx.x == 0) out[3 * VK_LIST_CAND + k] = (u64)__float_as_uint(dd);
+            if (blockIdx.x == 0) *ev_slot(out, 0, k, 3) = (u64)__float_as_uint(dd);
             const float ca = 1.0f - 2.0f * fmaxf(dd, 0.0f);
             const float sa = sqrtf(fmaxf(1.0f - ca * ca, 0.0f));
             const float cs = ca * 0.9f - sa * 0.43588990f;  // cos(angle(d_k) + acos(0.9))
@@ -815,6 +825,7 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
     const int groups_total = gridDim.x * EC_SLOTS;
     const int n_rounds = (n_nl + groups_total - 1) / groups_total;  // block-uniform
     const int own_k = tid & (VK_LIST_CAND - 1), own_p = tid / VK_LIST_CAND;
+    const int sub = blockIdx.x & (VK_EVAL_SUBS - 1);
     u64 r_dens = 0ull, r_dens_hi = 0ull;  // sums of candidate own_k over this owner's row slots, all rounds
     for (int round = 0; round < n_rounds; ++round) {
         const int j = round * groups_total + blockIdx.x * EC_SLOTS + g;
@@ -865,7 +876,7 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
             unsigned tot = 0;
 #pragma unroll
             for (int p = 0; p < EC_PARTS; ++p) tot += s_pcnt[p][tid];
-            if (tot) s_base[tid] = atomicAdd(&out[2 * VK_LIST_CAND + tid], (u64)tot);
+            if (tot) s_base[tid] = atomicAdd(ev_slot(out, sub, tid, 2), (u64)tot);
         }
         __syncthreads();
         if (cnt) {
@@ -875,7 +886,7 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
             for (int i = 0; i < EC_PER; ++i) {
                 const int slot = own_p * EC_PER + i;
                 if (s_cell[slot][own_k]) {
-                    if (pos < (u64)within_cap) within_dev[(size_t)own_k * within_cap + pos] = s_slot_row[slot];
+                    if (pos < (u64)within_cap) within_dev[((size_t)sub * VK_LIST_CAND + own_k) * within_cap + pos] = s_slot_row[slot];
                     ++pos;
                     s_cell[slot][own_k] = 0u;
                 }
@@ -897,7 +908,7 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
         u64 tot = 0ull;
 #pragma unroll
         for (int p = 0; p < EC_PARTS; ++p) tot += s_own[p][which][kk];
-        if (tot) atomicAdd(&out[which * VK_LIST_CAND + kk], tot);
+        if (tot) atomicAdd(ev_slot(out, sub, kk, which), tot);
     }
     __shared__ int s_last;
     tl_mark(4);
@@ -908,10 +919,20 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
     // ids with independent loads (a warp per candidate walked them one after the other: 6 us).
     __shared__ int s_off[VK_LIST_CAND + 1];
     __shared__ int s_len_k[VK_LIST_CAND];
-    if (tid < VK_LIST_CAND) {  // the counts: independent loads, then a serial prefix in shared memory
-        u64 cnt = tid < n_cand ? __ldcg(out + 2 * VK_LIST_CAND + tid) : 0ull;
+    __shared__ int s_sub_len[VK_EVAL_SUBS][VK_LIST_CAND];
+    static_assert(EC_THREADS >= VK_EVAL_SUBS * VK_LIST_CAND, "one thread per (sub, candidate)");
+    if (tid < VK_EVAL_SUBS * VK_LIST_CAND) {  // the counts: independent loads, then a serial prefix in shared memory
+        const int kk = tid & (VK_LIST_CAND - 1), sb = tid / VK_LIST_CAND;
+        u64 cnt = kk < n_cand ? __ldcg(ev_slot(out, sb, kk, 2)) : 0ull;
         if (cnt > (u64)within_cap) cnt = (u64)within_cap;
-        s_len_k[tid] = (int)cnt;
+        s_sub_len[sb][kk] = (int)cnt;
+    }
+    __syncthreads();
+    if (tid < VK_LIST_CAND) {
+        int tot = 0;
+#pragma unroll
+        for (int sb = 0; sb < VK_EVAL_SUBS; ++sb) tot += s_sub_len[sb][tid];
+        s_len_k[tid] = tot > within_cap ? within_cap : tot;
     }
     __syncthreads();
     if (tid == 0) {
@@ -930,14 +951,30 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
             if (s_off[mid] <= e) lo = mid;
             else hi = mid;
         }
-        const size_t idx = (size_t)lo * within_cap + (e - s_off[lo]);
-        within_mapped[idx] = __ldcg(within_dev + idx);
+        int r = e - s_off[lo], sb = 0;  // position in the candidate's list = the subs' lists one after the other
+        while (sb < VK_EVAL_SUBS - 1 && r >= s_sub_len[sb][lo]) {
+            r -= s_sub_len[sb][lo];
+            ++sb;
+        }
+        within_mapped[(size_t)lo * within_cap + (e - s_off[lo])] = __ldcg(within_dev + ((size_t)sb * VK_LIST_CAND + lo) * within_cap + r);
     }
     __syncthreads();  // every count has been read before the accumulators are zeroed below
-    if (tid < 4 * VK_LIST_CAND) {
-        out_mapped[tid] = __ldcg(out + tid);
-        out[tid] = 0ull;
+    if (tid < VK_LIST_CAND) {
+        u64 lo = 0ull, hi = 0ull, cnt = 0ull;
+#pragma unroll
+        for (int sb = 0; sb < VK_EVAL_SUBS; ++sb) {
+            lo += __ldcg(ev_slot(out, sb, tid, 0));
+            hi += __ldcg(ev_slot(out, sb, tid, 1));
+            cnt += __ldcg(ev_slot(out, sb, tid, 2));
+        }
+        out_mapped[tid] = lo;
+        out_mapped[VK_LIST_CAND + tid] = hi;
+        out_mapped[2 * VK_LIST_CAND + tid] = cnt;
+        out_mapped[3 * VK_LIST_CAND + tid] = __ldcg(ev_slot(out, 0, tid, 3));
     }
+    __syncthreads();
+    for (int i = tid; i < VK_EVAL_SUBS * VK_LIST_CAND * 4; i += EC_THREADS) *ev_slot(out, i >> 8, (i >> 2) & (VK_LIST_CAND - 1), i & 3) = 0ull;
+    static_assert(VK_LIST_CAND == 64, "index split above");
     tl_mark_any(6);
     vk_raise_flag(done_flag, seq);
     tl_mark_any(7);

@@ -518,9 +518,9 @@ extern "C" int vk_cluster_create(void **handle, const vk_cluster_config *cfg) {
         cudaMalloc((void **)&st->tickets_dev, sizeof(int32_t) * 4) != cudaSuccess ||
         cudaHostAlloc((void **)&st->cand2_pin, sizeof(uint64_t) * 4 * VK_LIST_CAND, cudaHostAllocMapped) != cudaSuccess ||
         cudaHostAlloc((void **)&st->within_pin, sizeof(int32_t) * VK_LIST_CAND * WITHIN_CAP, cudaHostAllocMapped) != cudaSuccess ||
-        cudaMalloc((void **)&st->cand2_dev, sizeof(uint64_t) * 4 * VK_LIST_CAND) != cudaSuccess ||
-        cudaMalloc((void **)&st->within_dev, sizeof(int32_t) * VK_LIST_CAND * WITHIN_CAP) != cudaSuccess ||
-        cudaMemsetAsync(st->cand2_dev, 0, sizeof(uint64_t) * 4 * VK_LIST_CAND, s) != cudaSuccess ||
+        cudaMalloc((void **)&st->cand2_dev, sizeof(uint64_t) * VK_EVAL_SCRATCH_U64) != cudaSuccess ||
+        cudaMalloc((void **)&st->within_dev, sizeof(int32_t) * VK_EVAL_SUBS * VK_LIST_CAND * WITHIN_CAP) != cudaSuccess ||
+        cudaMemsetAsync(st->cand2_dev, 0, sizeof(uint64_t) * VK_EVAL_SCRATCH_U64, s) != cudaSuccess ||
         cudaMemsetAsync(st->tickets_dev, 0, sizeof(int32_t) * 4, s) != cudaSuccess ||
         cudaMemsetAsync(cfg->hdr, 0, sizeof(vk_probe_header), s) != cudaSuccess ||
         cudaMemsetAsync(cfg->cand_out, 0, sizeof(uint64_t) * 3 * VK_MAX_CAND, s) != cudaSuccess ||
