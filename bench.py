@@ -444,7 +444,7 @@ def main_reference(args, rank):
     log("reference arm: one bounded sample of the workload on the host cores")
     base = cpu_baseline(ab, tnf, lens, args.nsamples, args.nepochs, args.seed, args.cpu_seconds)
     v = base["value"]
-    print(json.dumps({
+    emit_json({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "contigs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.n / v / max(1, args.steps),
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -455,11 +455,31 @@ def main_reference(args, rank):
                            "times ONE bounded sample of that pass (independent of --steps/--warmup) and extrapolates"},
         "cpu_baseline": base,
         "e2e": {"value": v, "unit": "contigs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
+
+
+_JSON_OUT = None
+
+
+def claim_stdout() -> None:
+    """stdout carries exactly ONE JSON line: keep a private handle on the real stdout for it and point file descriptor 1
+    at stderr for everything else (NCCL prints its version banner to stdout at NCCL_DEBUG=WARN/VERSION; child
+    processes and C libraries write to fd 1 directly)."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit_json(obj) -> None:
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
 
 
 def main():
     args = parse_args()
+    claim_stdout()
     ctx = Ctx(args)
     if args.impl == "reference":
         return main_reference(args, ctx.rank)
@@ -473,9 +493,6 @@ def main():
         import torch.distributed as dist
 
         torch.cuda.set_device(ctx.local_rank)
-        # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION) would precede it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", ctx.local_rank))
     else:
         torch.cuda.set_device(0)
@@ -582,7 +599,7 @@ def main():
                                                 "d2h_bytes_per_step": 0, "note": e2e_note},
             "gpu_launches": int(res["launches"]), "clocks": clocks,
         }
-        print(json.dumps(out), flush=True)
+        emit_json(out)
     if world > 1:
         import torch.distributed as dist
 
