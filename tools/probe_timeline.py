@@ -53,4 +53,10 @@ for n in (1_000_000, 5_000_000):
     print(f"   eval of {len(cands)} candidates over a {n_nl}-row list: event time {a.elapsed_time(b) * 1e3:.1f} us; [us after block-0 entry] "
           f"prologue {rel[1]:.1f}, rows done {rel[2]:.1f}, block barrier {rel[3]:.1f}, before ticket {rel[4]:.1f} | last block elected "
           f"{rel[5]:.1f}, published {rel[6]:.1f}, flag raised {rel[7]:.1f}")
+    nb = min((n_nl + 31) // 32, 592, 1024)
+    st = (buf[512:512 + nb].astype(np.int64) - int(g[0])) / 1e3
+    en = (buf[2560:2560 + nb].astype(np.int64) - int(g[0])) / 1e3
+    q = lambda x: " / ".join(f"{np.percentile(x, p):.1f}" for p in (0, 25, 50, 75, 90, 100))
+    print(f"      {nb} blocks: entry [min / 25 / 50 / 75 / 90 / max] {q(st)} us; exit (before ticket) {q(en)} us; "
+          f"time in block {q(en - st)} us")
     del gen, lat

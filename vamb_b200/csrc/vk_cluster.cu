@@ -745,10 +745,17 @@ static_assert(VK_EVAL_SUBS * VK_LIST_CAND * EV_LINE == VK_EVAL_SCRATCH_U64, "eva
 __global__ void __launch_bounds__(EC_THREADS)
 eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths, int d,
                              const int32_t *__restrict__ nl_rows, const float *__restrict__ nl_dists, int n_nl,
-                             float prune_radius, CandRowsL cand, int n_cand, int32_t base_row, u64 *out, u64 *out_mapped,
+                             float prune_radius, const __grid_constant__ CandRowsL cand, int n_cand, int32_t base_row, u64 *out, u64 *out_mapped,
                              int32_t *within_dev, int32_t *within_mapped, int within_cap, int32_t *done_ticket,
                              volatile int32_t *done_flag, int32_t seq) {
     tl_begin(1);
+#ifdef VK_TIMELINE
+    if (threadIdx.x == 0 && blockIdx.x < 1024) {  // per-block entry / exit stamps (tools/probe_timeline.py)
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        vk_tl[512 + blockIdx.x] = t;
+    }
+#endif
     extern __shared__ __align__(16) float s_qs[];  // [n_cand][dpad]
     // A hit = (row within 0.05 of candidate k).  The lane that scans a row of a dense core finds a hit for almost every
     // candidate; doing the bookkeeping there (shared atomics + a returning global atomic per hit) serialised 40 x ~1 us
@@ -767,17 +774,14 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
     __shared__ uint32_t s_slot_len[EC_SLOTS];
     __shared__ unsigned s_pcnt[EC_PARTS][VK_LIST_CAND];
     __shared__ u64 s_base[VK_LIST_CAND];
-    __shared__ int32_t s_crow[VK_LIST_CAND];  // candidate rows: copied out of the by-value parameter with STATIC indices
-                                              // (a dynamic index would make every thread spill the array to local memory)
+    __shared__ int32_t s_crow[VK_LIST_CAND];  // candidate rows out of the parameter
     __shared__ float s_reach[VK_LIST_CAND];
     const int tid = threadIdx.x, lane8 = tid & 7, g = tid >> 3;
     const unsigned gmask = group8_mask();
     const int dpad = (d + 3) & ~3;
     const bool vec4 = (d & 3) == 0;
     const bool fast = (d == 32);
-#pragma unroll
-    for (int k = 0; k < VK_LIST_CAND; ++k)
-        if (tid == k) s_crow[k] = k < n_cand ? cand.rows[k] : -1;
+    if (tid < VK_LIST_CAND) s_crow[tid] = tid < n_cand ? cand.rows[tid] : -1;  // __grid_constant__: indexed constant load
     for (int i = tid; i < EC_SLOTS * VK_LIST_CAND; i += EC_THREADS) (&s_cell[0][0])[i] = 0u;
     __syncthreads();
     if (fast) {  // 8 float4 per candidate row, all loads independent
@@ -859,7 +863,7 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
         }
         if (!__syncthreads_or(any)) continue;  // no hit in this block and round (the common case away from the core)
         unsigned cnt = 0;
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < EC_PER; ++i) {
             const int slot = own_p * EC_PER + i;
             const uint32_t c1 = s_cell[slot][own_k];
@@ -874,7 +878,7 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
         __syncthreads();
         if (tid < n_cand) {
             unsigned tot = 0;
-#pragma unroll
+#pragma unroll 1
             for (int p = 0; p < EC_PARTS; ++p) tot += s_pcnt[p][tid];
             if (tot) s_base[tid] = atomicAdd(ev_slot(out, sub, tid, 2), (u64)tot);
         }
@@ -882,7 +886,7 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
         if (cnt) {
             u64 pos = s_base[own_k];
             for (int p = 0; p < own_p; ++p) pos += s_pcnt[p][own_k];
-#pragma unroll
+#pragma unroll 1
             for (int i = 0; i < EC_PER; ++i) {
                 const int slot = own_p * EC_PER + i;
                 if (s_cell[slot][own_k]) {
@@ -906,12 +910,19 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
     if (tid < 2 * VK_LIST_CAND) {
         const int kk = tid & (VK_LIST_CAND - 1), which = tid / VK_LIST_CAND;
         u64 tot = 0ull;
-#pragma unroll
+#pragma unroll 1
         for (int p = 0; p < EC_PARTS; ++p) tot += s_own[p][which][kk];
         if (tot) atomicAdd(ev_slot(out, sub, kk, which), tot);
     }
     __shared__ int s_last;
     tl_mark(4);
+#ifdef VK_TIMELINE
+    if (threadIdx.x == 0 && blockIdx.x < 1024) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        vk_tl[2560 + blockIdx.x] = t;
+    }
+#endif
     if (!vk_last_block(done_ticket, &s_last)) return;
     tl_mark_any(5);
     // The last block publishes: the id lists (device -> pinned host memory), then the sums and counts; ONE system-scope
@@ -930,7 +941,7 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
     __syncthreads();
     if (tid < VK_LIST_CAND) {
         int tot = 0;
-#pragma unroll
+#pragma unroll 1
         for (int sb = 0; sb < VK_EVAL_SUBS; ++sb) tot += s_sub_len[sb][tid];
         s_len_k[tid] = tot > within_cap ? within_cap : tot;
     }
@@ -961,7 +972,7 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
     __syncthreads();  // every count has been read before the accumulators are zeroed below
     if (tid < VK_LIST_CAND) {
         u64 lo = 0ull, hi = 0ull, cnt = 0ull;
-#pragma unroll
+#pragma unroll 1
         for (int sb = 0; sb < VK_EVAL_SUBS; ++sb) {
             lo += __ldcg(ev_slot(out, sb, tid, 0));
             hi += __ldcg(ev_slot(out, sb, tid, 1));

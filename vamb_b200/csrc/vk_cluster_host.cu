@@ -133,6 +133,11 @@ struct State {
     int64_t n_moves_lazy = 0, n_rebases = 0, sum_nnl = 0;  // sum_nnl: neighbour-list sizes over all candidate evaluations
     bool lazy_enabled = true;  // VAMB_B200_CLUSTER_LAZY=0: a full scan per move, as round 1 (same clusters)
     std::vector<int64_t> members;
+    // per-wander sets over device rows as stamp arrays (row -> id of the wander that set it): `tried`, and the cache of
+    // candidate evaluations (stamp + slot in cache_vec).  Hash containers cost ~1 s of the 6.3 s C2 clustering.
+    std::vector<uint32_t> tried_stamp, cache_stamp;
+    std::vector<int32_t> cache_slot;
+    uint32_t wander_id = 0;
     int64_t n_probes, n_evals, n_packs;
     double t_probe = 0.0, t_eval = 0.0, t_select = 0.0, t_pack = 0.0, t_total = 0.0;  // host wall seconds per call kind
 
@@ -319,8 +324,20 @@ int do_eval_lists(State &st, const Probe &base, float prune, const std::vector<i
 // once for its histogram / neighbour list.  Densities are pure functions of (medoid, live rows), so the decisions --
 // and the Python RNG call sequence -- are exactly the reference's.
 int wander(State &st, int32_t seed, Probe &probe, int32_t &seed_rank) {
-    std::unordered_set<int32_t> tried;
-    tried.insert(seed);
+    if (st.tried_stamp.size() < (size_t)st.n_act) {  // rows only ever renumber downwards (compaction)
+        st.tried_stamp.assign((size_t)st.n_act, 0u);
+        st.cache_stamp.assign((size_t)st.n_act, 0u);
+        st.cache_slot.assign((size_t)st.n_act, 0);
+    }
+    if (++st.wander_id == 0u) {  // wrapped: stale stamps could alias
+        std::fill(st.tried_stamp.begin(), st.tried_stamp.end(), 0u);
+        std::fill(st.cache_stamp.begin(), st.cache_stamp.end(), 0u);
+        st.wander_id = 1u;
+    }
+    const uint32_t wid = st.wander_id;
+    auto is_tried = [&](int32_t r) { return st.tried_stamp[(size_t)r] == wid; };
+    auto set_tried = [&](int32_t r) { st.tried_stamp[(size_t)r] = wid; };
+    set_tried(seed);
     if (do_probe(st, seed, probe)) return 1;
     seed_rank = probe.rank;
     const bool list_is_everything = !(st.c.nl_radius < 1e30f);
@@ -336,8 +353,19 @@ int wander(State &st, int32_t seed, Probe &probe, int32_t &seed_rank) {
         unsigned __int128 dens;
         std::vector<int32_t> within;
         bool lists_ok;
+        bool sorted;  // `within` is sorted only when it becomes the current within-set (one winner per round, not 64 lists)
     };
-    std::unordered_map<int32_t, Cached> cache;  // row -> what a candidate evaluation of this wander returned
+    std::vector<Cached> cache_vec;  // what the candidate evaluations of this wander returned, by slot
+    auto cached = [&](int32_t r) -> Cached * {
+        return st.cache_stamp[(size_t)r] == wid ? &cache_vec[(size_t)st.cache_slot[(size_t)r]] : nullptr;
+    };
+    auto cache_new = [&](int32_t r) -> Cached & {
+        if (Cached *c = cached(r)) return *c;
+        st.cache_stamp[(size_t)r] = wid;
+        st.cache_slot[(size_t)r] = (int32_t)cache_vec.size();
+        cache_vec.emplace_back();
+        return cache_vec.back();
+    };
     std::vector<int32_t> batch;
     auto rebase = [&]() -> int {                // full scan at the current medoid
         const unsigned __int128 want = local;
@@ -352,7 +380,7 @@ int wander(State &st, int32_t seed, Probe &probe, int32_t &seed_rank) {
     for (;;) {
         cand.clear();
         for (int32_t r : cur_within)
-            if (!tried.count(r)) cand.push_back(r);
+            if (!is_tried(r)) cand.push_back(r);
         const int k = (int)std::min<size_t>(cand.size(), (size_t)st.c.maxsteps);
         st.rng.sample(cand, k, sampled);
         if (sampled.empty()) break;
@@ -361,7 +389,7 @@ int wander(State &st, int32_t seed, Probe &probe, int32_t &seed_rank) {
             if (cur != probe.medoid && rebase()) return 1;
             if (do_eval(st, probe, sampled, dens)) return 1;
             for (size_t i = 0; i < sampled.size(); ++i) {
-                tried.insert(sampled[i]);
+                set_tried(sampled[i]);
                 if (dens[i] > local) { winner = (int)i; break; }
             }
             if (winner < 0) break;
@@ -384,12 +412,12 @@ int wander(State &st, int32_t seed, Probe &probe, int32_t &seed_rank) {
         for (;;) {
             batch.clear();
             for (int32_t c : sampled)
-                if (!cache.count(c)) batch.push_back(c);
+                if (!cached(c)) batch.push_back(c);
             if (!batch.empty()) {
                 const size_t n_need = batch.size();
                 for (int32_t c : cur_within) {
                     if (batch.size() >= (size_t)VK_LIST_CAND) break;
-                    if (!tried.count(c) && !cache.count(c) && std::find(batch.begin(), batch.end(), c) == batch.end())
+                    if (!is_tried(c) && !cached(c) && std::find(batch.begin(), batch.end(), c) == batch.end())
                         batch.push_back(c);
                 }
                 const bool at_base = cur == probe.medoid;
@@ -398,13 +426,13 @@ int wander(State &st, int32_t seed, Probe &probe, int32_t &seed_rank) {
                 for (size_t i = 0; i < batch.size(); ++i) {
                     const bool ok = at_base || list_is_everything || ev.dbase[i] <= R_EVAL;
                     if (!ok) continue;  // the list may not cover this candidate's neighbourhood: not usable
-                    Cached &cc = cache[batch[i]];
+                    Cached &cc = cache_new(batch[i]);
                     cc.dens = ev.dens[i];
                     cc.lists_ok = ev.cnt[i] <= WITHIN_CAP;
+                    cc.sorted = false;
                     if (cc.lists_ok) {
                         const int32_t *ids = st.within_pin + i * WITHIN_CAP;
                         cc.within.assign(ids, ids + ev.cnt[i]);
-                        std::sort(cc.within.begin(), cc.within.end());
                     }
                 }
                 (void)n_need;
@@ -412,17 +440,17 @@ int wander(State &st, int32_t seed, Probe &probe, int32_t &seed_rank) {
             bool need_rebase = false;
             winner = -1;
             for (size_t i = 0; i < sampled.size(); ++i) {
-                const auto it = cache.find(sampled[i]);
-                if (it == cache.end()) { need_rebase = true; break; }  // beyond the coverage radius of the base
-                tried.insert(sampled[i]);
-                if (it->second.dens > local) { winner = (int)i; break; }
+                const Cached *it = cached(sampled[i]);
+                if (!it) { need_rebase = true; break; }  // beyond the coverage radius of the base
+                set_tried(sampled[i]);
+                if (it->dens > local) { winner = (int)i; break; }
             }
             if (!need_rebase) break;
             if (rebase()) return 1;  // then evaluate what is still unknown of the same sample against the new base
         }
         if (winner < 0) break;
         const size_t w = (size_t)winner;
-        const Cached &cw = cache[sampled[w]];
+        Cached &cw = *cached(sampled[w]);
         if (!cw.lists_ok) {  // id list truncated: take the winner's within-set from a full scan
             const unsigned __int128 want = cw.dens;
             if (do_probe(st, sampled[w], probe)) return 1;
@@ -432,6 +460,10 @@ int wander(State &st, int32_t seed, Probe &probe, int32_t &seed_rank) {
             }
             cur_within = probe.within;
         } else {
+            if (!cw.sorted) {  // ascending row order = the reference's candidate order (vamb/cluster.py:626)
+                std::sort(cw.within.begin(), cw.within.end());
+                cw.sorted = true;
+            }
             cur_within = cw.within;
             ++st.n_moves_lazy;
         }
