@@ -53,10 +53,13 @@ for n in (1_000_000, 5_000_000):
     print(f"   eval of {len(cands)} candidates over a {n_nl}-row list: event time {a.elapsed_time(b) * 1e3:.1f} us; [us after block-0 entry] "
           f"prologue {rel[1]:.1f}, rows done {rel[2]:.1f}, block barrier {rel[3]:.1f}, before ticket {rel[4]:.1f} | last block elected "
           f"{rel[5]:.1f}, published {rel[6]:.1f}, flag raised {rel[7]:.1f}")
-    nb = min((n_nl + 31) // 32, 592, 1024)
-    st = (buf[512:512 + nb].astype(np.int64) - int(g[0])) / 1e3
-    en = (buf[2560:2560 + nb].astype(np.int64) - int(g[0])) / 1e3
-    q = lambda x: " / ".join(f"{np.percentile(x, p):.1f}" for p in (0, 25, 50, 75, 90, 100))
-    print(f"      {nb} blocks: entry [min / 25 / 50 / 75 / 90 / max] {q(st)} us; exit (before ticket) {q(en)} us; "
-          f"time in block {q(en - st)} us")
+    nb = min((n_nl + 31) // 32, 592, 320)
+    pt = [(buf[(512 + 320 * i if i < 4 else 2560 + 320 * (i - 4)):][:nb].astype(np.int64) - int(g[0])) / 1e3 for i in range(5)]
+    slow = pt[4] > np.median(pt[4]) + 3.0
+    q = lambda x: " / ".join(f"{np.percentile(x, p):.1f}" for p in (0, 50, 90, 100)) if len(x) else "-"
+    names = ["entry", "scan done (last round)", "ranges reserved", "loop done", "before ticket"]
+    print(f"      first {nb} blocks, {int(slow.sum())} of them slow; per point [min / median / 90 % / max us]: " +
+          "; ".join(f"{nm} {q(p_)}" for nm, p_ in zip(names, pt)))
+    if slow.any():
+        print("      slow blocks only: " + "; ".join(f"{nm} {q(p_[slow])}" for nm, p_ in zip(names, pt)))
     del gen, lat

@@ -749,13 +749,20 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
                              int32_t *within_dev, int32_t *within_mapped, int within_cap, int32_t *done_ticket,
                              volatile int32_t *done_flag, int32_t seq) {
     tl_begin(1);
+    // per-block stamps (stamped build only; tools/probe_timeline.py): point i of block b < 320 at vk_tl[EVT_BASE(i) + b]
 #ifdef VK_TIMELINE
-    if (threadIdx.x == 0 && blockIdx.x < 1024) {  // per-block entry / exit stamps (tools/probe_timeline.py)
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        vk_tl[512 + blockIdx.x] = t;
-    }
+#define EVT(i)                                                                        \
+    do {                                                                              \
+        if (threadIdx.x == 0 && blockIdx.x < 320) {                                   \
+            unsigned long long t_;                                                    \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                    \
+            vk_tl[((i) < 4 ? 512 + 320 * (i) : 2560 + 320 * ((i) - 4)) + blockIdx.x] = t_; \
+        }                                                                             \
+    } while (0)
+#else
+#define EVT(i) ((void)0)
 #endif
+    EVT(0);
     extern __shared__ __align__(16) float s_qs[];  // [n_cand][dpad]
     // A hit = (row within 0.05 of candidate k).  The lane that scans a row of a dense core finds a hit for almost every
     // candidate; doing the bookkeeping there (shared atomics + a returning global atomic per hit) serialised 40 x ~1 us
@@ -861,6 +868,7 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
                 }
             }
         }
+        EVT(1);
         if (!__syncthreads_or(any)) continue;  // no hit in this block and round (the common case away from the core)
         unsigned cnt = 0;
 #pragma unroll 1
@@ -883,6 +891,7 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
             if (tot) s_base[tid] = atomicAdd(ev_slot(out, sub, tid, 2), (u64)tot);
         }
         __syncthreads();
+        EVT(2);
         if (cnt) {
             u64 pos = s_base[own_k];
             for (int p = 0; p < own_p; ++p) pos += s_pcnt[p][own_k];
@@ -898,6 +907,7 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
         }
         __syncthreads();
     }
+    EVT(3);
     tl_mark(2);
     tl_mark(3);
     // the owners of a candidate are combined in shared memory first: one pair of global atomics per (block, candidate)
@@ -916,13 +926,7 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
     }
     __shared__ int s_last;
     tl_mark(4);
-#ifdef VK_TIMELINE
-    if (threadIdx.x == 0 && blockIdx.x < 1024) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        vk_tl[2560 + blockIdx.x] = t;
-    }
-#endif
+    EVT(4);
     if (!vk_last_block(done_ticket, &s_last)) return;
     tl_mark_any(5);
     // The last block publishes: the id lists (device -> pinned host memory), then the sums and counts; ONE system-scope

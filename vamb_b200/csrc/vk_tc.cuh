@@ -298,7 +298,11 @@ __device__ __forceinline__ bool ws_mainloop(const float *A, int lda, int m0, con
                                             int kt0, int nk, uint8_t *smem, WsShared *sh, int slot_rows = 0,
                                             const void *tm_hi = nullptr, const void *tm_lo = nullptr,
                                             float (*racc)[16] = nullptr) {
-    constexpr int S = WS_STAGES, P = 2;
+    // PA: A tiles in flight as global loads into registers; PB: B tiles issued ahead into the shared-memory ring.
+    // A k-tile of A is 16 KB per CTA read from L2 with ~0.8 us of latency: two tiles in flight held the main loop to
+    // 0.43-0.47 us per k-tile (latency / 2) against the 0.29 us the 12 MMAs need (tools/kernel_timeline.py).
+    constexpr int S = WS_STAGES, PA = 4, PB = 3;
+    static_assert(PB < S && PA <= S, "ring depth");
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int bbytes = b_tile_bytes(TMA_B ? slot_rows : bn), sbytes = 2 * bbytes;
     const uint32_t smem_base = smem_u32(smem);
@@ -338,17 +342,17 @@ __device__ __forceinline__ bool ws_mainloop(const float *A, int lda, int m0, con
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] = __ldg(g + j * 128);
     };
-    // the first two tiles are in flight while barriers / tensor memory are set up
-    float4 ra[2][4];
+    // the first tiles are in flight while barriers / tensor memory are set up
+    float4 ra[PA][4];
     if (warp < 8) {
 #pragma unroll
-        for (int t = 0; t < P; ++t) {
-            if (t < nk) {
-                if (!TMA_B) issue_b(t, t);  // (the bulk copies need the barriers: issued after the set-up below)
-                load_a(t, ra[t]);
-            }
+        for (int t = 0; t < PB; ++t) {
+            if (t < nk && !TMA_B) issue_b(t, t);  // (the bulk copies need the barriers: issued after the set-up below)
             if (!TMA_B) cp_async_commit();
         }
+#pragma unroll
+        for (int t = 0; t < PA; ++t)
+            if (t < nk) load_a(t, ra[t]);
     }
     if (tid == 0) {
 #pragma unroll
@@ -372,7 +376,7 @@ __device__ __forceinline__ bool ws_mainloop(const float *A, int lda, int m0, con
     tl_mark(8);
     if (TMA_B && warp < 8) {
 #pragma unroll
-        for (int t = 0; t < P; ++t)
+        for (int t = 0; t < PB; ++t)
             if (t < nk) issue_b(t, t);
     }
     const uint32_t tmem_d = sh->tmem_base;
@@ -415,14 +419,9 @@ __device__ __forceinline__ bool ws_mainloop(const float *A, int lda, int m0, con
     }
     const uint32_t a_lane = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + 128u + (uint32_t)(warp >> 2) * 16u;
     auto produce = [&](int kt, float4(&v)[4]) {
-        const int nt = kt + P, slot = kt % S;
-        if (nt < nk) {
-            // stage nt % S was read by the MMAs of tile nt - S (issued two k-tiles ago)
-            if (nt >= S) mbar_wait(&sh->empty[nt % S], (uint32_t)(((nt / S) - 1) & 1));
-            issue_b(nt, nt % S);
-        }
-        if (!TMA_B) cp_async_commit();
-        // A tile kt: registers -> tensor memory (its stage was released before B of this tile was issued)
+        const int slot = kt % S;
+        // A tile kt: registers -> tensor memory.  Its stage is free: every producer thread waited for the MMAs of tile
+        // kt - S before B of tile kt was issued (PB tiles ago, below).
         float hi[16], lo[16];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -433,9 +432,9 @@ __device__ __forceinline__ bool ws_mainloop(const float *A, int lda, int m0, con
         tc_fence_after();
         tmem_st16(a_lane + 64u * slot, hi);
         tmem_st16(a_lane + 64u * slot + 32u, lo);
-        if (nt < nk) load_a(nt, v);  // v's registers are free again: next-but-one tile
+        if (kt + PA < nk) load_a(kt + PA, v);  // v's registers are free again
         if (!TMA_B) {
-            cp_async_wait<P>();      // this thread's B copies of tile kt have landed
+            cp_async_wait<PB - 1>();  // this thread's B copies of tile kt have landed (one group per produced tile)
             split_b(slot);
         }
         tmem_wait_st();
@@ -443,6 +442,14 @@ __device__ __forceinline__ bool ws_mainloop(const float *A, int lda, int m0, con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sh->full[slot]);
+        // B of tile kt + PB, AFTER this tile has been handed over: its stage was read by the MMAs of tile
+        // kt + PB - S (the previous tile for PB = S - 1), which run while the A part above is produced
+        const int nt = kt + PB;
+        if (nt < nk) {
+            if (nt >= S) mbar_wait(&sh->empty[nt % S], (uint32_t)(((nt / S) - 1) & 1));
+            issue_b(nt, nt % S);
+        }
+        if (!TMA_B) cp_async_commit();
         if (kt < 20) tl_mark(10 + kt);
     };
     // FLUSH: add a finished group (all but the last, which the epilogue reads) into the register accumulators
@@ -476,13 +483,13 @@ __device__ __forceinline__ bool ws_mainloop(const float *A, int lda, int m0, con
 #pragma unroll
             for (int j = 0; j < 16; ++j) racc[i][j] = 0.0f;
     }
-    for (int kt = 0; kt < nk; kt += 2) {
-        produce(kt, ra[0]);
-        drain_ready(kt);
-        if (kt + 1 < nk) {
-            produce(kt + 1, ra[1]);
-            drain_ready(kt + 1);
-        }
+    for (int kt = 0; kt < nk; kt += PA) {
+#pragma unroll
+        for (int i = 0; i < PA; ++i)
+            if (kt + i < nk) {
+                produce(kt + i, ra[i]);
+                drain_ready(kt + i);
+            }
     }
     if (FLUSH) {  // groups that completed inside the last WS_DRAIN_LAG tiles
         while ((next_drain + 1) * WS_FLUSH_KT < nk) drain_ready(1 << 28);
