@@ -19,8 +19,8 @@ lib = _lib.lib
 import ctypes
 lib.vk_tc_mma_rate_test.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
 out = torch.zeros(2, dtype=torch.int64, device="cuda")
-for sw in (0, 2):
-    for n in (32, 64, 128):
+for sw in (0, 2, 3):
+    for n in (16, 32, 64) if sw == 3 else (16, 32, 64, 128):
         for n_mma in (1, 12, 48, 768):
             _lib.check(lib.vk_tc_mma_rate_test(n_mma, n, sw, out.data_ptr(), s)); torch.cuda.synchronize()
             _lib.check(lib.vk_tc_mma_rate_test(n_mma, n, sw, out.data_ptr(), s)); torch.cuda.synchronize()

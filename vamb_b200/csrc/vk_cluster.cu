@@ -731,6 +731,8 @@ struct CandRowsL {
 // each other in the same L2 slices: the last block finished ~15 us after the first whatever was done inside the blocks
 // (tools/probe_timeline.py); one line per (sub, candidate) spreads them over 4 x n_cand lines.
 constexpr int EV_LINE = 16;  // u64 words per (sub, candidate)
+constexpr int EC_QS = 36;    // floats between candidate rows / row buffers in shared memory (d = 32): 8 lanes reading 8
+                             // different rows with float4 loads touch 8 distinct bank quads
 __device__ __forceinline__ u64 *ev_slot(u64 *out, int sub, int k, int field) {
     return out + ((size_t)(sub * VK_LIST_CAND + k) * EV_LINE + field);
 }
@@ -763,7 +765,8 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
 #define EVT(i) ((void)0)
 #endif
     EVT(0);
-    extern __shared__ __align__(16) float s_qs[];  // [n_cand][dpad]
+    extern __shared__ __align__(16) float s_qs[];  // [n_cand][qs]: qs = 36 for d = 32 (conflict-free float4 reads by 8 lanes
+                                                   // holding 8 different candidates), else dpad
     // A hit = (row within 0.05 of candidate k).  The lane that scans a row of a dense core finds a hit for almost every
     // candidate; doing the bookkeeping there (shared atomics + a returning global atomic per hit) serialised 40 x ~1 us
     // in that one lane, and folding recorded hits with 64-bit shared atomics (CAS loops, 32 hits of one candidate in
@@ -778,6 +781,7 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
     static_assert(EC_THREADS % VK_LIST_CAND == 0 && EC_SLOTS % EC_PARTS == 0, "eval ownership");
     __shared__ uint32_t s_cell[EC_SLOTS][VK_LIST_CAND];  // closeness + 1 of (row slot, candidate), 0 = no hit
     __shared__ int32_t s_slot_row[EC_SLOTS];
+    __shared__ __align__(16) float s_rowbuf[EC_SLOTS][EC_QS];  // the row of every slot, readable by all lanes of its group
     __shared__ uint32_t s_slot_len[EC_SLOTS];
     __shared__ unsigned s_pcnt[EC_PARTS][VK_LIST_CAND];
     __shared__ u64 s_base[VK_LIST_CAND];
@@ -788,12 +792,13 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
     const int dpad = (d + 3) & ~3;
     const bool vec4 = (d & 3) == 0;
     const bool fast = (d == 32);
+    const int qs = fast ? EC_QS : dpad;
     if (tid < VK_LIST_CAND) s_crow[tid] = tid < n_cand ? cand.rows[tid] : -1;  // __grid_constant__: indexed constant load
     for (int i = tid; i < EC_SLOTS * VK_LIST_CAND; i += EC_THREADS) (&s_cell[0][0])[i] = 0u;
     __syncthreads();
     if (fast) {  // 8 float4 per candidate row, all loads independent
         for (int i = tid; i < n_cand * 8; i += EC_THREADS)
-            *reinterpret_cast<float4 *>(s_qs + (i >> 3) * 32 + (i & 7) * 4) = ldg_stream4(matrix + (int64_t)s_crow[i >> 3] * 32 + (i & 7) * 4);
+            *reinterpret_cast<float4 *>(s_qs + (i >> 3) * EC_QS + (i & 7) * 4) = ldg_stream4(matrix + (int64_t)s_crow[i >> 3] * 32 + (i & 7) * 4);
     } else {
         for (int i = tid; i < n_cand * dpad; i += EC_THREADS) {
             const int k = i / dpad, c = i - k * dpad;
@@ -813,7 +818,7 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
     //     reach_k = 0.5 * (1 - ((1 - 2 d_k) * 0.9 - sqrt(1 - (1 - 2 d_k)^2) * sqrt(0.19)))      (+ 1e-4 of slack).
     // Neighbour-list entries beyond max_k reach_k (and beyond `prune_radius`) cannot matter and are not gathered.
     for (int k = g; k < n_cand; k += EC_THREADS / 8) {
-        const float *q = s_qs + k * dpad;
+        const float *q = s_qs + k * qs;
         float acc = fast ? chain4(xbv, *reinterpret_cast<const float4 *>(q + 4 * lane8)) : lane_chain_generic(xb, q, d, lane8, vec4);
         acc = group8_sum(acc, gmask);
         if (lane8 == 0) {
@@ -851,18 +856,44 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
                 s_slot_row[g] = row;
                 s_slot_len[g] = (uint32_t)__float2ull_rz(__ldg(lengths + row));  // integral, < 2^24 per contig
             }
+            if (fast) {
+                // Every lane of the group takes whole (row, candidate) pairs -- candidates lane8, lane8 + 8, ... -- with the
+                // full row in registers: 8 independent fmaf chains and the butterfly's additions in the same order
+                // ((p0+p1)+(p2+p3))+((p4+p5)+(p6+p7)), i.e. the same bits as group8_sum(chain4) without a shuffle.  (One
+                // candidate at a time per group was a serial chain of n_cand x ~150 cycles, and the four groups of a warp
+                // diverge on `dj`: blocks with rows near the candidates took 14 us against 3 us, tools/probe_timeline.py.)
+                *reinterpret_cast<float4 *>(&s_rowbuf[g][4 * lane8]) = xv;
+                __syncwarp(gmask);
+                float4 xr[8];
+#pragma unroll
+                for (int l = 0; l < 8; ++l) xr[l] = *reinterpret_cast<const float4 *>(&s_rowbuf[g][4 * l]);
+                for (int k = lane8; k < n_cand; k += 8) {
+                    if (geo && !(dj <= s_reach[k])) continue;  // this row cannot be within 0.05 of candidate k
+                    const float4 *q = reinterpret_cast<const float4 *>(s_qs + k * EC_QS);
+                    float p[8];
+#pragma unroll
+                    for (int l = 0; l < 8; ++l) p[l] = chain4(xr[l], q[l]);
+                    const float acc = __fadd_rn(__fadd_rn(__fadd_rn(p[0], p[1]), __fadd_rn(p[2], p[3])),
+                                                __fadd_rn(__fadd_rn(p[4], p[5]), __fadd_rn(p[6], p[7])));
+                    float dd = __fsub_rn(0.5f, acc);
+                    if (row == s_crow[k]) dd = 0.0f;
+                    if (dd <= rad) {
+                        s_cell[g][k] = (uint32_t)closeness_fx(rad, dd) + 1u;  // closeness <= 0.05 * 2^29 < 2^25
+                        any = true;
+                    }
+                }
+                __syncwarp(gmask);  // the row buffer is rewritten in the next round
+            } else
             for (int k = 0; k < n_cand; ++k) {
                 if (geo && !(dj <= s_reach[k])) continue;  // this row cannot be within 0.05 of candidate k
-                const float *q = s_qs + k * dpad;
-                float acc;
-                if (fast) acc = chain4(xv, *reinterpret_cast<const float4 *>(q + 4 * lane8));
-                else acc = lane_chain_generic(x, q, d, lane8, vec4);
+                const float *q = s_qs + k * qs;
+                float acc = lane_chain_generic(x, q, d, lane8, vec4);
                 acc = group8_sum(acc, gmask);
                 if (lane8 == 0) {
                     float dd = __fsub_rn(0.5f, acc);
                     if (row == s_crow[k]) dd = 0.0f;
                     if (dd <= rad) {
-                        s_cell[g][k] = (uint32_t)closeness_fx(rad, dd) + 1u;  // closeness <= 0.05 * 2^29 < 2^25
+                        s_cell[g][k] = (uint32_t)closeness_fx(rad, dd) + 1u;
                         any = true;
                     }
                 }
@@ -1014,7 +1045,7 @@ extern "C" int vk_eval_candidates_lists(const float *matrix, const float *length
     memset(&cand, 0, sizeof(cand));
     for (int k = 0; k < n_cand; ++k) cand.rows[k] = cand_rows_host[k];
     const int dpad = (d + 3) & ~3;
-    const size_t smem = sizeof(float) * (size_t)n_cand * dpad;
+    const size_t smem = sizeof(float) * (size_t)n_cand * (d == 32 ? EC_QS : dpad);
     if (smem > 48 * 1024)
         VK_CUDA(cudaFuncSetAttribute(eval_candidates_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int per_block = EC_THREADS / 8;

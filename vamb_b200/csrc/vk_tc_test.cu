@@ -159,12 +159,16 @@ __global__ void __launch_bounds__(tc::TC_THREADS, 1) tc_mma_rate_kernel(int n_mm
     tc::tc_fence_after();
     if (tid == 0) {
         uint64_t d = tc::make_smem_desc(tc::smem_u32(smem), swizzle ? 16 : 128, 1024);
-        if (swizzle) d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+        if (swizzle) d |= (uint64_t)2 << 61;  // SWIZZLE_128B (modes 1, 2, 3)
         const uint64_t da = d, db = d + (32768 >> 4);
         const uint32_t idesc = tc::make_idesc_tf32(128, n, 0, 0);
         const long long t0 = clock64();
         if (swizzle == 2)  // A operand from tensor memory (columns 128..), B from shared memory
             for (int i = 0; i < n_mma; ++i) tc::umma_tf32_ts(sh.tmem_base, sh.tmem_base + 128u + 8u * (i & 3), db, idesc, 1u);
+        else if (swizzle == 3)  // as 2, successive MMAs into two DIFFERENT accumulators (n <= 64): is the per-MMA cost a
+                                // dependency on the accumulator or an issue cost?
+            for (int i = 0; i < n_mma; ++i)
+                tc::umma_tf32_ts(sh.tmem_base + ((i & 1) ? 192u : 0u), sh.tmem_base + 128u + 8u * (i & 3), db, idesc, 1u);
         else
             for (int i = 0; i < n_mma; ++i) tc::umma_tf32(sh.tmem_base, da + (uint64_t)((i & 3) * (swizzle ? 2 : 16)), db, idesc, 1u);
         tc::umma_commit(&sh.bar_done);

@@ -370,6 +370,7 @@ struct FwdArgs {
     // B operand (W and its tf32 remainder) through TMA: 128B-swizzled tensor maps, box = 32 floats x tile_n rows
     int use_tma; VkTmap tm_b_hi, tm_b_lo;
     int cluster_rt;       // > 0: the row tiles of one column tile form a thread-block cluster of this size (cluster fold)
+    int b_pow2; double inv_b, unbias;  // B is a power of two; 1 / B; B / (B - 1)
 };
 
 // Fold the per-row-tile column sums of P and P^2 into the BatchNorm affine, the saved batch statistics
@@ -635,6 +636,7 @@ struct BwdArgs {
     int stage; float *stage_a; int stage_a_ld; float *stage_t; int stage_t_ld; float slope; int has_dropout;
     int use_tma; VkTmap tm_dg_hi, tm_dg_lo;  // dgrad B operand (W^T and its tf32 remainder) through TMA
     int cluster_rt, n_wg_pad;  // cluster fold: dgrad row tiles of one column tile = one cluster; wgrad CTAs padded to whole clusters
+    int b_pow2; double inv_b;  // B is a power of two; 1 / B
 };
 
 // Fold the per-row-tile column sums of dH and dH*Phat: BatchNorm weight/bias gradients and the two
@@ -1113,11 +1115,14 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) fwd_layer_tc_kernel(const _
             const int n = n0 + tid;
             float k0 = 0.0f, k1 = 0.0f;
             if (n < a.N) {
-                // torch.nn.BatchNorm1d in training mode (as bn_forward_finalize)
-                const double mean = sm / a.B;
-                double var = q / a.B - mean * mean;
+                // torch.nn.BatchNorm1d in training mode (as bn_forward_finalize).  fp64 divisions and square roots are
+                // ~100-instruction software sequences at 1/64 rate on this part -- the fold was 2.2 us of a 15 us layer
+                // kernel -- so: x / B as x * (1 / B) when B is a power of two (the same bits), one rsqrt instead of
+                // sqrt + division (<= 1 ulp in double either way, rounded to float), B / (B - 1) from the host.
+                const double mean = a.b_pow2 ? sm * a.inv_b : sm / a.B;
+                double var = (a.b_pow2 ? q * a.inv_b : q / a.B) - mean * mean;
                 if (var < 0.0) var = 0.0;
-                const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+                const float rstd = (float)rsqrt(var + 1e-5);
                 const float fm = (float)mean;
                 k0 = a.gamma[n] * rstd;
                 k1 = a.beta[n] - fm * k0;
@@ -1126,7 +1131,7 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) fwd_layer_tc_kernel(const _
                     a.bn_rstd[n] = rstd;
                     a.bn_a[n] = k0;
                     a.bn_c[n] = k1;
-                    const float unb = a.B > 1 ? (float)(var * ((double)a.B / (double)(a.B - 1))) : (float)var;
+                    const float unb = a.B > 1 ? (float)(var * a.unbias) : (float)var;
                     a.running_mean[n] = 0.9f * a.running_mean[n] + 0.1f * fm;
                     a.running_var[n] = 0.9f * a.running_var[n] + 0.1f * unb;
                     if (n == 0) *a.nbt += 1;
@@ -1335,7 +1340,7 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(const _
             if (n < a.K) {
                 // BatchNorm weight / bias gradients and the folded dL/dY constants (as bn_backward_finalize)
                 const float rs = a.rstd_prev[n], mu = a.mean_prev[n];
-                const float m1 = (float)(u / a.B), m2 = (float)(v / a.B);
+                const float m1 = (float)(a.b_pow2 ? u * a.inv_b : u / a.B), m2 = (float)(a.b_pow2 ? v * a.inv_b : v / a.B);
                 k0 = a.inv_keep * a.gamma_prev[n] * rs;
                 k1 = -k0 * rs * m2;
                 k2 = -k0 * m1 - k1 * mu;
@@ -2029,6 +2034,7 @@ static int launch_forward(const vk_vae *net, int B, int training, int upto /*exc
         a.mask_bits = mask_bits;
         a.latent_out = (L.kind == VK_LAYER_MU) ? latent_out : nullptr;
         a.ctl = net->ctl; a.layer_id = j; a.slope = net->slope;
+        a.b_pow2 = (B & (B - 1)) == 0; a.inv_b = 1.0 / (double)B; a.unbias = B > 1 ? (double)B / (double)(B - 1) : 1.0;
         const bool tcp = use_tc(net, B);
         const bool fused = tcp && fused_staging(net, B);
         if (tcp && (!fused || j == 0))  // fused: layer j - 1 staged this layer's operands from its output tile
@@ -2137,6 +2143,7 @@ static int launch_backward(const vk_vae *net, int B, cudaStream_t s) {
         a.gW = net->grads + L.w_off;
         a.gb = net->grads + L.b_off;
         a.B = B; a.K = L.k_in; a.N = L.n_out;
+        a.b_pow2 = (B & (B - 1)) == 0; a.inv_b = 1.0 / (double)B;
         a.wg_tiles_m = (L.n_out + 63) / 64;
         a.wg_tiles_n = (L.k_in + 1 + 63) / 64;
         a.in_kind = L.in_kind;
