@@ -115,11 +115,13 @@ int vk_eval_candidates_mapped(const float *matrix, const float *lengths, int d, 
  * still tells), and out_pinned (4 * VK_LIST_CAND uint64) = density_lo[k] | density_hi[k] | counts[k] | fp32 bits of
  * d(candidate k, base_row).  `base_row` = the medoid whose neighbour list (radius nl_radius = 0.3) is passed in: the list
  * covers the whole 0.05-neighbourhood of a candidate iff d(candidate, base) <= 0.12 (angles add: acos(0.76) +
- * acos(0.9) = acos(0.4)), which the caller checks.  Mapped completion as vk_eval_candidates_mapped (out_dev:
+ * acos(0.9) = acos(0.4)), which the caller checks.  The id list of candidate k is only published if its density exceeds
+ * min_density = min_density_hi * 4096 + min_density_lo (the current medoid's: nothing else can be moved to; 0, 0 = all).  Mapped completion as vk_eval_candidates_mapped (out_dev:
  * VK_EVAL_SCRATCH_U64 uint64 of device scratch, all zero on entry, left zeroed; n_cand <= VK_LIST_CAND). */
 int vk_eval_candidates_lists(const float *matrix, const float *lengths, int d, const int32_t *nl_rows,
                              const float *nl_dists, int32_t n_nl, float prune_radius, const int32_t *cand_rows_host,
-                             int n_cand, int32_t base_row, uint64_t *out_dev, uint64_t *out_pinned,
+                             int n_cand, int32_t base_row, uint64_t min_density_hi, uint64_t min_density_lo,
+                             uint64_t *out_dev, uint64_t *out_pinned,
                              int32_t *within_dev /* device scratch [VK_EVAL_SUBS * VK_LIST_CAND * within_cap] */, int32_t *within_pinned,
                              int32_t within_cap, int32_t *done_ticket, int32_t *done_flag_pinned, int32_t seq, void *stream);
 

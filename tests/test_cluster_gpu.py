@@ -245,7 +245,7 @@ def test_eval_candidates_lists_matches_oracle(vk):
     flag = torch.zeros(1, dtype=torch.int32).pin_memory()
     arr = (vk.c_int32 * len(cands))(*[int(c) for c in cands])
     vk.check(vk.lib.vk_eval_candidates_lists(dm.data_ptr(), dl.data_ptr(), d, nl_rows.data_ptr(), nl_d.data_ptr(), n_nl,
-                                             0.3, arr, len(cands), base, out_dev.data_ptr(), out_pin.data_ptr(),
+                                             0.3, arr, len(cands), base, 0, 0, out_dev.data_ptr(), out_pin.data_ptr(),
                                              within_dev.data_ptr(), within_pin.data_ptr(), cap, ticket.data_ptr(),
                                              flag.data_ptr(), 7, s))
     assert int(flag[0]) == 7 and int(out_dev.abs().sum()) == 0  # accumulators left zeroed for the next call
@@ -267,6 +267,22 @@ def test_eval_candidates_lists_matches_oracle(vk):
         assert (int(res[C + k]) << 12) + int(res[k]) == (int(od[1]) << 12) + int(od[0])
         got = np.sort(within_pin.numpy()[k * cap:k * cap + cnt])
         assert np.array_equal(got, sel[idx[:cnt]])
+    # with a density threshold the sums and counts are the same and only denser candidates get their ids published
+    dens = [(int(res[C + k]) << 12) + int(res[k]) for k in range(len(cands))]
+    thr = sorted(dens)[len(dens) // 2]
+    first = out_pin.clone()
+    within_pin.fill_(-7)
+    vk.check(vk.lib.vk_eval_candidates_lists(dm.data_ptr(), dl.data_ptr(), d, nl_rows.data_ptr(), nl_d.data_ptr(), n_nl,
+                                             0.3, arr, len(cands), base, thr >> 12, thr & 4095, out_dev.data_ptr(),
+                                             out_pin.data_ptr(), within_dev.data_ptr(), within_pin.data_ptr(), cap,
+                                             ticket.data_ptr(), flag.data_ptr(), 8, s))
+    assert int(flag[0]) == 8 and torch.equal(out_pin, first)
+    for k, c in enumerate(cands):
+        ids = within_pin.numpy()[k * cap:k * cap + int(res[2 * C + k])]
+        if dens[k] > thr:
+            assert (ids >= 0).all() and len(np.unique(ids)) == len(ids)
+        else:
+            assert (ids == -7).all()
 
 
 @pytest.mark.parametrize("n,d,spread,seed", [(30000, 32, 0.3, 41), (30000, 32, 0.08, 42), (6000, 40, 0.2, 43)])

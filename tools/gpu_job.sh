@@ -10,19 +10,18 @@ leg() { # name timeout command...
 }
 : > gpurun_out/job_summary.log
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader | tee -a gpurun_out/job_summary.log
-leg r02o_mma_rate 200 env MMA_ONLY=1 python tools/tc_fixed_cost.py
-leg r02o_pt_cluster 400 python -m pytest tests/test_cluster_gpu.py tests/test_c2_scale_gpu.py -m gpu -q
-leg r02o_pt_vae 300 python -m pytest tests/test_vae_gpu.py tests/test_tc_gpu.py tests/test_trajectory_gpu.py -m gpu -q
-leg r02o_probe_timeline 200 env VAMB_B200_SO=vamb_b200/_vk_timeline.so python tools/probe_timeline.py
-leg r02o_clusterbench 300 python tools/cluster_speed.py
-leg r02o_train_speed 300 env TC_MIN=128 python tools/train_speed.py
-leg r02o_timeline 300 env VK_PDL=0 BATCHES=256 VAMB_B200_SO=vamb_b200/_vk_timeline.so python tools/kernel_timeline.py
-leg r02o_bench 760 bash -c 'python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02o_bench.json'
-for f in gpurun_out/r02o_pt_*.log; do echo "== $f"; grep -E "^FAILED|^ERROR|passed|failed" $f | tail -8; done
-cat gpurun_out/job_summary.log; grep "mma rate" gpurun_out/r02o_mma_rate.log; grep -E "N=|eval of|blocks" gpurun_out/r02o_probe_timeline.log; grep "lazy=" gpurun_out/r02o_clusterbench.log; grep -h "B=" gpurun_out/r02o_train_speed.log | cut -c1-250; grep -E "==|L[0-9]:|layer|backward" gpurun_out/r02o_timeline.log | cut -c1-250
+leg r02p_pt_cluster 400 python -m pytest tests/test_cluster_gpu.py tests/test_c2_scale_gpu.py -m gpu -q
+leg r02p_pt_vae 300 python -m pytest tests/test_vae_gpu.py tests/test_tc_gpu.py tests/test_trajectory_gpu.py -m gpu -q
+leg r02p_probe_timeline 200 env VAMB_B200_SO=vamb_b200/_vk_timeline.so python tools/probe_timeline.py
+leg r02p_clusterbench 300 python tools/cluster_speed.py
+leg r02p_train_speed 300 env TC_MIN=128 python tools/train_speed.py
+leg r02p_timeline 300 env VK_PDL=0 BATCHES=256 VAMB_B200_SO=vamb_b200/_vk_timeline.so python tools/kernel_timeline.py
+leg r02p_bench 760 bash -c 'python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02p_bench.json'
+for f in gpurun_out/r02p_pt_*.log; do echo "== $f"; grep -E "^FAILED|^ERROR|passed|failed" $f | tail -8; done
+cat gpurun_out/job_summary.log; grep -E "N=|eval of|blocks" gpurun_out/r02p_probe_timeline.log; grep "lazy=" gpurun_out/r02p_clusterbench.log; grep -h "B=" gpurun_out/r02p_train_speed.log | cut -c1-250; grep -E "==|L[0-9]:|layer|backward" gpurun_out/r02p_timeline.log | cut -c1-250
 python - <<'PY'
 import json
-d = json.load(open("gpurun_out/r02o_bench.json"))
+d = json.load(open("gpurun_out/r02p_bench.json"))
 print({k: d[k] for k in ("value", "phases_s", "cluster_host_seconds", "clusters", "final_loss")})
 print(d["e2e"]); print(d["roofline"]["achieved"], d["roofline"]["frac"], d["roofline_cluster"]["achieved"], d["roofline_cluster"]["frac"])
 PY

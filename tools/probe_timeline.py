@@ -43,7 +43,7 @@ for n in (1_000_000, 5_000_000):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         _lib.check(_lib.lib.vk_eval_candidates_lists(gen._m.data_ptr(), gen._len.data_ptr(), 32, gen._nl_rows.data_ptr(),
-                                                     gen._nl_d.data_ptr(), n_nl, 0.2, arr, len(cands), base, out_dev.data_ptr(),
+                                                     gen._nl_d.data_ptr(), n_nl, 0.2, arr, len(cands), base, 0, 0, out_dev.data_ptr(),
                                                      out_pin.data_ptr(), wdev.data_ptr(), wpin.data_ptr(), cap, ticket.data_ptr(),
                                                      flag.data_ptr(), seq, gen._stream))
         b.record(); torch.cuda.synchronize()

@@ -66,7 +66,8 @@ _SIGNATURES = {
     "vk_eval_candidates_sync": [_p, _p, c_int, _p, _p, c_int32, c_float, POINTER(c_int32), c_int, _p, _p, _p],
     "vk_eval_candidates_mapped": [_p, _p, c_int, _p, _p, c_int32, c_float, POINTER(c_int32), c_int, _p, _p, _p, _p,
                                   c_int32, _p],
-    "vk_eval_candidates_lists": [_p, _p, c_int, _p, _p, c_int32, c_float, POINTER(c_int32), c_int, c_int32, _p, _p, _p, _p,
+    "vk_eval_candidates_lists": [_p, _p, c_int, _p, _p, c_int32, c_float, POINTER(c_int32), c_int, c_int32, c_uint64, c_uint64,
+                                 _p, _p, _p, _p,
                                  c_int32, _p, _p, c_int32, _p],
     "vk_select_members_sync": [_p, _p, c_int32, c_float, _p, _p, _p, _p, c_int32, _p],
     "vk_mask_clear": [_p, _p, c_int32, _p],

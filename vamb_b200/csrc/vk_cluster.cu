@@ -747,7 +747,8 @@ static_assert(VK_EVAL_SUBS * VK_LIST_CAND * EV_LINE == VK_EVAL_SCRATCH_U64, "eva
 __global__ void __launch_bounds__(EC_THREADS)
 eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__restrict__ lengths, int d,
                              const int32_t *__restrict__ nl_rows, const float *__restrict__ nl_dists, int n_nl,
-                             float prune_radius, const __grid_constant__ CandRowsL cand, int n_cand, int32_t base_row, u64 *out, u64 *out_mapped,
+                             float prune_radius, const __grid_constant__ CandRowsL cand, int n_cand, int32_t base_row, u64 thr_hi, u64 thr_lo, u64 *out,
+                             u64 *out_mapped,
                              int32_t *within_dev, int32_t *within_mapped, int within_cap, int32_t *done_ticket,
                              volatile int32_t *done_flag, int32_t seq) {
     tl_begin(1);
@@ -975,10 +976,26 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
     }
     __syncthreads();
     if (tid < VK_LIST_CAND) {
+        u64 lo = 0ull, hi = 0ull, cnt = 0ull;
+#pragma unroll 1
+        for (int sb = 0; sb < VK_EVAL_SUBS; ++sb) {
+            lo += __ldcg(ev_slot(out, sb, tid, 0));
+            hi += __ldcg(ev_slot(out, sb, tid, 1));
+            cnt += __ldcg(ev_slot(out, sb, tid, 2));
+        }
+        out_mapped[tid] = lo;
+        out_mapped[VK_LIST_CAND + tid] = hi;
+        out_mapped[2 * VK_LIST_CAND + tid] = cnt;
+        out_mapped[3 * VK_LIST_CAND + tid] = __ldcg(ev_slot(out, 0, tid, 3));
+        // The ids are only ever needed for a candidate the medoid can MOVE to: one whose density exceeds the current
+        // medoid's (thr = that density, which only grows during a wander).  density = hi * 4096 + lo, compared in the
+        // normalised form (hi + (lo >> 12), lo & 4095).  Everything else skips the copy to host memory.
+        const u64 nh = hi + (lo >> 12), nl = lo & 4095ull;
+        const bool wanted = nh > thr_hi || (nh == thr_hi && nl > thr_lo);
         int tot = 0;
 #pragma unroll 1
         for (int sb = 0; sb < VK_EVAL_SUBS; ++sb) tot += s_sub_len[sb][tid];
-        s_len_k[tid] = tot > within_cap ? within_cap : tot;
+        s_len_k[tid] = !wanted ? 0 : (tot > within_cap ? within_cap : tot);
     }
     __syncthreads();
     if (tid == 0) {
@@ -1005,20 +1022,6 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
         within_mapped[(size_t)lo * within_cap + (e - s_off[lo])] = __ldcg(within_dev + ((size_t)sb * VK_LIST_CAND + lo) * within_cap + r);
     }
     __syncthreads();  // every count has been read before the accumulators are zeroed below
-    if (tid < VK_LIST_CAND) {
-        u64 lo = 0ull, hi = 0ull, cnt = 0ull;
-#pragma unroll 1
-        for (int sb = 0; sb < VK_EVAL_SUBS; ++sb) {
-            lo += __ldcg(ev_slot(out, sb, tid, 0));
-            hi += __ldcg(ev_slot(out, sb, tid, 1));
-            cnt += __ldcg(ev_slot(out, sb, tid, 2));
-        }
-        out_mapped[tid] = lo;
-        out_mapped[VK_LIST_CAND + tid] = hi;
-        out_mapped[2 * VK_LIST_CAND + tid] = cnt;
-        out_mapped[3 * VK_LIST_CAND + tid] = __ldcg(ev_slot(out, 0, tid, 3));
-    }
-    __syncthreads();
     for (int i = tid; i < VK_EVAL_SUBS * VK_LIST_CAND * 4; i += EC_THREADS) *ev_slot(out, i >> 8, (i >> 2) & (VK_LIST_CAND - 1), i & 3) = 0ull;
     static_assert(VK_LIST_CAND == 64, "index split above");
     tl_mark_any(6);
@@ -1028,7 +1031,8 @@ eval_candidates_lists_kernel(const float *__restrict__ matrix, const float *__re
 
 extern "C" int vk_eval_candidates_lists(const float *matrix, const float *lengths, int d, const int32_t *nl_rows,
                                         const float *nl_dists, int32_t n_nl, float prune_radius,
-                                        const int32_t *cand_rows_host, int n_cand, int32_t base_row, uint64_t *out_dev,
+                                        const int32_t *cand_rows_host, int n_cand, int32_t base_row,
+                                        uint64_t min_density_hi, uint64_t min_density_lo, uint64_t *out_dev,
                                         uint64_t *out_pinned, int32_t *within_dev, int32_t *within_pinned,
                                         int32_t within_cap, int32_t *done_ticket, int32_t *done_flag_pinned, int32_t seq,
                                         void *stream) {
@@ -1053,7 +1057,8 @@ extern "C" int vk_eval_candidates_lists(const float *matrix, const float *length
     const int cap = vk_num_sms() * 4;
     if (grid > cap) grid = cap;
     eval_candidates_lists_kernel<<<grid, EC_THREADS, smem, s>>>(matrix, lengths, d, nl_rows, nl_dists, n_nl, prune_radius,
-                                                                cand, n_cand, base_row, (u64 *)out_dev, (u64 *)out_pinned,
+                                                                cand, n_cand, base_row, (u64)min_density_hi, (u64)min_density_lo, (u64 *)out_dev,
+                                                                (u64 *)out_pinned,
                                                                 within_dev, within_pinned, within_cap, done_ticket,
                                                                 done_flag_pinned, seq);
     VK_LAUNCH_CHECK();

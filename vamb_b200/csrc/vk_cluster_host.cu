@@ -293,14 +293,15 @@ struct EvalLists {
     std::vector<float> dbase;
 };
 
-int do_eval_lists(State &st, const Probe &base, float prune, const std::vector<int32_t> &rows, EvalLists &out) {
+int do_eval_lists(State &st, const Probe &base, float prune, const std::vector<int32_t> &rows, unsigned __int128 min_density,
+                  EvalLists &out) {
     Stopwatch sw(st.t_eval);
     const vk_cluster_config &c = st.c;
     const int n = (int)rows.size();
     ++st.n_evals;
     st.sum_nnl += base.n_nl;
     if (vk_eval_candidates_lists(st.M(), st.LEN(), c.d, c.nl_rows, c.nl_dists, base.n_nl, prune, rows.data(), n, base.medoid,
-                                 st.cand2_dev, st.cand2_pin, st.within_dev, st.within_pin, WITHIN_CAP, st.tickets_dev + 1,
+                                 (uint64_t)(min_density >> 12), (uint64_t)(min_density & 4095), st.cand2_dev, st.cand2_pin, st.within_dev, st.within_pin, WITHIN_CAP, st.tickets_dev + 1,
                                  st.flags_pin + 1, ++st.seq, c.stream))
         return 1;
     out.dens.resize((size_t)n);
@@ -422,13 +423,15 @@ int wander(State &st, int32_t seed, Probe &probe, int32_t &seed_rank) {
                 }
                 const bool at_base = cur == probe.medoid;
                 // candidates of the base itself lie within 0.05 of it: rows near them are within 0.19 (prune radius)
-                if (do_eval_lists(st, probe, at_base ? st.c.prune_radius : st.c.nl_radius, batch, ev)) return 1;
+                // id lists come back only for candidates denser than the current medoid: `local` only grows during a
+                // wander, so no other candidate can ever be moved to
+                if (do_eval_lists(st, probe, at_base ? st.c.prune_radius : st.c.nl_radius, batch, local, ev)) return 1;
                 for (size_t i = 0; i < batch.size(); ++i) {
                     const bool ok = at_base || list_is_everything || ev.dbase[i] <= R_EVAL;
                     if (!ok) continue;  // the list may not cover this candidate's neighbourhood: not usable
                     Cached &cc = cache_new(batch[i]);
                     cc.dens = ev.dens[i];
-                    cc.lists_ok = ev.cnt[i] <= WITHIN_CAP;
+                    cc.lists_ok = ev.cnt[i] <= WITHIN_CAP && ev.dens[i] > local;  // else: never a move target (or truncated)
                     cc.sorted = false;
                     if (cc.lists_ok) {
                         const int32_t *ids = st.within_pin + i * WITHIN_CAP;

@@ -284,6 +284,19 @@ constexpr int WS_FLUSH_KT = 4;
 constexpr int WS_DRAIN_LAG = 2;  // a group is drained once the producers are this many k-tiles into the next one
 constexpr uint32_t WS_ACC1_COL = 384u;
 
+// Stacked B: the tf32 remainder tile of B lies directly behind its hi tile in every ring stage, with the same layout, so
+// ONE MMA with N' = 2 bn rows of B computes A_hi x B_hi (accumulator columns [0, bn)) and A_hi x B_lo (columns
+// [bn, 2 bn)); a second one adds A_lo x B_hi into [0, bn); the epilogue adds the two column ranges.  A k-step is then 2
+// tcgen05.mma instead of 3 -- and an MMA with M = 128 costs the issuing thread ~47 cycles for any N <= 64 (64 cycles at
+// N = 128; tools/tc_fixed_cost.py, also with alternating accumulators: an issue cost, not a dependency), which is what
+// bounds the main loop of the narrow tiles small batches use.  Needs 2 bn <= 128 accumulator columns, a single
+// accumulator (no FLUSH) and, with TMA boxes of slot_rows rows, a full tile (bn == slot_rows).
+constexpr bool WS_STACK_B = true;
+template <bool TMA_B, bool FLUSH>
+__device__ __forceinline__ bool ws_stacked(int bn, int slot_rows) {
+    return WS_STACK_B && !FLUSH && 2 * bn <= 128 && (!TMA_B || bn == slot_rows);
+}
+
 // D[128 x bn] = sum over k-tiles [kt0, kt0 + nk) of A[m0.., k] * B[n0.., k]^T.  A: lane-major (m0 a multiple
 // of 128), B: plain K-major; both fp32, zero padded to whole tiles (ld = floats per row, multiple of 32).
 // Returns true for the 256 epilogue threads (accumulator complete), false for the MMA warp (which is done).
@@ -383,6 +396,8 @@ __device__ __forceinline__ bool ws_mainloop(const float *A, int lda, int m0, con
     if (warp == 8) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(TC_BM, bn, 0, 0);
+            const bool stk = ws_stacked<TMA_B, FLUSH>(bn, slot_rows);
+            const uint32_t idesc2 = make_idesc_tf32(TC_BM, 2 * bn, 0, 0);
             const uint64_t desc0 = TMA_B ? make_smem_desc_sw128(smem_base) : make_smem_desc(smem_base, 128, 1024);
             const uint32_t kstep = TMA_B ? 2u : 16u;  // start-address units (16 bytes) per K = 8 step
             int slot = 0;
@@ -400,11 +415,19 @@ __device__ __forceinline__ bool ws_mainloop(const float *A, int lda, int m0, con
                 // descriptors differ only in the 14-bit start-address field: add (byte offset >> 4)
                 const uint64_t bh = desc0 + (uint64_t)((uint32_t)(slot * sbytes) >> 4);
                 const uint64_t bl = bh + (uint64_t)((uint32_t)bbytes >> 4);
+                if (stk) {
 #pragma unroll
-                for (int j = 0; j < KT / 8; ++j) {
-                    umma_tf32_ts(tmem_acc, al + 8u * j, bh + kstep * j, idesc, (grp_first && j == 0) ? 0u : 1u);  // small terms first
-                    umma_tf32_ts(tmem_acc, ah + 8u * j, bl + kstep * j, idesc, 1u);
-                    umma_tf32_ts(tmem_acc, ah + 8u * j, bh + kstep * j, idesc, 1u);
+                    for (int j = 0; j < KT / 8; ++j) {
+                        umma_tf32_ts(tmem_acc, ah + 8u * j, bh + kstep * j, idesc2, (grp_first && j == 0) ? 0u : 1u);  // hi x [hi; lo]
+                        umma_tf32_ts(tmem_acc, al + 8u * j, bh + kstep * j, idesc, 1u);                                // lo x hi
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < KT / 8; ++j) {
+                        umma_tf32_ts(tmem_acc, al + 8u * j, bh + kstep * j, idesc, (grp_first && j == 0) ? 0u : 1u);  // small terms first
+                        umma_tf32_ts(tmem_acc, ah + 8u * j, bl + kstep * j, idesc, 1u);
+                        umma_tf32_ts(tmem_acc, ah + 8u * j, bh + kstep * j, idesc, 1u);
+                    }
                 }
                 umma_commit(&sh->empty[slot]);
                 if (FLUSH && grp_last && kt != nk - 1) umma_commit(&sh->acc_full[grp & 1]);
@@ -505,7 +528,7 @@ __device__ __forceinline__ bool ws_mainloop(const float *A, int lda, int m0, con
 // racc != nullptr (FLUSH): the last group sits in accumulator ((nk - 1) / WS_FLUSH_KT) & 1 and the earlier groups in
 // the register sums of ws_mainloop.
 __device__ __forceinline__ void ws_acc_to_tile(const WsShared *sh, int bn, int nk, float *tile, int ts,
-                                               const float (*racc)[16] = nullptr) {
+                                               const float (*racc)[16] = nullptr, bool stacked = false) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t acc_col = (racc && nk > 0 && (((nk - 1) / WS_FLUSH_KT) & 1)) ? WS_ACC1_COL : 0u;
@@ -521,6 +544,12 @@ __device__ __forceinline__ void ws_acc_to_tile(const WsShared *sh, int bn, int n
         if (racc) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] += racc[i][j];
+        }
+        if (stacked && nk > 0) {  // + A_hi x B_lo, accumulated in the columns behind the tile's own (ws_stacked)
+            float w[16];
+            tmem_ld16(sh->tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(bn + c), w);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += w[j];
         }
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4)

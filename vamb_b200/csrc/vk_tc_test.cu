@@ -30,7 +30,7 @@ ws_gemm_test_kernel(const float *A, int lda, const float *B, int ldb, float *C, 
     constexpr int TS = 132;
     float *tile = reinterpret_cast<float *>(smem);
     if (tm.flush) tc::ws_acc_to_tile(&sh, bn, nk, tile, TS, racc);
-    else tc::ws_acc_to_tile(&sh, bn, nk, tile, TS);
+    else tc::ws_acc_to_tile(&sh, bn, nk, tile, TS, nullptr, tm.use_tma ? tc::ws_stacked<true, false>(bn, tile_n) : tc::ws_stacked<false, false>(bn, 0));
     tc::ws_tile_end(&sh);
     for (int q = threadIdx.x; q < 128 * bn; q += tc::WS_EPI_THREADS) {
         const int r = q / bn, c = q - r * bn;

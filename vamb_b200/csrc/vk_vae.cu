@@ -959,7 +959,7 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) fwd_layer_tc_kernel(const _
         return;
     tl_mark(2);
     float *tile = reinterpret_cast<float *>(smem);  // [128][TS]; the operand stages are dead now
-    tc::ws_acc_to_tile(&sh, bn, nk, tile, TS, FLUSH ? racc : nullptr);
+    tc::ws_acc_to_tile(&sh, bn, nk, tile, TS, FLUSH ? racc : nullptr, tc::ws_stacked<TMA, FLUSH>(bn, a.tile_n));
     tl_mark(3);
     tc::ws_tile_end(&sh);
     tl_mark(44);
@@ -1199,7 +1199,7 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(const _
                                            nullptr, nullptr, FLUSH ? racc : nullptr))
             return;
         tl_mark(2);
-        tc::ws_acc_to_tile(&sh, bn, nk, tile, TS, FLUSH ? racc : nullptr);
+        tc::ws_acc_to_tile(&sh, bn, nk, tile, TS, FLUSH ? racc : nullptr, tc::ws_stacked<false, FLUSH>(bn, 0));
         tl_mark(3);
         tc::ws_tile_end(&sh);
         float *gW = a.gW + (int64_t)split * x.slab, *gb = a.gb + (int64_t)split * x.slab;
@@ -1268,7 +1268,7 @@ __global__ void __launch_bounds__(tc::WS_THREADS, 1) bwd_layer_tc_kernel(const _
             *reinterpret_cast<float4 *>(ptile + r * TS + c) = pv;
         }
     }
-    tc::ws_acc_to_tile(&sh, bn, nk, tile, TS);
+    tc::ws_acc_to_tile(&sh, bn, nk, tile, TS, nullptr, tc::ws_stacked<TMA, false>(bn, a.tile_n));
     tc::ws_tile_end(&sh);
     TLD(3);
     const bool vec = ((a.K & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.d_in) & 15) == 0);
