@@ -6,10 +6,8 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/r02_launches.csv \
     python tools/prof_steps.py > gpurun_out/r02_ncu_launches.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:probe_kernel -s 2 -c 2 -f -o gpurun_out/r02_prof_probe \
-    python tools/prof_steps.py > gpurun_out/r02_ncu_probe.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:eval_candidates -s 2 -c 2 -f -o gpurun_out/r02_prof_eval \
-    python tools/prof_steps.py > gpurun_out/r02_ncu_eval.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'probe_kernel|eval_candidates' -s 4 -c 4 -f -o gpurun_out/r02_prof_cluster \
+    python tools/prof_steps.py > gpurun_out/r02_ncu_cluster.log 2>&1
 # training kernels: one whole step at B = 4096 (6 forward + loss + 6 backward + optimiser) ...
 timeout 400 env STEPS=1 CLUSTERS=0 ncu --set full --clock-control none \
     -k regex:'layer_tc_kernel|loss_kernel|dadapt_kernel' -c 14 -f -o gpurun_out/r02_prof_vae4096 \
