@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VK_ABI_VERSION 1
+#define VK_ABI_VERSION 2
 #define VK_NBINS 60          /* ceil(0.3 / 0.005), vamb/cluster.py:231 */
 #define VK_MAX_CAND 32       /* candidates evaluated per vk_eval_candidates launch */
 #define VK_LIST_CAND 64      /* candidates evaluated per vk_eval_candidates_lists launch */

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # VAMB_B200_SO selects another build of the same library (tools/kernel_timeline.py uses the stamped one)
 _SO = os.environ.get("VAMB_B200_SO") or os.path.join(_HERE, "_vk.so")
 
-VK_ABI_VERSION = 1
+VK_ABI_VERSION = 2
 VK_NBINS = 60
 VK_MAX_CAND = 32
 VK_LIST_CAND = 64
