@@ -72,6 +72,13 @@ def main():
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json"), "w") as fh:
         json.dump(traffic, fh, indent=1)
+    # every captured launch, in capture order
+    lines += ["", "| report | kernel | grid | duration us | DRAM read / write MB | tensor pipe % | dram % | inst executed |",
+              "|---|---|---|---|---|---|---|---|"]
+    for d in table:
+        lines.append(f"| {d['report'].replace('.ncu-rep', '')} | `{d['kernel']}` | {int(d.get('grid', 0))} | {d.get('dur', 0.0):.1f} | "
+                     f"{d.get('rd', 0.0) / 1e6:.2f} / {d.get('wr', 0.0) / 1e6:.2f} | "
+                     f"{max(d.get('tensor_pct', 0.0), d.get('tensor_pct2', 0.0)):.1f} | {d.get('dram_pct', 0.0):.1f} | {int(d.get('inst', 0))} |")
     print("\n".join(lines))
     with open(os.path.join(ROOT, "profiles", "r02_ncu_table.md"), "w") as fh:
         fh.write("\n".join(lines) + "\n")
