@@ -21,6 +21,20 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib.vk_abi_version() == _lib.VK_ABI_VERSION
 
 
+def test_binding_constants_match_the_header():
+    """The Python binding restates the header's sizes (scratch buffers are allocated from them)."""
+    from vamb_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "vamb_b200.h")).read()
+    macros = dict(re.findall(r"#define\s+(VK_[A-Z0-9_]+)\s+([0-9]+)\b", header))
+    for name in ("VK_ABI_VERSION", "VK_LIST_CAND", "VK_EVAL_SUBS", "VK_NBINS", "VK_PROBE_INLINE", "VK_MAX_CAND"):
+        if hasattr(_lib, name) and name in macros:
+            assert int(macros[name]) == getattr(_lib, name), name
+    assert "VK_LIST_CAND" in macros and "VK_EVAL_SUBS" in macros and "VK_ABI_VERSION" in macros
+    assert _lib.VK_EVAL_SCRATCH_U64 == _lib.VK_EVAL_SUBS * _lib.VK_LIST_CAND * 16
+    assert re.search(r"#define\s+VK_EVAL_SCRATCH_U64\s+\(VK_EVAL_SUBS \* VK_LIST_CAND \* 16\)", header)
+
+
 def test_probe_header_layout_matches_binding():
     from vamb_b200 import _lib
 
